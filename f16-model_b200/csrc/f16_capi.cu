@@ -1,0 +1,437 @@
+// f16_capi.cu -- the C ABI (include/f16_b200.h): argument checking, per-device table images,
+// launch geometry, and the host-buffer (end-to-end) step pipeline.  No torch types, no
+// exceptions across the boundary.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "../../include/f16_b200.h"
+#include "f16_launch.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) return fail(F16_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_));     \
+    } while (0)
+
+constexpr int kMaxDev = 64;
+
+struct HostPipe {   // scratch of f16_env_step_host
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t done_ev[3] = {nullptr, nullptr, nullptr};
+    void *actions = nullptr, *obs = nullptr, *reward = nullptr;
+    uint8_t *done = nullptr;
+    size_t cap_actions = 0, cap_obs = 0, cap_reward = 0, cap_done = 0;
+};
+
+struct DeviceCtx {
+    bool ready = false;
+    int n_sm = 0;
+    f16::Tables<float> *t32 = nullptr;
+    f16::Tables<double> *t64 = nullptr;
+    int occ[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};   // [dtype][fast][autoreset]
+    HostPipe pipe;
+};
+
+DeviceCtx g_ctx[kMaxDev];
+std::mutex g_mu;
+
+int ensure_device(int device, DeviceCtx **out)
+{
+    if (device < 0 || device >= kMaxDev) return fail(F16_EINVAL, "device %d out of range", device);
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceCtx &c = g_ctx[device];
+    if (!c.ready) {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+            cudaGetLastError();
+            return fail(F16_ENODEV, "no CUDA device visible: the F-16 simulator has no CPU fallback");
+        }
+        if (device >= count) return fail(F16_ENODEV, "device %d not present (%d visible)", device, count);
+        int prev = 0;
+        CUDA_TRY(cudaGetDevice(&prev));
+        CUDA_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            return fail(F16_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+                        prop.minor);
+        c.n_sm = prop.multiProcessorCount;
+        auto *h32 = new (std::nothrow) f16::Tables<float>;
+        auto *h64 = new (std::nothrow) f16::Tables<double>;
+        if (!h32 || !h64) return fail(F16_EINVAL, "out of host memory");
+        f16::build_tables(*h32);
+        f16::build_tables(*h64);
+        CUDA_TRY(cudaMalloc(&c.t32, sizeof *h32));
+        CUDA_TRY(cudaMalloc(&c.t64, sizeof *h64));
+        CUDA_TRY(cudaMemcpy(c.t32, h32, sizeof *h32, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(c.t64, h64, sizeof *h64, cudaMemcpyHostToDevice));
+        delete h32;
+        delete h64;
+        for (int f = 0; f < 2; ++f)
+            for (int a = 0; a < 2; ++a) {
+                c.occ[F16_F32][f][a] = f16::env_step_occupancy_f32(f != 0, a != 0);
+                c.occ[F16_F64][f][a] = f16::env_step_occupancy_f64(a != 0);
+            }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaSetDevice(prev));
+        c.ready = true;
+    }
+    *out = &c;
+    return F16_OK;
+}
+
+int current_device(int *dev)
+{
+    cudaError_t e = cudaGetDevice(dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(F16_ENODEV, "cudaGetDevice: %s (the F-16 simulator has no CPU fallback)", cudaGetErrorString(e));
+    }
+    return F16_OK;
+}
+
+f16::LaunchGeom geom(const DeviceCtx &c, int dtype, bool fast, bool autoreset)
+{
+    int occ = c.occ[dtype][fast ? 1 : 0][autoreset ? 1 : 0];
+    if (occ < 1) occ = 1;
+    return {c.n_sm, occ};
+}
+
+int check_cfg(const f16_config *cfg)
+{
+    if (!cfg) return fail(F16_EINVAL, "cfg is NULL");
+    if (cfg->dtype != F16_F32 && cfg->dtype != F16_F64) return fail(F16_EINVAL, "dtype must be F16_F32 or F16_F64");
+    if (cfg->n_envs <= 0) return fail(F16_EINVAL, "n_envs must be positive");
+    if (!(cfg->dt > 0)) return fail(F16_EINVAL, "dt must be positive");
+    if (cfg->ref_len <= 0 || cfg->n_ref <= 0) return fail(F16_EINVAL, "reference bank must hold >= 1 signal of >= 1 sample");
+    if (cfg->init_mode < 0 || cfg->init_mode > 2) return fail(F16_EINVAL, "bad init_mode");
+    if (cfg->obs_layout != F16_OBS_AOS && cfg->obs_layout != F16_OBS_SOA) return fail(F16_EINVAL, "bad obs_layout");
+    return F16_OK;
+}
+
+int check_env(const f16_config *cfg, const f16_env_buffers *env)
+{
+    if (!env) return fail(F16_EINVAL, "env buffers are NULL");
+    if (!env->state || !env->ep_len || !env->ref_idx || !env->done || !env->episode_no || !env->ref_bank)
+        return fail(F16_EINVAL, "state, ep_len, ref_idx, done, episode_no and ref_bank are required");
+    if (cfg->init_mode == F16_INIT_PER_ENV && !env->init_state)
+        return fail(F16_EINVAL, "init_mode F16_INIT_PER_ENV needs env->init_state");
+    return F16_OK;
+}
+
+template <typename R>
+f16::EnvArgs<R> make_env_args(const f16_config *cfg, const f16_env_buffers *env, const f16::Tables<R> *tables)
+{
+    f16::EnvArgs<R> A;
+    A.tables = tables;
+    A.n = cfg->n_envs;
+    A.dt = static_cast<R>(cfg->dt);
+    A.horizon = cfg->horizon;
+    A.ref_len = cfg->ref_len;
+    A.n_ref = cfg->n_ref;
+    A.autoreset = cfg->autoreset;
+    A.init_mode = cfg->init_mode;
+    A.obs_layout = cfg->obs_layout;
+    A.noise = cfg->noise;
+    A.seed = cfg->seed;
+    A.id_base = cfg->env_id_base;
+    for (int j = 0; j < 9; ++j) A.x0[j] = static_cast<R>(cfg->x0[j]);
+    A.state = static_cast<R *>(env->state);
+    A.ep_len = env->ep_len;
+    A.total_return = static_cast<R *>(env->total_return);
+    A.ref_idx = env->ref_idx;
+    A.done = env->done;
+    A.episode_no = env->episode_no;
+    A.ref_bank = static_cast<const R *>(env->ref_bank);
+    A.init_state = static_cast<const R *>(env->init_state);
+    return A;
+}
+
+template <typename R>
+f16::StepArgs<R> make_step_args(const f16_config *cfg, const f16_step_io *io, int K)
+{
+    f16::StepArgs<R> S;
+    S.actions = static_cast<const R *>(io->actions);
+    S.obs = static_cast<R *>(io->obs);
+    S.reward = static_cast<R *>(io->reward);
+    S.done = io->done;
+    S.final_obs = static_cast<R *>(io->final_obs);
+    S.final_ep_len = io->final_ep_len;
+    S.final_return = static_cast<R *>(io->final_return);
+    S.obs_every_step = io->obs_every_step;
+    S.K = K;
+    S.i_begin = 0;
+    S.i_end = cfg->n_envs;
+    return S;
+}
+
+int check_step(const f16_step_io *io, int K)
+{
+    if (!io) return fail(F16_EINVAL, "io is NULL");
+    if (K <= 0) return fail(F16_EINVAL, "K must be >= 1");
+    if (!io->actions || !io->reward || !io->done) return fail(F16_EINVAL, "actions, reward and done are required");
+    if (io->obs_every_step && !io->obs) return fail(F16_EINVAL, "obs_every_step needs obs");
+    return F16_OK;
+}
+
+int step_range(DeviceCtx *ctx, const f16_config *cfg, const f16_env_buffers *env, const f16_step_io *io, int K, int64_t i0, int64_t i1,
+               cudaStream_t st)
+{
+    const bool fast = cfg->dtype == F16_F32 && cfg->fast_math != 0;
+    const f16::LaunchGeom g = geom(*ctx, cfg->dtype, fast, cfg->autoreset != 0);
+    if (cfg->dtype == F16_F32) {
+        auto A = make_env_args<float>(cfg, env, ctx->t32);
+        auto S = make_step_args<float>(cfg, io, K);
+        S.i_begin = i0;
+        S.i_end = i1;
+        CUDA_TRY(f16::launch_env_step(A, S, fast, g, st));
+    } else {
+        auto A = make_env_args<double>(cfg, env, ctx->t64);
+        auto S = make_step_args<double>(cfg, io, K);
+        S.i_begin = i0;
+        S.i_end = i1;
+        CUDA_TRY(f16::launch_env_step(A, S, false, g, st));
+    }
+    return F16_OK;
+}
+
+int grow(void **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return F16_OK;
+    if (*p) CUDA_TRY(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    CUDA_TRY(cudaMalloc(p, need));
+    *cap = need;
+    return F16_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int f16_abi_version(void) { return F16_ABI_VERSION; }
+
+const char *f16_last_error(void) { return g_err; }
+
+int f16_init(int device)
+{
+    DeviceCtx *c;
+    return ensure_device(device, &c);
+}
+
+int f16_launch_geometry(int device, int dtype, int *n_sm, int *cta_threads, int *ctas_per_sm)
+{
+    DeviceCtx *c;
+    int rc = ensure_device(device, &c);
+    if (rc) return rc;
+    if (dtype != F16_F32 && dtype != F16_F64) return fail(F16_EINVAL, "bad dtype");
+    if (n_sm) *n_sm = c->n_sm;
+    if (cta_threads) *cta_threads = 256;
+    if (ctas_per_sm) *ctas_per_sm = c->occ[dtype][dtype == F16_F32 ? 1 : 0][0];
+    return F16_OK;
+}
+
+int f16_env_reset(const f16_config *cfg, const f16_env_buffers *env, const uint8_t *mask, int keep_ref, void *obs, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if ((rc = check_env(cfg, env))) return rc;
+    int dev;
+    if ((rc = current_device(&dev))) return rc;
+    DeviceCtx *ctx;
+    if ((rc = ensure_device(dev, &ctx))) return rc;
+    const f16::LaunchGeom g{ctx->n_sm, 8};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cfg->dtype == F16_F32) {
+        auto A = make_env_args<float>(cfg, env, ctx->t32);
+        CUDA_TRY(f16::launch_env_reset(A, mask, keep_ref, static_cast<float *>(obs), g, st));
+    } else {
+        auto A = make_env_args<double>(cfg, env, ctx->t64);
+        CUDA_TRY(f16::launch_env_reset(A, mask, keep_ref, static_cast<double *>(obs), g, st));
+    }
+    return F16_OK;
+}
+
+int f16_env_step(const f16_config *cfg, const f16_env_buffers *env, const f16_step_io *io, int K, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if ((rc = check_env(cfg, env))) return rc;
+    if ((rc = check_step(io, K))) return rc;
+    int dev;
+    if ((rc = current_device(&dev))) return rc;
+    DeviceCtx *ctx;
+    if ((rc = ensure_device(dev, &ctx))) return rc;
+    return step_range(ctx, cfg, env, io, K, 0, cfg->n_envs, static_cast<cudaStream_t>(stream));
+}
+
+int f16_env_step_host(const f16_config *cfg, const f16_env_buffers *env, const void *actions_host, void *obs_host, void *reward_host,
+                      uint8_t *done_host, int K, int device)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if ((rc = check_env(cfg, env))) return rc;
+    if (K <= 0) return fail(F16_EINVAL, "K must be >= 1");
+    if (!actions_host || !reward_host || !done_host) return fail(F16_EINVAL, "actions_host, reward_host and done_host are required");
+    DeviceCtx *ctx;
+    if ((rc = ensure_device(device, &ctx))) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    HostPipe &P = ctx->pipe;
+    const int64_t n = cfg->n_envs;
+    const size_t es = cfg->dtype == F16_F32 ? 4 : 8;
+    if (!P.streams[0])
+        for (int s = 0; s < 3; ++s) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&P.streams[s], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&P.done_ev[s], cudaEventDisableTiming));
+        }
+    if ((rc = grow(&P.actions, &P.cap_actions, es * K * n))) return rc;
+    if ((rc = grow(&P.obs, &P.cap_obs, es * 5 * n))) return rc;
+    if ((rc = grow(&P.reward, &P.cap_reward, es * K * n))) return rc;
+    if ((rc = grow(reinterpret_cast<void **>(&P.done), &P.cap_done, (size_t)K * n))) return rc;
+
+    f16_step_io io;
+    std::memset(&io, 0, sizeof io);
+    io.actions = P.actions;
+    io.obs = obs_host ? P.obs : nullptr;
+    io.reward = P.reward;
+    io.done = P.done;
+
+    // chunk the env range so that H2D(c+1), kernel(c) and D2H(c-1) overlap on three streams
+    int64_t chunks = n >= (1 << 18) ? 8 : (n >= (1 << 15) ? 4 : 1);
+    int64_t per = ((n + chunks - 1) / chunks + 255) / 256 * 256;
+    for (int64_t c = 0, i0 = 0; i0 < n; ++c, i0 += per) {
+        const int64_t i1 = i0 + per < n ? i0 + per : n;
+        const int64_t cnt = i1 - i0;
+        cudaStream_t st = P.streams[c % 3];
+        for (int k = 0; k < K; ++k)
+            CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(P.actions) + es * ((size_t)k * n + i0),
+                                     static_cast<const char *>(actions_host) + es * ((size_t)k * n + i0), es * cnt,
+                                     cudaMemcpyHostToDevice, st));
+        if ((rc = step_range(ctx, cfg, env, &io, K, i0, i1, st))) return rc;
+        for (int k = 0; k < K; ++k) {
+            CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(reward_host) + es * ((size_t)k * n + i0),
+                                     static_cast<const char *>(P.reward) + es * ((size_t)k * n + i0), es * cnt,
+                                     cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(done_host + (size_t)k * n + i0, P.done + (size_t)k * n + i0, (size_t)cnt, cudaMemcpyDeviceToHost,
+                                     st));
+        }
+        if (obs_host) {
+            if (cfg->obs_layout == F16_OBS_AOS) {
+                CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(obs_host) + es * 5 * (size_t)i0,
+                                         static_cast<const char *>(P.obs) + es * 5 * (size_t)i0, es * 5 * cnt, cudaMemcpyDeviceToHost,
+                                         st));
+            } else {
+                for (int j = 0; j < 5; ++j)
+                    CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(obs_host) + es * ((size_t)j * n + i0),
+                                             static_cast<const char *>(P.obs) + es * ((size_t)j * n + i0), es * cnt,
+                                             cudaMemcpyDeviceToHost, st));
+            }
+        }
+    }
+    for (int s = 0; s < 3; ++s) CUDA_TRY(cudaStreamSynchronize(P.streams[s]));
+    return F16_OK;
+}
+
+#define DISPATCH_SIMPLE(call32, call64)                 \
+    do {                                                \
+        if (dtype == F16_F32) CUDA_TRY(call32);         \
+        else if (dtype == F16_F64) CUDA_TRY(call64);    \
+        else return fail(F16_EINVAL, "bad dtype");      \
+    } while (0)
+
+static int prep(int64_t n, DeviceCtx **ctx, f16::LaunchGeom *g)
+{
+    if (n <= 0) return fail(F16_EINVAL, "n must be positive");
+    int dev, rc;
+    if ((rc = current_device(&dev))) return rc;
+    if ((rc = ensure_device(dev, ctx))) return rc;
+    *g = f16::LaunchGeom{(*ctx)->n_sm, 4};
+    return F16_OK;
+}
+
+int f16_rhs(int dtype, int64_t n, const void *x, const void *u, void *dx, void *stream)
+{
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(n, &c, &g);
+    if (rc) return rc;
+    if (!x || !u || !dx) return fail(F16_EINVAL, "NULL pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DISPATCH_SIMPLE(f16::launch_rhs(c->t32, n, (const float *)x, (const float *)u, (float *)dx, g, st),
+                    f16::launch_rhs(c->t64, n, (const double *)x, (const double *)u, (double *)dx, g, st));
+    return F16_OK;
+}
+
+int f16_model_step(int dtype, int64_t n, void *x, const void *u, double dt, int K, void *stream)
+{
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(n, &c, &g);
+    if (rc) return rc;
+    if (!x || !u || K <= 0) return fail(F16_EINVAL, "NULL pointer or K <= 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DISPATCH_SIMPLE(f16::launch_model_step(c->t32, n, (float *)x, (const float *)u, (float)dt, K, g, st),
+                    f16::launch_model_step(c->t64, n, (double *)x, (const double *)u, dt, K, g, st));
+    return F16_OK;
+}
+
+int f16_coeffs(int dtype, int64_t n, const void *alpha, const void *fi, const void *wz, const void *V, void *out, void *stream)
+{
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(n, &c, &g);
+    if (rc) return rc;
+    if (!alpha || !fi || !wz || !V || !out) return fail(F16_EINVAL, "NULL pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DISPATCH_SIMPLE(
+        f16::launch_coeffs(c->t32, n, (const float *)alpha, (const float *)fi, (const float *)wz, (const float *)V, (float *)out, g, st),
+        f16::launch_coeffs(c->t64, n, (const double *)alpha, (const double *)fi, (const double *)wz, (const double *)V, (double *)out, g, st));
+    return F16_OK;
+}
+
+int f16_thrust(int dtype, int64_t n, const void *H, const void *M, const void *Pa, void *out, void *stream)
+{
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(n, &c, &g);
+    if (rc) return rc;
+    if (!H || !M || !Pa || !out) return fail(F16_EINVAL, "NULL pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DISPATCH_SIMPLE(f16::launch_thrust(c->t32, n, (const float *)H, (const float *)M, (const float *)Pa, (float *)out, g, st),
+                    f16::launch_thrust(c->t64, n, (const double *)H, (const double *)M, (const double *)Pa, (double *)out, g, st));
+    return F16_OK;
+}
+
+int f16_atmosphere(int dtype, int64_t n, const void *h, void *rho, void *a, void *stream)
+{
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(n, &c, &g);
+    if (rc) return rc;
+    if (!h || !rho || !a) return fail(F16_EINVAL, "NULL pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DISPATCH_SIMPLE(f16::launch_isa(n, (const float *)h, (float *)rho, (float *)a, g, st),
+                    f16::launch_isa(n, (const double *)h, (double *)rho, (double *)a, g, st));
+    return F16_OK;
+}
+
+}  // extern "C"

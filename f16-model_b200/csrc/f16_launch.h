@@ -1,0 +1,73 @@
+// f16_launch.h -- typed kernel arguments and launcher prototypes shared by the two kernel
+// translation units (f32 / f64) and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "f16_tables.h"
+
+namespace f16 {
+
+struct LaunchGeom {
+    int n_sm;
+    int ctas_per_sm;
+};
+
+// typed view of f16_config + f16_env_buffers (include/f16_b200.h)
+template <typename R>
+struct EnvArgs {
+    const Tables<R> *tables;
+    int64_t n;
+    R dt;
+    int horizon, ref_len, n_ref;
+    int autoreset, init_mode, obs_layout, noise;
+    uint64_t seed;
+    int64_t id_base;
+    R x0[9];
+    R *state;
+    int32_t *ep_len;
+    R *total_return;
+    int32_t *ref_idx;
+    uint8_t *done;
+    uint32_t *episode_no;
+    const R *ref_bank;
+    const R *init_state;
+};
+
+// typed view of f16_step_io
+template <typename R>
+struct StepArgs {
+    const R *actions;
+    R *obs;
+    R *reward;
+    uint8_t *done;
+    R *final_obs;
+    int32_t *final_ep_len;
+    R *final_return;
+    int obs_every_step;
+    int K;
+    int64_t i_begin, i_end;   // env sub-range advanced by this launch (host-buffer path pipelines chunks)
+};
+
+// f16_kernels_f32.cu
+cudaError_t launch_env_step(const EnvArgs<float> &, const StepArgs<float> &, bool fast, const LaunchGeom &, cudaStream_t);
+cudaError_t launch_env_reset(const EnvArgs<float> &, const uint8_t *mask, int keep_ref, float *obs, const LaunchGeom &, cudaStream_t);
+cudaError_t launch_rhs(const Tables<float> *, int64_t n, const float *x, const float *u, float *dx, const LaunchGeom &, cudaStream_t);
+cudaError_t launch_model_step(const Tables<float> *, int64_t n, float *x, const float *u, float dt, int K, const LaunchGeom &, cudaStream_t);
+cudaError_t launch_coeffs(const Tables<float> *, int64_t n, const float *, const float *, const float *, const float *, float *, const LaunchGeom &, cudaStream_t);
+cudaError_t launch_thrust(const Tables<float> *, int64_t n, const float *, const float *, const float *, float *, const LaunchGeom &, cudaStream_t);
+cudaError_t launch_isa(int64_t n, const float *, float *, float *, const LaunchGeom &, cudaStream_t);
+int env_step_occupancy_f32(bool fast, bool autoreset);
+
+// f16_kernels_f64.cu
+cudaError_t launch_env_step(const EnvArgs<double> &, const StepArgs<double> &, bool fast, const LaunchGeom &, cudaStream_t);
+cudaError_t launch_env_reset(const EnvArgs<double> &, const uint8_t *mask, int keep_ref, double *obs, const LaunchGeom &, cudaStream_t);
+cudaError_t launch_rhs(const Tables<double> *, int64_t n, const double *x, const double *u, double *dx, const LaunchGeom &, cudaStream_t);
+cudaError_t launch_model_step(const Tables<double> *, int64_t n, double *x, const double *u, double dt, int K, const LaunchGeom &, cudaStream_t);
+cudaError_t launch_coeffs(const Tables<double> *, int64_t n, const double *, const double *, const double *, const double *, double *, const LaunchGeom &, cudaStream_t);
+cudaError_t launch_thrust(const Tables<double> *, int64_t n, const double *, const double *, const double *, double *, const LaunchGeom &, cudaStream_t);
+cudaError_t launch_isa(int64_t n, const double *, double *, double *, const LaunchGeom &, cudaStream_t);
+int env_step_occupancy_f64(bool autoreset);
+
+}  // namespace f16

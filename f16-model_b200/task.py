@@ -1,0 +1,152 @@
+"""Pitch reference signals -- host-side mirror of ``ReferenceSignal`` (F16model/env/task.py:6-118).
+
+Signals are built once on the host (NumPy, fp64) and uploaded as a bank ``[R, T]`` of
+``wz_ref = theta_ref / 2``; every env follows one row of the bank and the step kernel reads
+``wz_ref[ref_idx][episode_length]``.  Random draws go through Python's ``random`` module in
+the reference's order, so ``random.seed(s)`` reproduces the reference's signal for seed s."""
+import itertools
+import random as _random
+
+import numpy as np
+
+SCENARIOS = ("step", "cos", "pure_step", "combo")
+_AMPS6 = (20, 10, 5, -5, -10, -20)
+
+
+class ReferenceSignal:
+    def __init__(self, dt, tn, determenistic=False, scenario=None, rng=None):
+        self.dt = dt
+        self.tn = tn
+        self.t = np.arange(0, tn, dt)
+        self.determenistic = determenistic
+        self._rng = _random if rng is None else rng
+        if scenario is None:
+            scenario = self._rng.choice(["step", "cos", "pure_step"])
+        if scenario not in SCENARIOS:
+            raise ValueError(f"unknown scenario {scenario!r}")
+        self.scenario = scenario
+        theta = getattr(self, f"_build_{scenario}")()
+        self.theta_ref = theta
+        self.wz_ref = theta / 2
+
+    # -- building blocks ---------------------------------------------------
+    def _nearest(self, time):
+        return int(np.abs(self.t - time).argmin())
+
+    def cosstep(self, start_time, w):
+        """Raised-cosine ramp 0 -> 1 of width w starting at start_time (task.py:105-118)."""
+        i0, i1 = self._nearest(start_time), self._nearest(start_time + w)
+        ramp = -(np.cos(1 / w * np.pi * (self.t - start_time)) - 1) / 2
+        if start_time >= 0:
+            ramp[:i0] = 0.0
+        ramp[i1:] = 1.0
+        return ramp
+
+    # -- scenarios ---------------------------------------------------------
+    def _build_step(self):
+        if self.determenistic:
+            amp = 10 * np.pi / 180
+        else:
+            amp = np.radians(self._rng.choice(list(_AMPS6)))
+        sig = amp * self.cosstep(-1, 2) * 2 - amp
+        sig -= amp * self.cosstep(self.tn * 0.25, 1)
+        sig -= amp * self.cosstep(self.tn * 0.50, 1)
+        sig += amp * self.cosstep(self.tn * 0.75, 1)
+        return sig[::-1]
+
+    def _build_cos(self):
+        if self.determenistic:
+            amp, freq = 20 * np.pi / 180, 0.25
+        else:
+            amp = np.radians(self._rng.choice([10, 5, -5, -10]))
+            freq = self._rng.choice([0.125, 0.25, 0.45, 0.5])
+        return np.sin(2 * np.pi * freq * self.t) * amp
+
+    def _build_pure_step(self):
+        if self.determenistic:
+            amp, t_step = np.radians(10), 1
+        else:
+            amp = np.radians(self._rng.choice(list(_AMPS6)))
+            t_step = self._rng.choice([1, 2, 3, 4])
+        sig = np.zeros(self.t.shape)
+        sig[self._nearest(t_step):] = amp
+        return sig
+
+    def _build_combo(self):
+        if self.determenistic:
+            a_step, a_sin, freq, a_cos = np.radians(10), np.radians(10), 0.25, np.radians(20)
+        else:
+            a_step = np.radians(self._rng.choice(list(_AMPS6)))
+            a_sin = np.radians(self._rng.choice(list(_AMPS6)))
+            freq = self._rng.choice([0.125, 0.25, 0.45, 0.5, 0.75])
+            a_cos = np.radians(self._rng.choice(list(_AMPS6)))
+        return self._combo_from(a_step, a_sin, freq, a_cos, order=None)
+
+    def _combo_segments(self, a_step, a_sin, freq, a_cos):
+        n1 = int(1 / self.dt)
+        rect = np.concatenate(([0] * int(n1 / 2), [a_step] * int(n1 * 2), [0] * int(n1 / 2)))
+        sine = np.sin(2 * np.pi * freq * np.arange(0, 3, self.dt)) * a_sin
+        ramp = self.cosstep(0, 1)[:n1]
+        bump = np.concatenate((ramp * a_cos, [a_cos] * n1, ramp[::-1] * a_cos))
+        return [rect, sine, bump]
+
+    def _combo_from(self, a_step, a_sin, freq, a_cos, order):
+        segs = []
+        for _ in range(int(self.tn / 10)):
+            segs += self._combo_segments(a_step, a_sin, freq, a_cos)
+        if order is not None:
+            segs = [segs[j] for j in order]
+        elif not self.determenistic:
+            self._rng.shuffle(segs)
+        flat = np.concatenate(segs)   # tn < 10 -> ValueError, exactly like the reference
+        sig = np.zeros(self.t.shape)
+        sig[: len(flat)] = flat
+        return sig
+
+
+def build_reference_bank(dt, tn, scenario, determenistic, bank_size=256, seed=0):
+    """Bank of ``wz_ref`` rows for a batch of envs, shape [R, T] (fp64).
+
+    Deterministic configs give one row (three when ``scenario`` is None, which the
+    reference still draws at random).  Random configs enumerate the reference's whole
+    discrete parameter space when it has at most ``bank_size`` members (pure_step 24,
+    cos 16, step 6) and otherwise (combo: 6*6*5*6 parameter sets x segment orders) hold
+    ``bank_size`` draws made exactly as the reference makes them, from ``random.Random(seed)``.
+    A reset picks a row uniformly, so resets are distributed like the reference's.
+    """
+    rows = []
+    if determenistic:
+        for sc in ([scenario] if scenario is not None else ["step", "cos", "pure_step"]):
+            rows.append(ReferenceSignal(dt, tn, True, sc).wz_ref)
+        return np.ascontiguousarray(np.stack(rows))
+    scen = [scenario] if scenario is not None else ["step", "cos", "pure_step"]
+    proto = ReferenceSignal(dt, tn, True, "pure_step")
+    enumerable = {"step": 6, "cos": 16, "pure_step": 24}
+    if all(s in enumerable for s in scen) and max(enumerable[s] for s in scen) * len(scen) <= max(bank_size, 24 * 3):
+        # equal weight per scenario: replicate to the lcm so that uniform row choice == choice of
+        # scenario followed by uniform choice of parameters
+        per = int(np.lcm.reduce([enumerable[s] for s in scen]))
+        for sc in scen:
+            sigs = []
+            if sc == "step":
+                for a in _AMPS6:
+                    amp = np.radians(a)
+                    s_ = amp * proto.cosstep(-1, 2) * 2 - amp
+                    s_ -= amp * proto.cosstep(tn * 0.25, 1)
+                    s_ -= amp * proto.cosstep(tn * 0.50, 1)
+                    s_ += amp * proto.cosstep(tn * 0.75, 1)
+                    sigs.append(s_[::-1] / 2)
+            elif sc == "cos":
+                for a, f in itertools.product([10, 5, -5, -10], [0.125, 0.25, 0.45, 0.5]):
+                    sigs.append(np.sin(2 * np.pi * f * proto.t) * np.radians(a) / 2)
+            else:
+                for a, ts in itertools.product(_AMPS6, [1, 2, 3, 4]):
+                    s_ = np.zeros(proto.t.shape)
+                    s_[proto._nearest(ts):] = np.radians(a)
+                    sigs.append(s_ / 2)
+            rows += sigs * (per // len(sigs))
+        return np.ascontiguousarray(np.stack(rows))
+    rng = _random.Random(seed)
+    for _ in range(bank_size):
+        rows.append(ReferenceSignal(dt, tn, False, scenario, rng=rng).wz_ref)
+    return np.ascontiguousarray(np.stack(rows))

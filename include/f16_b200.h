@@ -1,0 +1,146 @@
+/* f16_b200.h -- C ABI of the B200-native batched F-16 longitudinal simulator.
+ *
+ * Drop-in boundary for the per-step NumPy path of lalapopa/F16-model
+ * (F16model/model + F16model/env).  The reference has no FFI of its own (it is
+ * pure Python); each entry point below names the reference function it
+ * replaces (paths relative to the reference root).  All pointers are DEVICE
+ * pointers unless the name ends in _host; the caller (PyTorch, or any other
+ * allocator) owns every buffer, the library only enqueues work on the given
+ * CUDA stream and keeps no reference past the call.  No torch types cross the
+ * boundary.  Functions return 0 on success or a negative F16_E* code and never
+ * throw; f16_last_error() returns a thread-local message.
+ *
+ * Batch layout: structure-of-arrays.  A "state" is real[9][n] in the field
+ * order of States.to_array() (model/_interface.py:18-31):
+ *     0 Ox [m], 1 Oy [m], 2 wz [rad/s], 3 theta [rad], 4 V [m/s],
+ *     5 alpha [rad], 6 stab [rad], 7 dstab [rad/s], 8 Pa [%]
+ * `real` is float (F16_F32) or double (F16_F64) as selected by `dtype`.
+ */
+#ifndef F16_B200_H
+#define F16_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F16_ABI_VERSION 1
+
+enum { F16_F32 = 0, F16_F64 = 1 };
+
+enum {
+    F16_OK = 0,
+    F16_EINVAL = -1,  /* bad argument (null pointer, bad dtype, n <= 0, ...) */
+    F16_ECUDA = -2,   /* CUDA runtime error, see f16_last_error() */
+    F16_ENODEV = -3   /* no CUDA device / wrong architecture */
+};
+
+/* How an episode's initial state is produced by f16_env_reset and by the
+ * in-kernel autoreset (reference: F16._get_init_state, env/env.py:172-195). */
+enum {
+    F16_INIT_RANDOM = 0,  /* get_random_state(), env/env.py:221-243, counter RNG */
+    F16_INIT_FIXED = 1,   /* config["init_state"]/["init_control"]: cfg.x0 for every env */
+    F16_INIT_PER_ENV = 2  /* explicit per-env states in f16_env_buffers.init_state */
+};
+
+enum { F16_OBS_AOS = 0 /* obs[n][5], the reference's layout */, F16_OBS_SOA = 1 /* obs[5][n] */ };
+
+/* Scalar configuration of a batch of envs (reference: the config dict of
+ * F16.__init__, env/env.py:18-35, plus what SyncVectorEnv adds). */
+typedef struct f16_config {
+    int32_t dtype;        /* F16_F32 | F16_F64 */
+    int32_t fast_math;    /* F32 only: 1 = MUFU intrinsics for sin/cos/log2/exp2/rcp (within the 1e-4 bound) */
+    int64_t n_envs;
+    double dt;            /* config["dt"] */
+    int32_t horizon;      /* episode_length value at which `done` fires: tn/dt - 1 (env/env.py:115) */
+    int32_t ref_len;      /* samples per reference signal: len(arange(0, tn, dt)) (env/task.py:12) */
+    int32_t n_ref;        /* number of signals in the bank */
+    int32_t autoreset;    /* 1 = gymnasium SyncVectorEnv semantics: reset in the same step, return the reset obs */
+    int32_t init_mode;    /* F16_INIT_* */
+    int32_t obs_layout;   /* F16_OBS_* */
+    int32_t noise;        /* config["noise"] truthy: wz_obs += radians(N(0, 0.5)) (env/env.py:139-152) */
+    int32_t reserved;
+    uint64_t seed;        /* key of the counter-based RNG (reset + noise) */
+    int64_t env_id_base;  /* global id of env 0 of this shard: RNG streams are keyed by the GLOBAL env id, so
+                             results do not depend on how the batch is sharded over GPUs */
+    double x0[9];         /* F16_INIT_FIXED: the initial state */
+} f16_config;
+
+/* Persistent per-env buffers (device).  What the reference keeps in the F16
+ * object: model.state_prev, episode_length, total_return, done, ref_signal. */
+typedef struct f16_env_buffers {
+    void *state;             /* real[9][n]   r/w */
+    int32_t *ep_len;         /* [n]          r/w  F16.episode_length */
+    void *total_return;      /* real[n]      r/w  F16.total_return; may be NULL */
+    int32_t *ref_idx;        /* [n]          r/w  row of ref_bank followed by each env */
+    uint8_t *done;           /* [n]          r/w  F16.done (sticky until reset; always 0 after an autoreset) */
+    uint32_t *episode_no;    /* [n]          r/w  episodes started so far (RNG counter) */
+    const void *ref_bank;    /* real[n_ref][ref_len]  wz_ref = theta_ref/2 (env/task.py:25-26) */
+    const void *init_state;  /* real[9][n]   F16_INIT_PER_ENV only, else NULL */
+} f16_env_buffers;
+
+/* Per-call tensors of f16_env_step. */
+typedef struct f16_step_io {
+    const void *actions;  /* real[K][n]  normalised stick in [-1,1] (clipped like env/env.py:204) */
+    void *obs;            /* real[n][5] (or [5][n]): observation after the LAST of the K steps; with
+                             obs_every_step: real[K][n][5] (or [K][5][n]) */
+    void *reward;         /* real[K][n] */
+    uint8_t *done;        /* [K][n]  1 on the step that terminated an episode (and, without autoreset, after) */
+    void *final_obs;      /* real[n][5]/[5][n]: terminal observation of the most recent episode that ended
+                             inside this call (gymnasium "final_observation"); only written where done fired;
+                             may be NULL */
+    int32_t *final_ep_len;   /* [n] episode_length of that episode ("final_info"); may be NULL */
+    void *final_return;      /* real[n] total_return of that episode; may be NULL */
+    int32_t obs_every_step;  /* 0: only the last observation is written */
+    int32_t reserved;
+} f16_step_io;
+
+/* ---- library ---------------------------------------------------------- */
+int f16_abi_version(void);
+const char *f16_last_error(void);
+/* Upload the table images for `device` (idempotent; done lazily otherwise). */
+int f16_init(int device);
+/* SMs of `device`, CTA size and the resident-CTA count the step kernel is launched with. */
+int f16_launch_geometry(int device, int dtype, int *n_sm, int *cta_threads, int *ctas_per_sm);
+
+/* ---- env level -------------------------------------------------------- */
+/* F16.reset (env/env.py:154-170) for every env whose mask byte is non-zero
+ * (mask == NULL: all).  Draws/copies the initial state, zeroes the counters,
+ * picks a reference signal (uniformly from the bank unless n_ref == 1 or
+ * keep_ref != 0) and writes the reset observation. */
+int f16_env_reset(const f16_config *cfg, const f16_env_buffers *env, const uint8_t *mask, int keep_ref,
+                  void *obs /* real[n][5] or [5][n], may be NULL */, void *stream);
+
+/* K consecutive F16.step calls (env/env.py:46-70) for all n envs in ONE kernel
+ * launch; state stays in registers across the K steps. */
+int f16_env_step(const f16_config *cfg, const f16_env_buffers *env, const f16_step_io *io, int K, void *stream);
+
+/* Same step through HOST buffers (pinned or pageable): H2D of actions, kernel,
+ * D2H of obs/reward/done, chunked and double-buffered over internal streams.
+ * The env's persistent buffers stay on the device. Blocks until the results are
+ * in the host buffers. */
+int f16_env_step_host(const f16_config *cfg, const f16_env_buffers *env, const void *actions_host, void *obs_host,
+                      void *reward_host, uint8_t *done_host, int K, int device);
+
+/* ---- model level ------------------------------------------------------ */
+/* ODE_3DoF.solve (model/ODE_3DoF.py:8-60): dx = f(x, u); x real[9][n], u real[2][n] (stab cmd [rad],
+ * throttle), dx real[9][n] (all nine derivatives, including the V_dot the integrator discards). */
+int f16_rhs(int dtype, int64_t n, const void *x, const void *u, void *dx, void *stream);
+/* K x F16model.step (model/_interface.py:116-122): explicit Euler with the SAME control held for the K
+ * steps, wz clipped to +-60 deg/s, V frozen.  x real[9][n] is updated in place. */
+int f16_model_step(int dtype, int64_t n, void *x, const void *u, double dt, int K, void *stream);
+
+/* ---- data level (parity probes of the table/atmosphere code) ----------- */
+/* coeff.get_Cx/get_Cy/get_Mz (data/coeff.py:37,8,225) at beta=0, lef=0, sb=0: out real[3][n] */
+int f16_coeffs(int dtype, int64_t n, const void *alpha, const void *fi, const void *wz, const void *V, void *out,
+               void *stream);
+/* thrust.get_thrust(H, M, Pa) (data/thrust.py:6-14): out real[n] */
+int f16_thrust(int dtype, int64_t n, const void *H, const void *M, const void *Pa, void *out, void *stream);
+/* atmosphere.get_density / get_speed_of_sound (data/atmosphere.py:5-11): rho, a real[n] */
+int f16_atmosphere(int dtype, int64_t n, const void *h, void *rho, void *a, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F16_B200_H */

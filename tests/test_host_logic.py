@@ -1,0 +1,173 @@
+"""CPU tests of the host-side logic and of the C-ABI library's surface (no compute calls:
+this container has no GPU).  Reference-signal construction is pinned bit-exactly against
+vectors produced by the unmodified reference (tests/golden/make_golden.py)."""
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import f16_model_b200 as f16
+from f16_model_b200 import _capi
+from f16_model_b200.sharding import shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------- reference signals
+@pytest.mark.parametrize("scenario", ["step", "cos", "pure_step", "combo"])
+def test_reference_signal_deterministic_bit_exact(golden, scenario):
+    sig = f16.ReferenceSignal(0.01, 10, determenistic=True, scenario=scenario)
+    assert np.array_equal(sig.theta_ref, golden[f"ref_det_{scenario}"])
+    assert np.array_equal(sig.wz_ref, golden[f"ref_det_{scenario}"] / 2)
+
+
+@pytest.mark.parametrize("scenario", ["step", "cos", "pure_step", "combo"])
+@pytest.mark.parametrize("seed", [1, 2, 3, 11, 12345])
+def test_reference_signal_random_follows_reference_draw_order(golden, scenario, seed):
+    random.seed(seed)
+    sig = f16.ReferenceSignal(0.01, 10, determenistic=False, scenario=scenario)
+    assert np.array_equal(sig.theta_ref, golden[f"ref_rnd_{scenario}_{seed}"])
+
+
+@pytest.mark.parametrize("seed", [4, 5, 6, 7, 8, 9])
+def test_reference_signal_random_scenario_choice(golden, seed):
+    random.seed(seed)
+    sig = f16.ReferenceSignal(0.01, 10, determenistic=False, scenario=None)
+    assert np.array_equal(sig.theta_ref, golden[f"ref_rnd_None_{seed}"])
+
+
+def test_reference_signal_other_horizons(golden):
+    assert np.array_equal(f16.ReferenceSignal(0.01, 5, True, "pure_step").theta_ref, golden["ref_det_pure_step_tn5"])
+    assert np.array_equal(f16.ReferenceSignal(0.02, 20, True, "step").theta_ref, golden["ref_det_step_tn20_dt02"])
+    assert np.array_equal(f16.ReferenceSignal(0.01, 20, True, "combo").theta_ref, golden["ref_det_combo_tn20"])
+
+
+def test_reference_signal_known_shapes():
+    """det. pure_step -> wz_ref[100:] = radians(5); det. combo plateaus."""
+    ps = f16.ReferenceSignal(0.01, 10, True, "pure_step")
+    assert np.all(ps.wz_ref[:100] == 0) and np.all(ps.wz_ref[100:] == np.radians(10) / 2)
+    cb = f16.ReferenceSignal(0.01, 10, True, "combo")
+    assert np.all(cb.theta_ref[50:250] == np.radians(10)) and np.all(cb.theta_ref[:50] == 0)
+    assert np.all(cb.theta_ref[700:800] == np.radians(20)) and np.all(cb.theta_ref[900:] == 0)
+
+
+def test_combo_needs_ten_seconds():
+    with pytest.raises(ValueError):    # the reference fails the same way (np.concatenate of nothing)
+        f16.ReferenceSignal(0.01, 5, True, "combo")
+
+
+def test_reference_bank_enumerates_discrete_space():
+    bank = f16.build_reference_bank(0.01, 10, "pure_step", False)
+    assert bank.shape == (24, 1000)
+    assert len({row.tobytes() for row in bank}) == 24
+    bank = f16.build_reference_bank(0.01, 10, None, False)
+    # scenario chosen uniformly, then parameters uniformly: equal mass per scenario
+    assert bank.shape[0] % 3 == 0
+    random.seed(3)
+    sig = f16.ReferenceSignal(0.01, 10, False, None)
+    assert any(np.array_equal(sig.wz_ref, row) for row in bank)
+    bank = f16.build_reference_bank(0.01, 10, "combo", False, bank_size=16, seed=5)
+    assert bank.shape == (16, 1000)
+    assert np.array_equal(bank, f16.build_reference_bank(0.01, 10, "combo", False, bank_size=16, seed=5))
+    assert f16.build_reference_bank(0.01, 10, "combo", True).shape == (1, 1000)
+
+
+# ---------------------------------------------------------------- env statics
+def test_rescale_action_matches_reference(golden):
+    out = np.array([float(f16.F16.rescale_action(np.array([v]))) for v in golden["rescale_in"]])
+    assert np.array_equal(out, golden["rescale_out"])
+
+
+def test_device_action_constants_are_the_float32_cast_bounds():
+    lo, hi = np.float32(-np.radians(25)), np.float32(np.radians(25))
+    src = open(os.path.join(ROOT, "f16-model_b200", "csrc", "f16_device.cuh")).read()
+    assert repr(float(lo)) in src and repr(float(hi - lo)) in src
+
+
+def test_normalize_denormalize_roundtrip():
+    raw = [1234.5, 0.3, 210.0]
+    n = f16.F16.normalize(raw)
+    assert np.allclose(n, [1234.5 / 35000, (0.3 + np.radians(150)) / (2 * np.radians(150)), 0.42])
+    back = f16.F16.denormalize(np.array(n + [0.01, 0.02]))
+    assert np.allclose(back[:3], raw) and np.allclose(back[3:], [0.01, 0.02])
+
+
+def test_trimmed_state_and_thrust_position(golden):
+    x0, u0 = f16.get_trimmed_state_control()
+    assert np.array_equal(x0, golden["trim_x0"]) and np.array_equal(u0, golden["trim_u0"])
+    mine = np.array([f16.find_correct_thrust_position(t) for t in golden["thrpos_in"]])
+    assert np.max(np.abs(mine - golden["thrpos_out"])) < 1e-9     # closed form vs the reference's fsolve
+
+
+def test_get_random_state_draw_order(golden):
+    for seed, ref in zip(golden["random_state_seeds"], golden["random_state_out"]):
+        np.random.seed(int(seed))
+        assert np.array_equal(f16.get_random_state().to_array(), ref)
+
+
+def test_states_arithmetic():
+    a = f16.States(*range(9))
+    b = 0.5 * a + a
+    assert np.allclose(b.to_array(), 1.5 * np.arange(9))
+    assert np.allclose((f16.Control(0.1, 0.5) * 2).to_array(), [0.2, 1.0])
+
+
+# ---------------------------------------------------------------- sharding
+def test_shard_range_covers_batch():
+    for total, world in [(1 << 20, 8), (4097, 4), (10, 3), (7, 8)]:
+        spans = [shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        sizes = [e - b for b, e in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+# ---------------------------------------------------------------- C ABI surface
+def _header_functions():
+    hdr = open(os.path.join(ROOT, "include", "f16_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(f16_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    f16.build()
+    lib = ctypes.CDLL(f16.library_path())
+    names = _header_functions()
+    assert len(names) >= 12
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/f16_b200.h but not exported"
+    assert sorted(_capi.EXPORTS) == names
+    lib.f16_abi_version.restype = ctypes.c_int
+    assert lib.f16_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors of the ABI structs: sizes as the C compiler lays them out."""
+    assert ctypes.sizeof(_capi.Config) == 4 + 4 + 8 + 8 + 8 * 4 + 8 + 8 + 9 * 8
+    assert ctypes.sizeof(_capi.EnvBuffers) == 8 * 8
+    assert ctypes.sizeof(_capi.StepIO) == 7 * 8 + 8
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _capi.load_library()
+    assert lib.f16_init(0) != 0
+    assert b"no CPU fallback" in lib.f16_last_error()
+    cfg = {"dt": 0.01, "tn": 10, "debug_state": False, "determenistic_ref": True, "scenario": "combo"}
+    with pytest.raises(f16.F16Error):
+        f16.F16VecEnv(cfg, 4)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "f16-model_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in text.lower() or fn == "f16_tables_data.h", f"{fn} mentions the oracle"

@@ -1,0 +1,49 @@
+"""Seeded synthetic workloads shared by the GPU parity tests (BASELINE config 2)."""
+import numpy as np
+
+T = 1000
+
+
+def config2_inputs(n=4096, seed=1234, T=T):
+    """Random initial states per plane.random_state_bound, plus stick programs:
+    3/4 piecewise-constant U(-0.3,0.1) held 25 steps, 1/8 i.i.d. U(-1,1), 1/8 sustained +-1
+    from a random onset (forces the 50 deg/s termination), and a few hand-made states next to
+    the altitude limits.  Everything fp64, generated on the host."""
+    rng = np.random.default_rng(seed)
+    d5 = np.radians(5)
+    al = rng.uniform(-d5, d5, n)
+    x0 = np.zeros((n, 9))
+    x0[:, 1] = rng.uniform(2000, 4000, n)
+    x0[:, 2] = rng.uniform(-d5, d5, n)
+    x0[:, 3] = al
+    x0[:, 4] = rng.uniform(90, 250, n)
+    x0[:, 5] = al
+    acts = np.repeat(rng.uniform(-0.3, 0.1, (T // 25, n)), 25, axis=0)
+    kind = rng.permutation(n) % 8
+    iid = kind == 6
+    acts[:, iid] = rng.uniform(-1, 1, (T, int(iid.sum())))
+    slam = np.nonzero(kind == 7)[0]
+    onset = rng.integers(20, 800, slam.size)
+    sign = rng.choice([-1.0, 1.0], slam.size)
+    for j, o, s in zip(slam, onset, sign):
+        acts[o:, j] = s
+    # altitude terminations
+    k = min(8, n // 4)
+    x0[:k, 1] = np.linspace(301.0, 340.0, k)
+    x0[:k, 3] = np.radians(-10.0)
+    x0[:k, 5] = np.radians(2.0)
+    x0[k:2 * k, 1] = np.linspace(29950.0, 29999.0, k)
+    x0[k:2 * k, 3] = np.radians(25.0)
+    x0[k:2 * k, 4] = 250.0
+    x0[k:2 * k, 5] = np.radians(3.0)
+    return x0, acts
+
+
+FIELD_SCALE = np.array([1.0, 1.0, 1e-2, 1e-2, 1.0, 1e-2, 1e-2, 1e-2, 1e-2])
+"""Per-field floor of the relative error |d| / max(|ref|, scale): many fields pass through 0
+(wz, dstab ~ 1e-16 at trim), so 'relative' needs a floor (SURVEY section 7, hard parts)."""
+
+
+def rel_err(a, ref, scale):
+    a, ref = np.asarray(a, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    return np.abs(a - ref) / np.maximum(np.abs(ref), scale)
