@@ -289,8 +289,8 @@ def main():
     if not args.no_cpu:
         probe_steps, probe_dt, cores = cpu_oracle_run(1 << 13, 16)
         rate = probe_steps / probe_dt
-        n_steps = 64
-        n_envs = int(min(1 << 20, max(1 << 12, rate * 12 / n_steps)))        # ~12 s of CPU work
+        n_envs = 1 << 17
+        n_steps = int(min(1000, max(16, rate * 12 / n_envs)))                 # ~12 s of CPU work
         steps_done, dt, cores = cpu_oracle_run(n_envs, n_steps)
         cpu = {"value": steps_done / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n_envs} envs x {n_steps} env-steps ({dt:.1f} s), same distributions, C oracle port (gcc -O2, OpenMP)"}
