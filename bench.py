@@ -34,6 +34,7 @@ METRIC = "env-steps/sec (F-16 long., batched)"
 UNIT = "env-steps/s"
 ENVS_PER_GPU = 1 << 20
 BYTES_PER_ENV_STEP_F32 = 113      # 48 B read + 65 B written per env-step, fp32, K = 1
+# (the kernel really moves 117 B: + total_return r/w 8, - the V row write 4)
 CFG = {"dt": 0.01, "tn": 10, "debug_state": False, "determenistic_ref": False, "scenario": "combo"}
 
 
@@ -186,13 +187,21 @@ def main():
     pool = torch.rand((16, N), device=device, generator=g) * 2 - 1          # 16 different stick tensors, cycled
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)          # > 126 MB L2
 
-    def timed_steps(n_steps, do_flush=True):
+    static_actions = pool[0].clone()
+    graph, _ = env.make_graphed_step(static_actions)                          # same launch, replayed from a CUDA graph
+
+    def timed_steps(n_steps, do_flush=True, graphed=False):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
         for s in range(n_steps):
+            if graphed:
+                static_actions.copy_(pool[s % 16])
             if do_flush:
                 flush.fill_(s & 0xFF)
             ev[s][0].record()
-            env.step(pool[s % 16])
+            if graphed:
+                graph.replay()
+            else:
+                env.step(pool[s % 16])
             ev[s][1].record()
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in ev)                          # ms on the device
@@ -210,6 +219,8 @@ def main():
     wall_s = time.perf_counter() - t_wall0
     warm_ms = timed_steps(args.steps, do_flush=False)                         # L2-warm variant, reported separately
     barrier()
+    graph_ms = max_over_ranks_later = timed_steps(args.steps, do_flush=True, graphed=True)
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     def max_over_ranks(x):
@@ -221,6 +232,7 @@ def main():
 
     dev_ms = max_over_ranks(dev_ms)
     warm_ms = max_over_ranks(warm_ms)
+    graph_ms = max_over_ranks(graph_ms)
     total_env_steps = N * world * args.steps
     value = total_env_steps / (dev_ms * 1e-3)
 
@@ -304,7 +316,8 @@ def main():
                    "envs_per_gpu": N, "substeps_per_launch": 1, "fast_math": fast, "parallelism": f"env-shard x{world}, no collective",
                    "l2": "flushed before every timed step (256 MiB fill, outside the CUDA-event bracket)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu,
-        "value_l2_warm": total_env_steps / (warm_ms * 1e-3), "wall_s_timed_region_incl_flush": wall_s,
+        "value_l2_warm": total_env_steps / (warm_ms * 1e-3), "value_cuda_graph_replay": total_env_steps / (graph_ms * 1e-3),
+        "wall_s_timed_region_incl_flush": wall_s,
         "substeps_sweep_env_steps_per_s": sweep,
     }
     print(json.dumps(line), flush=True)

@@ -34,7 +34,8 @@ class Config(C.Structure):
 
 class EnvBuffers(C.Structure):
     _fields_ = [("state", C.c_void_p), ("ep_len", C.c_void_p), ("total_return", C.c_void_p), ("ref_idx", C.c_void_p),
-                ("done", C.c_void_p), ("episode_no", C.c_void_p), ("ref_bank", C.c_void_p), ("init_state", C.c_void_p)]
+                ("done", C.c_void_p), ("episode_no", C.c_void_p), ("ref_bank", C.c_void_p), ("init_state", C.c_void_p),
+                ("pos_comp", C.c_void_p)]
 
 
 class StepIO(C.Structure):

@@ -162,6 +162,7 @@ f16::EnvArgs<R> make_env_args(const f16_config *cfg, const f16_env_buffers *env,
     A.episode_no = env->episode_no;
     A.ref_bank = static_cast<const R *>(env->ref_bank);
     A.init_state = static_cast<const R *>(env->init_state);
+    A.pos_comp = static_cast<R *>(env->pos_comp);
     return A;
 }
 
@@ -178,18 +179,44 @@ f16::StepArgs<R> make_step_args(const f16_config *cfg, const f16_step_io *io, in
     S.final_return = static_cast<R *>(io->final_return);
     S.obs_every_step = io->obs_every_step;
     S.K = K;
+    S.obs_vec_ok = (reinterpret_cast<uintptr_t>(io->obs) % 16 == 0 &&
+                    (!io->obs_every_step || (static_cast<size_t>(cfg->n_envs) * 5 * sizeof(R)) % 16 == 0))
+                       ? 1
+                       : 0;
+    S.tma_ok = 0;   // set by step_range once the env buffers are known
     S.i_begin = 0;
     S.i_end = cfg->n_envs;
     return S;
 }
 
-int check_step(const f16_step_io *io, int K)
+int check_step(const f16_config *cfg, const f16_step_io *io, int K)
 {
     if (!io) return fail(F16_EINVAL, "io is NULL");
     if (K <= 0) return fail(F16_EINVAL, "K must be >= 1");
+    // the kernels index with 32 bits: every array must stay below 2^32 elements
+    const double lim = 4294967296.0;
+    const double n = static_cast<double>(cfg->n_envs);
+    if (9.0 * n >= lim || static_cast<double>(K) * n * (io->obs_every_step ? 5.0 : 1.0) >= lim || 5.0 * n >= lim ||
+        static_cast<double>(cfg->n_ref) * cfg->ref_len >= lim)
+        return fail(F16_EINVAL, "batch too large for 32-bit indexing (n_envs * max(9, K, 5K with obs_every_step) must be < 2^32): "
+                                "shard the envs or lower K");
     if (!io->actions || !io->reward || !io->done) return fail(F16_EINVAL, "actions, reward and done are required");
     if (io->obs_every_step && !io->obs) return fail(F16_EINVAL, "obs_every_step needs obs");
     return F16_OK;
+}
+
+// TMA bulk copies need 16-byte aligned global addresses and sizes: every SoA row of every full tile
+// starts at base + (j * n + i_begin + 256 * t) * elem, so bases, n and i_begin must be aligned.
+int tma_aligned(const f16_config *cfg, const f16_env_buffers *env, const f16_step_io *io, int64_t i0)
+{
+    const size_t es = cfg->dtype == F16_F32 ? 4 : 8;
+    auto ok = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+    if (!ok(env->state) || !ok(env->ep_len) || !ok(env->ref_idx) || !ok(env->done) || !ok(io->actions)) return 0;
+    if (env->total_return && !ok(env->total_return)) return 0;
+    if (env->pos_comp && !ok(env->pos_comp)) return 0;
+    if ((static_cast<size_t>(cfg->n_envs) * es) % 16 != 0) return 0;
+    if (i0 % 16 != 0) return 0;
+    return 1;
 }
 
 int step_range(DeviceCtx *ctx, const f16_config *cfg, const f16_env_buffers *env, const f16_step_io *io, int K, int64_t i0, int64_t i1,
@@ -202,12 +229,14 @@ int step_range(DeviceCtx *ctx, const f16_config *cfg, const f16_env_buffers *env
         auto S = make_step_args<float>(cfg, io, K);
         S.i_begin = i0;
         S.i_end = i1;
+        S.tma_ok = tma_aligned(cfg, env, io, i0);
         CUDA_TRY(f16::launch_env_step(A, S, fast, g, st));
     } else {
         auto A = make_env_args<double>(cfg, env, ctx->t64);
         auto S = make_step_args<double>(cfg, io, K);
         S.i_begin = i0;
         S.i_end = i1;
+        S.tma_ok = tma_aligned(cfg, env, io, i0);
         CUDA_TRY(f16::launch_env_step(A, S, false, g, st));
     }
     return F16_OK;
@@ -276,7 +305,7 @@ int f16_env_step(const f16_config *cfg, const f16_env_buffers *env, const f16_st
     int rc = check_cfg(cfg);
     if (rc) return rc;
     if ((rc = check_env(cfg, env))) return rc;
-    if ((rc = check_step(io, K))) return rc;
+    if ((rc = check_step(cfg, io, K))) return rc;
     int dev;
     if ((rc = current_device(&dev))) return rc;
     DeviceCtx *ctx;

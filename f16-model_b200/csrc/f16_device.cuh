@@ -205,8 +205,9 @@ __device__ __forceinline__ void aero_coeffs(const Tables<R> &T, R alpha, R fi, R
     const R *row = T.arow[ia];
     const Vec4<R> r3 = Vec4<R>::ld(row + 12);                                            // dmz1 y0, slope, alpha_i
     const R a_i = r3.z;
-    const R f1_i = i1 == 0 ? R(K::fi_m25) : (i1 == 1 ? R(K::fi_m10) : (i1 == 2 ? R(0) : R(K::fi_p10)));
-    const R f3_i = i3 <= 3 ? f1_i : (i3 == 4 ? R(K::fi_p15) : R(K::fi_p20));
+    // interval origins as select chains on the same predicates (a switch on i1 compiles to a jump table)
+    const R f1_i = fc >= R(K::fi_p10) ? R(K::fi_p10) : (fc >= R(0) ? R(0) : (fc >= R(K::fi_m10) ? R(K::fi_m10) : R(K::fi_m25)));
+    const R f3_i = fc >= R(K::fi_p20) ? R(K::fi_p20) : (fc >= R(K::fi_p15) ? R(K::fi_p15) : f1_i);
     const R sa = ac - a_i;      // linear tables: clipped alpha
     const R s = alpha - a_i;    // PCHIP: raw alpha
     const R sf = fc - f1_i;
@@ -318,16 +319,39 @@ __device__ __forceinline__ void rhs(const Tables<R> &T, const R (&x)[9], R u_sta
     dx[8] = power_level<R>(Pa, cth);
 }
 
-// F16model.step: explicit Euler, clip wz, V frozen (dx[4] ignored)
+// F16model.step: explicit Euler, clip wz, V frozen (dx[4] ignored).
+// comp: Kahan-compensated accumulation of the two position integrals (fp32 mode): Ox, Oy are pure
+// accumulators of ~1e-4-relative increments, where plain fp32 drifts by up to 1 ulp per step; the
+// carries (ox_lo, oy_lo) persist across steps and launches.
 template <typename R, bool FAST>
-__device__ __forceinline__ void euler_step(const Tables<R> &T, R (&x)[9], R u_stab, R u_thr, R dt)
+__device__ __forceinline__ void euler_step(const Tables<R> &T, R (&x)[9], R u_stab, R u_thr, R dt, bool comp, R &ox_lo, R &oy_lo)
 {
     R dx[9];
     rhs<R, FAST, false>(T, x, u_stab, u_thr, dx);
+    if (comp) {
+        R y = dx[0] * dt + ox_lo;
+        R t = x[0] + y;
+        ox_lo = y - (t - x[0]);
+        x[0] = t;
+        y = dx[1] * dt + oy_lo;
+        t = x[1] + y;
+        oy_lo = y - (t - x[1]);
+        x[1] = t;
+    } else {
+        x[0] = dx[0] * dt + x[0];
+        x[1] = dx[1] * dt + x[1];
+    }
 #pragma unroll
-    for (int i = 0; i < 9; ++i)
+    for (int i = 2; i < 9; ++i)
         if (i != 4) x[i] = dx[i] * dt + x[i];
     x[2] = clampr(x[2], R(-K::wz_clip), R(K::wz_clip));
+}
+
+template <typename R, bool FAST>
+__device__ __forceinline__ void euler_step(const Tables<R> &T, R (&x)[9], R u_stab, R u_thr, R dt)
+{
+    R a = R(0), b = R(0);
+    euler_step<R, FAST>(T, x, u_stab, u_thr, dt, false, a, b);
 }
 
 }  // namespace f16

@@ -183,60 +183,198 @@ __device__ __forceinline__ R obs_noise(const EnvArgs<R> &A, int64_t i, uint32_t 
 // ---------------------------------------------------------------------------
 // THE hot kernel: K x F16.step for n envs
 // ---------------------------------------------------------------------------
-template <typename R, bool FAST, bool AUTORESET>
-__global__ void __launch_bounds__(kCtaThreads) env_step_kernel(const EnvArgs<R> A, const StepArgs<R> S)
+// Resident CTAs per SM the register allocator is asked to make room for: fp32 64 regs/thread
+// (4 x 256 threads = 32 warps/SM hide the HBM latency of the K = 1 gym step), fp64 128 regs.
+template <typename R> struct MinCtas;
+template <> struct MinCtas<float> { static constexpr int v = 4; };
+template <> struct MinCtas<double> { static constexpr int v = 2; };
+
+// 16-byte global store of a staged shared-memory vector
+struct alignas(16) V16 { unsigned x, y, z, w; };
+
+// Coalesced store of one warp's 32 x 5 observations in the reference's AoS layout obs[n][5]:
+// the warp transposes through its private shared-memory slab (stride 5 words: conflict-free)
+// and writes 16-byte vectors, instead of five 20-byte-strided scalar stores per lane.
+template <typename R>
+__device__ __forceinline__ void store_obs_warp_aos(R *slab, R *dst /* obs + 5 * first env of the warp */, const R (&o)[5])
 {
-    __shared__ Tables<R> tbl;
-    __shared__ alignas(8) uint64_t bar;
-    tables_issue(&tbl, A.tables, &bar);
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) slab[lane * 5 + j] = o[j];
+    __syncwarp();
+    constexpr unsigned kVec = 160 * sizeof(R) / 16;   // 40 (fp32) / 80 (fp64)
+    const V16 *src = reinterpret_cast<const V16 *>(slab);
+    V16 *out = reinterpret_cast<V16 *>(dst);
+#pragma unroll
+    for (unsigned v = 0; v < (kVec + 31) / 32; ++v) {
+        const unsigned idx = v * 32 + lane;
+        if (idx < kVec) out[idx] = src[idx];
+    }
+    __syncwarp();
+}
+
+// Input staging.  A tile is kCtaThreads consecutive envs; its per-env inputs are up to 16
+// contiguous SoA rows (9 state rows, the first action row, ep_len, ref_idx, total_return, the two
+// position carries, done).  One elected thread streams them global -> shared with TMA bulk
+// copies two tiles ahead of the compute (2-stage ring, one mbarrier per stage), so HBM latency
+// is hidden by the pipeline instead of by occupancy, and nobody spends registers or address
+// arithmetic on the loads.  Tiles that are partial or not 16-byte aligned fall back to plain
+// coalesced loads.
+constexpr int kInRows = 16;
+enum { ROW_ACTION = 9, ROW_EPLEN = 10, ROW_REFIDX = 11, ROW_RET = 12, ROW_OXLO = 13, ROW_OYLO = 14, ROW_DONE = 15 };
+
+template <typename R>
+struct alignas(16) StepSmem {
+    Tables<R> tbl;
+    R in[2][kInRows][kCtaThreads];
+    R obs_slab[kCtaThreads / 32][160];
+    uint64_t bar_tbl;
+    uint64_t bar_in[2];
+};
+
+template <typename R, bool AUTORESET>
+__device__ __forceinline__ void issue_tile(const EnvArgs<R> &A, const StepArgs<R> &S, StepSmem<R> *sm, int stage, unsigned i0)
+{
+    // called by ONE thread; i0 = first env of a full, aligned tile
+    const unsigned n = static_cast<unsigned>(A.n);
+    constexpr uint32_t rb = kCtaThreads * sizeof(R), ib = kCtaThreads * 4u;
+    uint32_t total = 10u * rb + 2u * ib;
+    if (A.total_return) total += rb;
+    if (A.pos_comp) total += 2u * rb;
+    if (!AUTORESET) total += kCtaThreads;
+    uint64_t *bar = &sm->bar_in[stage];
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(total) : "memory");
+    auto cp = [&](void *dst, const void *src, uint32_t bytes) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                     "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                     : "memory");
+    };
+    R(*in)[kCtaThreads] = sm->in[stage];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) cp(in[j], A.state + static_cast<size_t>(j) * n + i0, rb);
+    cp(in[ROW_ACTION], S.actions + i0, rb);
+    cp(in[ROW_EPLEN], A.ep_len + i0, ib);
+    cp(in[ROW_REFIDX], A.ref_idx + i0, ib);
+    if (A.total_return) cp(in[ROW_RET], A.total_return + i0, rb);
+    if (A.pos_comp) {
+        cp(in[ROW_OXLO], A.pos_comp + i0, rb);
+        cp(in[ROW_OYLO], A.pos_comp + static_cast<size_t>(n) + i0, rb);
+    }
+    if (!AUTORESET) cp(in[ROW_DONE], A.done + i0, kCtaThreads);
+}
+
+template <typename R, bool FAST, bool AUTORESET>
+__global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(const EnvArgs<R> A, const StepArgs<R> S)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StepSmem<R> *sm = reinterpret_cast<StepSmem<R> *>(smem_raw);
+    const Tables<R> &tbl = sm->tbl;
+
+    // 32-bit element indices (the C ABI rejects batches whose arrays exceed 2^32 elements)
+    const unsigned n = static_cast<unsigned>(A.n);
+    const unsigned i_begin = static_cast<unsigned>(S.i_begin), i_end = static_cast<unsigned>(S.i_end);
+    const unsigned n_tiles = (i_end - i_begin + kCtaThreads - 1) / kCtaThreads;
+    const unsigned n_full = (i_end - i_begin) / kCtaThreads;     // tiles [0, n_full) are full
+    const bool tma = S.tma_ok != 0;
+    const R dt = A.dt;
+    const bool comp = A.pos_comp != nullptr;
+    const bool aos_fast = A.obs_layout == 0 && S.obs_vec_ok;
+    R *const slab = sm->obs_slab[threadIdx.x >> 5];
+
+    if (threadIdx.x == 0) {
+        mbar_init(&sm->bar_tbl, 1);
+        mbar_init(&sm->bar_in[0], 1);
+        mbar_init(&sm->bar_in[1], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma_bulk_g2s(&sm->tbl, A.tables, static_cast<uint32_t>(sizeof(Tables<R>)), &sm->bar_tbl);
+        if (tma) {   // prologue: two tiles in flight
+            unsigned t0 = blockIdx.x, t1 = blockIdx.x + gridDim.x;
+            if (t0 < n_full) issue_tile<R, AUTORESET>(A, S, sm, 0, i_begin + t0 * kCtaThreads);
+            if (t1 < n_full) issue_tile<R, AUTORESET>(A, S, sm, 1, i_begin + t1 * kCtaThreads);
+        }
+    }
     bool tables_ready = false;
 
-    const int64_t n = A.n;
-    const int64_t n_tiles = (S.i_end - S.i_begin + kCtaThreads - 1) / kCtaThreads;
-    const R dt = A.dt;
-
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t i = S.i_begin + tile * kCtaThreads + threadIdx.x;
-        const bool live = i < S.i_end;
+    unsigned it = 0;
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const unsigned i = i_begin + tile * kCtaThreads + threadIdx.x;
+        const bool live = i < i_end;
+        const unsigned warp_first = i - (threadIdx.x & 31u);
+        const bool warp_full = warp_first + 32u <= i_end;      // warp-uniform
+        const bool staged = tma && tile < n_full;              // CTA-uniform
+        const int stage = it & 1;
         R x[9];
+        R ox_lo = R(0), oy_lo = R(0), a0 = R(0);
         int ep_len = 0, ref_idx = 0;
-        uint32_t done_sticky = 0, episode = 0;
+        uint32_t done_sticky = 0;
+        bool was_reset = false;
         R ret = R(0);
-        if (live) {
+        if (staged) {
+            mbar_wait(&sm->bar_in[stage], (it >> 1) & 1u);
+            const R(*in)[kCtaThreads] = sm->in[stage];
+            const unsigned t = threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) x[j] = in[j][t];
+            a0 = in[ROW_ACTION][t];
+            ep_len = reinterpret_cast<const int *>(in[ROW_EPLEN])[t];
+            ref_idx = reinterpret_cast<const int *>(in[ROW_REFIDX])[t];
+            if (A.total_return) ret = in[ROW_RET][t];
+            if (comp) {
+                ox_lo = in[ROW_OXLO][t];
+                oy_lo = in[ROW_OYLO][t];
+            }
+            if (!AUTORESET) done_sticky = reinterpret_cast<const uint8_t *>(in[ROW_DONE])[t];
+            __syncthreads();                                   // everyone has drained this stage
+            const unsigned next = tile + 2 * gridDim.x;
+            if (threadIdx.x == 0 && next < n_full) issue_tile<R, AUTORESET>(A, S, sm, stage, i_begin + next * kCtaThreads);
+        } else if (live) {
 #pragma unroll
             for (int j = 0; j < 9; ++j) x[j] = A.state[j * n + i];
+            a0 = S.actions[i];
             ep_len = A.ep_len[i];
             ref_idx = A.ref_idx[i];
             done_sticky = AUTORESET ? 0u : A.done[i];
             if (A.total_return) ret = A.total_return[i];
-            if (AUTORESET || A.noise) episode = A.episode_no[i];
+            if (comp) {
+                ox_lo = A.pos_comp[i];
+                oy_lo = A.pos_comp[n + i];
+            }
         }
-        if (!tables_ready) {   // first tile only: the state loads above overlapped the TMA copy
-            tables_wait(&bar);
+        if (!tables_ready) {   // first tile only: the input loads above overlapped the table copy
+            mbar_wait(&sm->bar_tbl, 0);
             tables_ready = true;
         }
         if (!live) continue;
 
+        const R *ref_row = A.ref_bank + static_cast<unsigned>(ref_idx) * static_cast<unsigned>(A.ref_len);
         R o[5];
         bool have_obs = false;
+        R a_k = a0;
         for (int k = 0; k < S.K; ++k) {
+            const unsigned kn = static_cast<unsigned>(k) * n + i;
+            // issue next step's loads before this step's arithmetic: the reference sample (a gather
+            // that depends on ref_idx / ep_len) and the next action row
+            const R ref = ref_row[min(ep_len, A.ref_len - 1)];
+            R a_next = R(0);
+            if (k + 1 < S.K) a_next = S.actions[kn + n];
             R reward = R(0);
             uint32_t done_now = done_sticky;
             if (!done_sticky) {
                 // F16.rescale_action (env.py:200-211): clip to [-1,1], float32-cast bounds
-                const R a = clampr(S.actions[(int64_t)k * n + i], R(-1), R(1));
+                const R a = clampr(a_k, R(-1), R(1));
                 const R u_stab = R(K::act_lo) + R(0.5) * (a + R(1.0)) * R(K::act_span);
-                euler_step<R, FAST>(tbl, x, u_stab, R(0), dt);   // Control(action, 0), env.py:49
+                euler_step<R, FAST>(tbl, x, u_stab, R(0), dt, comp, ox_lo, oy_lo);   // Control(action, 0), env.py:49
                 // check_state (env.py:103-117) on the post-step state, pre-increment counter
                 R pen = R(0);
                 if (!(x[1] > R(300))) { pen += R(-1000); done_now = 1; }
                 if (x[1] >= R(30000)) { pen += R(-1000); done_now = 1; }
                 if (Mth<R, FAST>::fabs(x[2]) >= R(K::wz_term)) { pen += R(-1000); done_now = 1; }
                 if (ep_len == A.horizon) done_now = 1;
-                const R ref = A.ref_bank[(int64_t)ref_idx * A.ref_len + min(ep_len, A.ref_len - 1)];
                 reward = pen + tracking_reward<R, FAST>(ref, x[2]);
                 R wz_obs = x[2];
-                if (A.noise) wz_obs += obs_noise<R>(A, i, episode, ep_len);
+                if (A.noise) wz_obs += obs_noise<R>(A, i, A.episode_no[i], ep_len);
                 make_obs<R, FAST>(x[1], wz_obs, x[4], ref, o);
                 have_obs = true;
                 ep_len += 1;
@@ -246,50 +384,57 @@ __global__ void __launch_bounds__(kCtaThreads) env_step_kernel(const EnvArgs<R> 
                     if (S.final_ep_len) S.final_ep_len[i] = ep_len;
                     if (S.final_return) S.final_return[i] = ret;
                     if (AUTORESET) {
-                        // gymnasium SyncVectorEnv: reset immediately, hand back the reset observation
-                        episode += 1;
+                        // gymnasium SyncVectorEnv: reset immediately, hand back the reset observation.
+                        // Everything only a reset touches (episode counter, reference row, V) is read and
+                        // written here, off the per-step path.
+                        const uint32_t episode = A.episode_no[i] + 1u;
+                        A.episode_no[i] = episode;
                         init_episode<R>(A, i, episode, false, x, ref_idx);
+                        A.ref_idx[i] = ref_idx;
+                        ref_row = A.ref_bank + static_cast<unsigned>(ref_idx) * static_cast<unsigned>(A.ref_len);
+                        was_reset = true;
                         ep_len = 0;
                         ret = R(0);
-                        const R ref0 = A.ref_bank[(int64_t)ref_idx * A.ref_len];
-                        make_obs<R, FAST>(x[1], x[2], x[4], ref0, o);
+                        ox_lo = R(0);
+                        oy_lo = R(0);
+                        make_obs<R, FAST>(x[1], x[2], x[4], ref_row[0], o);
                     } else {
                         done_sticky = 1;
                     }
                 }
             }
-            S.reward[(int64_t)k * n + i] = reward;
-            S.done[(int64_t)k * n + i] = static_cast<uint8_t>(done_now);
+            a_k = a_next;
+            S.reward[kn] = reward;
+            S.done[kn] = static_cast<uint8_t>(done_now);
             if (S.obs_every_step) {
                 if (!have_obs) {   // env was already done when the launch started
-                    const R ref = A.ref_bank[(int64_t)ref_idx * A.ref_len + min(max(ep_len - 1, 0), A.ref_len - 1)];
-                    make_obs<R, FAST>(x[1], x[2], x[4], ref, o);
+                    make_obs<R, FAST>(x[1], x[2], x[4], ref_row[min(max(ep_len - 1, 0), A.ref_len - 1)], o);
                     have_obs = true;
                 }
-                store_obs<R>(S.obs + (int64_t)k * n * 5, A.obs_layout, n, i, o);
+                R *obs_k = S.obs + static_cast<size_t>(k) * n * 5;
+                if (aos_fast && warp_full) store_obs_warp_aos<R>(slab, obs_k + static_cast<size_t>(warp_first) * 5, o);
+                else store_obs<R>(obs_k, A.obs_layout, n, i, o);
             }
         }
         // write back
 #pragma unroll
         for (int j = 0; j < 9; ++j)
-            if (j != 4 || AUTORESET) A.state[j * n + i] = x[j];
+            if (j != 4) A.state[j * n + i] = x[j];
+        if (AUTORESET && was_reset) A.state[4 * n + i] = x[4];   // V only changes at a reset
         A.ep_len[i] = ep_len;
         if (A.total_return) A.total_return[i] = ret;
-        if (AUTORESET) {
-            A.ref_idx[i] = ref_idx;
-            A.episode_no[i] = episode;
-        } else {
-            A.done[i] = static_cast<uint8_t>(done_sticky);
+        if (comp) {
+            A.pos_comp[i] = ox_lo;
+            A.pos_comp[n + i] = oy_lo;
         }
+        if (!AUTORESET) A.done[i] = static_cast<uint8_t>(done_sticky);
         if (!S.obs_every_step && S.obs) {
-            if (!have_obs) {
-                const R ref = A.ref_bank[(int64_t)ref_idx * A.ref_len + min(max(ep_len - 1, 0), A.ref_len - 1)];
-                make_obs<R, FAST>(x[1], x[2], x[4], ref, o);
-            }
-            store_obs<R>(S.obs, A.obs_layout, n, i, o);
+            if (!have_obs) make_obs<R, FAST>(x[1], x[2], x[4], ref_row[min(max(ep_len - 1, 0), A.ref_len - 1)], o);
+            if (aos_fast && warp_full) store_obs_warp_aos<R>(slab, S.obs + static_cast<size_t>(warp_first) * 5, o);
+            else store_obs<R>(S.obs, A.obs_layout, n, i, o);
         }
     }
-    if (!tables_ready) tables_wait(&bar);   // CTA had no tile: still drain the copy before exit
+    if (!tables_ready) mbar_wait(&sm->bar_tbl, 0);   // CTA had no tile: still drain the copy before exit
 }
 
 // ---------------------------------------------------------------------------
@@ -308,6 +453,10 @@ __global__ void __launch_bounds__(kCtaThreads) env_reset_kernel(const EnvArgs<R>
         for (int j = 0; j < 9; ++j) A.state[j * A.n + i] = x[j];
         A.ep_len[i] = 0;
         if (A.total_return) A.total_return[i] = R(0);
+        if (A.pos_comp) {
+            A.pos_comp[i] = R(0);
+            A.pos_comp[A.n + i] = R(0);
+        }
         A.ref_idx[i] = ref_idx;
         A.done[i] = 0;
         A.episode_no[i] = episode;
@@ -411,9 +560,21 @@ template <typename R, bool FAST>
 cudaError_t launch_env_step_t(const EnvArgs<R> &A, const StepArgs<R> &S, const LaunchGeom &g, cudaStream_t st)
 {
     const int grid = grid_for(S.i_end - S.i_begin, g);
-    if (A.autoreset) env_step_kernel<R, FAST, true><<<grid, kCtaThreads, 0, st>>>(A, S);
-    else env_step_kernel<R, FAST, false><<<grid, kCtaThreads, 0, st>>>(A, S);
+    const size_t smem = sizeof(StepSmem<R>);
+    if (A.autoreset) env_step_kernel<R, FAST, true><<<grid, kCtaThreads, smem, st>>>(A, S);
+    else env_step_kernel<R, FAST, false><<<grid, kCtaThreads, smem, st>>>(A, S);
     return cudaGetLastError();
+}
+
+// Opt the step kernels into > 48 KB of dynamic shared memory and report resident CTAs per SM.
+template <typename R, bool FAST, bool AUTORESET>
+int prepare_env_step()
+{
+    auto fn = env_step_kernel<R, FAST, AUTORESET>;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StepSmem<R>)));
+    int b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, kCtaThreads, sizeof(StepSmem<R>));
+    return b;
 }
 
 }  // namespace f16

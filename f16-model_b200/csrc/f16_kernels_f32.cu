@@ -41,12 +41,8 @@ cudaError_t launch_isa(int64_t n, const float *h, float *rho, float *a, const La
 }
 int env_step_occupancy_f32(bool fast, bool autoreset)
 {
-    int b = 0;
-    if (fast && autoreset) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, env_step_kernel<float, true, true>, kCtaThreads, 0);
-    else if (fast) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, env_step_kernel<float, true, false>, kCtaThreads, 0);
-    else if (autoreset) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, env_step_kernel<float, false, true>, kCtaThreads, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, env_step_kernel<float, false, false>, kCtaThreads, 0);
-    return b;
+    if (fast) return autoreset ? prepare_env_step<float, true, true>() : prepare_env_step<float, true, false>();
+    return autoreset ? prepare_env_step<float, false, true>() : prepare_env_step<float, false, false>();
 }
 
 }  // namespace f16

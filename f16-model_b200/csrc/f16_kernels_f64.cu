@@ -42,10 +42,7 @@ cudaError_t launch_isa(int64_t n, const double *h, double *rho, double *a, const
 }
 int env_step_occupancy_f64(bool autoreset)
 {
-    int b = 0;
-    if (autoreset) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, env_step_kernel<double, false, true>, kCtaThreads, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, env_step_kernel<double, false, false>, kCtaThreads, 0);
-    return b;
+    return autoreset ? prepare_env_step<double, false, true>() : prepare_env_step<double, false, false>();
 }
 
 }  // namespace f16

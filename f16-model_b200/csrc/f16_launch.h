@@ -33,6 +33,7 @@ struct EnvArgs {
     uint32_t *episode_no;
     const R *ref_bank;
     const R *init_state;
+    R *pos_comp;   // [2][n] Kahan carry of Ox, Oy (fp32 mode), or nullptr
 };
 
 // typed view of f16_step_io
@@ -47,6 +48,8 @@ struct StepArgs {
     R *final_return;
     int obs_every_step;
     int K;
+    int tma_ok;               // every input row of a full tile is 16-byte aligned: TMA-staged loads allowed
+    int obs_vec_ok;           // obs base is 16-byte aligned: warp-transposed vector stores allowed
     int64_t i_begin, i_end;   // env sub-range advanced by this launch (host-buffer path pipelines chunks)
 };
 

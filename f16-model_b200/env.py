@@ -95,6 +95,10 @@ class F16VecEnv:
         observation, terminal observation in ``info["final_observation"]``).  With False a
         finished env freezes until ``reset``.
     fast_math : fp32 only -- MUFU intrinsics for sin/cos/pow/div.
+    compensated_position : keep a Kahan carry for the Ox / Oy position integrals (default off; +16 B per
+        env-step).  Plain fp32 accumulation of ~2 m increments onto ~2000 m rounds once per step; the carry
+        removes that drift (median Oy error 7e-7 -> 6e-8 over an episode).  Meant for fp32 runs much
+        longer than the reference's 1000-step episodes.
     env_id_base : global id of this shard's env 0 (multi-GPU: rank * num_envs); the device RNG is
         keyed by global env id, so a sharded run reproduces the single-GPU run env for env.
     obs_layout : "aos" -> obs [N, 5] contiguous (reference layout); "soa" -> stored [5, N],
@@ -104,7 +108,7 @@ class F16VecEnv:
     metadata = {}
 
     def __init__(self, config, num_envs, device="cuda", dtype=None, autoreset=True, seed=0, fast_math=False,
-                 obs_layout="aos", bank_size=256, reference_bank=None, env_id_base=0):
+                 obs_layout="aos", bank_size=256, reference_bank=None, env_id_base=0, compensated_position=None):
         import torch
 
         self._torch = torch
@@ -168,6 +172,8 @@ class F16VecEnv:
         self.ref_idx = torch.zeros(N, dtype=torch.int32, device=dev)
         self.done = torch.zeros(N, dtype=torch.uint8, device=dev)
         self.episode_no = torch.zeros(N, dtype=torch.int32, device=dev)
+        compensated_position = bool(compensated_position) and dt_ == torch.float32
+        self.pos_comp = torch.zeros((2, N), dtype=dt_, device=dev) if compensated_position else None
         obs_shape = (N, 5) if obs_layout == "aos" else (5, N)
         self._obs = torch.zeros(obs_shape, dtype=dt_, device=dev)
         self._final_obs = torch.zeros(obs_shape, dtype=dt_, device=dev)
@@ -214,6 +220,7 @@ class F16VecEnv:
         b.episode_no = self.episode_no.data_ptr()
         b.ref_bank = self.ref_bank.data_ptr()
         b.init_state = self.init_state_tensor.data_ptr() if self.init_state_tensor is not None else None
+        b.pos_comp = self.pos_comp.data_ptr() if self.pos_comp is not None else None
         self._buf = b
         io = _capi.StepIO()
         io.obs = self._obs.data_ptr()
@@ -224,6 +231,21 @@ class F16VecEnv:
         io.final_return = self._final_ret.data_ptr()
         io.obs_every_step = 0
         self._io1 = io
+        # prebuilt call arguments / results of the K = 1 fast path
+        self._Tensor = self._torch.Tensor
+        self._step_fn = self._lib.f16_env_step
+        self._cfg_ref, self._buf_ref, self._io1_ref = C.byref(self._cfg), C.byref(self._buf), C.byref(self._io1)
+        terminated = self._done_out[0].view(self._torch.bool)
+        info = {
+            "episode_length": self.episode_length,
+            "total_return": self.total_return,
+            "state": self.state,
+            "_final_info": terminated,
+            "_final_observation": terminated,
+            "final_observation": self._obs_view(self._final_obs),
+            "final_info": {"episode_length": self._final_len, "total_return": self._final_ret},
+        }
+        self._step_result = (self._obs_view(self._obs), self._reward[0], terminated, self._truncated, info)
 
     def _stream(self):
         return C.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)
@@ -269,23 +291,40 @@ class F16VecEnv:
 
     def step(self, actions):
         """One ``F16.step`` for every env (env.py:46-70) -> (obs [N,5], reward [N], terminated [N] bool,
-        truncated [N] bool (all False, as in the reference), info)."""
+        truncated [N] bool (all False, as in the reference), info).
+
+        The returned tensors (and those in ``info``) are the env's own output buffers: the next
+        ``step`` overwrites them, so copy what you keep (a rollout buffer does)."""
+        a = actions
+        if not (a.__class__ is self._Tensor and a.dtype == self.dtype and a.device == self.device
+                and a.is_contiguous() and a.numel() == self.num_envs):
+            a = self._actions(a)
+        self._io1.actions = a.data_ptr()
+        stream = self._torch.cuda.current_stream(self.device).cuda_stream
+        if self._torch.cuda.current_device() == self.device.index:
+            rc = self._step_fn(self._cfg_ref, self._buf_ref, self._io1_ref, 1, stream)
+        else:
+            with self._torch.cuda.device(self.device):
+                rc = self._step_fn(self._cfg_ref, self._buf_ref, self._io1_ref, 1, stream)
+        if rc:
+            _capi.check(rc)
+        return self._step_result
+
+    def make_graphed_step(self, actions):
+        """Capture ``step(actions)`` into a CUDA graph (launch-bound inner loops: one graph launch
+        instead of a Python call + kernel launch).  ``actions`` is a static device buffer the
+        caller refills before each ``replay()``; outputs land in the usual step buffers."""
         torch = self._torch
         a = self._actions(actions)
-        self._io1.actions = a.data_ptr()
-        with torch.cuda.device(self.device):
-            _capi.check(self._lib.f16_env_step(C.byref(self._cfg), C.byref(self._buf), C.byref(self._io1), 1, self._stream()))
-        terminated = self._done_out[0].view(torch.bool)
-        info = {
-            "episode_length": self.episode_length,
-            "total_return": self.total_return,
-            "state": self.state,
-            "_final_info": terminated,
-            "_final_observation": terminated,
-            "final_observation": self._obs_view(self._final_obs),
-            "final_info": {"episode_length": self._final_len, "total_return": self._final_ret},
-        }
-        return self._obs_view(self._obs), self._reward[0], terminated, self._truncated, info
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.step(a)                    # warm up outside capture (table upload, lazy init)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step(a)
+        return graph, self._step_result
 
     def step_k(self, actions, obs_every_step=False, out=None):
         """K consecutive steps in ONE launch with the state held in registers.  actions [K, N]
@@ -350,6 +389,8 @@ class F16VecEnv:
         self.state.copy_(t.to(device=self.device, dtype=self.dtype))
         self.done.zero_()
         self.total_return.zero_()
+        if self.pos_comp is not None:
+            self.pos_comp.zero_()
         if episode_length is None:
             self.episode_length.zero_()
         else:

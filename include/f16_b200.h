@@ -78,6 +78,9 @@ typedef struct f16_env_buffers {
     uint32_t *episode_no;    /* [n]          r/w  episodes started so far (RNG counter) */
     const void *ref_bank;    /* real[n_ref][ref_len]  wz_ref = theta_ref/2 (env/task.py:25-26) */
     const void *init_state;  /* real[9][n]   F16_INIT_PER_ENV only, else NULL */
+    void *pos_comp;          /* real[2][n]   r/w  Kahan carry of the Ox, Oy position integrals, or NULL: keeps the
+                                fp32 mode's positions within ~1e-7 of the fp64 reference over an episode (plain fp32
+                                accumulation drifts up to 1 ulp per step). Leave NULL in fp64 parity mode. */
 } f16_env_buffers;
 
 /* Per-call tensors of f16_env_step. */
