@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "lib", "libf16b200.so")
+# F16B200_LIB: alternative build of the same library (kernel-tuning experiments only)
+_LIB = os.environ.get("F16B200_LIB") or os.path.join(_HERE, "lib", "libf16b200.so")
 _lib = None
 
 F16_F32, F16_F64 = 0, 1

@@ -130,8 +130,9 @@ int check_cfg(const f16_config *cfg)
 int check_env(const f16_config *cfg, const f16_env_buffers *env)
 {
     if (!env) return fail(F16_EINVAL, "env buffers are NULL");
-    if (!env->state || !env->ep_len || !env->ref_idx || !env->done || !env->episode_no || !env->ref_bank)
-        return fail(F16_EINVAL, "state, ep_len, ref_idx, done, episode_no and ref_bank are required");
+    if (!env->state || !env->ep_len || !env->total_return || !env->ref_idx || !env->done || !env->episode_no || !env->ref_bank)
+        return fail(F16_EINVAL, "state, ep_len, total_return, ref_idx, done, episode_no and ref_bank are required");
+    if (env->pos_comp && cfg->dtype != F16_F32) return fail(F16_EINVAL, "pos_comp is an fp32-mode feature; leave it NULL in fp64");
     if (cfg->init_mode == F16_INIT_PER_ENV && !env->init_state)
         return fail(F16_EINVAL, "init_mode F16_INIT_PER_ENV needs env->init_state");
     return F16_OK;
@@ -212,7 +213,7 @@ int tma_aligned(const f16_config *cfg, const f16_env_buffers *env, const f16_ste
     const size_t es = cfg->dtype == F16_F32 ? 4 : 8;
     auto ok = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
     if (!ok(env->state) || !ok(env->ep_len) || !ok(env->ref_idx) || !ok(env->done) || !ok(io->actions)) return 0;
-    if (env->total_return && !ok(env->total_return)) return 0;
+    if (!ok(env->total_return)) return 0;
     if (env->pos_comp && !ok(env->pos_comp)) return 0;
     if ((static_cast<size_t>(cfg->n_envs) * es) % 16 != 0) return 0;
     if (i0 % 16 != 0) return 0;

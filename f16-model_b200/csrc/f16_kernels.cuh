@@ -48,11 +48,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(2000u)   // suspend-time hint [ns]: a waiting warp sleeps instead of burning issue slots
         : "memory");
 }
 
@@ -107,14 +107,15 @@ __device__ __forceinline__ void make_obs(R Oy, R wz_obs, R V, R ref, R (&o)[5])
 }
 
 template <typename R>
-__device__ __forceinline__ void store_obs(R *obs, int layout, int64_t n, int64_t i, const R (&o)[5])
+__device__ __forceinline__ void store_obs(R *obs, int layout, unsigned n, unsigned i, const R (&o)[5])
 {
     if (layout == 0) {
+        R *p = obs + static_cast<size_t>(i) * 5;   // one address, five immediate-offset stores (L2 merges the sectors)
 #pragma unroll
-        for (int j = 0; j < 5; ++j) obs[i * 5 + j] = o[j];
+        for (int j = 0; j < 5; ++j) p[j] = o[j];
     } else {
 #pragma unroll
-        for (int j = 0; j < 5; ++j) obs[j * n + i] = o[j];
+        for (int j = 0; j < 5; ++j) obs[static_cast<size_t>(j) * n + i] = o[j];
     }
 }
 
@@ -186,32 +187,11 @@ __device__ __forceinline__ R obs_noise(const EnvArgs<R> &A, int64_t i, uint32_t 
 // Resident CTAs per SM the register allocator is asked to make room for: fp32 64 regs/thread
 // (4 x 256 threads = 32 warps/SM hide the HBM latency of the K = 1 gym step), fp64 128 regs.
 template <typename R> struct MinCtas;
-template <> struct MinCtas<float> { static constexpr int v = 4; };
+#ifndef F16_MINCTAS_F32
+#define F16_MINCTAS_F32 4
+#endif
+template <> struct MinCtas<float> { static constexpr int v = F16_MINCTAS_F32; };
 template <> struct MinCtas<double> { static constexpr int v = 2; };
-
-// 16-byte global store of a staged shared-memory vector
-struct alignas(16) V16 { unsigned x, y, z, w; };
-
-// Coalesced store of one warp's 32 x 5 observations in the reference's AoS layout obs[n][5]:
-// the warp transposes through its private shared-memory slab (stride 5 words: conflict-free)
-// and writes 16-byte vectors, instead of five 20-byte-strided scalar stores per lane.
-template <typename R>
-__device__ __forceinline__ void store_obs_warp_aos(R *slab, R *dst /* obs + 5 * first env of the warp */, const R (&o)[5])
-{
-    const unsigned lane = threadIdx.x & 31u;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) slab[lane * 5 + j] = o[j];
-    __syncwarp();
-    constexpr unsigned kVec = 160 * sizeof(R) / 16;   // 40 (fp32) / 80 (fp64)
-    const V16 *src = reinterpret_cast<const V16 *>(slab);
-    V16 *out = reinterpret_cast<V16 *>(dst);
-#pragma unroll
-    for (unsigned v = 0; v < (kVec + 31) / 32; ++v) {
-        const unsigned idx = v * 32 + lane;
-        if (idx < kVec) out[idx] = src[idx];
-    }
-    __syncwarp();
-}
 
 // Input staging.  A tile is kCtaThreads consecutive envs; its per-env inputs are up to 16
 // contiguous SoA rows (9 state rows, the first action row, ep_len, ref_idx, total_return, the two
@@ -227,21 +207,18 @@ template <typename R>
 struct alignas(16) StepSmem {
     Tables<R> tbl;
     R in[2][kInRows][kCtaThreads];
-    R obs_slab[kCtaThreads / 32][160];
     uint64_t bar_tbl;
-    uint64_t bar_in[2];
+    uint64_t bar_in[2];      // "full": TMA bytes of a stage have landed
+    unsigned drained[2];     // warps that have copied a stage into registers; the last one refills it
 };
 
-template <typename R, bool AUTORESET>
+template <typename R, bool AUTORESET, bool COMP>
 __device__ __forceinline__ void issue_tile(const EnvArgs<R> &A, const StepArgs<R> &S, StepSmem<R> *sm, int stage, unsigned i0)
 {
     // called by ONE thread; i0 = first env of a full, aligned tile
     const unsigned n = static_cast<unsigned>(A.n);
     constexpr uint32_t rb = kCtaThreads * sizeof(R), ib = kCtaThreads * 4u;
-    uint32_t total = 10u * rb + 2u * ib;
-    if (A.total_return) total += rb;
-    if (A.pos_comp) total += 2u * rb;
-    if (!AUTORESET) total += kCtaThreads;
+    constexpr uint32_t total = 11u * rb + 2u * ib + (COMP ? 2u * rb : 0u) + (AUTORESET ? 0u : kCtaThreads);
     uint64_t *bar = &sm->bar_in[stage];
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(total) : "memory");
     auto cp = [&](void *dst, const void *src, uint32_t bytes) {
@@ -255,15 +232,17 @@ __device__ __forceinline__ void issue_tile(const EnvArgs<R> &A, const StepArgs<R
     cp(in[ROW_ACTION], S.actions + i0, rb);
     cp(in[ROW_EPLEN], A.ep_len + i0, ib);
     cp(in[ROW_REFIDX], A.ref_idx + i0, ib);
-    if (A.total_return) cp(in[ROW_RET], A.total_return + i0, rb);
-    if (A.pos_comp) {
+    cp(in[ROW_RET], A.total_return + i0, rb);
+    if (COMP) {
         cp(in[ROW_OXLO], A.pos_comp + i0, rb);
         cp(in[ROW_OYLO], A.pos_comp + static_cast<size_t>(n) + i0, rb);
     }
     if (!AUTORESET) cp(in[ROW_DONE], A.done + i0, kCtaThreads);
 }
 
-template <typename R, bool FAST, bool AUTORESET>
+// SINGLE: the K = 1 gym step (one action row, one observation) with the K-loop bookkeeping compiled out.
+// COMP: Kahan carries for the position integrals (fp32 only).
+template <typename R, bool FAST, bool AUTORESET, bool SINGLE, bool COMP>
 __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(const EnvArgs<R> A, const StepArgs<R> S)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -277,22 +256,22 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
     const unsigned n_full = (i_end - i_begin) / kCtaThreads;     // tiles [0, n_full) are full
     const bool tma = S.tma_ok != 0;
     const R dt = A.dt;
-    const bool comp = A.pos_comp != nullptr;
-    const bool aos_fast = A.obs_layout == 0 && S.obs_vec_ok;
-    R *const slab = sm->obs_slab[threadIdx.x >> 5];
+    constexpr bool comp = COMP;
 
     if (threadIdx.x == 0) {
         mbar_init(&sm->bar_tbl, 1);
         mbar_init(&sm->bar_in[0], 1);
         mbar_init(&sm->bar_in[1], 1);
+        sm->drained[0] = 0;
+        sm->drained[1] = 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         tma_bulk_g2s(&sm->tbl, A.tables, static_cast<uint32_t>(sizeof(Tables<R>)), &sm->bar_tbl);
         if (tma) {   // prologue: two tiles in flight
             unsigned t0 = blockIdx.x, t1 = blockIdx.x + gridDim.x;
-            if (t0 < n_full) issue_tile<R, AUTORESET>(A, S, sm, 0, i_begin + t0 * kCtaThreads);
-            if (t1 < n_full) issue_tile<R, AUTORESET>(A, S, sm, 1, i_begin + t1 * kCtaThreads);
+            if (t0 < n_full) issue_tile<R, AUTORESET, COMP>(A, S, sm, 0, i_begin + t0 * kCtaThreads);
+            if (t1 < n_full) issue_tile<R, AUTORESET, COMP>(A, S, sm, 1, i_begin + t1 * kCtaThreads);
         }
     }
     bool tables_ready = false;
@@ -301,8 +280,6 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
     for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const unsigned i = i_begin + tile * kCtaThreads + threadIdx.x;
         const bool live = i < i_end;
-        const unsigned warp_first = i - (threadIdx.x & 31u);
-        const bool warp_full = warp_first + 32u <= i_end;      // warp-uniform
         const bool staged = tma && tile < n_full;              // CTA-uniform
         const int stage = it & 1;
         R x[9];
@@ -320,15 +297,25 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
             a0 = in[ROW_ACTION][t];
             ep_len = reinterpret_cast<const int *>(in[ROW_EPLEN])[t];
             ref_idx = reinterpret_cast<const int *>(in[ROW_REFIDX])[t];
-            if (A.total_return) ret = in[ROW_RET][t];
+            ret = in[ROW_RET][t];
             if (comp) {
                 ox_lo = in[ROW_OXLO][t];
                 oy_lo = in[ROW_OYLO][t];
             }
             if (!AUTORESET) done_sticky = reinterpret_cast<const uint8_t *>(in[ROW_DONE])[t];
-            __syncthreads();                                   // everyone has drained this stage
-            const unsigned next = tile + 2 * gridDim.x;
-            if (threadIdx.x == 0 && next < n_full) issue_tile<R, AUTORESET>(A, S, sm, stage, i_begin + next * kCtaThreads);
+            // This warp has drained the stage.  The LAST warp of the CTA to get here refills the stage
+            // with the tile two ahead -- at the earliest possible moment and with no CTA-wide barrier.
+            // (A fixed producer thread does not work: the SM's scheduler favours high warp ids, so
+            // warp 0 runs last and every other warp ends up waiting for its refill.)
+            __syncwarp();
+            if ((threadIdx.x & 31u) == 0) {
+                const unsigned prior = atomicAdd(&sm->drained[stage], 1u);
+                if (prior == kCtaThreads / 32 - 1) {
+                    sm->drained[stage] = 0;
+                    const unsigned next = tile + 2 * gridDim.x;
+                    if (next < n_full) issue_tile<R, AUTORESET, COMP>(A, S, sm, stage, i_begin + next * kCtaThreads);
+                }
+            }
         } else if (live) {
 #pragma unroll
             for (int j = 0; j < 9; ++j) x[j] = A.state[j * n + i];
@@ -336,7 +323,7 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
             ep_len = A.ep_len[i];
             ref_idx = A.ref_idx[i];
             done_sticky = AUTORESET ? 0u : A.done[i];
-            if (A.total_return) ret = A.total_return[i];
+            ret = A.total_return[i];
             if (comp) {
                 ox_lo = A.pos_comp[i];
                 oy_lo = A.pos_comp[n + i];
@@ -352,13 +339,15 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
         R o[5];
         bool have_obs = false;
         R a_k = a0;
-        for (int k = 0; k < S.K; ++k) {
+        const int K_steps = SINGLE ? 1 : S.K;
+        const bool every = !SINGLE && S.obs_every_step;
+        for (int k = 0; k < K_steps; ++k) {
             const unsigned kn = static_cast<unsigned>(k) * n + i;
             // issue next step's loads before this step's arithmetic: the reference sample (a gather
             // that depends on ref_idx / ep_len) and the next action row
             const R ref = ref_row[min(ep_len, A.ref_len - 1)];
             R a_next = R(0);
-            if (k + 1 < S.K) a_next = S.actions[kn + n];
+            if (!SINGLE && k + 1 < K_steps) a_next = S.actions[kn + n];
             R reward = R(0);
             uint32_t done_now = done_sticky;
             if (!done_sticky) {
@@ -406,32 +395,34 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
             a_k = a_next;
             S.reward[kn] = reward;
             S.done[kn] = static_cast<uint8_t>(done_now);
-            if (S.obs_every_step) {
+            if (every) {
                 if (!have_obs) {   // env was already done when the launch started
                     make_obs<R, FAST>(x[1], x[2], x[4], ref_row[min(max(ep_len - 1, 0), A.ref_len - 1)], o);
                     have_obs = true;
                 }
-                R *obs_k = S.obs + static_cast<size_t>(k) * n * 5;
-                if (aos_fast && warp_full) store_obs_warp_aos<R>(slab, obs_k + static_cast<size_t>(warp_first) * 5, o);
-                else store_obs<R>(obs_k, A.obs_layout, n, i, o);
+                store_obs<R>(S.obs + static_cast<size_t>(k) * n * 5, A.obs_layout, n, i, o);
             }
         }
         // write back
+        {
+            R *p = A.state + i;   // row pointers by repeated "+= n": one IMAD.WIDE per row, no per-row induction variables
 #pragma unroll
-        for (int j = 0; j < 9; ++j)
-            if (j != 4) A.state[j * n + i] = x[j];
-        if (AUTORESET && was_reset) A.state[4 * n + i] = x[4];   // V only changes at a reset
+            for (int j = 0; j < 9; ++j) {
+                if (j != 4) *p = x[j];
+                else if (AUTORESET && was_reset) *p = x[4];   // V only changes at a reset
+                p += n;
+            }
+        }
         A.ep_len[i] = ep_len;
-        if (A.total_return) A.total_return[i] = ret;
+        A.total_return[i] = ret;
         if (comp) {
             A.pos_comp[i] = ox_lo;
             A.pos_comp[n + i] = oy_lo;
         }
         if (!AUTORESET) A.done[i] = static_cast<uint8_t>(done_sticky);
-        if (!S.obs_every_step && S.obs) {
+        if (!every && S.obs) {
             if (!have_obs) make_obs<R, FAST>(x[1], x[2], x[4], ref_row[min(max(ep_len - 1, 0), A.ref_len - 1)], o);
-            if (aos_fast && warp_full) store_obs_warp_aos<R>(slab, S.obs + static_cast<size_t>(warp_first) * 5, o);
-            else store_obs<R>(S.obs, A.obs_layout, n, i, o);
+            store_obs<R>(S.obs, A.obs_layout, n, i, o);
         }
     }
     if (!tables_ready) mbar_wait(&sm->bar_tbl, 0);   // CTA had no tile: still drain the copy before exit
@@ -561,8 +552,19 @@ cudaError_t launch_env_step_t(const EnvArgs<R> &A, const StepArgs<R> &S, const L
 {
     const int grid = grid_for(S.i_end - S.i_begin, g);
     const size_t smem = sizeof(StepSmem<R>);
-    if (A.autoreset) env_step_kernel<R, FAST, true><<<grid, kCtaThreads, smem, st>>>(A, S);
-    else env_step_kernel<R, FAST, false><<<grid, kCtaThreads, smem, st>>>(A, S);
+    const bool single = S.K == 1;
+    const bool comp = A.pos_comp != nullptr && sizeof(R) == 4;
+#define F16_LAUNCH(AR, SG, CP) env_step_kernel<R, FAST, AR, SG, CP><<<grid, kCtaThreads, smem, st>>>(A, S)
+    if (comp) {
+        if constexpr (sizeof(R) == 4) {
+            if (A.autoreset) { if (single) F16_LAUNCH(true, true, true); else F16_LAUNCH(true, false, true); }
+            else             { if (single) F16_LAUNCH(false, true, true); else F16_LAUNCH(false, false, true); }
+        }
+    } else {
+        if (A.autoreset) { if (single) F16_LAUNCH(true, true, false); else F16_LAUNCH(true, false, false); }
+        else             { if (single) F16_LAUNCH(false, true, false); else F16_LAUNCH(false, false, false); }
+    }
+#undef F16_LAUNCH
     return cudaGetLastError();
 }
 
@@ -570,11 +572,19 @@ cudaError_t launch_env_step_t(const EnvArgs<R> &A, const StepArgs<R> &S, const L
 template <typename R, bool FAST, bool AUTORESET>
 int prepare_env_step()
 {
-    auto fn = env_step_kernel<R, FAST, AUTORESET>;
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StepSmem<R>)));
-    int b = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, kCtaThreads, sizeof(StepSmem<R>));
-    return b;
+    int b1 = 0, bk = 0;
+    auto prep = [](auto fn, int &b) {
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StepSmem<R>)));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, kCtaThreads, sizeof(StepSmem<R>));
+    };
+    prep(env_step_kernel<R, FAST, AUTORESET, true, false>, b1);
+    prep(env_step_kernel<R, FAST, AUTORESET, false, false>, bk);
+    if constexpr (sizeof(R) == 4) {
+        int c1 = 0, ck = 0;
+        prep(env_step_kernel<R, FAST, AUTORESET, true, true>, c1);
+        prep(env_step_kernel<R, FAST, AUTORESET, false, true>, ck);
+    }
+    return b1 < bk ? b1 : bk;
 }
 
 }  // namespace f16

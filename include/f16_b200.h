@@ -72,7 +72,7 @@ typedef struct f16_config {
 typedef struct f16_env_buffers {
     void *state;             /* real[9][n]   r/w */
     int32_t *ep_len;         /* [n]          r/w  F16.episode_length */
-    void *total_return;      /* real[n]      r/w  F16.total_return; may be NULL */
+    void *total_return;      /* real[n]      r/w  F16.total_return */
     int32_t *ref_idx;        /* [n]          r/w  row of ref_bank followed by each env */
     uint8_t *done;           /* [n]          r/w  F16.done (sticky until reset; always 0 after an autoreset) */
     uint32_t *episode_no;    /* [n]          r/w  episodes started so far (RNG counter) */

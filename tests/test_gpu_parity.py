@@ -384,7 +384,8 @@ def test_graphed_step_equals_eager_step(f16):
     b_env = f16.F16VecEnv(CFG, n, seed=9)
     static = torch.zeros(n, device="cuda")
     graph, (obs_g, rew_g, term_g, _, _) = b_env.make_graphed_step(static)
-    b_env.reset(seed=9)                                 # undo the warm-up + capture steps
+    for name in ("state", "episode_length", "total_return", "ref_idx", "done", "episode_no"):
+        getattr(b_env, name).copy_(getattr(a_env, name))    # undo the warm-up step
     acts = torch.rand((5, n), device="cuda") * 2 - 1
     for k in range(5):
         o, r, d, _, _ = a_env.step(acts[k])
