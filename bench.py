@@ -49,42 +49,66 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (one streaming
+    `nvidia-smi -lms` process, the recipe's query in B200_PROFILING.md)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=20):
         super().__init__(daemon=True)
-        self.index, self.samples, self._halt = index, [], threading.Event()
+        self.samples, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.1)
+        if self.proc is None:
+            return
+        for line in self.proc.stdout:
+            parts = [c.strip() for c in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append((time.perf_counter(), parts))
 
-    def stop(self):
-        self._halt.set()
-        self.join(timeout=6)
-        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+    def stop(self, t0=None, t1=None):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        self.join(timeout=5)
+        rows = [p for t, p in self.samples if (t0 is None or t >= t0) and (t1 is None or t <= t1)] or [p for _, p in self.samples]
+
+        def num(v):
+            try:
+                return int(float(v))
+            except ValueError:
+                return None
+        sm = sorted(v for v in (num(r[0]) for r in rows) if v is not None)
+        mx = [v for v in (num(r[1]) for r in rows) if v is not None]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "", 1).isdigit()]
         reasons = set()
-        for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(pw) if pw else None}
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_run(n_envs, n_steps, threads=0, seed=0):
+def host_threads():
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm ignores that)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_oracle_run(n_envs, n_steps, threads=None, seed=0):
     """Time the CPU oracle on a bounded sample of the same workload: n_envs aircraft from the
     same initial-state distribution, uniform random stick, n_steps env-steps each."""
     import numpy as np
@@ -101,10 +125,11 @@ def cpu_oracle_run(n_envs, n_steps, threads=0, seed=0):
     acts = rng.uniform(-1, 1, (n_steps, n_envs))
     bank = f16.build_reference_bank(0.01, 10, "combo", False, bank_size=64, seed=seed)
     idx = rng.integers(0, bank.shape[0], n_envs).astype(np.int32)
+    threads = threads or host_threads()
     t0 = time.perf_counter()
     out = orc.rollout(x0, acts, bank, idx, want_states=False, want_obs=True, nthreads=threads)
     dt = time.perf_counter() - t0
-    return out["env_steps"], dt, orc.num_threads() if threads == 0 else threads
+    return out["env_steps"], dt, threads
 
 
 def reference_arm(args, rank, world):
@@ -141,8 +166,8 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--no-sweep", action="store_true", help="skip the K-substeps sweep")
@@ -181,47 +206,70 @@ def main():
 
     N = args.envs
     fast = bool(args.fast_math)
-    env = make_sharded_env(CFG, N * world, rank, world, device, dtype=torch.float32, autoreset=True, seed=1,
-                           fast_math=fast, bank_size=256)
+    # R_SETS independent batches of N envs resident in HBM, stepped round-robin: the cycle touches
+    # R_SETS x 77 MB (state + actions + outputs) = 308 MB >> 126 MB of L2, so every step's inputs come
+    # from HBM and its dirty lines are written back while the next batches run -- the steady state of a
+    # streaming workload, with no flush kernel inside the timed region.
+    R_SETS, POOL = 4, 8
+    envs = [make_sharded_env(CFG, N * world, rank, world, device, dtype=torch.float32, autoreset=True, seed=1 + j,
+                             fast_math=fast, bank_size=256) for j in range(R_SETS)]
+    env = envs[0]
     g = torch.Generator(device=device).manual_seed(1000 + rank)
-    pool = torch.rand((16, N), device=device, generator=g) * 2 - 1          # 16 different stick tensors, cycled
+    pools = [torch.rand((POOL, N), device=device, generator=g) * 2 - 1 for _ in range(R_SETS)]   # stick tensors, cycled
+    pool = pools[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)          # > 126 MB L2
 
-    static_actions = pool[0].clone()
-    graph, _ = env.make_graphed_step(static_actions)                          # same launch, replayed from a CUDA graph
+    def enqueue_steps(n_steps, first=0):
+        for s in range(first, first + n_steps):
+            envs[s % R_SETS].step(pools[s % R_SETS][(s // R_SETS) % POOL])
 
-    def timed_steps(n_steps, do_flush=True, graphed=False):
+    for _ in range(max(args.warmup, 3)):
+        enqueue_steps(R_SETS)
+    torch.cuda.synchronize()
+
+    # The K = 1 gym step is launch-bound from Python (~30 us of interpreter + ctypes per call vs a
+    # ~25 us kernel), so the timed loop replays a CUDA graph of G consecutive steps.
+    G = min(48, args.steps)
+    graphs = {}
+
+    def graph_of(n_steps):
+        if n_steps not in graphs:
+            side = torch.cuda.Stream(device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                enqueue_steps(R_SETS)
+            torch.cuda.current_stream(device).wait_stream(side)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                enqueue_steps(n_steps)
+            graphs[n_steps] = gr
+        return graphs[n_steps]
+
+    def timed_graph_steps(n_steps):
+        plan = [G] * (n_steps // G) + ([n_steps % G] if n_steps % G else [])
+        for k in set(plan):
+            graph_of(k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for k in plan:
+            graphs[k].replay()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)                                             # ms on the device for exactly n_steps
+
+    def timed_steps(n_steps, do_flush=True):
+        """Secondary measurement: eager API calls, one CUDA-event pair per step, optional write-flush of L2."""
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
         for s in range(n_steps):
-            if graphed:
-                static_actions.copy_(pool[s % 16])
             if do_flush:
                 flush.fill_(s & 0xFF)
             ev[s][0].record()
-            if graphed:
-                graph.replay()
-            else:
-                env.step(pool[s % 16])
+            env.step(pool[s % POOL])
             ev[s][1].record()
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in ev)                          # ms on the device
-
-    for _ in range(max(args.warmup, 3)):
-        flush.fill_(0)
-        env.step(pool[0])
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    t_wall0 = time.perf_counter()
-    dev_ms = timed_steps(args.steps, do_flush=True)
-    barrier()
-    wall_s = time.perf_counter() - t_wall0
-    warm_ms = timed_steps(args.steps, do_flush=False)                         # L2-warm variant, reported separately
-    barrier()
-    graph_ms = max_over_ranks_later = timed_steps(args.steps, do_flush=True, graphed=True)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
+        return sum(a.elapsed_time(b) for a, b in ev)
 
     def max_over_ranks(x):
         if world == 1:
@@ -230,9 +278,27 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    timed_graph_steps(min(args.steps, 4 * G))                                  # warm the graphs themselves
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.1)
+    t_wall0 = time.perf_counter()
+    dev_ms = timed_graph_steps(args.steps)
+    t_wall1 = time.perf_counter()
+    wall_s = t_wall1 - t_wall0
+    n_sec = min(args.steps, 500)
+    flushed_ms = timed_steps(n_sec, do_flush=True)
+    eager_t0 = time.perf_counter()
+    enqueue_steps(n_sec)
+    torch.cuda.synchronize()
+    eager_s = time.perf_counter() - eager_t0
+    barrier()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
     dev_ms = max_over_ranks(dev_ms)
-    warm_ms = max_over_ranks(warm_ms)
-    graph_ms = max_over_ranks(graph_ms)
+    flushed_ms = max_over_ranks(flushed_ms)
+    eager_s = max_over_ranks(eager_s)
     total_env_steps = N * world * args.steps
     value = total_env_steps / (dev_ms * 1e-3)
 
@@ -245,7 +311,7 @@ def main():
         for s in range(3):
             env.step_host(a_host[s % 4], out=out)
         barrier()
-        n_e2e = max(10, min(args.steps, 50))
+        n_e2e = max(10, min(args.steps, 100))
         t0 = time.perf_counter()
         for s in range(n_e2e):
             env.step_host(a_host[s % 4], out=out)
@@ -295,17 +361,24 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": traffic, "peak_kind": f"of {peak_kind}", "kernel": "env_step_kernel<float,fast,autoreset>",
                 "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP_F32, "units_per_launch": N,
-                "avg_launch_us": per_launch_s * 1e6, "l2_warm_frac": BYTES_PER_ENV_STEP_F32 * N / (warm_ms * 1e-3 / args.steps) / 1e9 / peaks["hbm_gbs"]}
+                "avg_launch_us": per_launch_s * 1e6,
+                "timing": "CUDA events around the whole timed region (graph replays of consecutive steps) / steps: includes inter-kernel gaps",
+                "frac_single_launch_write_flushed_l2": BYTES_PER_ENV_STEP_F32 * N / (flushed_ms * 1e-3 / n_sec) / 1e9 / peaks["hbm_gbs"]}
 
     cpu = None
     if not args.no_cpu:
         probe_steps, probe_dt, cores = cpu_oracle_run(1 << 13, 16)
         rate = probe_steps / probe_dt
-        n_envs = 1 << 17
-        n_steps = int(min(1000, max(16, rate * 12 / n_envs)))                 # ~12 s of CPU work
-        steps_done, dt, cores = cpu_oracle_run(n_envs, n_steps)
+        n_envs, n_steps = 1 << 17, 500
+        reps = int(min(64, max(1, round(rate * 12 / (n_envs * n_steps)))))    # ~12 s of CPU work
+        steps_done = dt = 0
+        for r in range(reps):
+            s_, d_, cores = cpu_oracle_run(n_envs, n_steps, seed=r)
+            steps_done += s_
+            dt += d_
         cpu = {"value": steps_done / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_envs} envs x {n_steps} env-steps ({dt:.1f} s), same distributions, C oracle port (gcc -O2, OpenMP)"}
+               "sample": f"{reps} x ({n_envs} envs x {n_steps} env-steps) = {steps_done:.3g} env-steps in {dt:.1f} s, same "
+                         "distributions as the GPU workload, C oracle port (gcc -O2, OpenMP)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -314,10 +387,13 @@ def main():
         "config": {"workload": "BASELINE configs[2]: 2^20 envs per GPU, fp32, random init + random combo refs + uniform stick, "
                                "gym step K=1 with autoreset, obs [N,5] + reward + done emitted every step",
                    "envs_per_gpu": N, "substeps_per_launch": 1, "fast_math": fast, "parallelism": f"env-shard x{world}, no collective",
-                   "l2": "flushed before every timed step (256 MiB fill, outside the CUDA-event bracket)"},
+                   "l2": "inputs larger than L2: 4 resident batches of 2^20 envs stepped round-robin (308 MB per cycle vs 126 MB L2), "
+                         "no flush kernel in the timed region",
+                   "launch": f"CUDA graph of {G} consecutive steps, replayed"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu,
-        "value_l2_warm": total_env_steps / (warm_ms * 1e-3), "value_cuda_graph_replay": total_env_steps / (graph_ms * 1e-3),
-        "wall_s_timed_region_incl_flush": wall_s,
+        "value_eager_python_loop": N * world * n_sec / eager_s,
+        "value_single_launch_events_write_flushed_l2": N * world * n_sec / (flushed_ms * 1e-3),
+        "wall_s_timed_region": wall_s,
         "substeps_sweep_env_steps_per_s": sweep,
     }
     print(json.dumps(line), flush=True)
