@@ -11,6 +11,7 @@
 
 #include "../../include/f16_b200.h"
 #include "f16_launch.h"
+#include "f16_policy.h"
 
 namespace {
 
@@ -461,6 +462,35 @@ int f16_atmosphere(int dtype, int64_t n, const void *h, void *rho, void *a, void
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     DISPATCH_SIMPLE(f16::launch_isa(n, (const float *)h, (float *)rho, (float *)a, g, st),
                     f16::launch_isa(n, (const double *)h, (double *)rho, (double *)a, g, st));
+    return F16_OK;
+}
+
+int f16_policy_blob_bytes(void) { return static_cast<int>(sizeof(f16::PolicyBlob)); }
+
+int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void *logstd, void *mean, void *value, void *action,
+                       void *logprob, int sample, uint64_t seed, uint32_t step, int64_t env_id_base, void *stream)
+{
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(n, &c, &g);
+    if (rc) return rc;
+    if (!obs || !blob) return fail(F16_EINVAL, "obs and blob are required");
+    if (reinterpret_cast<uintptr_t>(blob) % 16 != 0) return fail(F16_EINVAL, "blob must be 16-byte aligned");
+    if (action && !logstd) return fail(F16_EINVAL, "sampling an action needs logstd");
+    f16::PolicyArgs P;
+    P.blob = static_cast<const f16::PolicyBlob *>(blob);
+    P.obs = static_cast<const float *>(obs);
+    P.logstd = static_cast<const float *>(logstd);
+    P.mean = static_cast<float *>(mean);
+    P.value = static_cast<float *>(value);
+    P.action = static_cast<float *>(action);
+    P.logprob = static_cast<float *>(logprob);
+    P.n = n;
+    P.sample = sample;
+    P.step = step;
+    P.seed = seed;
+    P.id_base = env_id_base;
+    CUDA_TRY(f16::launch_policy_forward(P, c->n_sm, static_cast<cudaStream_t>(stream)));
     return F16_OK;
 }
 

@@ -1,0 +1,125 @@
+"""Agent MLPs on the tensor cores -- mirror of the network part of ``Agent``
+(control/ppo/ppo_model_gsde.py:37-66,81-99): ``actor_mean`` and ``critic`` are
+``Linear(5,64) Tanh Linear(64,64) Tanh Linear(64,1)``; the policy is Gaussian with a
+state-independent log-std.
+
+``TensorCorePolicy`` owns ordinary torch parameters (so the PPO update can use autograd) and
+evaluates them for the rollout with the hand-written tcgen05 kernel (csrc/f16_policy.cu) through
+the C ABI: one launch gives mean, value, a sampled action and its log-probability for all envs.
+No CPU path: the forward raises without the CUDA library / a B200."""
+import ctypes as C
+import math
+
+from . import _capi
+
+
+def _layer_init(layer, std=math.sqrt(2), bias_const=0.0):
+    import torch
+
+    torch.nn.init.orthogonal_(layer.weight, std)
+    torch.nn.init.constant_(layer.bias, bias_const)
+    return layer
+
+
+def pack_policy_blob(actor, critic, out=None):
+    """Arrange the six Linear layers of (actor, critic) in the kernel's layout (csrc/f16_policy.h,
+    ``PolicyBlob``): K-major 16-byte chunks ``[chunk][row][4]`` for the two tensor-core layers."""
+    import torch
+
+    la = [m for m in actor if isinstance(m, torch.nn.Linear)]
+    lc = [m for m in critic if isinstance(m, torch.nn.Linear)]
+    dev = la[0].weight.device
+    with torch.no_grad():
+        w1 = torch.zeros(128, 8, device=dev)
+        w1[:64, :5] = la[0].weight
+        w1[64:, :5] = lc[0].weight
+        w1p = w1.reshape(128, 2, 4).permute(1, 0, 2).contiguous()                    # [chunk][row][4]
+        w2 = torch.stack([la[1].weight, lc[1].weight])                               # [2][64 out][64 in]
+        w2p = w2.reshape(2, 64, 16, 4).permute(0, 2, 1, 3).contiguous()              # [net][chunk][row][4]
+        b1 = torch.cat([la[0].bias, lc[0].bias])
+        b2 = torch.cat([la[1].bias, lc[1].bias])
+        w3 = torch.cat([la[2].weight.reshape(-1), lc[2].weight.reshape(-1)])
+        b3 = torch.cat([la[2].bias.reshape(-1), lc[2].bias.reshape(-1), torch.zeros(2, device=dev)])
+        flat = torch.cat([w1p.reshape(-1), w2p.reshape(-1), b1, b2, w3, b3]).float()
+    n_bytes = _capi.load_library().f16_policy_blob_bytes()
+    assert flat.numel() * 4 == n_bytes, (flat.numel() * 4, n_bytes)
+    if out is None:
+        return flat.contiguous()
+    out.copy_(flat)
+    return out
+
+
+class TensorCorePolicy:
+    """actor_mean + critic + log-std, with a tensor-core forward for rollouts."""
+
+    def __init__(self, device="cuda", seed=0, logstd_init=0.0, env_id_base=0):
+        import torch
+        from torch import nn
+
+        self._torch = torch
+        self._lib = _capi.load_library()
+        self.device = torch.device(device if str(device) != "cuda" else f"cuda:{torch.cuda.current_device()}")
+        g = torch.random.fork_rng(devices=[])
+        with g:
+            torch.manual_seed(seed)
+            self.actor_mean = nn.Sequential(_layer_init(nn.Linear(5, 64)), nn.Tanh(), _layer_init(nn.Linear(64, 64)), nn.Tanh(),
+                                            _layer_init(nn.Linear(64, 1), std=0.01)).to(self.device)
+            self.critic = nn.Sequential(_layer_init(nn.Linear(5, 64)), nn.Tanh(), _layer_init(nn.Linear(64, 64)), nn.Tanh(),
+                                        _layer_init(nn.Linear(64, 1), std=1.0)).to(self.device)
+        self.actor_logstd = nn.Parameter(torch.full((1,), float(logstd_init), device=self.device))
+        self.seed = int(seed)
+        self.env_id_base = int(env_id_base)
+        self._blob = pack_policy_blob(self.actor_mean, self.critic)
+        self._step = 0
+
+    def parameters(self):
+        return list(self.actor_mean.parameters()) + list(self.critic.parameters()) + [self.actor_logstd]
+
+    def sync_weights(self):
+        """Re-pack the tensor-core blob after an optimiser step."""
+        pack_policy_blob(self.actor_mean, self.critic, out=self._blob)
+
+    # ---- tensor-core inference ------------------------------------------------------------
+    def act(self, obs, sample=True, step=None, want_mean=False):
+        """obs [N,5] fp32 CUDA -> (action [N], logprob [N], value [N]) in one kernel launch."""
+        torch = self._torch
+        obs = _capi.require_cuda(obs, "obs")
+        if obs.dtype != torch.float32 or obs.dim() != 2 or obs.shape[1] != 5:
+            raise ValueError("obs must be float32 [N, 5]")
+        n = obs.shape[0]
+        action = torch.empty(n, device=obs.device)
+        logprob = torch.empty(n, device=obs.device)
+        value = torch.empty(n, device=obs.device)
+        mean = torch.empty(n, device=obs.device) if want_mean else None
+        if step is None:
+            step = self._step
+            self._step += 1
+        with torch.cuda.device(obs.device):
+            _capi.check(self._lib.f16_policy_forward(
+                n, obs.data_ptr(), self._blob.data_ptr(), self.actor_logstd.data_ptr(), mean.data_ptr() if want_mean else None,
+                value.data_ptr(), action.data_ptr(), logprob.data_ptr(), int(bool(sample)), self.seed & 0xFFFFFFFFFFFFFFFF,
+                int(step) & 0xFFFFFFFF, self.env_id_base, _capi.stream_ptr(obs.device)))
+        return (action, logprob, value, mean) if want_mean else (action, logprob, value)
+
+    def mean_value(self, obs):
+        """(actor mean [N], critic value [N]) on the tensor cores, no sampling."""
+        torch = self._torch
+        obs = _capi.require_cuda(obs, "obs")
+        n = obs.shape[0]
+        mean = torch.empty(n, device=obs.device)
+        value = torch.empty(n, device=obs.device)
+        with torch.cuda.device(obs.device):
+            _capi.check(self._lib.f16_policy_forward(n, obs.data_ptr(), self._blob.data_ptr(), None, mean.data_ptr(), value.data_ptr(),
+                                                     None, None, 0, 0, 0, 0, _capi.stream_ptr(obs.device)))
+        return mean, value
+
+    # ---- differentiable evaluation for the PPO update (torch autograd) ---------------------
+    def evaluate(self, obs, action):
+        """(logprob, entropy, value) of given actions, differentiable (ppo_model_gsde.py:81-99)."""
+        torch = self._torch
+        mean = self.actor_mean(obs).squeeze(-1)
+        logstd = self.actor_logstd.expand_as(mean)
+        std = torch.exp(logstd)
+        logprob = -0.5 * ((action - mean) / std) ** 2 - logstd - 0.5 * math.log(2 * math.pi)
+        entropy = 0.5 + 0.5 * math.log(2 * math.pi) + logstd
+        return logprob, entropy, self.critic(obs).squeeze(-1)

@@ -143,6 +143,18 @@ int f16_thrust(int dtype, int64_t n, const void *H, const void *M, const void *P
 /* atmosphere.get_density / get_speed_of_sound (data/atmosphere.py:5-11): rho, a real[n] */
 int f16_atmosphere(int dtype, int64_t n, const void *h, void *rho, void *a, void *stream);
 
+/* ---- agent level -------------------------------------------------------- */
+/* Agent.get_action_and_value / get_value (control/ppo/ppo_model_gsde.py:81-99,158-160): the two tanh MLPs
+ * 5->64->64->1 (actor_mean, critic) on the tensor cores (tcgen05, TF32 operands, fp32 accumulate), fused with the
+ * Gaussian policy head.  obs float[n][5]; blob = weights packed by f16_policy_blob layout (see
+ * f16-model_b200/policy.py); logstd float[1]; outputs float[n], each may be NULL.
+ * action = mean + exp(logstd) * eps with eps ~ N(0,1) from the counter RNG keyed by (seed, env id, step), or
+ * eps = 0 when sample == 0; logprob is the Gaussian log-density of that action. */
+int f16_policy_blob_bytes(void);
+int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void *logstd, void *mean, void *value,
+                       void *action, void *logprob, int sample, uint64_t seed, uint32_t step, int64_t env_id_base,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif
