@@ -494,4 +494,19 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
     return F16_OK;
 }
 
+int f16_gae(int T, int64_t n, const void *rewards, const void *values, const void *dones, const void *next_value,
+            const void *next_done, double gamma, double gae_lambda, void *advantages, void *returns, void *stream)
+{
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(n, &c, &g);
+    if (rc) return rc;
+    if (T <= 0 || !rewards || !values || !dones || !next_value || !next_done || !advantages || !returns)
+        return fail(F16_EINVAL, "NULL pointer or T <= 0");
+    CUDA_TRY(f16::launch_gae(T, n, (const float *)rewards, (const float *)values, (const float *)dones, (const float *)next_value,
+                             (const float *)next_done, (float)gamma, (float)gae_lambda, (float *)advantages, (float *)returns,
+                             c->n_sm, static_cast<cudaStream_t>(stream)));
+    return F16_OK;
+}
+
 }  // extern "C"

@@ -275,7 +275,44 @@ __global__ void __launch_bounds__(kRows, 2) policy_forward_kernel(const PolicyAr
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
 }
 
+// Generalised advantage estimation, the reverse scan of ppo_model_gsde.py:244-268 (gae=True):
+//   delta_t = r_t + gamma * V_{t+1} * (1 - d_{t+1}) - V_t ;  A_t = delta_t + gamma * lambda * (1 - d_{t+1}) * A_{t+1}
+// with d_t = "env was done BEFORE step t" (dones[t] = next_done of step t-1) and (V_T, d_T) = the bootstrap
+// value / done after the last step.  One thread per env walks its T steps backwards; every access of a warp is
+// one contiguous row segment of the [T][n] buffers.
+__global__ void __launch_bounds__(256) gae_kernel(int T, int64_t n, const float *__restrict__ rewards, const float *__restrict__ values,
+                                                  const float *__restrict__ dones, const float *__restrict__ next_value,
+                                                  const float *__restrict__ next_done, float gamma, float lam,
+                                                  float *__restrict__ advantages, float *__restrict__ returns)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float nextnonterminal = 1.0f - next_done[i];
+        float nextvalues = next_value[i];
+        float lastgaelam = 0.f;
+        for (int t = T - 1; t >= 0; --t) {
+            const int64_t k = (int64_t)t * n + i;
+            const float v = values[k];
+            const float delta = rewards[k] + gamma * nextvalues * nextnonterminal - v;
+            lastgaelam = delta + gamma * lam * nextnonterminal * lastgaelam;
+            advantages[k] = lastgaelam;
+            returns[k] = lastgaelam + v;
+            nextnonterminal = 1.0f - dones[k];
+            nextvalues = v;
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *values, const float *dones, const float *next_value,
+                       const float *next_done, float gamma, float lam, float *advantages, float *returns, int n_sm, cudaStream_t st)
+{
+    const int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)n_sm * 8;
+    gae_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(T, n, rewards, values, dones, next_value, next_done, gamma, lam,
+                                                                   advantages, returns);
+    return cudaGetLastError();
+}
 
 size_t policy_smem_bytes() { return sizeof(PolicySmem); }
 

@@ -34,6 +34,8 @@ struct PolicyArgs {
     int64_t id_base;          // global id of env 0 (sharding-invariant noise)
 };
 
+cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *values, const float *dones, const float *next_value,
+                       const float *next_done, float gamma, float lam, float *advantages, float *returns, int n_sm, cudaStream_t st);
 size_t policy_smem_bytes();
 cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, cudaStream_t st);
 

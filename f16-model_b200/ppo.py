@@ -1,0 +1,192 @@
+"""On-device PPO -- mirror of ``Agent.train`` (control/ppo/ppo_model_gsde.py:181-398) with the
+host round trips removed: the rollout loop is ``tensor-core policy -> fused env-step kernel``
+on device tensors, GAE is one CUDA kernel, the clipped-PPO update uses torch autograd on the
+same parameters and Adam(amsgrad), and with more than one rank the flat gradient (~9.3 k floats)
+is all-reduced over NCCL once per minibatch.
+
+Flags keep the reference's names and defaults (control/ppo/utils.py:11-142).  Deliberate
+deviations: the reference's gSDE noise path is broken as committed
+(``theta_gsde`` is never created in ``train``); here exploration is the standard Gaussian policy
+``a = mean + exp(logstd) * eps`` with eps drawn by the counter RNG inside the policy kernel."""
+import dataclasses
+import time
+
+from . import _capi
+
+
+@dataclasses.dataclass
+class PPOConfig:
+    learning_rate: float = 3e-4
+    seed: int = 1
+    total_timesteps: int = 200000
+    num_steps: int = 2048
+    anneal_lr: bool = True
+    gae: bool = True
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    num_minibatches: int = 64
+    update_epochs: int = 10
+    norm_adv: bool = True
+    clip_coef: float = 0.5
+    clip_vloss: bool = True
+    ent_coef: float = 0.0
+    vf_coef: float = 0.5
+    max_grad_norm: float = 0.5
+    target_kl: float = None
+    reset_every_update: bool = True      # the reference re-resets the envs at every update (:210)
+
+
+def gae(rewards, values, dones, next_value, next_done, gamma, gae_lambda):
+    """Advantages and returns [T, N] by the CUDA reverse scan (f16_gae)."""
+    import torch
+
+    T, N = rewards.shape
+    adv = torch.empty_like(rewards)
+    ret = torch.empty_like(rewards)
+    L = _capi.load_library()
+    for t in (rewards, values, dones, next_value, next_done):
+        _capi.require_cuda(t, "gae input")
+        if t.dtype != torch.float32:
+            raise ValueError("gae inputs must be float32")
+    with torch.cuda.device(rewards.device):
+        _capi.check(L.f16_gae(T, N, rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), next_value.data_ptr(),
+                              next_done.data_ptr(), float(gamma), float(gae_lambda), adv.data_ptr(), ret.data_ptr(),
+                              _capi.stream_ptr(rewards.device)))
+    return adv, ret
+
+
+class PPOTrainer:
+    def __init__(self, envs, policy, config=None):
+        import torch
+
+        self._torch = torch
+        self.envs, self.policy, self.cfg = envs, policy, config or PPOConfig()
+        self.N = envs.num_envs
+        self.device = envs.device
+        self.batch_size = self.N * self.cfg.num_steps
+        self.minibatch_size = self.batch_size // self.cfg.num_minibatches
+        self.optimizer = torch.optim.Adam(policy.parameters(), lr=self.cfg.learning_rate, amsgrad=True)
+        T, N, dev = self.cfg.num_steps, self.N, self.device
+        self.obs = torch.zeros((T, N, 5), device=dev)
+        self.actions = torch.zeros((T, N), device=dev)
+        self.logprobs = torch.zeros((T, N), device=dev)
+        self.rewards = torch.zeros((T, N), device=dev)
+        self.dones = torch.zeros((T, N), device=dev)
+        self.values = torch.zeros((T, N), device=dev)
+        self.global_step = 0
+        self.update_idx = 0
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size()
+        self._gen = torch.Generator(device=dev).manual_seed(self.cfg.seed)
+
+    # ------------------------------------------------------------------ rollout
+    def rollout(self):
+        """num_steps closed-loop steps for all envs, everything device-resident."""
+        torch, cfg = self._torch, self.cfg
+        if cfg.reset_every_update:
+            next_obs, _ = self.envs.reset(seed=cfg.seed + self.update_idx + 1)
+            next_done = torch.zeros(self.N, device=self.device)
+        else:
+            next_obs, next_done = self._next_obs, self._next_done
+        ep_returns, ep_count = torch.zeros((), device=self.device), torch.zeros((), device=self.device)
+        for step in range(cfg.num_steps):
+            self.obs[step].copy_(next_obs)
+            self.dones[step].copy_(next_done)
+            action, logprob, value = self.policy.act(next_obs, sample=True, step=self.global_step // max(self.N, 1))
+            self.values[step], self.actions[step], self.logprobs[step] = value, action, logprob
+            next_obs, reward, done, _, info = self.envs.step(action)
+            self.rewards[step].copy_(reward)
+            next_done = done.float()
+            ep_returns += (info["final_info"]["total_return"] * done).sum()
+            ep_count += done.sum()
+            self.global_step += self.N
+        self._next_obs, self._next_done = next_obs.clone(), next_done
+        _, next_value = self.policy.mean_value(self._next_obs)
+        adv, ret = gae(self.rewards, self.values, self.dones, next_value, self._next_done, cfg.gamma, cfg.gae_lambda)
+        return adv, ret, ep_returns, ep_count
+
+    # ------------------------------------------------------------------ update
+    def _allreduce_grads(self):
+        if self.world == 1:
+            return
+        torch = self._torch
+        params = [p for p in self.policy.parameters() if p.grad is not None]
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        torch.distributed.all_reduce(flat)                      # one NCCL call, ~37 KB: latency-bound
+        flat /= self.world
+        off = 0
+        for p in params:
+            p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+            off += p.numel()
+
+    def update(self, advantages, returns):
+        torch, cfg = self._torch, self.cfg
+        b_obs = self.obs.reshape(-1, 5)
+        b_logprobs, b_actions = self.logprobs.reshape(-1), self.actions.reshape(-1)
+        b_adv, b_ret, b_val = advantages.reshape(-1), returns.reshape(-1), self.values.reshape(-1)
+        stats = {}
+        clipfracs = []
+        for epoch in range(cfg.update_epochs):
+            perm = torch.randperm(self.batch_size, device=self.device, generator=self._gen)
+            for start in range(0, self.batch_size, self.minibatch_size):
+                mb = perm[start:start + self.minibatch_size]
+                newlogprob, entropy, newvalue = self.policy.evaluate(b_obs[mb], b_actions[mb])
+                logratio = newlogprob - b_logprobs[mb]
+                ratio = logratio.exp()
+                with torch.no_grad():
+                    old_approx_kl = (-logratio).mean()
+                    approx_kl = ((ratio - 1) - logratio).mean()
+                    clipfracs.append(((ratio - 1.0).abs() > cfg.clip_coef).float().mean())
+                mb_adv = b_adv[mb]
+                if cfg.norm_adv:
+                    mb_adv = (mb_adv - mb_adv.mean()) / (mb_adv.std() + 1e-8)
+                pg_loss = torch.max(-mb_adv * ratio, -mb_adv * torch.clamp(ratio, 1 - cfg.clip_coef, 1 + cfg.clip_coef)).mean()
+                if cfg.clip_vloss:
+                    v_unclipped = (newvalue - b_ret[mb]) ** 2
+                    v_clipped = b_val[mb] + torch.clamp(newvalue - b_val[mb], -cfg.clip_coef, cfg.clip_coef)
+                    v_loss = 0.5 * torch.max(v_unclipped, (v_clipped - b_ret[mb]) ** 2).mean()
+                else:
+                    v_loss = 0.5 * ((newvalue - b_ret[mb]) ** 2).mean()
+                entropy_loss = entropy.mean()
+                loss = pg_loss - cfg.ent_coef * entropy_loss + v_loss * cfg.vf_coef
+                self.optimizer.zero_grad(set_to_none=False)
+                loss.backward()
+                self._allreduce_grads()
+                torch.nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
+                self.optimizer.step()
+            if cfg.target_kl is not None and approx_kl.item() > cfg.target_kl:
+                break
+        self.policy.sync_weights()                                  # refresh the tensor-core weight blob
+        stats.update(value_loss=v_loss.item(), policy_loss=pg_loss.item(), entropy=entropy_loss.item(),
+                     old_approx_kl=old_approx_kl.item(), approx_kl=approx_kl.item(),
+                     clipfrac=torch.stack(clipfracs).mean().item())
+        return stats
+
+    def train(self, num_updates=None, log=None):
+        """The reference's outer loop: lr annealing, rollout, GAE, update; returns per-update stats."""
+        torch, cfg = self._torch, self.cfg
+        if num_updates is None:
+            num_updates = max(1, cfg.total_timesteps // self.batch_size)
+        history = []
+        for update in range(1, num_updates + 1):
+            self.update_idx = update - 1
+            if cfg.anneal_lr:
+                self.optimizer.param_groups[0]["lr"] = (1.0 - (update - 1.0) / num_updates) * cfg.learning_rate
+            t0 = time.perf_counter()
+            adv, ret, ep_ret, ep_cnt = self.rollout()
+            torch.cuda.synchronize(self.device)
+            t1 = time.perf_counter()
+            stats = self.update(adv, ret)
+            torch.cuda.synchronize(self.device)
+            t2 = time.perf_counter()
+            y_pred, y_true = self.values.reshape(-1), ret.reshape(-1)
+            var_y = y_true.var()
+            stats.update(update=update, global_step=self.global_step, rollout_s=t1 - t0, update_s=t2 - t1,
+                         rollout_sps=self.batch_size / (t1 - t0), mean_step_reward=self.rewards.mean().item(),
+                         episodes=int(ep_cnt.item()), mean_episode_return=(ep_ret / ep_cnt.clamp(min=1)).item(),
+                         explained_variance=(1 - (y_true - y_pred).var() / var_y).item() if var_y > 0 else float("nan"))
+            history.append(stats)
+            if log:
+                log(stats)
+        return history

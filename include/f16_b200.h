@@ -155,6 +155,12 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
                        void *action, void *logprob, int sample, uint64_t seed, uint32_t step, int64_t env_id_base,
                        void *stream);
 
+/* The GAE reverse scan of Agent.train (control/ppo/ppo_model_gsde.py:244-268): float [T][n] rewards, values,
+ * dones (dones[t] = env was done before step t), bootstrap next_value / next_done float[n] ->
+ * advantages, returns float[T][n]. */
+int f16_gae(int T, int64_t n, const void *rewards, const void *values, const void *dones, const void *next_value,
+            const void *next_done, double gamma, double gae_lambda, void *advantages, void *returns, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
