@@ -465,6 +465,19 @@ int f16_atmosphere(int dtype, int64_t n, const void *h, void *rho, void *a, void
     return F16_OK;
 }
 
+int f16_trim(int n_cells, const void *V, const void *H, int n_starts, const void *starts, void *out_x, void *out_cost, void *out_iters,
+             void *stream)
+{
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(n_cells, &c, &g);
+    if (rc) return rc;
+    if (n_starts <= 0 || !V || !H || !starts || !out_x || !out_cost) return fail(F16_EINVAL, "NULL pointer or n_starts <= 0");
+    CUDA_TRY(f16::launch_trim(c->t64, n_cells, n_starts, (const double *)V, (const double *)H, (const double *)starts, (double *)out_x,
+                              (double *)out_cost, (int *)out_iters, g, static_cast<cudaStream_t>(stream)));
+    return F16_OK;
+}
+
 int f16_policy_blob_bytes(void) { return static_cast<int>(sizeof(f16::PolicyBlob)); }
 
 int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void *logstd, void *mean, void *value, void *action,

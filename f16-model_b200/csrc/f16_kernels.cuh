@@ -538,6 +538,109 @@ __global__ void __launch_bounds__(kCtaThreads) isa_kernel(int64_t n, const R *h,
 }
 
 // ---------------------------------------------------------------------------
+// Batched trim search (F16model/utils/find_trim_position.py:11-113): one thread runs one
+// Nelder-Mead search (scipy.optimize.fmin semantics: rho=1, chi=2, psi=sigma=0.5, 5 % initial
+// simplex, xtol=ftol=1e-10, maxiter=1000, maxfun=5000) over u = (stab, throttle, alpha) for one
+// (V, H) cell from one start, minimising the reference's cost
+//   10*Oy_dot^2 + 10*wz_dot^2 + 15*theta_dot^2 + 30*V_dot^2 + 20*alpha_dot^2
+// of the RHS at x0 = (0, H, 0, alpha, V, alpha, stab, 0, Pc(throttle)).  fp64 only.
+// ---------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ R trim_cost(const Tables<R> &T, R V, R H, const R (&u)[3])
+{
+    const R thr = u[1];
+    const R Pa = thr <= R(0.77) ? R(64.94) * thr : R(217.38) * thr - R(117.38);   // find_correct_thrust_position
+    const R x[9] = {R(0), H, R(0), u[2], V, u[2], u[0], R(0), Pa};
+    R d[9];
+    rhs<R, false, true>(T, x, u[0], thr, d);
+    // np.matmul(weight, step**2) over [Ox,Oy,wz,theta,V,alpha,stab,dstab,Pa] with weight (0,10,10,15,30,20,0,0,0)
+    R c = R(0) * (d[0] * d[0]);
+    c += R(10) * (d[1] * d[1]);
+    c += R(10) * (d[2] * d[2]);
+    c += R(15) * (d[3] * d[3]);
+    c += R(30) * (d[4] * d[4]);
+    c += R(20) * (d[5] * d[5]);
+    return c;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(128) trim_kernel(const Tables<R> *tables, int n_cells, int n_starts, const R *Vc, const R *Hc,
+                                                    const R *starts /*[S][3]*/, R *out_x /*[cells][S][3]*/, R *out_cost /*[cells][S]*/,
+                                                    int *out_iters /*[cells][S] or null*/)
+{
+    __shared__ Tables<R> tbl;
+    __shared__ alignas(8) uint64_t bar;
+    tables_issue(&tbl, tables, &bar);
+    tables_wait(&bar);
+    const int64_t total = (int64_t)n_cells * n_starts;
+    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
+        const int cell = (int)(id / n_starts), st = (int)(id % n_starts);
+        const R V = Vc[cell], H = Hc[cell];
+        R sim[4][3], fs[4];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sim[0][j] = starts[st * 3 + j];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) sim[k + 1][j] = sim[0][j];
+            sim[k + 1][k] = sim[0][k] != R(0) ? (R(1) + R(0.05)) * sim[0][k] : R(0.00025);
+        }
+        int fcalls = 0, iters = 1;
+        for (int k = 0; k < 4; ++k) { fs[k] = trim_cost<R>(tbl, V, H, sim[k]); ++fcalls; }
+        auto sort4 = [&]() {   // stable insertion sort == np.argsort(kind='stable') on 4 keys
+            for (int a = 1; a < 4; ++a)
+                for (int b = a; b > 0 && fs[b] < fs[b - 1]; --b) {
+                    const R tf = fs[b]; fs[b] = fs[b - 1]; fs[b - 1] = tf;
+                    for (int j = 0; j < 3; ++j) { const R tx = sim[b][j]; sim[b][j] = sim[b - 1][j]; sim[b - 1][j] = tx; }
+                }
+        };
+        sort4();
+        while (fcalls < 5000 && iters < 1000) {
+            R dx = R(0), df = R(0);
+            for (int k = 1; k < 4; ++k) {
+                for (int j = 0; j < 3; ++j) dx = fmax(dx, fabs(sim[k][j] - sim[0][j]));
+                df = fmax(df, fabs(fs[0] - fs[k]));
+            }
+            if (dx <= R(1e-10) && df <= R(1e-10)) break;
+            R xbar[3], xr[3], xt[3];
+            for (int j = 0; j < 3; ++j) xbar[j] = ((sim[0][j] + sim[1][j]) + sim[2][j]) / R(3);
+            for (int j = 0; j < 3; ++j) xr[j] = (R(1) + R(1)) * xbar[j] - R(1) * sim[3][j];
+            const R fxr = trim_cost<R>(tbl, V, H, xr); ++fcalls;
+            bool shrink = false;
+            if (fxr < fs[0]) {
+                for (int j = 0; j < 3; ++j) xt[j] = (R(1) + R(2)) * xbar[j] - R(2) * sim[3][j];
+                const R fxe = trim_cost<R>(tbl, V, H, xt); ++fcalls;
+                if (fxe < fxr) { for (int j = 0; j < 3; ++j) sim[3][j] = xt[j]; fs[3] = fxe; }
+                else { for (int j = 0; j < 3; ++j) sim[3][j] = xr[j]; fs[3] = fxr; }
+            } else if (fxr < fs[2]) {
+                for (int j = 0; j < 3; ++j) sim[3][j] = xr[j];
+                fs[3] = fxr;
+            } else if (fxr < fs[3]) {
+                for (int j = 0; j < 3; ++j) xt[j] = (R(1) + R(0.5)) * xbar[j] - R(0.5) * sim[3][j];
+                const R fxc = trim_cost<R>(tbl, V, H, xt); ++fcalls;
+                if (fxc <= fxr) { for (int j = 0; j < 3; ++j) sim[3][j] = xt[j]; fs[3] = fxc; }
+                else shrink = true;
+            } else {
+                for (int j = 0; j < 3; ++j) xt[j] = (R(1) - R(0.5)) * xbar[j] + R(0.5) * sim[3][j];
+                const R fxcc = trim_cost<R>(tbl, V, H, xt); ++fcalls;
+                if (fxcc < fs[3]) { for (int j = 0; j < 3; ++j) sim[3][j] = xt[j]; fs[3] = fxcc; }
+                else shrink = true;
+            }
+            if (shrink)
+                for (int k = 1; k < 4; ++k) {
+                    for (int j = 0; j < 3; ++j) sim[k][j] = sim[0][j] + R(0.5) * (sim[k][j] - sim[0][j]);
+                    fs[k] = trim_cost<R>(tbl, V, H, sim[k]); ++fcalls;
+                }
+            ++iters;
+            sort4();
+        }
+        for (int j = 0; j < 3; ++j) out_x[id * 3 + j] = sim[0][j];
+        out_cost[id] = fs[0];
+        if (out_iters) out_iters[id] = iters;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // typed launchers
 // ---------------------------------------------------------------------------
 inline int grid_for(int64_t n, const LaunchGeom &g)

@@ -40,6 +40,15 @@ cudaError_t launch_isa(int64_t n, const double *h, double *rho, double *a, const
     isa_kernel<double><<<grid_for(n, g), kCtaThreads, 0, st>>>(n, h, rho, a);
     return cudaGetLastError();
 }
+cudaError_t launch_trim(const Tables<double> *T, int n_cells, int n_starts, const double *V, const double *H, const double *starts,
+                        double *out_x, double *out_cost, int *out_iters, const LaunchGeom &g, cudaStream_t st)
+{
+    const int64_t total = (int64_t)n_cells * n_starts;
+    const int64_t blocks = (total + 127) / 128;
+    const int64_t cap = (int64_t)g.n_sm * 8;
+    trim_kernel<double><<<(int)(blocks < cap ? blocks : cap), 128, 0, st>>>(T, n_cells, n_starts, V, H, starts, out_x, out_cost, out_iters);
+    return cudaGetLastError();
+}
 int env_step_occupancy_f64(bool autoreset)
 {
     return autoreset ? prepare_env_step<double, false, true>() : prepare_env_step<double, false, false>();

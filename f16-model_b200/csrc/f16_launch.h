@@ -72,5 +72,7 @@ cudaError_t launch_coeffs(const Tables<double> *, int64_t n, const double *, con
 cudaError_t launch_thrust(const Tables<double> *, int64_t n, const double *, const double *, const double *, double *, const LaunchGeom &, cudaStream_t);
 cudaError_t launch_isa(int64_t n, const double *, double *, double *, const LaunchGeom &, cudaStream_t);
 int env_step_occupancy_f64(bool autoreset);
+cudaError_t launch_trim(const Tables<double> *, int n_cells, int n_starts, const double *V, const double *H, const double *starts,
+                        double *out_x, double *out_cost, int *out_iters, const LaunchGeom &, cudaStream_t);
 
 }  // namespace f16

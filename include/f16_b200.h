@@ -143,6 +143,16 @@ int f16_thrust(int dtype, int64_t n, const void *H, const void *M, const void *P
 /* atmosphere.get_density / get_speed_of_sound (data/atmosphere.py:5-11): rho, a real[n] */
 int f16_atmosphere(int dtype, int64_t n, const void *h, void *rho, void *a, void *stream);
 
+/* ---- trim search ------------------------------------------------------- */
+/* find_trim_position.optimize_loop / Cost.calculate (F16model/utils/find_trim_position.py:27-66) for a grid of
+ * flight conditions: for every (V[c], H[c]) cell and every start u0 = starts[s] = (stab [rad], throttle,
+ * alpha [rad]) one Nelder-Mead search with scipy.optimize.fmin's parameters (xtol = ftol = 1e-10, maxiter 1000,
+ * maxfun 5000) minimises the reference's weighted squared-derivative cost.  All fp64.
+ * out_x double[n_cells][n_starts][3], out_cost double[n_cells][n_starts], out_iters int32[n_cells][n_starts] or NULL.
+ * The caller takes the arg-min over starts (the reference stops at the first start with cost <= 1e-5). */
+int f16_trim(int n_cells, const void *V, const void *H, int n_starts, const void *starts, void *out_x, void *out_cost,
+             void *out_iters, void *stream);
+
 /* ---- agent level -------------------------------------------------------- */
 /* Agent.get_action_and_value / get_value (control/ppo/ppo_model_gsde.py:81-99,158-160): the two tanh MLPs
  * 5->64->64->1 (actor_mean, critic) on the tensor cores (tcgen05, TF32 operands, fp32 accumulate), fused with the

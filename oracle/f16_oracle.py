@@ -55,6 +55,9 @@ def lib():
         L.orc_rollout.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, _dp, _dp, _dp, _ip, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _ip, _dp, _dp, C.c_int]
         L.orc_rollout.restype = C.c_longlong
+        L.orc_trim_cost.argtypes = [C.c_double, C.c_double, _dp]
+        L.orc_trim_cost.restype = C.c_double
+        L.orc_trim.argtypes = [C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp, _ip, C.c_int]
         L.orc_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -143,6 +146,23 @@ def rollout(x0, actions, ref_bank, ref_idx, dt=0.01, horizon=999, want_states=Tr
                               p(states), p(obs), p(rew), p(done), ep_len, xf, ret, nthreads)
     return dict(states=states, obs=obs, reward=rew, done=done, ep_len=ep_len, final_state=xf,
                 total_return=ret, env_steps=int(total))
+
+
+def trim_cost(V, H, u):
+    """Cost.calculate (utils/find_trim_position.py:27-42)."""
+    return lib().orc_trim_cost(float(V), float(H), _f64(u))
+
+
+def trim(V, H, starts, nthreads=0):
+    """Nelder-Mead trim search for every (cell, start): returns x [cells, S, 3], cost [cells, S], iters."""
+    V, H = np.atleast_1d(_f64(V)), np.atleast_1d(_f64(H))
+    starts = _f64(starts).reshape(-1, 3)
+    n, S = V.size, starts.shape[0]
+    x = np.empty((n, S, 3))
+    cost = np.empty((n, S))
+    iters = np.empty((n, S), dtype=np.int32)
+    lib().orc_trim(n, V, H, S, starts, x, cost, iters.reshape(-1), nthreads)
+    return x, cost, iters
 
 
 def num_threads():
