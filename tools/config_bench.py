@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Timings for the BASELINE configs that are not the headline bench line (GPU box):
+  config 4: PPO rollout + update with 65536 envs on device (control/ppo MLP policy)
+  config 5b: batched trim-state search over an altitude/speed grid
+  plus a short "does PPO learn" run.  Prints one JSON object per section.
+    python tools/config_bench.py [--updates 3] [--learn-updates 40]
+Under torchrun the envs are sharded over ranks and the PPO gradients all-reduced over NCCL."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import f16_model_b200 as f16  # noqa: E402
+from f16_model_b200.sharding import make_sharded_env, shard_range  # noqa: E402
+
+CFG = {"dt": 0.01, "tn": 10, "debug_state": False, "determenistic_ref": False, "scenario": "combo"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--updates", type=int, default=3)
+    ap.add_argument("--learn-updates", type=int, default=0)
+    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--num-steps", type=int, default=128)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+
+    # ---- config 4 -------------------------------------------------------------------------
+    envs = make_sharded_env(CFG, args.envs * world, rank, world, dev, seed=1, fast_math=True)
+    pol = f16.TensorCorePolicy(device=dev, seed=1, logstd_init=-1.0, env_id_base=shard_range(args.envs * world, rank, world)[0])
+    cfg = f16.PPOConfig(num_steps=args.num_steps, num_minibatches=32, update_epochs=4)
+    tr = f16.PPOTrainer(envs, pol, cfg)
+    hist = tr.train(num_updates=args.updates)
+    if rank == 0:
+        h = hist[-1]
+        print(json.dumps({"config": "4: PPO rollout+update, %d envs/GPU x %d steps, %d GPU(s)" % (args.envs, args.num_steps, world),
+                          "rollout_env_steps_per_s": h["rollout_sps"] * world, "rollout_s": h["rollout_s"], "update_s": h["update_s"],
+                          "minibatches_per_update": cfg.num_minibatches * cfg.update_epochs, "value_loss": h["value_loss"],
+                          "approx_kl": h["approx_kl"]}), flush=True)
+
+    # policy forward alone (tensor-core kernel), CUDA events
+    obs = torch.rand((args.envs, 5), device=dev) * 2 - 1
+    for _ in range(5):
+        pol.act(obs, step=0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(50):
+        pol.act(obs, step=k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 50
+    flops = 2 * (8 * 128 + 2 * 64 * 64) * args.envs          # tensor-core MACs actually issued (K padded to 8)
+    if rank == 0:
+        print(json.dumps({"kernel": "policy_forward_kernel (tcgen05 tf32)", "envs": args.envs, "us_per_launch": ms * 1e3,
+                          "envs_per_s": args.envs / (ms * 1e-3), "tensor_tflops": flops / (ms * 1e-3) / 1e12}), flush=True)
+
+    # ---- config 5b --------------------------------------------------------------------------
+    Vg, Hg = np.meshgrid(np.linspace(100, 300, 41), np.linspace(1000, 10000, 37))
+    b, e = shard_range(Vg.size, rank, world)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    g = f16.trim_grid(Vg.ravel()[b:e], Hg.ravel()[b:e], device=dev)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    res = torch.tensor(np.stack([g["stab"], g["throttle"], g["alpha"], g["cost"]], 1), device=dev)
+    if world > 1:     # one all_gather of [cells, 4] doubles; shards differ by at most one cell -> pad
+        n_max = (Vg.size + world - 1) // world
+        pad = torch.zeros((n_max, 4), dtype=res.dtype, device=dev)
+        pad[: res.shape[0]] = res
+        out = [torch.empty_like(pad) for _ in range(world)]
+        torch.distributed.all_gather(out, pad)
+        res = torch.cat([o[: shard_range(Vg.size, r, world)[1] - shard_range(Vg.size, r, world)[0]] for r, o in enumerate(out)])
+    if rank == 0:
+        print(json.dumps({"config": "5b: trim grid %d cells x %d starts (reference grid), %d GPU(s)" % (Vg.size, g["n_starts"], world),
+                          "seconds_rank0": dt, "searches_per_s": (e - b) * g["n_starts"] * world / dt,
+                          "accepted_fraction": float((res[:, 3] <= 1e-5).double().mean())}), flush=True)
+
+    # ---- learning curve ---------------------------------------------------------------------
+    if args.learn_updates and world == 1:
+        det = dict(CFG, determenistic_ref=True)
+        envs = f16.F16VecEnv(det, 4096, device=dev, seed=3, fast_math=True)
+        pol = f16.TensorCorePolicy(device=dev, seed=3, logstd_init=-1.0)
+        tr = f16.PPOTrainer(envs, pol, f16.PPOConfig(num_steps=250, num_minibatches=16, update_epochs=5, learning_rate=1e-3,
+                                                      clip_coef=0.2, anneal_lr=False))
+        hist = tr.train(num_updates=args.learn_updates)
+        curve = [round(h["mean_step_reward"], 4) for h in hist]
+        print(json.dumps({"ppo_learning": "4096 envs x 250 steps per update, det. combo reference", "mean_step_reward_per_update": curve,
+                          "explained_variance_last": hist[-1]["explained_variance"]}), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
