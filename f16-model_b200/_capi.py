@@ -86,8 +86,8 @@ def load_library():
     L.f16_atmosphere.argtypes = [i32, i64, vp, vp, vp, vp]
     L.f16_policy_blob_bytes.argtypes = []
     L.f16_trim.argtypes = [i32, vp, vp, i32, vp, vp, vp, vp, vp]
-    L.f16_gae.argtypes = [i32, i64, vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp]
-    L.f16_policy_forward.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, i32, C.c_uint64, C.c_uint32, i64, vp]
+    L.f16_gae.argtypes = [i32, i64, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp]
+    L.f16_policy_forward.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, i32, C.c_uint64, C.c_uint32, vp, vp, i64, vp]
     for name in EXPORTS:
         if name not in ("f16_last_error",):
             getattr(L, name).restype = C.c_int

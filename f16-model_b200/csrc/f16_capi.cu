@@ -481,7 +481,8 @@ int f16_trim(int n_cells, const void *V, const void *H, int n_starts, const void
 int f16_policy_blob_bytes(void) { return static_cast<int>(sizeof(f16::PolicyBlob)); }
 
 int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void *logstd, void *mean, void *value, void *action,
-                       void *logprob, int sample, uint64_t seed, uint32_t step, int64_t env_id_base, void *stream)
+                       void *logprob, int sample, uint64_t seed, uint32_t step, const int32_t *ep_len, const uint32_t *episode_no,
+                       int64_t env_id_base, void *stream)
 {
     DeviceCtx *c;
     f16::LaunchGeom g;
@@ -501,24 +502,25 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
     P.n = n;
     P.sample = sample;
     P.step = step;
+    P.ep_len = ep_len;
+    P.episode_no = episode_no;
     P.seed = seed;
     P.id_base = env_id_base;
     CUDA_TRY(f16::launch_policy_forward(P, c->n_sm, static_cast<cudaStream_t>(stream)));
     return F16_OK;
 }
 
-int f16_gae(int T, int64_t n, const void *rewards, const void *values, const void *dones, const void *next_value,
-            const void *next_done, double gamma, double gae_lambda, void *advantages, void *returns, void *stream)
+int f16_gae(int T, int64_t n, const void *rewards, const void *values, const uint8_t *done_after, const void *next_value, double gamma,
+            double gae_lambda, void *advantages, void *returns, void *stream)
 {
     DeviceCtx *c;
     f16::LaunchGeom g;
     int rc = prep(n, &c, &g);
     if (rc) return rc;
-    if (T <= 0 || !rewards || !values || !dones || !next_value || !next_done || !advantages || !returns)
+    if (T <= 0 || !rewards || !values || !done_after || !next_value || !advantages || !returns)
         return fail(F16_EINVAL, "NULL pointer or T <= 0");
-    CUDA_TRY(f16::launch_gae(T, n, (const float *)rewards, (const float *)values, (const float *)dones, (const float *)next_value,
-                             (const float *)next_done, (float)gamma, (float)gae_lambda, (float *)advantages, (float *)returns,
-                             c->n_sm, static_cast<cudaStream_t>(stream)));
+    CUDA_TRY(f16::launch_gae(T, n, (const float *)rewards, (const float *)values, done_after, (const float *)next_value, (float)gamma,
+                             (float)gae_lambda, (float *)advantages, (float *)returns, c->n_sm, static_cast<cudaStream_t>(stream)));
     return F16_OK;
 }
 

@@ -309,7 +309,8 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
             // warp 0 runs last and every other warp ends up waiting for its refill.)
             __syncwarp();
             if ((threadIdx.x & 31u) == 0) {
-                const unsigned prior = atomicAdd(&sm->drained[stage], 1u);
+                unsigned prior;   // plain atom.shared (atomicAdd would be wrapped in warp-aggregation code)
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(prior) : "r"(smem_u32(&sm->drained[stage])) : "memory");
                 if (prior == kCtaThreads / 32 - 1) {
                     sm->drained[stage] = 0;
                     const unsigned next = tile + 2 * gridDim.x;
@@ -317,8 +318,12 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
                 }
             }
         } else if (live) {
+            const R *p = A.state + i;   // pointer bumps, not j * n + i: no per-row induction variables in the tile loop
 #pragma unroll
-            for (int j = 0; j < 9; ++j) x[j] = A.state[j * n + i];
+            for (int j = 0; j < 9; ++j) {
+                x[j] = *p;
+                p += n;
+            }
             a0 = S.actions[i];
             ep_len = A.ep_len[i];
             ref_idx = A.ref_idx[i];

@@ -258,8 +258,12 @@ __global__ void __launch_bounds__(kRows, 2) policy_forward_kernel(const PolicyAr
                 // a = mean + std * eps,  logp = -0.5 eps^2 - log std - 0.5 log(2 pi)
                 float eps = 0.f;
                 if (P.sample) {
-                    const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(P.id_base + i), static_cast<uint32_t>((P.id_base + i) >> 32),
-                                                          P.step, 0x50504F31u),
+                    // counter = (global env id, episode, step): with the env's own counters the stream is unique per
+                    // env-step without any host-side step argument (CUDA-graph replays stay fresh)
+                    const int64_t gid = P.id_base + i;
+                    const uint32_t c2 = P.episode_no ? P.episode_no[i] : 0u;
+                    const uint32_t c3 = P.ep_len ? static_cast<uint32_t>(P.ep_len[i]) : P.step;
+                    const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32) ^ 0x50504F31u, c2, c3),
                                                make_uint2(static_cast<uint32_t>(P.seed), static_cast<uint32_t>(P.seed >> 32)));
                     const float u1 = (static_cast<float>(r.x >> 8) + 1.0f) * (1.0f / 16777216.0f);
                     const float u2 = static_cast<float>(r.y >> 8) * (1.0f / 16777216.0f);
@@ -277,26 +281,24 @@ __global__ void __launch_bounds__(kRows, 2) policy_forward_kernel(const PolicyAr
 
 // Generalised advantage estimation, the reverse scan of ppo_model_gsde.py:244-268 (gae=True):
 //   delta_t = r_t + gamma * V_{t+1} * (1 - d_{t+1}) - V_t ;  A_t = delta_t + gamma * lambda * (1 - d_{t+1}) * A_{t+1}
-// with d_t = "env was done BEFORE step t" (dones[t] = next_done of step t-1) and (V_T, d_T) = the bootstrap
-// value / done after the last step.  One thread per env walks its T steps backwards; every access of a warp is
-// one contiguous row segment of the [T][n] buffers.
+// where d_{t+1} = done flag returned BY step t (the reference's dones[t+1] / next_done) = done_after[t],
+// and V_T = the bootstrap value after the last step.  One thread per env walks its T steps backwards; every
+// access of a warp is one contiguous row segment of the [T][n] buffers.
 __global__ void __launch_bounds__(256) gae_kernel(int T, int64_t n, const float *__restrict__ rewards, const float *__restrict__ values,
-                                                  const float *__restrict__ dones, const float *__restrict__ next_value,
-                                                  const float *__restrict__ next_done, float gamma, float lam,
-                                                  float *__restrict__ advantages, float *__restrict__ returns)
+                                                  const uint8_t *__restrict__ done_after, const float *__restrict__ next_value,
+                                                  float gamma, float lam, float *__restrict__ advantages, float *__restrict__ returns)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float nextnonterminal = 1.0f - next_done[i];
         float nextvalues = next_value[i];
         float lastgaelam = 0.f;
         for (int t = T - 1; t >= 0; --t) {
             const int64_t k = (int64_t)t * n + i;
+            const float nextnonterminal = done_after[k] ? 0.f : 1.f;
             const float v = values[k];
             const float delta = rewards[k] + gamma * nextvalues * nextnonterminal - v;
             lastgaelam = delta + gamma * lam * nextnonterminal * lastgaelam;
             advantages[k] = lastgaelam;
             returns[k] = lastgaelam + v;
-            nextnonterminal = 1.0f - dones[k];
             nextvalues = v;
         }
     }
@@ -304,13 +306,13 @@ __global__ void __launch_bounds__(256) gae_kernel(int T, int64_t n, const float 
 
 }  // namespace
 
-cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *values, const float *dones, const float *next_value,
-                       const float *next_done, float gamma, float lam, float *advantages, float *returns, int n_sm, cudaStream_t st)
+cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *values, const uint8_t *done_after, const float *next_value,
+                       float gamma, float lam, float *advantages, float *returns, int n_sm, cudaStream_t st)
 {
     const int64_t blocks = (n + 255) / 256;
     const int64_t cap = (int64_t)n_sm * 8;
-    gae_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(T, n, rewards, values, dones, next_value, next_done, gamma, lam,
-                                                                   advantages, returns);
+    gae_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(T, n, rewards, values, done_after, next_value, gamma, lam, advantages,
+                                                                   returns);
     return cudaGetLastError();
 }
 

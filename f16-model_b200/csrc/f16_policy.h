@@ -29,13 +29,15 @@ struct PolicyArgs {
     float *logprob;           // [n] or nullptr
     int64_t n;
     int sample;               // 0: eps = 0 (deterministic action)
-    uint32_t step;            // RNG counter (rollout step)
+    uint32_t step;            // RNG counter (rollout step), used when ep_len is null
+    const int32_t *ep_len;    // [n] env step counters / episode counters as RNG counters, or nullptr
+    const uint32_t *episode_no;
     uint64_t seed;
     int64_t id_base;          // global id of env 0 (sharding-invariant noise)
 };
 
-cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *values, const float *dones, const float *next_value,
-                       const float *next_done, float gamma, float lam, float *advantages, float *returns, int n_sm, cudaStream_t st);
+cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *values, const uint8_t *done_after, const float *next_value,
+                       float gamma, float lam, float *advantages, float *returns, int n_sm, cudaStream_t st);
 size_t policy_smem_bytes();
 cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, cudaStream_t st);
 

@@ -80,25 +80,34 @@ class TensorCorePolicy:
         pack_policy_blob(self.actor_mean, self.critic, out=self._blob)
 
     # ---- tensor-core inference ------------------------------------------------------------
-    def act(self, obs, sample=True, step=None, want_mean=False):
-        """obs [N,5] fp32 CUDA -> (action [N], logprob [N], value [N]) in one kernel launch."""
+    def act(self, obs, sample=True, step=None, want_mean=False, out=None, env=None):
+        """obs [N,5] fp32 CUDA -> (action [N], logprob [N], value [N]) in one kernel launch.
+        ``out=(action, logprob, value)`` writes into caller buffers (e.g. rows of a rollout buffer);
+        ``env`` (an ``F16VecEnv``) keys the exploration noise by the env's own episode / step
+        counters instead of ``step`` -- nothing host-side changes between launches, so the call can
+        be captured in a CUDA graph and replayed."""
         torch = self._torch
         obs = _capi.require_cuda(obs, "obs")
         if obs.dtype != torch.float32 or obs.dim() != 2 or obs.shape[1] != 5:
             raise ValueError("obs must be float32 [N, 5]")
         n = obs.shape[0]
-        action = torch.empty(n, device=obs.device)
-        logprob = torch.empty(n, device=obs.device)
-        value = torch.empty(n, device=obs.device)
+        if out is None:
+            action = torch.empty(n, device=obs.device)
+            logprob = torch.empty(n, device=obs.device)
+            value = torch.empty(n, device=obs.device)
+        else:
+            action, logprob, value = out
         mean = torch.empty(n, device=obs.device) if want_mean else None
-        if step is None:
+        if step is None and env is None:
             step = self._step
             self._step += 1
+        ep_len = env.episode_length.data_ptr() if env is not None else None
+        ep_no = env.episode_no.data_ptr() if env is not None else None
         with torch.cuda.device(obs.device):
             _capi.check(self._lib.f16_policy_forward(
                 n, obs.data_ptr(), self._blob.data_ptr(), self.actor_logstd.data_ptr(), mean.data_ptr() if want_mean else None,
                 value.data_ptr(), action.data_ptr(), logprob.data_ptr(), int(bool(sample)), self.seed & 0xFFFFFFFFFFFFFFFF,
-                int(step) & 0xFFFFFFFF, self.env_id_base, _capi.stream_ptr(obs.device)))
+                int(step or 0) & 0xFFFFFFFF, ep_len, ep_no, self.env_id_base, _capi.stream_ptr(obs.device)))
         return (action, logprob, value, mean) if want_mean else (action, logprob, value)
 
     def mean_value(self, obs):
@@ -110,7 +119,7 @@ class TensorCorePolicy:
         value = torch.empty(n, device=obs.device)
         with torch.cuda.device(obs.device):
             _capi.check(self._lib.f16_policy_forward(n, obs.data_ptr(), self._blob.data_ptr(), None, mean.data_ptr(), value.data_ptr(),
-                                                     None, None, 0, 0, 0, 0, _capi.stream_ptr(obs.device)))
+                                                     None, None, 0, 0, 0, None, None, 0, _capi.stream_ptr(obs.device)))
         return mean, value
 
     # ---- differentiable evaluation for the PPO update (torch autograd) ---------------------

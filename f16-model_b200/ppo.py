@@ -34,24 +34,28 @@ class PPOConfig:
     max_grad_norm: float = 0.5
     target_kl: float = None
     reset_every_update: bool = True      # the reference re-resets the envs at every update (:210)
+    use_cuda_graph: bool = True          # replay the whole rollout (2 kernels per step) from one CUDA graph
 
 
-def gae(rewards, values, dones, next_value, next_done, gamma, gae_lambda):
-    """Advantages and returns [T, N] by the CUDA reverse scan (f16_gae)."""
+def gae(rewards, values, done_after, next_value, gamma, gae_lambda):
+    """Advantages and returns [T, N] by the CUDA reverse scan (f16_gae).  ``done_after`` is the uint8
+    [T, N] done flag returned by each step (``dones[t+1]`` / ``next_done`` in the reference's loop)."""
     import torch
 
     T, N = rewards.shape
     adv = torch.empty_like(rewards)
     ret = torch.empty_like(rewards)
     L = _capi.load_library()
-    for t in (rewards, values, dones, next_value, next_done):
+    for t in (rewards, values, next_value):
         _capi.require_cuda(t, "gae input")
         if t.dtype != torch.float32:
             raise ValueError("gae inputs must be float32")
+    _capi.require_cuda(done_after, "done_after")
+    if done_after.dtype not in (torch.uint8, torch.bool):
+        raise ValueError("done_after must be uint8 / bool")
     with torch.cuda.device(rewards.device):
-        _capi.check(L.f16_gae(T, N, rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), next_value.data_ptr(),
-                              next_done.data_ptr(), float(gamma), float(gae_lambda), adv.data_ptr(), ret.data_ptr(),
-                              _capi.stream_ptr(rewards.device)))
+        _capi.check(L.f16_gae(T, N, rewards.data_ptr(), values.data_ptr(), done_after.data_ptr(), next_value.data_ptr(),
+                              float(gamma), float(gae_lambda), adv.data_ptr(), ret.data_ptr(), _capi.stream_ptr(rewards.device)))
     return adv, ret
 
 
@@ -67,11 +71,12 @@ class PPOTrainer:
         self.minibatch_size = self.batch_size // self.cfg.num_minibatches
         self.optimizer = torch.optim.Adam(policy.parameters(), lr=self.cfg.learning_rate, amsgrad=True)
         T, N, dev = self.cfg.num_steps, self.N, self.device
-        self.obs = torch.zeros((T, N, 5), device=dev)
+        aos = envs.obs_layout == "aos"
+        self.obs = torch.zeros((T + 1, N, 5) if aos else (T + 1, 5, N), device=dev)   # obs[t] feeds step t; obs[T] bootstraps
         self.actions = torch.zeros((T, N), device=dev)
         self.logprobs = torch.zeros((T, N), device=dev)
         self.rewards = torch.zeros((T, N), device=dev)
-        self.dones = torch.zeros((T, N), device=dev)
+        self.done_after = torch.zeros((T, N), dtype=torch.uint8, device=dev)            # done flag returned by step t
         self.values = torch.zeros((T, N), device=dev)
         self.global_step = 0
         self.update_idx = 0
@@ -79,31 +84,51 @@ class PPOTrainer:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size()
         self._gen = torch.Generator(device=dev).manual_seed(self.cfg.seed)
+        self._graph = None
 
     # ------------------------------------------------------------------ rollout
+    def _obs_at(self, t):
+        return self.obs[t] if self.envs.obs_layout == "aos" else self.obs[t].t()
+
+    def _enqueue_rollout(self):
+        """2 kernels per step, no host work in between: the policy kernel writes action / log-prob / value
+        straight into row t of the rollout buffers, the env kernel reads the action row and writes
+        reward / done rows and the NEXT observation row."""
+        for t in range(self.cfg.num_steps):
+            self.policy.act(self._obs_at(t), sample=True, env=self.envs,
+                            out=(self.actions[t], self.logprobs[t], self.values[t]))
+            self.envs.step_k(self.actions[t:t + 1], out=(self.obs[t + 1], self.rewards[t:t + 1], self.done_after[t:t + 1]))
+
     def rollout(self):
-        """num_steps closed-loop steps for all envs, everything device-resident."""
+        """num_steps closed-loop steps for all envs, everything device-resident; replayed from a CUDA
+        graph (one launch per rollout) unless ``use_cuda_graph=False``."""
         torch, cfg = self._torch, self.cfg
-        if cfg.reset_every_update:
-            next_obs, _ = self.envs.reset(seed=cfg.seed + self.update_idx + 1)
-            next_done = torch.zeros(self.N, device=self.device)
+        if cfg.reset_every_update or self.update_idx == 0:
+            obs0, _ = self.envs.reset(seed=cfg.seed + self.update_idx + 1)
+            self._obs_at(0).copy_(obs0)
         else:
-            next_obs, next_done = self._next_obs, self._next_done
-        ep_returns, ep_count = torch.zeros((), device=self.device), torch.zeros((), device=self.device)
-        for step in range(cfg.num_steps):
-            self.obs[step].copy_(next_obs)
-            self.dones[step].copy_(next_done)
-            action, logprob, value = self.policy.act(next_obs, sample=True, step=self.global_step // max(self.N, 1))
-            self.values[step], self.actions[step], self.logprobs[step] = value, action, logprob
-            next_obs, reward, done, _, info = self.envs.step(action)
-            self.rewards[step].copy_(reward)
-            next_done = done.float()
-            ep_returns += (info["final_info"]["total_return"] * done).sum()
-            ep_count += done.sum()
-            self.global_step += self.N
-        self._next_obs, self._next_done = next_obs.clone(), next_done
-        _, next_value = self.policy.mean_value(self._next_obs)
-        adv, ret = gae(self.rewards, self.values, self.dones, next_value, self._next_done, cfg.gamma, cfg.gae_lambda)
+            self.obs[0].copy_(self.obs[cfg.num_steps])
+        if not cfg.use_cuda_graph:
+            self._enqueue_rollout()
+        else:
+            if self._graph is None:
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):                      # warm-up outside capture
+                    self.policy.act(self._obs_at(0), sample=True, env=self.envs,
+                                    out=(self.actions[0], self.logprobs[0], self.values[0]))
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._enqueue_rollout()
+            self._graph.replay()
+        self.global_step += self.N * cfg.num_steps
+        _, next_value = self.policy.mean_value(self._obs_at(cfg.num_steps))
+        adv, ret = gae(self.rewards, self.values, self.done_after, next_value, cfg.gamma, cfg.gae_lambda)
+        done = self.done_after.bool()
+        ep_count = done.sum()
+        # episode statistics from the buffers (the env's final_* outputs are overwritten every step)
+        ep_returns = self.rewards.sum() * (ep_count > 0)
         return adv, ret, ep_returns, ep_count
 
     # ------------------------------------------------------------------ update
@@ -122,7 +147,8 @@ class PPOTrainer:
 
     def update(self, advantages, returns):
         torch, cfg = self._torch, self.cfg
-        b_obs = self.obs.reshape(-1, 5)
+        T = cfg.num_steps
+        b_obs = (self.obs[:T] if self.envs.obs_layout == "aos" else self.obs[:T].transpose(1, 2)).reshape(-1, 5)
         b_logprobs, b_actions = self.logprobs.reshape(-1), self.actions.reshape(-1)
         b_adv, b_ret, b_val = advantages.reshape(-1), returns.reshape(-1), self.values.reshape(-1)
         stats = {}
@@ -184,7 +210,7 @@ class PPOTrainer:
             var_y = y_true.var()
             stats.update(update=update, global_step=self.global_step, rollout_s=t1 - t0, update_s=t2 - t1,
                          rollout_sps=self.batch_size / (t1 - t0), mean_step_reward=self.rewards.mean().item(),
-                         episodes=int(ep_cnt.item()), mean_episode_return=(ep_ret / ep_cnt.clamp(min=1)).item(),
+                         episodes=int(ep_cnt.item()), mean_return_per_finished_episode=(ep_ret / ep_cnt.clamp(min=1)).item(),
                          explained_variance=(1 - (y_true - y_pred).var() / var_y).item() if var_y > 0 else float("nan"))
             history.append(stats)
             if log:

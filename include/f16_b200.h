@@ -158,18 +158,19 @@ int f16_trim(int n_cells, const void *V, const void *H, int n_starts, const void
  * 5->64->64->1 (actor_mean, critic) on the tensor cores (tcgen05, TF32 operands, fp32 accumulate), fused with the
  * Gaussian policy head.  obs float[n][5]; blob = weights packed by f16_policy_blob layout (see
  * f16-model_b200/policy.py); logstd float[1]; outputs float[n], each may be NULL.
- * action = mean + exp(logstd) * eps with eps ~ N(0,1) from the counter RNG keyed by (seed, env id, step), or
- * eps = 0 when sample == 0; logprob is the Gaussian log-density of that action. */
+ * action = mean + exp(logstd) * eps with eps ~ N(0,1) from the counter RNG keyed by (seed, env id, episode_no[i],
+ * ep_len[i]) -- the env's own counters, so CUDA-graph replays draw fresh noise -- or by (seed, env id, step) when
+ * ep_len is NULL; eps = 0 when sample == 0; logprob is the Gaussian log-density of that action. */
 int f16_policy_blob_bytes(void);
 int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void *logstd, void *mean, void *value,
-                       void *action, void *logprob, int sample, uint64_t seed, uint32_t step, int64_t env_id_base,
-                       void *stream);
+                       void *action, void *logprob, int sample, uint64_t seed, uint32_t step, const int32_t *ep_len,
+                       const uint32_t *episode_no, int64_t env_id_base, void *stream);
 
-/* The GAE reverse scan of Agent.train (control/ppo/ppo_model_gsde.py:244-268): float [T][n] rewards, values,
- * dones (dones[t] = env was done before step t), bootstrap next_value / next_done float[n] ->
- * advantages, returns float[T][n]. */
-int f16_gae(int T, int64_t n, const void *rewards, const void *values, const void *dones, const void *next_value,
-            const void *next_done, double gamma, double gae_lambda, void *advantages, void *returns, void *stream);
+/* The GAE reverse scan of Agent.train (control/ppo/ppo_model_gsde.py:244-268): float [T][n] rewards, values;
+ * done_after u8[T][n] = the done flag returned by step t (the reference's dones[t+1], and next_done for the last
+ * step) exactly as f16_env_step writes it; bootstrap next_value float[n] -> advantages, returns float[T][n]. */
+int f16_gae(int T, int64_t n, const void *rewards, const void *values, const uint8_t *done_after, const void *next_value,
+            double gamma, double gae_lambda, void *advantages, void *returns, void *stream);
 
 #ifdef __cplusplus
 }

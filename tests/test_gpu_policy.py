@@ -121,7 +121,8 @@ def test_gae_kernel_matches_reference_loop(f16):
     dones = (torch.rand((T, N), device="cuda", generator=g) < 0.02).float()
     next_value = torch.randn(N, device="cuda", generator=g)
     next_done = (torch.rand(N, device="cuda", generator=g) < 0.02).float()
-    adv, ret = f16.gae(rewards, values, dones, next_value, next_done, 0.99, 0.95)
+    done_after = torch.cat([dones[1:], next_done[None]]).to(torch.uint8)        # flag returned BY step t
+    adv, ret = f16.gae(rewards, values, done_after, next_value, 0.99, 0.95)
     radv, rret = _gae_reference(rewards, values, dones, next_value, next_done, 0.99, 0.95)
     assert (adv - radv).abs().max().item() < 2e-4 and (ret - rret).abs().max().item() < 2e-4
 
@@ -137,10 +138,26 @@ def test_ppo_updates_run_on_device(f16):
     blob_before = pol._blob.clone()
     hist = trainer.train(num_updates=2)
     assert len(hist) == 2 and all(np.isfinite(h["value_loss"]) and np.isfinite(h["policy_loss"]) for h in hist)
+    assert trainer._graph is not None                       # the rollout was replayed from a CUDA graph
     assert any(not torch.equal(a, b) for a, b in zip(before, pol.parameters()))
     assert not torch.equal(blob_before, pol._blob)
     assert hist[-1]["global_step"] == 2 * 64 * 4096 and hist[-1]["rollout_sps"] > 1e6
     obs = trainer.obs[0]
+    # graph replays draw fresh exploration noise (RNG keyed by the env's own counters)
+    a_first = trainer.actions[5].clone()
+    trainer.rollout()
+    assert not torch.equal(a_first, trainer.actions[5])
+    # eager rollout == graph rollout, bit for bit
+    envs2 = f16.F16VecEnv(cfg, 4096, seed=1)
+    pol2 = f16.TensorCorePolicy(seed=1, logstd_init=-1.0)
+    t_graph = f16.PPOTrainer(envs2, pol2, f16.PPOConfig(num_steps=16))
+    envs3 = f16.F16VecEnv(cfg, 4096, seed=1)
+    pol3 = f16.TensorCorePolicy(seed=1, logstd_init=-1.0)
+    t_eager = f16.PPOTrainer(envs3, pol3, f16.PPOConfig(num_steps=16, use_cuda_graph=False))
+    ag, rg, _, _ = t_graph.rollout()
+    ae, re, _, _ = t_eager.rollout()
+    assert torch.equal(t_graph.actions, t_eager.actions) and torch.equal(t_graph.rewards, t_eager.rewards)
+    assert torch.equal(ag, ae) and torch.equal(rg, re)
     m, v = pol.mean_value(obs)
     with torch.no_grad():
         assert (m - pol.actor_mean(obs).squeeze(-1)).abs().max().item() < 3e-3     # blob re-packed after the update
