@@ -17,8 +17,9 @@ from .policy import TensorCorePolicy, pack_policy_blob         # noqa: F401
 from .ppo import PPOConfig, PPOTrainer, gae                     # noqa: F401
 from .trim import trim_grid, reference_starts                   # noqa: F401
 from . import trim as find_trim_position                        # noqa: F401
+from . import artifacts                                         # noqa: F401
 from ._capi import build, load_library, library_path, F16Error   # noqa: F401
 
 __all__ = ["F16", "F16VecEnv", "ReferenceSignal", "build_reference_bank", "States", "Control", "F16model", "rhs",
            "model_step", "get_trimmed_state_control", "get_random_state", "find_correct_thrust_position", "plane",
-           "TensorCorePolicy", "pack_policy_blob", "PPOConfig", "PPOTrainer", "gae", "trim_grid", "reference_starts", "find_trim_position", "build", "load_library", "library_path", "F16Error"]
+           "TensorCorePolicy", "pack_policy_blob", "PPOConfig", "PPOTrainer", "gae", "trim_grid", "reference_starts", "find_trim_position", "artifacts", "build", "load_library", "library_path", "F16Error"]

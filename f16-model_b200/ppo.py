@@ -208,7 +208,7 @@ class PPOTrainer:
             t2 = time.perf_counter()
             y_pred, y_true = self.values.reshape(-1), ret.reshape(-1)
             var_y = y_true.var()
-            stats.update(update=update, global_step=self.global_step, rollout_s=t1 - t0, update_s=t2 - t1,
+            stats.update(update=update, global_step=self.global_step, learning_rate=self.optimizer.param_groups[0]["lr"], rollout_s=t1 - t0, update_s=t2 - t1,
                          rollout_sps=self.batch_size / (t1 - t0), mean_step_reward=self.rewards.mean().item(),
                          episodes=int(ep_cnt.item()), mean_return_per_finished_episode=(ep_ret / ep_cnt.clamp(min=1)).item(),
                          explained_variance=(1 - (y_true - y_pred).var() / var_y).item() if var_y > 0 else float("nan"))
