@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -113,7 +114,11 @@ f16::LaunchGeom geom(const DeviceCtx &c, int dtype, bool fast, bool autoreset)
 {
     int occ = c.occ[dtype][fast ? 1 : 0][autoreset ? 1 : 0];
     if (occ < 1) occ = 1;
-    return {c.n_sm, occ};
+    static const int pdl = [] {
+        const char *e = std::getenv("F16B200_PDL");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return {c.n_sm, occ, pdl};
 }
 
 int check_cfg(const f16_config *cfg)

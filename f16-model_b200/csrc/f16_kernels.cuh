@@ -266,8 +266,14 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
         sm->drained[1] = 0;
     }
     __syncthreads();
+    // Programmatic dependent launch: let the NEXT launch in the stream start its own prologue (barrier
+    // init, table staging) while this grid is still running ...
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) tma_bulk_g2s(&sm->tbl, A.tables, static_cast<uint32_t>(sizeof(Tables<R>)), &sm->bar_tbl);
+    // ... and do not touch anything the PREVIOUS launch may still be writing (state, counters, actions)
+    // until it has completed.  (No-op when the launch carries no programmatic dependency.)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) {
-        tma_bulk_g2s(&sm->tbl, A.tables, static_cast<uint32_t>(sizeof(Tables<R>)), &sm->bar_tbl);
         if (tma) {   // prologue: two tiles in flight
             unsigned t0 = blockIdx.x, t1 = blockIdx.x + gridDim.x;
             if (t0 < n_full) issue_tile<R, AUTORESET, COMP>(A, S, sm, 0, i_begin + t0 * kCtaThreads);
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
                 R pen = R(0);
                 if (!(x[1] > R(300))) { pen += R(-1000); done_now = 1; }
                 if (x[1] >= R(30000)) { pen += R(-1000); done_now = 1; }
-                if (Mth<R, FAST>::fabs(x[2]) >= R(K::wz_term)) { pen += R(-1000); done_now = 1; }
+                if (!(Mth<R, FAST>::fabs(x[2]) < R(K::wz_term))) { pen += R(-1000); done_now = 1; }   // >= for finite wz; NaN terminates too
                 if (ep_len == A.horizon) done_now = 1;
                 reward = pen + tracking_reward<R, FAST>(ref, x[2]);
                 R wz_obs = x[2];
@@ -662,7 +668,18 @@ cudaError_t launch_env_step_t(const EnvArgs<R> &A, const StepArgs<R> &S, const L
     const size_t smem = sizeof(StepSmem<R>);
     const bool single = S.K == 1;
     const bool comp = A.pos_comp != nullptr && sizeof(R) == 4;
-#define F16_LAUNCH(AR, SG, CP) env_step_kernel<R, FAST, AR, SG, CP><<<grid, kCtaThreads, smem, st>>>(A, S)
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kCtaThreads);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this launch's prologue with the previous tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = g.pdl ? 1 : 0;
+    cudaError_t le = cudaSuccess;
+#define F16_LAUNCH(AR, SG, CP) le = cudaLaunchKernelEx(&lc, env_step_kernel<R, FAST, AR, SG, CP>, A, S)
     if (comp) {
         if constexpr (sizeof(R) == 4) {
             if (A.autoreset) { if (single) F16_LAUNCH(true, true, true); else F16_LAUNCH(true, false, true); }
@@ -673,6 +690,7 @@ cudaError_t launch_env_step_t(const EnvArgs<R> &A, const StepArgs<R> &S, const L
         else             { if (single) F16_LAUNCH(false, true, false); else F16_LAUNCH(false, false, false); }
     }
 #undef F16_LAUNCH
+    if (le != cudaSuccess) return le;
     return cudaGetLastError();
 }
 

@@ -12,6 +12,7 @@ namespace f16 {
 struct LaunchGeom {
     int n_sm;
     int ctas_per_sm;
+    int pdl = 1;   // launch the step kernel with programmatic stream serialization (F16B200_PDL=0 disables)
 };
 
 // typed view of f16_config + f16_env_buffers (include/f16_b200.h)

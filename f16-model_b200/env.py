@@ -156,12 +156,10 @@ class F16VecEnv:
                 init_mode = _capi.INIT_FIXED
             else:
                 t = torch.as_tensor(s)
-                if t.dim() != 2 or 9 not in t.shape:
-                    raise ValueError("per-env init_state must have shape [9, N] or [N, 9]")
-                if t.shape[0] != 9 or (t.shape[0] == 9 and t.shape[1] != N and t.shape[0] == N):
+                if t.dim() == 2 and t.shape == (N, 9) and N != 9:
                     t = t.t()
-                if t.shape != (9, N):
-                    raise ValueError(f"per-env init_state must cover {N} envs")
+                if t.dim() != 2 or t.shape != (9, N):
+                    raise ValueError(f"per-env init_state must have shape [9, {N}] (or [{N}, 9])")
                 self.init_state_tensor = t.to(device=dev, dtype=dt_).contiguous()
                 init_mode = _capi.INIT_PER_ENV
 
@@ -331,6 +329,8 @@ class F16VecEnv:
         -> (obs, reward [K, N], done [K, N] uint8); obs is the last observation [N, 5], or
         [K, N, 5] with ``obs_every_step``.  ``out`` may carry preallocated (obs, reward, done)."""
         torch = self._torch
+        if getattr(actions, "ndim", 0) != 2:
+            raise ValueError("step_k takes actions of shape [K, N]")
         K = int(actions.shape[0])
         a = self._actions(actions, K)
         N, dev, dt_ = self.num_envs, self.device, self.dtype

@@ -433,6 +433,19 @@ def test_soa_observation_layout(f16):
     assert ob.shape == (4096, 5) and torch.equal(oa, ob.contiguous())
 
 
+def test_non_finite_state_terminates_instead_of_trapping(f16):
+    """The reference raises ValueError from inside the atmosphere / interpolators on a NaN state
+    (SURVEY section 5); the kernel flags the episode as terminated instead."""
+    env = f16.F16VecEnv(CFG, 64, dtype=torch.float64, autoreset=False, seed=1)
+    st = env.state.clone()
+    st[1, 3] = float("nan")       # altitude of env 3
+    st[2, 5] = float("nan")       # pitch rate of env 5
+    env.set_state(st)
+    _, r, d, _, _ = env.step(torch.zeros(64, dtype=torch.float64, device="cuda"))
+    d = d.cpu().numpy()
+    assert d[3] and d[5] and d.sum() == 2
+
+
 def test_bad_arguments_raise(f16):
     env = f16.F16VecEnv(CFG, 64)
     with pytest.raises(ValueError):
@@ -443,3 +456,7 @@ def test_bad_arguments_raise(f16):
         f16.F16VecEnv(CFG, 64, dtype=torch.float16)
     with pytest.raises(KeyError):
         f16.F16VecEnv({"dt": 0.01, "tn": 10}, 64)
+    with pytest.raises(ValueError):
+        env.step_k(torch.zeros(64, device="cuda"))
+    with pytest.raises(ValueError):
+        f16.F16VecEnv(dict(CFG, init_state=np.zeros((5, 9))), 64)
