@@ -347,7 +347,7 @@ def main():
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": N * world * n_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": 25 * N,
                "steps": n_e2e, "ms_per_step": 1e3 * e2e_s / n_e2e,
-               "path": "f16_env_step_host: pinned host actions -> H2D -> kernel -> D2H obs/reward/done, 8 chunks on 3 streams"}
+               "path": "f16_env_step_host: pinned host actions -> H2D -> kernel -> D2H obs/reward/done, 3 chunks on 3 streams (PCIe-bound)"}
 
     # ---- K-substeps sweep (state in registers across K env-steps per launch) -----------------
     sweep = None

@@ -351,8 +351,13 @@ int f16_env_step_host(const f16_config *cfg, const f16_env_buffers *env, const v
     io.reward = P.reward;
     io.done = P.done;
 
-    // chunk the env range so that H2D(c+1), kernel(c) and D2H(c-1) overlap on three streams
-    int64_t chunks = n >= (1 << 18) ? 8 : (n >= (1 << 15) ? 4 : 1);
+    // chunk the env range so that H2D(c+1), kernel(c) and D2H(c-1) overlap on three streams; the transfer is
+    // D2H-bound (25 B per env-step out), so few large copies beat many small ones
+    int64_t chunks = n >= (1 << 17) ? 3 : 1;   // measured on B200 / PCIe Gen5 (tools/e2e_probe.py): 3 chunks 1.78e9, 1: 1.72e9, 8: 1.60e9 env-steps/s
+    if (const char *e = std::getenv("F16B200_HOST_CHUNKS")) {   // tuning knob
+        const long v = std::atol(e);
+        if (v >= 1 && v <= 64) chunks = v;
+    }
     int64_t per = ((n + chunks - 1) / chunks + 255) / 256 * 256;
     for (int64_t c = 0, i0 = 0; i0 < n; ++c, i0 += per) {
         const int64_t i1 = i0 + per < n ? i0 + per : n;
