@@ -292,6 +292,76 @@ def test_sharding_invariance_full_size(f16):
         assert torch.equal(p.ref_idx, whole.ref_idx[rk * h:(rk + 1) * h])
 
 
+def test_full_size_batch_fp64_subset_vs_oracle(f16, orc):
+    """BASELINE config 3/5 size in the parity mode: 2^20 envs x 120 steps in fp64 (K = 40 per launch);
+    a strided subset of 2048 envs is re-flown by the oracle from the same inputs -- the result for an env
+    must not depend on the batch it sits in."""
+    n, T = 1 << 20, 120
+    rng = np.random.default_rng(99)
+    d5 = np.radians(5)
+    al = rng.uniform(-d5, d5, n)
+    x0 = np.zeros((n, 9))
+    x0[:, 1], x0[:, 2], x0[:, 3] = rng.uniform(2000, 4000, n), rng.uniform(-d5, d5, n), al
+    x0[:, 4], x0[:, 5] = rng.uniform(90, 250, n), al
+    bank = __import__("f16_model_b200").build_reference_bank(0.01, 10, None, False)
+    ref_idx = rng.integers(0, bank.shape[0], n).astype(np.int32)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    acts = torch.rand((T, n), device="cuda", dtype=torch.float64, generator=g) * 2 - 1
+    acts[:, ::3] = 1.0                                   # a third of the fleet pulls full aft stick -> terminations
+    env = f16.F16VecEnv(CFG, n, dtype=torch.float64, autoreset=False, reference_bank=bank)
+    env.set_state(x0.T, ref_idx=ref_idx)
+    dones = []
+    for c in range(3):
+        _, _, d = env.step_k(acts[c * 40:(c + 1) * 40])
+        dones.append(d)
+    sub = np.arange(0, n, 512)
+    ref = orc.rollout(x0[sub], acts[:, sub].cpu().numpy(), bank, ref_idx[sub], want_obs=False)
+    st = env.state.T.cpu().numpy()[sub]
+    assert np.array_equal(torch.cat(dones).cpu().numpy()[:, sub], ref["done"])
+    assert np.array_equal(env.episode_length.cpu().numpy()[sub], ref["ep_len"])
+    assert int((ref["ep_len"] < T).sum()) > 300
+    assert rel_err(st, ref["final_state"], FIELD_SCALE).max() < FP64_RTOL
+    assert rel_err(env.total_return.cpu().numpy()[sub], ref["total_return"], 1.0).max() < FP64_RTOL
+
+
+def test_eight_million_envs_sharding_invariance(f16):
+    """BASELINE config 5 size (8 Mi envs, here on one GPU): one batch == four shards keyed by global env id."""
+    from f16_model_b200.sharding import make_sharded_env
+
+    n = 1 << 23
+    cfg = dict(CFG, determenistic_ref=False)
+    whole = f16.F16VecEnv(cfg, n, dtype=torch.float32, autoreset=True, seed=21, bank_size=32, fast_math=True)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    acts = torch.rand((4, n), device="cuda", generator=g) * 2 - 1
+    _, r, d = whole.step_k(acts)
+    q = n // 4
+    for rk in (0, 3):
+        part = make_sharded_env(cfg, n, rk, 4, "cuda", dtype=torch.float32, autoreset=True, seed=21, bank_size=32, fast_math=True)
+        _, rp, dp = part.step_k(acts[:, rk * q:(rk + 1) * q].contiguous())
+        assert torch.equal(rp, r[:, rk * q:(rk + 1) * q]) and torch.equal(dp, d[:, rk * q:(rk + 1) * q])
+        assert torch.equal(part.state, whole.state[:, rk * q:(rk + 1) * q])
+        del part
+
+
+@pytest.mark.parametrize("dt,tn,scenario", [(0.01, 5, "pure_step"), (0.02, 20, "step"), (0.005, 10, "cos")])
+def test_other_step_sizes_and_horizons(f16, orc, dt, tn, scenario):
+    """config["dt"] / config["tn"] other than 0.01 / 10 (test/env_test.py uses tn=5): the horizon
+    tn/dt - 1 and the reference length follow, trajectories still match the oracle."""
+    cfg = dict(CFG, dt=dt, tn=tn, scenario=scenario)
+    T = int(round(tn / dt))
+    x0, acts = config2_inputs(256, seed=11, T=1000)
+    acts = np.tile(acts, (3, 1))[:T]
+    bank = __import__("f16_model_b200").build_reference_bank(dt, tn, scenario, True)
+    assert bank.shape == (1, T)
+    env = f16.F16VecEnv(cfg, 256, dtype=torch.float64, autoreset=False)
+    env.set_state(x0.T)
+    _, r, d = env.step_k(dev(acts))
+    ref = orc.rollout(x0, acts, bank, np.zeros(256, dtype=np.int32), dt=dt, horizon=T - 1, want_obs=False)
+    assert np.array_equal(d.cpu().numpy(), ref["done"]) and np.array_equal(env.episode_length.cpu().numpy(), ref["ep_len"])
+    assert ref["ep_len"].max() == T                       # the time-out fires on step tn/dt
+    assert rel_err(env.state.T.cpu().numpy(), ref["final_state"], FIELD_SCALE).max() < FP64_RTOL
+
+
 def test_determinism_and_seed_sensitivity(f16):
     a = f16.F16VecEnv(CFG, 4096, seed=5)
     b = f16.F16VecEnv(CFG, 4096, seed=5)
