@@ -186,10 +186,6 @@ f16::StepArgs<R> make_step_args(const f16_config *cfg, const f16_step_io *io, in
     S.final_return = static_cast<R *>(io->final_return);
     S.obs_every_step = io->obs_every_step;
     S.K = K;
-    S.obs_vec_ok = (reinterpret_cast<uintptr_t>(io->obs) % 16 == 0 &&
-                    (!io->obs_every_step || (static_cast<size_t>(cfg->n_envs) * 5 * sizeof(R)) % 16 == 0))
-                       ? 1
-                       : 0;
     S.tma_ok = 0;   // set by step_range once the env buffers are known
     S.i_begin = 0;
     S.i_end = cfg->n_envs;

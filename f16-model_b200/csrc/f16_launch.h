@@ -50,7 +50,6 @@ struct StepArgs {
     int obs_every_step;
     int K;
     int tma_ok;               // every input row of a full tile is 16-byte aligned: TMA-staged loads allowed
-    int obs_vec_ok;           // obs base is 16-byte aligned: warp-transposed vector stores allowed
     int64_t i_begin, i_end;   // env sub-range advanced by this launch (host-buffer path pipelines chunks)
 };
 

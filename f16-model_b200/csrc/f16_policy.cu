@@ -5,7 +5,8 @@
 // 5 -> 64 -> 64 -> 1 evaluated on the observation batch.  This is the one dense contraction on
 // the hot path, so it runs on the tensor cores:
 //
-//   tile = 128 envs = one CTA of 128 threads; thread t owns env row t (= TMEM lane t).
+//   tile = 128 envs = one CTA of 256 threads; threads t and t + 128 share env row t (= TMEM lane t): one
+//   handles the actor columns, the other the critic columns.
 //   layer 1:  D1[128 x 128] = X[128 x 8] * W1cat^T      one tcgen05.mma (M=128, N=128, K=8, kind::tf32);
 //             W1cat stacks actor (rows 0-63) and critic (rows 64-127), K is 5 padded to 8
 //   layer 2:  D2[:, 0:64]   = H1[:, 0:64]   * W2actor^T  eight tcgen05.mma (K=64 in steps of 8)
@@ -28,7 +29,8 @@
 namespace f16 {
 namespace {
 
-constexpr int kRows = 128;          // envs per tile == threads per CTA == UMMA M
+constexpr int kRows = 128;          // envs per tile == UMMA M
+constexpr int kThreads = 256;       // two threads per env row (actor half / critic half)
 constexpr int kHid = 64;
 constexpr uint32_t kTmemCols = 256;  // D1: columns [0,128), D2: columns [128,256)
 
@@ -131,7 +133,7 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key)
     return ctr;
 }
 
-__global__ void __launch_bounds__(kRows, 2) policy_forward_kernel(const PolicyArgs P)
+__global__ void __launch_bounds__(kThreads, 2) policy_forward_kernel(const PolicyArgs P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PolicySmem *sm = reinterpret_cast<PolicySmem *>(smem_raw);
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(kRows, 2) policy_forward_kernel(const PolicyAr
     constexpr uint32_t idesc2 = umma_idesc_tf32(128, 64);
     const uint32_t a1 = smem_u32(sm->a1), a2 = smem_u32(sm->a2);
     const uint32_t w1 = smem_u32(sm->w.w1), w2a = smem_u32(sm->w.w2[0]), w2c = smem_u32(sm->w.w2[1]);
-    const uint32_t lane_base = tmem + ((warp * 32u) << 16);   // this warp's 32 TMEM lanes
+    const uint32_t lane_base = tmem + (((warp & 3u) * 32u) << 16);   // this warp's 32 TMEM lanes (quarter = warp % 4)
     uint32_t phase = 0;
 
     const unsigned n = static_cast<unsigned>(P.n);
@@ -173,18 +175,24 @@ __global__ void __launch_bounds__(kRows, 2) policy_forward_kernel(const PolicyAr
     const float std_dev = P.logstd ? __expf(P.logstd[0]) : 0.f;
     const float log_std = P.logstd ? P.logstd[0] : 0.f;
 
+    // Two threads per env row: thread (row, half) with half 0 = actor columns, half 1 = critic columns.  That
+    // halves every thread's epilogue and doubles the resident warps (16 per SM), which is what this
+    // latency-bound kernel needs; TMEM lanes are reachable from warps w and w + 4 alike (lane quarter = w % 4).
+    const unsigned row = t & (kRows - 1), half = t >> 7;
     for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned i = tile * kRows + t;
+        const unsigned i = tile * kRows + row;
         const bool live = i < n;
-        // ---- layer-1 operand: this thread's observation row, K padded 5 -> 8 -------------------
-        float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        if (live) {
-            const float *src = P.obs + static_cast<size_t>(i) * 5;
-#pragma unroll
-            for (int j = 0; j < 5; ++j) o[j] = src[j];
+        // ---- layer-1 operand: the observation row, K padded 5 -> 8 (half 0 writes chunk 0, half 1 chunk 1) ----
+        if (half == 0) {
+            float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                const float *src = P.obs + static_cast<size_t>(i) * 5;
+                c0 = make_float4(src[0], src[1], src[2], src[3]);
+            }
+            *reinterpret_cast<float4 *>(sm->a1[0][row]) = c0;
+        } else {
+            *reinterpret_cast<float4 *>(sm->a1[1][row]) = make_float4(live ? P.obs[static_cast<size_t>(i) * 5 + 4] : 0.f, 0.f, 0.f, 0.f);
         }
-        *reinterpret_cast<float4 *>(sm->a1[0][t]) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4 *>(sm->a1[1][t]) = make_float4(o[4], 0.f, 0.f, 0.f);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -199,18 +207,19 @@ __global__ void __launch_bounds__(kRows, 2) policy_forward_kernel(const PolicyAr
 
         // ---- hidden layer 1: tanh(D1 + b1) -> layer-2 operand (same canonical layout) ----------
 #pragma unroll
-        for (int blk = 0; blk < 4; ++blk) {
+        for (int blk = 0; blk < 2; ++blk) {
             float v[32];
-            tmem_ld32(lane_base + blk * 32, v);
+            const int col0 = half * 64 + blk * 32;
+            tmem_ld32(lane_base + col0, v);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const int j = blk * 32 + c * 4;
+                const int j = col0 + c * 4;
                 float4 h;
                 h.x = fast_tanh(v[c * 4 + 0] + sm->w.b1[j + 0]);
                 h.y = fast_tanh(v[c * 4 + 1] + sm->w.b1[j + 1]);
                 h.z = fast_tanh(v[c * 4 + 2] + sm->w.b1[j + 2]);
                 h.w = fast_tanh(v[c * 4 + 3] + sm->w.b1[j + 3]);
-                *reinterpret_cast<float4 *>(sm->a2[blk * 8 + c][t]) = h;
+                *reinterpret_cast<float4 *>(sm->a2[j >> 2][row]) = h;
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -234,25 +243,25 @@ __global__ void __launch_bounds__(kRows, 2) policy_forward_kernel(const PolicyAr
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        // ---- hidden layer 2 + output layer -----------------------------------------------------
-        float mean = sm->w.b3[0], value = sm->w.b3[1];
+        // ---- hidden layer 2 + output layer: half 0 -> actor mean, half 1 -> critic value ----------------
+        float head = sm->w.b3[half];
 #pragma unroll
-        for (int blk = 0; blk < 4; ++blk) {
+        for (int blk = 0; blk < 2; ++blk) {
             float v[32];
-            tmem_ld32(lane_base + 128 + blk * 32, v);
+            const int col0 = half * 64 + blk * 32;
+            tmem_ld32(lane_base + 128 + col0, v);
             float acc = 0.f;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int j = blk * 32 + c;
-                acc = fmaf(fast_tanh(v[c] + sm->w.b2[j]), sm->w.w3[j], acc);
-            }
-            if (blk < 2) mean += acc; else value += acc;
+            for (int c = 0; c < 32; ++c) acc = fmaf(fast_tanh(v[c] + sm->w.b2[col0 + c]), sm->w.w3[col0 + c], acc);
+            head += acc;
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM reads done before the next tile's MMAs
 
-        if (live) {
+        if (live && half == 1) {
+            if (P.value) P.value[i] = head;
+        } else if (live) {
+            const float mean = head;
             if (P.mean) P.mean[i] = mean;
-            if (P.value) P.value[i] = value;
             if (P.action) {
                 // Gaussian policy head (ppo_model_gsde.py:81-99 with the state-independent log-std):
                 // a = mean + std * eps,  logp = -0.5 eps^2 - log std - 0.5 log(2 pi)
@@ -332,7 +341,7 @@ cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, cudaStream_t st
     const int64_t tiles = (P.n + kRows - 1) / kRows;
     const int64_t cap = static_cast<int64_t>(n_sm) * 2;
     const int grid = static_cast<int>(tiles < cap ? tiles : cap);
-    policy_forward_kernel<<<grid, kRows, sizeof(PolicySmem), st>>>(P);
+    policy_forward_kernel<<<grid, kThreads, sizeof(PolicySmem), st>>>(P);
     return cudaGetLastError();
 }
 
