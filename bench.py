@@ -166,7 +166,7 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=24000)
+    ap.add_argument("--steps", type=int, default=12000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")

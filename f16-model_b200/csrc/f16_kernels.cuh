@@ -274,10 +274,9 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
     // until it has completed.  (No-op when the launch carries no programmatic dependency.)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) {
-        if (tma) {   // prologue: two tiles in flight
-            unsigned t0 = blockIdx.x, t1 = blockIdx.x + gridDim.x;
+        if (tma) {   // prologue: only the FIRST tile of every CTA -- the opening burst is half as deep, so it lands sooner
+            const unsigned t0 = blockIdx.x;
             if (t0 < n_full) issue_tile<R, AUTORESET, COMP>(A, S, sm, 0, i_begin + t0 * kCtaThreads);
-            if (t1 < n_full) issue_tile<R, AUTORESET, COMP>(A, S, sm, 1, i_begin + t1 * kCtaThreads);
         }
     }
     bool tables_ready = false;
@@ -296,6 +295,10 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
         R ret = R(0);
         if (staged) {
             mbar_wait(&sm->bar_in[stage], (it >> 1) & 1u);
+            if (it == 0 && threadIdx.x == 0) {   // first tile has landed: now put the second one in flight
+                const unsigned t1 = tile + gridDim.x;
+                if (t1 < n_full) issue_tile<R, AUTORESET, COMP>(A, S, sm, 1, i_begin + t1 * kCtaThreads);
+            }
             const R(*in)[kCtaThreads] = sm->in[stage];
             const unsigned t = threadIdx.x;
 #pragma unroll
