@@ -132,6 +132,11 @@ def golden_refsignals():
     g["random_state_out"] = np.array(rs)
     x0, u0 = get_trimmed_state_control()
     g["trim_x0"], g["trim_u0"] = x0, u0
+    # airframe constants and bounds (data/plane.py)
+    names = ["m", "l", "S", "b_a", "Jz", "rcgx", "Tstab", "Xistab", "maxabsstab", "maxabsdstab", "minthrottle", "maxthrottle", "lef", "sb"]
+    g["plane_scalars"] = np.array([float(getattr(plane, k)) for k in names])
+    g["plane_state_bound"] = np.array([plane.state_bound[k] for k in ("Oy", "wz", "V")], dtype=float)
+    g["plane_random_state_bound"] = np.array([plane.random_state_bound[k] for k in ("Oy", "wz", "V", "alpha", "maxabsstab")], dtype=float)
     return g
 
 

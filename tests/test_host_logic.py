@@ -108,6 +108,17 @@ def test_get_random_state_draw_order(golden):
         assert np.array_equal(f16.get_random_state().to_array(), ref)
 
 
+def test_plane_constants_match_reference(golden):
+    from f16_model_b200 import plane
+
+    names = ["m", "l", "S", "b_a", "Jz", "rcgx", "Tstab", "Xistab", "maxabsstab", "maxabsdstab", "minthrottle", "maxthrottle", "lef", "sb"]
+    assert np.array_equal(np.array([float(getattr(plane, k)) for k in names]), golden["plane_scalars"])
+    assert list(plane.state_bound) == ["Oy", "wz", "V"]          # dict order = observation order
+    assert np.array_equal(np.array([plane.state_bound[k] for k in ("Oy", "wz", "V")], dtype=float), golden["plane_state_bound"])
+    rb = np.array([plane.random_state_bound[k] for k in ("Oy", "wz", "V", "alpha", "maxabsstab")], dtype=float)
+    assert np.array_equal(rb, golden["plane_random_state_bound"])
+
+
 def test_states_arithmetic():
     a = f16.States(*range(9))
     b = 0.5 * a + a
