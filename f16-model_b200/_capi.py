@@ -43,7 +43,7 @@ class EnvBuffers(C.Structure):
 class StepIO(C.Structure):
     _fields_ = [("actions", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
                 ("final_obs", C.c_void_p), ("final_ep_len", C.c_void_p), ("final_return", C.c_void_p),
-                ("obs_every_step", C.c_int32), ("reserved", C.c_int32)]
+                ("obs_every_step", C.c_int32), ("reserved", C.c_int32), ("stats", C.c_void_p)]
 
 
 def library_path():

@@ -184,6 +184,7 @@ f16::StepArgs<R> make_step_args(const f16_config *cfg, const f16_step_io *io, in
     S.final_obs = static_cast<R *>(io->final_obs);
     S.final_ep_len = io->final_ep_len;
     S.final_return = static_cast<R *>(io->final_return);
+    S.stats = io->stats;
     S.obs_every_step = io->obs_every_step;
     S.K = K;
     S.tma_ok = 0;   // set by step_range once the env buffers are known

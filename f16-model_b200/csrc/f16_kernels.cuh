@@ -131,6 +131,33 @@ __device__ __forceinline__ R tracking_reward(R ref, R wz)
     return asym + R(0.04) * lin;
 }
 
+// Episode statistics with warp primitives, called from the rare termination branch only: the lanes that
+// are here together (__activemask) elect the lowest one, it gathers their returns and lengths by shuffle and
+// adds them to the CTA's shared-memory accumulators; the CTA flushes to global memory once, at kernel end
+// (hierarchical reduction: shuffle -> shared atomics -> 3 global atomics per CTA).  Out of line so that it
+// costs the hot path no registers.
+struct CtaStats {
+    double ret;
+    int count, length;
+};
+static __device__ __noinline__ void episode_stats_add(CtaStats *cta, double ret, int ep_len)
+{
+    const unsigned grp = __activemask();
+    const unsigned leader = __ffs(grp) - 1;
+    double sum_ret = 0.0;
+    int sum_len = 0;
+    for (unsigned m = grp; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        sum_ret += __shfl_sync(grp, ret, src);
+        sum_len += __shfl_sync(grp, ep_len, src);
+    }
+    if ((threadIdx.x & 31u) == leader) {
+        atomicAdd(&cta->count, __popc(grp));
+        atomicAdd(&cta->length, sum_len);
+        atomicAdd(&cta->ret, sum_ret);
+    }
+}
+
 // Draw / copy an episode's initial state (env.py:172-195,221-243) and pick its reference signal.
 template <typename R>
 __device__ __forceinline__ void init_episode(const EnvArgs<R> &A, int64_t i, uint32_t episode, bool keep_ref, R (&x)[9],
@@ -210,6 +237,7 @@ struct alignas(16) StepSmem {
     uint64_t bar_tbl;
     uint64_t bar_in[2];      // "full": TMA bytes of a stage have landed
     unsigned drained[2];     // warps that have copied a stage into registers; the last one refills it
+    CtaStats stats;          // episodes finished by this CTA (flushed to global once, at kernel end)
 };
 
 template <typename R, bool AUTORESET, bool COMP>
@@ -264,6 +292,9 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
         mbar_init(&sm->bar_in[1], 1);
         sm->drained[0] = 0;
         sm->drained[1] = 0;
+        sm->stats.count = 0;
+        sm->stats.length = 0;
+        sm->stats.ret = 0.0;
     }
     __syncthreads();
     // Programmatic dependent launch: let the NEXT launch in the stream start its own prologue (barrier
@@ -383,6 +414,7 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
                 ep_len += 1;
                 ret += reward;
                 if (done_now) {
+                    if (S.stats) episode_stats_add(&sm->stats, static_cast<double>(ret), ep_len);
                     if (S.final_obs) store_obs<R>(S.final_obs, A.obs_layout, n, i, o);
                     if (S.final_ep_len) S.final_ep_len[i] = ep_len;
                     if (S.final_return) S.final_return[i] = ret;
@@ -440,6 +472,14 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
         }
     }
     if (!tables_ready) mbar_wait(&sm->bar_tbl, 0);   // CTA had no tile: still drain the copy before exit
+    if (S.stats) {
+        __syncthreads();
+        if (threadIdx.x == 0 && sm->stats.count) {
+            atomicAdd(S.stats + 0, static_cast<double>(sm->stats.count));
+            atomicAdd(S.stats + 1, sm->stats.ret);
+            atomicAdd(S.stats + 2, static_cast<double>(sm->stats.length));
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------

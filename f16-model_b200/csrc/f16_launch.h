@@ -47,6 +47,7 @@ struct StepArgs {
     R *final_obs;
     int32_t *final_ep_len;
     R *final_return;
+    double *stats;            // [4] accumulators: episodes finished, sum of their returns, sum of their lengths, spare
     int obs_every_step;
     int K;
     int tma_ok;               // every input row of a full tile is 16-byte aligned: TMA-staged loads allowed

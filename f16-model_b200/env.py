@@ -180,6 +180,8 @@ class F16VecEnv:
         self._reward = torch.zeros((1, N), dtype=dt_, device=dev)
         self._done_out = torch.zeros((1, N), dtype=torch.uint8, device=dev)
         self._truncated = torch.zeros(N, dtype=torch.bool, device=dev)
+        # in-kernel episode statistics (warp ballot + shuffle reduction, one atomic set per warp with a termination)
+        self.episode_stats = torch.zeros(4, dtype=torch.float64, device=dev)
 
         cfg = _capi.Config()
         cfg.dtype = _capi.dtype_code(dt_)
@@ -228,6 +230,7 @@ class F16VecEnv:
         io.final_ep_len = self._final_len.data_ptr()
         io.final_return = self._final_ret.data_ptr()
         io.obs_every_step = 0
+        io.stats = self.episode_stats.data_ptr()
         self._io1 = io
         # prebuilt call arguments / results of the K = 1 fast path
         self._Tensor = self._torch.Tensor
@@ -352,6 +355,7 @@ class F16VecEnv:
         io.final_ep_len = self._final_len.data_ptr()
         io.final_return = self._final_ret.data_ptr()
         io.obs_every_step = int(obs_every_step)
+        io.stats = self.episode_stats.data_ptr()
         with torch.cuda.device(dev):
             _capi.check(self._lib.f16_env_step(C.byref(self._cfg), C.byref(self._buf), C.byref(io), K, self._stream()))
         return self._obs_view(obs), reward, done
@@ -398,6 +402,14 @@ class F16VecEnv:
         if ref_idx is not None:
             self.ref_idx.copy_(torch.as_tensor(ref_idx, dtype=torch.int32))
         self.init_state = self.state.clone()
+
+    def pop_episode_stats(self):
+        """(episodes finished, mean return, mean length) since the last call -- the counters the kernel keeps
+        with warp-level reductions (replaces the per-env Python loop of control/ppo/utils.py:197-235)."""
+        s = self.episode_stats.clone()
+        self.episode_stats.zero_()
+        n = s[0].clamp(min=1.0)
+        return int(s[0].item()), (s[1] / n).item(), (s[2] / n).item()
 
     @property
     def clock(self):

@@ -28,12 +28,16 @@ def global_episode_stats(env, group=None):
     import torch
     import torch.distributed as dist
 
-    done = env._done_out[0].bool()
-    stats = torch.stack([
-        (env._final_ret * done).sum().double(),
-        (env._final_len * done).sum().double(),
-        done.sum().double(),
-    ])
+    if hasattr(env, "episode_stats"):          # kernel-side accumulators (sum of returns, sum of lengths, count)
+        s = env.episode_stats
+        stats = torch.stack([s[1], s[2], s[0]]).double()
+    else:
+        done = env._done_out[0].bool()
+        stats = torch.stack([
+            (env._final_ret * done).sum().double(),
+            (env._final_len * done).sum().double(),
+            done.sum().double(),
+        ])
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     return stats

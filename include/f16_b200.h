@@ -97,6 +97,9 @@ typedef struct f16_step_io {
     void *final_return;      /* real[n] total_return of that episode; may be NULL */
     int32_t obs_every_step;  /* 0: only the last observation is written */
     int32_t reserved;
+    double *stats;           /* double[4] accumulators (+=, never cleared by the library): episodes finished, sum of their
+                                total_return, sum of their episode_length, spare.  One atomic set per group of lanes that
+                                terminate together (active-mask election + shuffle reduction).  May be NULL. */
 } f16_step_io;
 
 /* ---- library ---------------------------------------------------------- */

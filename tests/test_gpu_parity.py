@@ -413,6 +413,11 @@ def test_autoreset_matches_syncvectorenv_semantics(f16, orc):
     assert np.abs(fo[:, :3] - ref["obs"][0][:, :3]).max() < 1e-12
     assert np.all(info["final_info"]["episode_length"].cpu().numpy()[idx] == first_done + 1)
     assert torch.equal(info["_final_info"], term)
+    # in-kernel episode statistics (ballot + shuffle reduction): count / mean return / mean length of the finished episodes
+    n_fin, mean_ret, mean_len = env.pop_episode_stats()
+    assert n_fin == int(m.sum()) and mean_len == first_done + 1
+    assert abs(mean_ret - info["final_info"]["total_return"].cpu().numpy()[m].mean()) < 1e-9
+    assert env.pop_episode_stats()[0] == 0
     # a second env with the same seed but autoreset off freezes instead
     env2 = f16.F16VecEnv(CFG, n, dtype=torch.float64, autoreset=False, seed=2)
     assert torch.equal(env2.state, x_init)

@@ -159,7 +159,7 @@ def test_struct_layouts_match_header():
     """ctypes mirrors of the ABI structs: sizes as the C compiler lays them out."""
     assert ctypes.sizeof(_capi.Config) == 4 + 4 + 8 + 8 + 8 * 4 + 8 + 8 + 9 * 8   # 144 bytes
     assert ctypes.sizeof(_capi.EnvBuffers) == 9 * 8
-    assert ctypes.sizeof(_capi.StepIO) == 7 * 8 + 8
+    assert ctypes.sizeof(_capi.StepIO) == 7 * 8 + 8 + 8
 
 
 def test_no_cpu_fallback_without_a_gpu():
