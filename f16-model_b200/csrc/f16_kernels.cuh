@@ -7,14 +7,18 @@
 // Kernel shape (SURVEY.md section 7 / BASELINE north_star):
 //   * one thread per aircraft, state SoA real[9][n] -> every global access of a warp is one
 //     contiguous 128 B (fp32) / 256 B (fp64) segment;
-//   * the packed table image (8.4 KB fp32 / 16.7 KB fp64) is staged ONCE per CTA into
-//     shared memory by a single TMA bulk copy (cp.async.bulk + mbarrier) that overlaps the
-//     CTA's first state loads; the grid is persistent (SMs x resident CTAs, grid-stride over
-//     256-env tiles) so the staging cost is paid ~10^3 times per launch, not per tile;
-//   * the nine state values, the episode counter and the return live in registers across
-//     the K env-steps of a launch; only action / reward / done stream per step;
-//   * episode termination, gymnasium-style autoreset (counter-based Philox RNG) and the
-//     observation are fused into the same kernel.
+//   * persistent grid (SMs x resident CTAs, grid-stride over 256-env tiles);
+//   * the packed table image (8.4 KB fp32 / 16.7 KB fp64) is staged ONCE per CTA into shared
+//     memory by a single TMA bulk copy (cp.async.bulk + mbarrier);
+//   * the per-env inputs of every full tile (state rows, first action row, counters) are staged
+//     by TMA bulk copies into a 2-stage shared-memory ring two tiles ahead of the compute; the
+//     last warp to drain a stage re-arms it (no CTA-wide barrier, no fixed producer warp);
+//   * the nine state values, the episode counter and the return live in registers across the K
+//     env-steps of a launch; only action / reward / done stream per step;
+//   * episode termination, gymnasium-style autoreset (counter-based Philox RNG), the observation
+//     and hierarchical episode statistics (shuffle -> shared atomics -> one flush per CTA) are
+//     fused into the same kernel;
+//   * launched with programmatic dependent launch: the next launch's prologue overlaps this tail.
 #pragma once
 #include <cstdint>
 

@@ -125,10 +125,10 @@ class PPOTrainer:
         self.global_step += self.N * cfg.num_steps
         _, next_value = self.policy.mean_value(self._obs_at(cfg.num_steps))
         adv, ret = gae(self.rewards, self.values, self.done_after, next_value, cfg.gamma, cfg.gae_lambda)
-        done = self.done_after.bool()
-        ep_count = done.sum()
-        # episode statistics from the buffers (the env's final_* outputs are overwritten every step)
-        ep_returns = self.rewards.sum() * (ep_count > 0)
+        # episode statistics come from the env kernel's own accumulators (warp-level reductions)
+        s = self.envs.episode_stats.clone()
+        self.envs.episode_stats.zero_()
+        ep_count, ep_returns = s[0], s[1]
         return adv, ret, ep_returns, ep_count
 
     # ------------------------------------------------------------------ update
