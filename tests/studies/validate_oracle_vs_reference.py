@@ -2,7 +2,7 @@
 """One-off, larger validation of the C oracle against the UNMODIFIED reference (build container only:
 needs /root/reference; uses the stand-ins in oracle/shims).  Flies N random episodes (config-2 style
 inputs) through the reference's F16 env and through the oracle, reports the worst deviations.
-    python tools/validate_oracle_vs_reference.py [n_envs=256]
+    python tests/studies/validate_oracle_vs_reference.py [n_envs=256]
 The committed goldens (tests/golden) hold 12 such episodes; this run is the wider check quoted in DESIGN.md."""
 import multiprocessing as mp
 import os
@@ -12,7 +12,7 @@ import warnings
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [os.path.join(ROOT, "oracle", "shims"), os.environ.get("F16_REFERENCE", "/root/reference"), ROOT,
                 os.path.join(ROOT, "tests")]
 warnings.simplefilter("ignore")

@@ -230,7 +230,7 @@ def test_config2_fp64_4096_envs_1000_steps(f16, config2):
 def test_config2_fp32_drift_bound(f16, config2, fast):
     """fp32 throughput mode on the config-2 inputs after 1000 steps, envs that flew the whole episode.
     STATED BOUND ('fp32 mode'): relative error <= 1e-4 for >= 99.9 % of envs and <= 2e-4 for
-    all.  Measured on these 3544 envs (tools/fp32_error_study.py): median 3e-7, 99.9th percentile
+    all.  Measured on these 3544 envs (tests/studies/fp32_error_study.py): median 3e-7, 99.9th percentile
     1.3e-5, and exactly one env above 5e-5 -- full-scale random stick with alpha pinned at the -20 deg
     table edge, whose error grows 40x over its last 200 steps (8.3e-5 accurate / 1.3e-4 fast-math):
     sensitivity of the model there, not accumulated rounding.  Early terminations may shift by a
