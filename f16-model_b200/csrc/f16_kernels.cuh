@@ -497,7 +497,12 @@ __global__ void __launch_bounds__(kCtaThreads) env_reset_kernel(const EnvArgs<R>
         R x[9];
         int ref_idx = A.ref_idx[i];
         const uint32_t episode = A.episode_no[i] + 1u;
-        init_episode<R>(A, i, episode, keep_ref != 0, x, ref_idx);
+        if (keep_ref & 2) {   // F16_RESET_KEEP_STATE: the caller has just written the state; only counters + observation
+#pragma unroll
+            for (int j = 0; j < 9; ++j) x[j] = A.state[j * A.n + i];
+        } else {
+            init_episode<R>(A, i, episode, (keep_ref & 1) != 0, x, ref_idx);
+        }
 #pragma unroll
         for (int j = 0; j < 9; ++j) A.state[j * A.n + i] = x[j];
         A.ep_len[i] = 0;

@@ -273,9 +273,11 @@ class F16VecEnv:
         return actions.contiguous()
 
     # ------------------------------------------------------------------ gym API
-    def reset(self, seed=None, options=None, mask=None, keep_reference=False):
+    def reset(self, seed=None, options=None, mask=None, keep_reference=False, keep_state=False):
         """``F16.reset`` for every env (env.py:154-170), or for those where ``mask`` is set.
-        ``seed`` re-keys the device RNG (the reference reseeds the process-global RNGs)."""
+        ``seed`` re-keys the device RNG (the reference reseeds the process-global RNGs).
+        ``keep_state`` keeps the states the caller has just loaded (``set_state``) and only clears the
+        counters and computes the reset observation on the device."""
         torch = self._torch
         if seed is not None:
             self._cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -284,7 +286,7 @@ class F16VecEnv:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
             mptr = mask.data_ptr()
         with torch.cuda.device(self.device):
-            _capi.check(self._lib.f16_env_reset(C.byref(self._cfg), C.byref(self._buf), mptr, int(keep_reference),
+            _capi.check(self._lib.f16_env_reset(C.byref(self._cfg), C.byref(self._buf), mptr, int(bool(keep_reference)) | (2 if keep_state else 0),
                                                 self._obs.data_ptr(), self._stream()))
         if mask is None:
             self.init_state = self.state.clone()
@@ -498,10 +500,10 @@ class F16:
         if v._cfg.init_mode == _capi.INIT_RANDOM:
             # reference semantics: the initial state comes from the (re)seeded global np.random
             v.set_state(self._torch.tensor(get_random_state().to_array().reshape(9, 1)))
-            obs = self.state_transform(States.from_array(v.state[:, 0].double().cpu().numpy()))
+            obs, _ = v.reset(keep_state=True, keep_reference=True)
         else:
             obs, _ = v.reset(seed=seed)
-            obs = obs[0].double().cpu().numpy()
+        obs = obs[0].double().cpu().numpy()
         self._sync_init()
         return obs, {}
 
@@ -520,13 +522,6 @@ class F16:
         info = {"episode_length": self.episode_length, "total_return": self.total_return, "clock": self.clock,
                 "state": self.prev_state}
         return obs[0].double().cpu().numpy(), float(reward[0]), self.done, False, info
-
-    def state_transform(self, state):
-        k = min(self.episode_length, len(self.ref_signal.wz_ref) - 1)
-        short = _normalize([state.Oy, state.wz, state.V])
-        short.append(self.ref_signal.wz_ref[k])
-        short.append(0.5 * (self.ref_signal.wz_ref[k] - state.wz))
-        return np.array(short)
 
     def render(self):
         raise UserWarning("TODO: Implement this function")

@@ -113,9 +113,13 @@ int f16_launch_geometry(int device, int dtype, int *n_sm, int *cta_threads, int 
 /* ---- env level -------------------------------------------------------- */
 /* F16.reset (env/env.py:154-170) for every env whose mask byte is non-zero
  * (mask == NULL: all).  Draws/copies the initial state, zeroes the counters,
- * picks a reference signal (uniformly from the bank unless n_ref == 1 or
- * keep_ref != 0) and writes the reset observation. */
-int f16_env_reset(const f16_config *cfg, const f16_env_buffers *env, const uint8_t *mask, int keep_ref,
+ * picks a reference signal (uniformly from the bank unless n_ref == 1) and
+ * writes the reset observation.  flags: F16_RESET_KEEP_REF keeps each env's
+ * reference row; F16_RESET_KEEP_STATE keeps the state the caller has just
+ * written (explicit initial states) and only clears the counters and computes
+ * the observation. */
+enum { F16_RESET_KEEP_REF = 1, F16_RESET_KEEP_STATE = 2 };
+int f16_env_reset(const f16_config *cfg, const f16_env_buffers *env, const uint8_t *mask, int flags,
                   void *obs /* real[n][5] or [5][n], may be NULL */, void *stream);
 
 /* K consecutive F16.step calls (env/env.py:46-70) for all n envs in ONE kernel

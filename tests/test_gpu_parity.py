@@ -194,6 +194,23 @@ def test_single_env_facade_config1(f16, golden):
     assert abs(total - golden["traj_return"][0]) < 1e-8 and abs(info["total_return"] - total) < 1e-9
 
 
+def test_single_env_reset_seed_follows_reference_draws(f16, golden):
+    """F16.reset(seed) reseeds the process-global RNGs like the reference (env/env.py:155-158): the random
+    initial state and the random reference signal are the reference's own draws for that seed."""
+    cfg = {"dt": 0.01, "tn": 10, "debug_state": False, "determenistic_ref": False, "scenario": "cos"}
+    env = f16.F16(cfg)
+    for k, seed in enumerate([1, 2, 3]):
+        obs, _ = env.reset(seed=seed)
+        x0 = golden["random_state_out"][k]
+        assert np.array_equal(env.init_state.to_array(), x0)
+        assert np.array_equal(env.ref_signal.theta_ref, golden[f"ref_rnd_cos_{seed}"])
+        w150 = np.radians(150)
+        ref0 = env.ref_signal.wz_ref[0]
+        expect = np.array([x0[1] / 35000, (x0[2] + w150) / (2 * w150), x0[4] / 500, ref0, 0.5 * (ref0 - x0[2])])
+        assert np.abs(obs - expect).max() < 1e-15
+        assert env.episode_length == 0 and not env.done
+
+
 # ------------------------------------------------------------------ BASELINE config 2
 @pytest.fixture(scope="module")
 def config2(orc):
