@@ -147,6 +147,13 @@ def test_ppo_updates_run_on_device(f16):
     a_first = trainer.actions[5].clone()
     trainer.rollout()
     assert not torch.equal(a_first, trainer.actions[5])
+    # kernel-side episode statistics seen through the trainer: a wild policy (std = e^1.5) crashes envs
+    envs4 = f16.F16VecEnv(cfg, 4096, seed=2)
+    pol4 = f16.TensorCorePolicy(seed=2, logstd_init=1.5)
+    t4 = f16.PPOTrainer(envs4, pol4, f16.PPOConfig(num_steps=64))
+    _, _, ep_ret, ep_cnt = t4.rollout()
+    assert int(ep_cnt.item()) == int(t4.done_after.sum().item()) > 0
+    assert ep_ret.item() < -900 * ep_cnt.item() * 0.5            # each crash carries the -1000 penalty
     # eager rollout == graph rollout, bit for bit
     envs2 = f16.F16VecEnv(cfg, 4096, seed=1)
     pol2 = f16.TensorCorePolicy(seed=1, logstd_init=-1.0)
