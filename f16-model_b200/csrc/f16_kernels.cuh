@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
                 oy_lo = A.pos_comp[n + i];
             }
         }
+        const R pa_in = x[8];
         if (!tables_ready) {   // first tile only: the input loads above overlapped the table copy
             mbar_wait(&sm->bar_tbl, 0);
             tables_ready = true;
@@ -458,8 +459,13 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
             R *p = A.state + i;   // row pointers by repeated "+= n": one IMAD.WIDE per row, no per-row induction variables
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
-                if (j != 4) *p = x[j];
-                else if (AUTORESET && was_reset) *p = x[4];   // V only changes at a reset
+                if (j == 4) {
+                    if (AUTORESET && was_reset) *p = x[4];      // V only changes at a reset
+                } else if (j == 8) {
+                    if (x[8] != pa_in) *p = x[8];               // engine power sits at exactly 0 with the throttle closed: don't rewrite it
+                } else {
+                    *p = x[j];
+                }
                 p += n;
             }
         }
