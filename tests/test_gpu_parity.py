@@ -80,6 +80,18 @@ def test_atmosphere_vs_reference(f16, golden):
     assert np.max(np.abs(out32 / golden["isa_out"] - 1)) < 3e-6
 
 
+def test_atmosphere_against_published_table(f16):
+    """Device ISA vs the published standard-atmosphere table (same table as tests/test_oracle_golden.py)."""
+    from f16_model_b200.model import atmosphere
+    from test_oracle_golden import ISA_TABLE
+
+    h = np.array([r[0] for r in ISA_TABLE], dtype=float)
+    for dtype, tol in ((torch.float64, 6e-5), (torch.float32, 7e-5)):
+        out = atmosphere(dev(h, dtype)).double().cpu().numpy()
+        assert np.max(np.abs(out[0] / np.array([r[1] for r in ISA_TABLE]) - 1)) < tol
+        assert np.max(np.abs(out[1] / np.array([r[2] for r in ISA_TABLE]) - 1)) < 3e-5
+
+
 # ------------------------------------------------------------------ model level
 def test_rhs_fp64_vs_reference(f16, golden, orc):
     x, u, ref = golden["rhs_x"], golden["rhs_u"], golden["rhs_dx"]
