@@ -111,7 +111,8 @@ def build_reference_bank(dt, tn, scenario, determenistic, bank_size=256, seed=0)
     reference still draws at random).  Random configs enumerate the reference's whole
     discrete parameter space when it has at most ``bank_size`` members (pure_step 24,
     cos 16, step 6) and otherwise (combo: 6*6*5*6 parameter sets x segment orders) hold
-    ``bank_size`` draws made exactly as the reference makes them, from ``random.Random(seed)``.
+    ``bank_size`` draws made exactly as the reference makes them, from ``random.Random(seed)``;
+    ``bank_size="full"`` enumerates all 6480 combo signals instead.
     A reset picks a row uniformly, so resets are distributed like the reference's.
     """
     rows = []
@@ -122,7 +123,7 @@ def build_reference_bank(dt, tn, scenario, determenistic, bank_size=256, seed=0)
     scen = [scenario] if scenario is not None else ["step", "cos", "pure_step"]
     proto = ReferenceSignal(dt, tn, True, "pure_step")
     enumerable = {"step": 6, "cos": 16, "pure_step": 24}
-    if all(s in enumerable for s in scen) and max(enumerable[s] for s in scen) * len(scen) <= max(bank_size, 24 * 3):
+    if all(s in enumerable for s in scen) and (bank_size == "full" or max(enumerable[s] for s in scen) * len(scen) <= max(bank_size, 24 * 3)):
         # equal weight per scenario: replicate to the lcm so that uniform row choice == choice of
         # scenario followed by uniform choice of parameters
         per = int(np.lcm.reduce([enumerable[s] for s in scen]))
@@ -145,6 +146,16 @@ def build_reference_bank(dt, tn, scenario, determenistic, bank_size=256, seed=0)
                     s_[proto._nearest(ts):] = np.radians(a)
                     sigs.append(s_ / 2)
             rows += sigs * (per // len(sigs))
+        return np.ascontiguousarray(np.stack(rows))
+    if bank_size == "full":
+        # the whole discrete space of the random `combo` scenario: 6 x 6 x 5 x 6 parameter sets x 3! segment orders
+        # = 6480 rows (26 MB in fp32).  Exact distribution equivalence, at the price of a bank that no longer stays
+        # hot in L2 when several large batches stream through it.
+        if scenario != "combo" or int(tn / 10) != 1:
+            raise ValueError('bank_size="full" enumerates the single-block combo scenario only')
+        for a_s, a_n, f, a_c in itertools.product(_AMPS6, _AMPS6, [0.125, 0.25, 0.45, 0.5, 0.75], _AMPS6):
+            for order in itertools.permutations(range(3)):
+                rows.append(proto._combo_from(np.radians(a_s), np.radians(a_n), f, np.radians(a_c), order) / 2)
         return np.ascontiguousarray(np.stack(rows))
     rng = _random.Random(seed)
     for _ in range(bank_size):

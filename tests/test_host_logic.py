@@ -73,6 +73,12 @@ def test_reference_bank_enumerates_discrete_space():
     assert bank.shape == (16, 1000)
     assert np.array_equal(bank, f16.build_reference_bank(0.01, 10, "combo", False, bank_size=16, seed=5))
     assert f16.build_reference_bank(0.01, 10, "combo", True).shape == (1, 1000)
+    full = f16.build_reference_bank(0.01, 10, "combo", False, bank_size="full")
+    assert full.shape == (6 * 6 * 5 * 6 * 6, 1000)
+    for seed in (1, 2, 3, 11, 12345):          # every seeded draw of the reference is one of the rows
+        random.seed(seed)
+        sig = f16.ReferenceSignal(0.01, 10, False, "combo").wz_ref
+        assert np.any(np.all(full == sig, axis=1))
 
 
 # ---------------------------------------------------------------- env statics
