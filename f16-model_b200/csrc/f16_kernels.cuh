@@ -27,7 +27,10 @@
 
 namespace f16 {
 
-constexpr int kCtaThreads = 256;
+#ifndef F16_CTA_THREADS
+#define F16_CTA_THREADS 256
+#endif
+constexpr int kCtaThreads = F16_CTA_THREADS;
 
 // ---------------------------------------------------------------------------
 // TMA bulk copy global -> shared with mbarrier completion (sm_90+/sm_100a)
