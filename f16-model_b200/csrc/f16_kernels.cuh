@@ -32,6 +32,15 @@ namespace f16 {
 #endif
 constexpr int kCtaThreads = F16_CTA_THREADS;
 
+// global stores of the step kernel's outputs.  F16_STREAMING_STORES=1 marks them evict-first (st.global.cs):
+// +0.9 % in the bench's streaming steady state, but it would evict state that a single L2-resident batch
+// re-reads on the next step, so it is off by default.
+#if defined(F16_STREAMING_STORES) && F16_STREAMING_STORES
+#define F16_ST(ptr, val) __stcs((ptr), (val))
+#else
+#define F16_ST(ptr, val) (*(ptr) = (val))
+#endif
+
 // ---------------------------------------------------------------------------
 // TMA bulk copy global -> shared with mbarrier completion (sm_90+/sm_100a)
 // ---------------------------------------------------------------------------
@@ -119,10 +128,10 @@ __device__ __forceinline__ void store_obs(R *obs, int layout, unsigned n, unsign
     if (layout == 0) {
         R *p = obs + static_cast<size_t>(i) * 5;   // one address, five immediate-offset stores (L2 merges the sectors)
 #pragma unroll
-        for (int j = 0; j < 5; ++j) p[j] = o[j];
+        for (int j = 0; j < 5; ++j) F16_ST(p + j, o[j]);
     } else {
 #pragma unroll
-        for (int j = 0; j < 5; ++j) obs[static_cast<size_t>(j) * n + i] = o[j];
+        for (int j = 0; j < 5; ++j) F16_ST(obs + static_cast<size_t>(j) * n + i, o[j]);
     }
 }
 
@@ -447,8 +456,8 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
                 }
             }
             a_k = a_next;
-            S.reward[kn] = reward;
-            S.done[kn] = static_cast<uint8_t>(done_now);
+            F16_ST(S.reward + kn, reward);
+            F16_ST(S.done + kn, static_cast<uint8_t>(done_now));
             if (every) {
                 if (!have_obs) {   // env was already done when the launch started
                     make_obs<R, FAST>(x[1], x[2], x[4], ref_row[min(max(ep_len - 1, 0), A.ref_len - 1)], o);
@@ -463,17 +472,17 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
                 if (j == 4) {
-                    if (AUTORESET && was_reset) *p = x[4];      // V only changes at a reset
+                    if (AUTORESET && was_reset) F16_ST(p, x[4]);      // V only changes at a reset
                 } else if (j == 8) {
-                    if (x[8] != pa_in) *p = x[8];               // engine power sits at exactly 0 with the throttle closed: don't rewrite it
+                    if (x[8] != pa_in) F16_ST(p, x[8]);               // engine power sits at exactly 0 with the throttle closed: don't rewrite it
                 } else {
-                    *p = x[j];
+                    F16_ST(p, x[j]);
                 }
                 p += n;
             }
         }
-        A.ep_len[i] = ep_len;
-        A.total_return[i] = ret;
+        F16_ST(A.ep_len + i, ep_len);
+        F16_ST(A.total_return + i, ret);
         if (comp) {
             A.pos_comp[i] = ox_lo;
             A.pos_comp[n + i] = oy_lo;
