@@ -408,7 +408,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic, "peak_kind": f"of {peak_kind}", "kernel": "env_step_kernel<float,fast,autoreset>",
+                "traffic": traffic, "peak_kind": f"of {peak_kind}", "kernel": "env_step2_kernel<float,fast,single> (two envs per thread)",
                 "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP_F32, "units_per_launch": N,
                 "avg_launch_us": per_launch_s * 1e6,
                 "timing": "CUDA events around the whole timed region (graph replays of consecutive steps) / steps: includes inter-kernel gaps",

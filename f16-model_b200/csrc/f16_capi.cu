@@ -49,6 +49,7 @@ struct DeviceCtx {
     f16::Tables<float> *t32 = nullptr;
     f16::Tables<double> *t64 = nullptr;
     int occ[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};   // [dtype][fast][autoreset]
+    int occ2[2] = {0, 0};                                     // two-envs-per-thread kernel, [fast]
     HostPipe pipe;
 };
 
@@ -92,6 +93,8 @@ int ensure_device(int device, DeviceCtx **out)
                 c.occ[F16_F32][f][a] = f16::env_step_occupancy_f32(f != 0, a != 0);
                 c.occ[F16_F64][f][a] = f16::env_step_occupancy_f64(a != 0);
             }
+        c.occ2[0] = f16::env_step2_occupancy_f32(false);
+        c.occ2[1] = f16::env_step2_occupancy_f32(true);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaSetDevice(prev));
         c.ready = true;
@@ -118,7 +121,14 @@ f16::LaunchGeom geom(const DeviceCtx &c, int dtype, bool fast, bool autoreset)
         const char *e = std::getenv("F16B200_PDL");
         return (e && e[0] == '0') ? 0 : 1;
     }();
-    return {c.n_sm, occ, pdl};
+    static const int x2 = [] {
+        const char *e = std::getenv("F16B200_TWO_PER_THREAD");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    f16::LaunchGeom g{c.n_sm, occ, pdl};
+    g.two_per_thread = (dtype == F16_F32) ? x2 : 0;
+    g.ctas2_per_sm = c.occ2[fast ? 1 : 0] > 0 ? c.occ2[fast ? 1 : 0] : 1;
+    return g;
 }
 
 int check_cfg(const f16_config *cfg)

@@ -146,34 +146,58 @@ struct Vec4<double> {
 // ---------------------------------------------------------------------------
 // ISA atmosphere: density and speed of sound at geometric height h
 // ---------------------------------------------------------------------------
+// troposphere branch (0 <= H < 11 km): every BASELINE workload lives here
+template <typename R, bool FAST>
+__device__ __forceinline__ void isa_troposphere(R H, R &T, R &p)
+{
+    using M = Mth<R, FAST>;
+    constexpr double Tb = 288.15, beta = -6.5e-3, pb = 1.01325e5;
+    constexpr double expo = (1.0 / beta) * (-K::isa_g0 / K::isa_R);
+    T = R(Tb) + R(beta) * (H - R(0));
+    p = R(pb) * M::pow(R(1) + R(beta / Tb) * (H - R(0)), R(expo));
+}
+
+// any other layer of the table (slow path)
+template <typename R, bool FAST>
+__device__ __forceinline__ void isa_layer(R H, R &T, R &p)
+{
+    using M = Mth<R, FAST>;
+    int L = 0;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) L = (H >= R(c_isa_layers[i].Hb)) ? i : L;
+    const R Hb = R(c_isa_layers[L].Hb), Tb = R(c_isa_layers[L].Tb), beta = R(c_isa_layers[L].beta);
+    const R pb = R(c_isa_layers[L].pb);
+    T = Tb + beta * (H - Hb);
+    if (beta == R(0)) {
+        p = pb * M::exp(M::div(R(-K::isa_g0), R(K::isa_R) * T) * (H - Hb));
+    } else {
+        const R expo = M::div(R(1), beta) * R(-K::isa_g0 / K::isa_R);
+        p = pb * M::pow(R(1) + M::div(beta, Tb) * (H - Hb), expo);
+    }
+}
+
+template <typename R, bool FAST>
+__device__ __forceinline__ R isa_geopotential(R h)
+{
+    return Mth<R, FAST>::div(R(K::isa_r) * h, R(K::isa_r) + h);
+}
+
+template <typename R, bool FAST>
+__device__ __forceinline__ void isa_finish(R T, R p, R &rho, R &a)
+{
+    using M = Mth<R, FAST>;
+    rho = M::div(p, R(K::isa_R) * T);
+    a = M::sqrt(R(K::isa_kappa) * R(K::isa_R) * T);
+}
+
 template <typename R, bool FAST>
 __device__ __forceinline__ void isa(R h, R &rho, R &a)
 {
-    using M = Mth<R, FAST>;
-    const R H = M::div(R(K::isa_r) * h, R(K::isa_r) + h);   // geopotential height
+    const R H = isa_geopotential<R, FAST>(h);
     R T, p;
-    if (H >= R(0) && H < R(11000)) {
-        // troposphere: every BASELINE workload lives here (warp-uniform branch)
-        constexpr double Tb = 288.15, beta = -6.5e-3, pb = 1.01325e5;
-        constexpr double expo = (1.0 / beta) * (-K::isa_g0 / K::isa_R);
-        T = R(Tb) + R(beta) * (H - R(0));
-        p = R(pb) * M::pow(R(1) + R(beta / Tb) * (H - R(0)), R(expo));
-    } else {
-        int L = 0;
-#pragma unroll
-        for (int i = 1; i < 8; ++i) L = (H >= R(c_isa_layers[i].Hb)) ? i : L;
-        const R Hb = R(c_isa_layers[L].Hb), Tb = R(c_isa_layers[L].Tb), beta = R(c_isa_layers[L].beta);
-        const R pb = R(c_isa_layers[L].pb);
-        T = Tb + beta * (H - Hb);
-        if (beta == R(0)) {
-            p = pb * M::exp(M::div(R(-K::isa_g0), R(K::isa_R) * T) * (H - Hb));
-        } else {
-            const R expo = M::div(R(1), beta) * R(-K::isa_g0 / K::isa_R);
-            p = pb * M::pow(R(1) + M::div(beta, Tb) * (H - Hb), expo);
-        }
-    }
-    rho = M::div(p, R(K::isa_R) * T);
-    a = M::sqrt(R(K::isa_kappa) * R(K::isa_R) * T);
+    if (H >= R(0) && H < R(11000)) isa_troposphere<R, FAST>(H, T, p);   // warp-uniform in practice
+    else isa_layer<R, FAST>(H, T, p);
+    isa_finish<R, FAST>(T, p, rho, a);
 }
 
 // ---------------------------------------------------------------------------
@@ -271,8 +295,9 @@ __device__ __forceinline__ R power_level(R Pa, R thr)
 // right-hand side.  x = [Ox,Oy,wz,theta,V,alpha,stab,dstab,Pa]; u = (stab cmd, throttle).
 // WANT_VDOT: also compute V_dot (the integrator discards it; trim search needs it).
 // ---------------------------------------------------------------------------
+// rhs_atm: the right-hand side with the atmosphere (rho, speed of sound at x[1]) supplied by the caller.
 template <typename R, bool FAST, bool WANT_VDOT>
-__device__ __forceinline__ void rhs(const Tables<R> &T, const R (&x)[9], R u_stab, R u_thr, R (&dx)[9])
+__device__ __forceinline__ void rhs_atm(const Tables<R> &T, const R (&x)[9], R u_stab, R u_thr, R rho, R asnd, R (&dx)[9])
 {
     using M = Mth<R, FAST>;
     const R Oy = x[1], wz = x[2], theta = x[3], V = x[4], alpha = x[5], stab = x[6], dstab = x[7], Pa = x[8];
@@ -282,8 +307,6 @@ __device__ __forceinline__ void rhs(const Tables<R> &T, const R (&x)[9], R u_sta
     const R Vx = V * ca;       // wind2body with beta = 0 (utils/cs_transform.py:11-15)
     const R Vy = -V * sa;
 
-    R rho, asnd;
-    isa<R, FAST>(Oy, rho, asnd);
     const R Mach = M::div(V, asnd);
     const R q = (rho * (V * V)) * R(0.5);
 
@@ -317,6 +340,14 @@ __device__ __forceinline__ void rhs(const Tables<R> &T, const R (&x)[9], R u_sta
     dx[7] = M::divc(R(-2 * K::Tstab) * R(K::Xistab) * dstab - stab + cs, R(K::Tstab * K::Tstab),
                     R(1.0 / (K::Tstab * K::Tstab)));
     dx[8] = power_level<R>(Pa, cth);
+}
+
+template <typename R, bool FAST, bool WANT_VDOT>
+__device__ __forceinline__ void rhs(const Tables<R> &T, const R (&x)[9], R u_stab, R u_thr, R (&dx)[9])
+{
+    R rho, asnd;
+    isa<R, FAST>(x[1], rho, asnd);
+    rhs_atm<R, FAST, WANT_VDOT>(T, x, u_stab, u_thr, rho, asnd, dx);
 }
 
 // F16model.step: explicit Euler, clip wz, V frozen (dx[4] ignored).

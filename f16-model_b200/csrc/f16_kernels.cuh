@@ -505,6 +505,232 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
 }
 
 // ---------------------------------------------------------------------------
+// Two aircraft per thread: the gym step (K = 1, autoreset, fp32) with instruction-level parallelism.
+//
+// The one-env kernel above is bound by dependency stalls (short scoreboard + fixed-latency waits are 37 % of
+// its stall samples, issue slots 64 % busy) and by per-tile bookkeeping.  Here every thread advances envs t and
+// t + 256 of a 512-env tile; the common path of a step is ONE branch-free basic block holding both envs'
+// arithmetic, so the scheduler interleaves two independent dependency chains, and the tile bookkeeping
+// (barrier wait, ring refill, parameter loads) is paid once per two envs.  Rare events -- an altitude outside
+// the troposphere, a termination with its autoreset -- are patched after the common path.  Handles full,
+// 16-byte aligned tiles only; the caller runs the one-env kernel on the remainder.
+// ---------------------------------------------------------------------------
+constexpr int kTile2 = 2 * kCtaThreads;
+constexpr int kIn2Rows = 13;   // 9 state rows, action, ep_len, ref_idx, total_return
+
+template <typename R>
+struct alignas(16) Step2Smem {
+    Tables<R> tbl;
+    R in[2][kIn2Rows][kTile2];
+    uint64_t bar_tbl;
+    uint64_t bar_in[2];
+    unsigned drained[2];
+    CtaStats stats;
+};
+
+template <typename R>
+__device__ __forceinline__ void issue_tile2(const EnvArgs<R> &A, const StepArgs<R> &S, Step2Smem<R> *sm, int stage, unsigned i0)
+{
+    const unsigned n = static_cast<unsigned>(A.n);
+    constexpr uint32_t rb = kTile2 * sizeof(R), ib = kTile2 * 4u;
+    constexpr uint32_t total = 11u * rb + 2u * ib;
+    uint64_t *bar = &sm->bar_in[stage];
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(total) : "memory");
+    auto cp = [&](void *dst, const void *src, uint32_t bytes) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                     "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                     : "memory");
+    };
+    R(*in)[kTile2] = sm->in[stage];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) cp(in[j], A.state + static_cast<size_t>(j) * n + i0, rb);
+    cp(in[9], S.actions + i0, rb);
+    cp(in[10], A.ep_len + i0, ib);
+    cp(in[11], A.ref_idx + i0, ib);
+    cp(in[12], A.total_return + i0, rb);
+}
+
+#ifndef F16_MINCTAS2
+#define F16_MINCTAS2 2
+#endif
+template <typename R, bool FAST, bool SINGLE>
+__global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(const EnvArgs<R> A, const StepArgs<R> S)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Step2Smem<R> *sm = reinterpret_cast<Step2Smem<R> *>(smem_raw);
+    const Tables<R> &tbl = sm->tbl;
+    using M = Mth<R, FAST>;
+
+    const unsigned n = static_cast<unsigned>(A.n);
+    const unsigned i_begin = static_cast<unsigned>(S.i_begin);
+    const unsigned n_tiles = static_cast<unsigned>(S.i_end - S.i_begin) / kTile2;   // full tiles only
+    const R dt = A.dt;
+    const unsigned t = threadIdx.x;
+
+    if (t == 0) {
+        mbar_init(&sm->bar_tbl, 1);
+        mbar_init(&sm->bar_in[0], 1);
+        mbar_init(&sm->bar_in[1], 1);
+        sm->drained[0] = 0;
+        sm->drained[1] = 0;
+        sm->stats.count = 0;
+        sm->stats.length = 0;
+        sm->stats.ret = 0.0;
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (t == 0) tma_bulk_g2s(&sm->tbl, A.tables, static_cast<uint32_t>(sizeof(Tables<R>)), &sm->bar_tbl);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (t == 0 && blockIdx.x < n_tiles) issue_tile2<R>(A, S, sm, 0, i_begin + blockIdx.x * kTile2);
+    bool tables_ready = false;
+
+    unsigned it = 0;
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const unsigned base = i_begin + tile * kTile2;
+        R x[2][9], a_in[2], ret[2];
+        int ep_len[2], ref_idx[2];
+        mbar_wait(&sm->bar_in[stage], (it >> 1) & 1u);
+        if (it == 0 && t == 0) {
+            const unsigned t1 = tile + gridDim.x;
+            if (t1 < n_tiles) issue_tile2<R>(A, S, sm, 1, i_begin + t1 * kTile2);
+        }
+        {
+            const R(*in)[kTile2] = sm->in[stage];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const unsigned c = t + e * kCtaThreads;
+#pragma unroll
+                for (int j = 0; j < 9; ++j) x[e][j] = in[j][c];
+                a_in[e] = in[9][c];
+                ep_len[e] = reinterpret_cast<const int *>(in[10])[c];
+                ref_idx[e] = reinterpret_cast<const int *>(in[11])[c];
+                ret[e] = in[12][c];
+            }
+        }
+        __syncwarp();
+        if ((t & 31u) == 0) {
+            unsigned prior;
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(prior) : "r"(smem_u32(&sm->drained[stage])) : "memory");
+            if (prior == kCtaThreads / 32 - 1) {
+                sm->drained[stage] = 0;
+                const unsigned next = tile + 2 * gridDim.x;
+                if (next < n_tiles) issue_tile2<R>(A, S, sm, stage, i_begin + next * kTile2);
+            }
+        }
+        if (!tables_ready) {
+            mbar_wait(&sm->bar_tbl, 0);
+            tables_ready = true;
+        }
+
+        R pa_in[2] = {x[0][8], x[1][8]};
+        bool was_reset[2] = {false, false};
+        R o[2][5];
+        const int K_steps = SINGLE ? 1 : S.K;
+        for (int k = 0; k < K_steps; ++k) {
+            // ---- common path: both envs in one basic block ------------------------------------------------
+            R ref[2], Hg[2], Tk[2], pk[2], a_next[2] = {R(0), R(0)};
+            bool slow[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                ref[e] = A.ref_bank[static_cast<unsigned>(ref_idx[e]) * static_cast<unsigned>(A.ref_len) + min(ep_len[e], A.ref_len - 1)];
+                if (!SINGLE && k + 1 < K_steps) a_next[e] = S.actions[static_cast<unsigned>(k + 1) * n + base + t + e * kCtaThreads];
+                Hg[e] = isa_geopotential<R, FAST>(x[e][1]);
+                slow[e] = !(Hg[e] >= R(0) && Hg[e] < R(11000));
+                isa_troposphere<R, FAST>(Hg[e], Tk[e], pk[e]);
+            }
+            if (slow[0] | slow[1]) {   // rare: some other layer of the standard atmosphere
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (slow[e]) isa_layer<R, FAST>(Hg[e], Tk[e], pk[e]);
+            }
+            R reward[2];
+            bool done[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                R rho, asnd, dx[9];
+                isa_finish<R, FAST>(Tk[e], pk[e], rho, asnd);
+                const R a = clampr(a_in[e], R(-1), R(1));
+                const R u_stab = R(K::act_lo) + R(0.5) * (a + R(1.0)) * R(K::act_span);
+                rhs_atm<R, FAST, false>(tbl, x[e], u_stab, R(0), rho, asnd, dx);
+#pragma unroll
+                for (int j = 0; j < 9; ++j)
+                    if (j != 4) x[e][j] = dx[j] * dt + x[e][j];
+                x[e][2] = clampr(x[e][2], R(-K::wz_clip), R(K::wz_clip));
+                R pen = R(0);
+                bool d = false;
+                if (!(x[e][1] > R(300))) { pen += R(-1000); d = true; }
+                if (x[e][1] >= R(30000)) { pen += R(-1000); d = true; }
+                if (!(M::fabs(x[e][2]) < R(K::wz_term))) { pen += R(-1000); d = true; }
+                d = d || (ep_len[e] == A.horizon);
+                reward[e] = pen + tracking_reward<R, FAST>(ref[e], x[e][2]);
+                make_obs<R, FAST>(x[e][1], x[e][2], x[e][4], ref[e], o[e]);
+                ep_len[e] += 1;
+                ret[e] += reward[e];
+                done[e] = d;
+                a_in[e] = a_next[e];
+            }
+
+            // ---- rare path: terminations (final_* outputs, statistics, autoreset) ---------------------------
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (done[e]) {
+                    const unsigned i = base + t + e * kCtaThreads;
+                    if (S.stats) episode_stats_add(&sm->stats, static_cast<double>(ret[e]), ep_len[e]);
+                    if (S.final_obs) store_obs<R>(S.final_obs, A.obs_layout, n, i, o[e]);
+                    if (S.final_ep_len) S.final_ep_len[i] = ep_len[e];
+                    if (S.final_return) S.final_return[i] = ret[e];
+                    const uint32_t episode = A.episode_no[i] + 1u;
+                    A.episode_no[i] = episode;
+                    init_episode<R>(A, i, episode, false, x[e], ref_idx[e]);
+                    A.ref_idx[i] = ref_idx[e];
+                    was_reset[e] = true;
+                    ep_len[e] = 0;
+                    ret[e] = R(0);
+                    make_obs<R, FAST>(x[e][1], x[e][2], x[e][4], A.ref_bank[static_cast<unsigned>(ref_idx[e]) * static_cast<unsigned>(A.ref_len)], o[e]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const unsigned kn = static_cast<unsigned>(k) * n + base + t + e * kCtaThreads;
+                S.reward[kn] = reward[e];
+                S.done[kn] = static_cast<uint8_t>(done[e]);
+            }
+        }
+
+        // ---- write back ---------------------------------------------------------------------------------------
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const unsigned i = base + t + e * kCtaThreads;
+            R *p = A.state + i;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                if (j == 4) {
+                    if (was_reset[e]) *p = x[e][4];
+                } else if (j == 8) {
+                    if (x[e][8] != pa_in[e]) *p = x[e][8];
+                } else {
+                    *p = x[e][j];
+                }
+                p += n;
+            }
+            A.ep_len[i] = ep_len[e];
+            A.total_return[i] = ret[e];
+            if (S.obs) store_obs<R>(S.obs, A.obs_layout, n, i, o[e]);
+        }
+    }
+    if (!tables_ready) mbar_wait(&sm->bar_tbl, 0);
+    if (S.stats) {
+        __syncthreads();
+        if (t == 0 && sm->stats.count) {
+            atomicAdd(S.stats + 0, static_cast<double>(sm->stats.count));
+            atomicAdd(S.stats + 1, sm->stats.ret);
+            atomicAdd(S.stats + 2, static_cast<double>(sm->stats.length));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // F16.reset for masked envs
 // ---------------------------------------------------------------------------
 template <typename R>
@@ -738,6 +964,33 @@ cudaError_t launch_env_step_t(const EnvArgs<R> &A, const StepArgs<R> &S, const L
     const size_t smem = sizeof(StepSmem<R>);
     const bool single = S.K == 1;
     const bool comp = A.pos_comp != nullptr && sizeof(R) == 4;
+    if constexpr (sizeof(R) == 4) {
+        // the gym step of the throughput mode: two envs per thread on the full 512-env tiles, one-env kernel on the rest
+        if (g.two_per_thread && A.autoreset && !comp && !A.noise && S.tma_ok && !(S.obs_every_step && !single) &&
+            (S.i_end - S.i_begin) >= kTile2) {
+            const int64_t n2 = (S.i_end - S.i_begin) / kTile2;
+            const int64_t cap2 = static_cast<int64_t>(g.n_sm) * g.ctas2_per_sm;
+            cudaLaunchConfig_t lc2 = {};
+            lc2.gridDim = dim3(static_cast<unsigned>(n2 < cap2 ? n2 : cap2));
+            lc2.blockDim = dim3(kCtaThreads);
+            lc2.dynamicSmemBytes = sizeof(Step2Smem<R>);
+            lc2.stream = st;
+            cudaLaunchAttribute at2[1];
+            at2[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at2[0].val.programmaticStreamSerializationAllowed = 1;
+            lc2.attrs = at2;
+            lc2.numAttrs = g.pdl ? 1 : 0;
+            cudaError_t e2 = single ? cudaLaunchKernelEx(&lc2, env_step2_kernel<R, FAST, true>, A, S)
+                                    : cudaLaunchKernelEx(&lc2, env_step2_kernel<R, FAST, false>, A, S);
+            if (e2 != cudaSuccess) return e2;
+            StepArgs<R> rest = S;
+            rest.i_begin = S.i_begin + n2 * kTile2;
+            if (rest.i_begin >= rest.i_end) return cudaGetLastError();
+            LaunchGeom g1 = g;
+            g1.two_per_thread = 0;
+            return launch_env_step_t<R, FAST>(A, rest, g1, st);
+        }
+    }
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid);
     lc.blockDim = dim3(kCtaThreads);
@@ -780,6 +1033,20 @@ int prepare_env_step()
         prep(env_step_kernel<R, FAST, AUTORESET, true, true>, c1);
         prep(env_step_kernel<R, FAST, AUTORESET, false, true>, ck);
     }
+    return b1 < bk ? b1 : bk;
+}
+
+// two-envs-per-thread gym-step kernel: opt into its shared memory, report resident CTAs per SM
+template <typename R, bool FAST>
+int prepare_env_step2()
+{
+    auto fn1 = env_step2_kernel<R, FAST, true>;
+    auto fnk = env_step2_kernel<R, FAST, false>;
+    cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Step2Smem<R>)));
+    cudaFuncSetAttribute(fnk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Step2Smem<R>)));
+    int b1 = 0, bk = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, fn1, kCtaThreads, sizeof(Step2Smem<R>));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bk, fnk, kCtaThreads, sizeof(Step2Smem<R>));
     return b1 < bk ? b1 : bk;
 }
 

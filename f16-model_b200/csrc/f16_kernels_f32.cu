@@ -45,4 +45,6 @@ int env_step_occupancy_f32(bool fast, bool autoreset)
     return autoreset ? prepare_env_step<float, false, true>() : prepare_env_step<float, false, false>();
 }
 
+int env_step2_occupancy_f32(bool fast) { return fast ? prepare_env_step2<float, true>() : prepare_env_step2<float, false>(); }
+
 }  // namespace f16

@@ -13,6 +13,8 @@ struct LaunchGeom {
     int n_sm;
     int ctas_per_sm;
     int pdl = 1;   // launch the step kernel with programmatic stream serialization (F16B200_PDL=0 disables)
+    int two_per_thread = 0;   // fp32 gym step: use the two-envs-per-thread kernel on full tiles
+    int ctas2_per_sm = 2;
 };
 
 // typed view of f16_config + f16_env_buffers (include/f16_b200.h)
@@ -63,6 +65,7 @@ cudaError_t launch_coeffs(const Tables<float> *, int64_t n, const float *, const
 cudaError_t launch_thrust(const Tables<float> *, int64_t n, const float *, const float *, const float *, float *, const LaunchGeom &, cudaStream_t);
 cudaError_t launch_isa(int64_t n, const float *, float *, float *, const LaunchGeom &, cudaStream_t);
 int env_step_occupancy_f32(bool fast, bool autoreset);
+int env_step2_occupancy_f32(bool fast);
 
 // f16_kernels_f64.cu
 cudaError_t launch_env_step(const EnvArgs<double> &, const StepArgs<double> &, bool fast, const LaunchGeom &, cudaStream_t);

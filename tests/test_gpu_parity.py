@@ -298,6 +298,29 @@ def test_k_invariance_bitwise(f16, dtype):
     assert torch.equal(envs[0].episode_length, envs[1].episode_length)
 
 
+@pytest.mark.parametrize("fast", [False, True])
+def test_two_envs_per_thread_kernel_equals_one_env_kernel(f16, fast):
+    """The fp32 autoreset path runs the two-envs-per-thread kernel on full 512-env tiles (and the one-env
+    kernel on the remainder); without autoreset everything runs the one-env kernel, which is the one held to
+    the reference above.  Same arithmetic -> bit-identical states, rewards and observations as long as no
+    episode ends."""
+    n = 70_000 + 37                      # full tiles + a ragged remainder
+    a_env = f16.F16VecEnv(CFG, n, dtype=torch.float32, autoreset=True, seed=8, fast_math=fast)
+    b_env = f16.F16VecEnv(CFG, n, dtype=torch.float32, autoreset=False, seed=8, fast_math=fast)
+    assert torch.equal(a_env.state, b_env.state)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    acts = (torch.rand((48, n), device="cuda", generator=g) - 0.5) * 0.2          # gentle stick: nobody terminates
+    for k in range(8):                                                             # K = 1 launches
+        oa, ra, da, _, _ = a_env.step(acts[k])
+        ob, rb, db, _, _ = b_env.step(acts[k])
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and not bool(da.any()) and not bool(db.any())
+    oa, ra, da = a_env.step_k(acts[8:])                                            # K = 40 in one launch
+    ob, rb, db = b_env.step_k(acts[8:])
+    assert torch.equal(ra, rb) and torch.equal(oa, ob) and int(da.sum()) == 0
+    assert torch.equal(a_env.state, b_env.state) and torch.equal(a_env.total_return, b_env.total_return)
+    assert torch.equal(a_env.episode_length, b_env.episode_length)
+
+
 def test_sharding_invariance_full_size(f16):
     """BASELINE config 3/5 size: 2^20 envs as one batch == two shards of 2^19 keyed by global env
     id (what two GPUs would hold): bitwise equal states, rewards, dones after resets + 64 steps."""
