@@ -69,7 +69,9 @@ class PPOTrainer:
         self.device = envs.device
         self.batch_size = self.N * self.cfg.num_steps
         self.minibatch_size = self.batch_size // self.cfg.num_minibatches
-        self.optimizer = torch.optim.Adam(policy.parameters(), lr=self.cfg.learning_rate, amsgrad=True)
+        # lr as a device tensor + capturable=True: the optimiser step can live inside a CUDA graph and still be annealed
+        self._lr = torch.tensor(float(self.cfg.learning_rate), device=envs.device)
+        self.optimizer = torch.optim.Adam(policy.parameters(), lr=self._lr, amsgrad=True, capturable=True)
         T, N, dev = self.cfg.num_steps, self.N, self.device
         aos = envs.obs_layout == "aos"
         self.obs = torch.zeros((T + 1, N, 5) if aos else (T + 1, 5, N), device=dev)   # obs[t] feeds step t; obs[T] bootstraps
@@ -85,6 +87,8 @@ class PPOTrainer:
             self.world = torch.distributed.get_world_size()
         self._gen = torch.Generator(device=dev).manual_seed(self.cfg.seed)
         self._graph = None
+        self._update_graph = None
+        self._flat = None
 
     # ------------------------------------------------------------------ rollout
     def _obs_at(self, t):
@@ -145,49 +149,108 @@ class PPOTrainer:
             p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
             off += p.numel()
 
-    def update(self, advantages, returns):
+    def _minibatch_step(self, mb):
+        """One clipped-PPO optimiser step on the minibatch indices ``mb`` (ppo_model_gsde.py:303-364).
+        Writes its diagnostics into persistent scalars so that it can be replayed from a CUDA graph."""
+        torch, cfg = self._torch, self.cfg
+        b = self._flat
+        newlogprob, entropy, newvalue = self.policy.evaluate(b["obs"][mb], b["actions"][mb])
+        logratio = newlogprob - b["logprobs"][mb]
+        ratio = logratio.exp()
+        with torch.no_grad():
+            self._diag[0].copy_((-logratio).mean())                                   # old_approx_kl
+            self._diag[1].copy_(((ratio - 1) - logratio).mean())                      # approx_kl
+            self._diag[2].add_(((ratio - 1.0).abs() > cfg.clip_coef).float().mean())  # clip fraction, summed
+        mb_adv = b["adv"][mb]
+        if cfg.norm_adv:
+            mb_adv = (mb_adv - mb_adv.mean()) / (mb_adv.std() + 1e-8)
+        pg_loss = torch.max(-mb_adv * ratio, -mb_adv * torch.clamp(ratio, 1 - cfg.clip_coef, 1 + cfg.clip_coef)).mean()
+        if cfg.clip_vloss:
+            v_unclipped = (newvalue - b["ret"][mb]) ** 2
+            v_clipped = b["val"][mb] + torch.clamp(newvalue - b["val"][mb], -cfg.clip_coef, cfg.clip_coef)
+            v_loss = 0.5 * torch.max(v_unclipped, (v_clipped - b["ret"][mb]) ** 2).mean()
+        else:
+            v_loss = 0.5 * ((newvalue - b["ret"][mb]) ** 2).mean()
+        entropy_loss = entropy.mean()
+        loss = pg_loss - cfg.ent_coef * entropy_loss + v_loss * cfg.vf_coef
+        self.optimizer.zero_grad(set_to_none=False)
+        loss.backward()
+        self._allreduce_grads()
+        torch.nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
+        self.optimizer.step()
+        with torch.no_grad():
+            self._diag[3].copy_(v_loss)
+            self._diag[4].copy_(pg_loss)
+            self._diag[5].copy_(entropy_loss)
+
+    def _prepare_update(self, advantages, returns):
         torch, cfg = self._torch, self.cfg
         T = cfg.num_steps
-        b_obs = (self.obs[:T] if self.envs.obs_layout == "aos" else self.obs[:T].transpose(1, 2)).reshape(-1, 5)
-        b_logprobs, b_actions = self.logprobs.reshape(-1), self.actions.reshape(-1)
-        b_adv, b_ret, b_val = advantages.reshape(-1), returns.reshape(-1), self.values.reshape(-1)
-        stats = {}
-        clipfracs = []
+        if self._flat is None:
+            self._adv = torch.empty_like(advantages)
+            self._ret = torch.empty_like(returns)
+            self._flat = {
+                "obs": (self.obs[:T] if self.envs.obs_layout == "aos" else self.obs[:T].transpose(1, 2)).reshape(-1, 5),
+                "logprobs": self.logprobs.reshape(-1), "actions": self.actions.reshape(-1),
+                "adv": self._adv.reshape(-1), "ret": self._ret.reshape(-1), "val": self.values.reshape(-1)}
+            self._diag = torch.zeros(6, device=self.device)
+            self._mb_idx = torch.zeros(self.minibatch_size, dtype=torch.long, device=self.device)
+        self._adv.copy_(advantages)
+        self._ret.copy_(returns)
+        self._diag.zero_()
+
+    def _capture_update(self):
+        """Capture one optimiser step (forward, backward, clip, Adam) in a CUDA graph: ~150 small launches
+        per minibatch become one."""
+        torch = self._torch
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        params = list(self.policy.parameters())
+        saved = [p.detach().clone() for p in params]
+        saved_opt = [{k: v.clone() for k, v in self.optimizer.state.get(p, {}).items() if torch.is_tensor(v)} for p in params]
+        with torch.cuda.stream(side):                      # warm-up iterations (allocator, autograd, optimiser state)
+            for _ in range(3):
+                self._minibatch_step(self._mb_idx)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._minibatch_step(self._mb_idx)
+        with torch.no_grad():                              # undo the warm-up steps IN PLACE (the graph holds these tensors)
+            for p, q, so in zip(params, saved, saved_opt):
+                p.copy_(q)
+                for k, v in self.optimizer.state[p].items():
+                    if torch.is_tensor(v):
+                        v.copy_(so[k]) if k in so else v.zero_()
+        self._diag.zero_()
+        return graph
+
+    def update(self, advantages, returns):
+        torch, cfg = self._torch, self.cfg
+        self._prepare_update(advantages, returns)
+        use_graph = cfg.use_cuda_graph and self.world == 1
+        if use_graph and self._update_graph is None:
+            try:
+                self._update_graph = self._capture_update()
+            except Exception as exc:                       # capture is an optimisation; fall back to eager launches
+                print(f"[ppo] update graph capture failed ({exc}); running eagerly")
+                self._update_graph = False
+        n_steps = 0
         for epoch in range(cfg.update_epochs):
             perm = torch.randperm(self.batch_size, device=self.device, generator=self._gen)
-            for start in range(0, self.batch_size, self.minibatch_size):
+            for start in range(0, self.batch_size - self.minibatch_size + 1, self.minibatch_size):
                 mb = perm[start:start + self.minibatch_size]
-                newlogprob, entropy, newvalue = self.policy.evaluate(b_obs[mb], b_actions[mb])
-                logratio = newlogprob - b_logprobs[mb]
-                ratio = logratio.exp()
-                with torch.no_grad():
-                    old_approx_kl = (-logratio).mean()
-                    approx_kl = ((ratio - 1) - logratio).mean()
-                    clipfracs.append(((ratio - 1.0).abs() > cfg.clip_coef).float().mean())
-                mb_adv = b_adv[mb]
-                if cfg.norm_adv:
-                    mb_adv = (mb_adv - mb_adv.mean()) / (mb_adv.std() + 1e-8)
-                pg_loss = torch.max(-mb_adv * ratio, -mb_adv * torch.clamp(ratio, 1 - cfg.clip_coef, 1 + cfg.clip_coef)).mean()
-                if cfg.clip_vloss:
-                    v_unclipped = (newvalue - b_ret[mb]) ** 2
-                    v_clipped = b_val[mb] + torch.clamp(newvalue - b_val[mb], -cfg.clip_coef, cfg.clip_coef)
-                    v_loss = 0.5 * torch.max(v_unclipped, (v_clipped - b_ret[mb]) ** 2).mean()
+                if use_graph and self._update_graph:
+                    self._mb_idx.copy_(mb)
+                    self._update_graph.replay()
                 else:
-                    v_loss = 0.5 * ((newvalue - b_ret[mb]) ** 2).mean()
-                entropy_loss = entropy.mean()
-                loss = pg_loss - cfg.ent_coef * entropy_loss + v_loss * cfg.vf_coef
-                self.optimizer.zero_grad(set_to_none=False)
-                loss.backward()
-                self._allreduce_grads()
-                torch.nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
-                self.optimizer.step()
-            if cfg.target_kl is not None and approx_kl.item() > cfg.target_kl:
+                    self._minibatch_step(mb)
+                n_steps += 1
+            if cfg.target_kl is not None and self._diag[1].item() > cfg.target_kl:
                 break
         self.policy.sync_weights()                                  # refresh the tensor-core weight blob
-        stats.update(value_loss=v_loss.item(), policy_loss=pg_loss.item(), entropy=entropy_loss.item(),
-                     old_approx_kl=old_approx_kl.item(), approx_kl=approx_kl.item(),
-                     clipfrac=torch.stack(clipfracs).mean().item())
-        return stats
+        d = self._diag.tolist()
+        return dict(old_approx_kl=d[0], approx_kl=d[1], clipfrac=d[2] / max(n_steps, 1), value_loss=d[3], policy_loss=d[4],
+                    entropy=d[5])
 
     def train(self, num_updates=None, log=None):
         """The reference's outer loop: lr annealing, rollout, GAE, update; returns per-update stats."""
@@ -198,7 +261,7 @@ class PPOTrainer:
         for update in range(1, num_updates + 1):
             self.update_idx = update - 1
             if cfg.anneal_lr:
-                self.optimizer.param_groups[0]["lr"] = (1.0 - (update - 1.0) / num_updates) * cfg.learning_rate
+                self._lr.fill_((1.0 - (update - 1.0) / num_updates) * cfg.learning_rate)
             t0 = time.perf_counter()
             adv, ret, ep_ret, ep_cnt = self.rollout()
             torch.cuda.synchronize(self.device)
@@ -208,7 +271,7 @@ class PPOTrainer:
             t2 = time.perf_counter()
             y_pred, y_true = self.values.reshape(-1), ret.reshape(-1)
             var_y = y_true.var()
-            stats.update(update=update, global_step=self.global_step, learning_rate=self.optimizer.param_groups[0]["lr"], rollout_s=t1 - t0, update_s=t2 - t1,
+            stats.update(update=update, global_step=self.global_step, learning_rate=float(self._lr.item()), rollout_s=t1 - t0, update_s=t2 - t1,
                          rollout_sps=self.batch_size / (t1 - t0), mean_step_reward=self.rewards.mean().item(),
                          episodes=int(ep_cnt.item()), mean_return_per_finished_episode=(ep_ret / ep_cnt.clamp(min=1)).item(),
                          explained_variance=(1 - (y_true - y_pred).var() / var_y).item() if var_y > 0 else float("nan"))

@@ -127,6 +127,21 @@ def test_gae_kernel_matches_reference_loop(f16):
     assert (adv - radv).abs().max().item() < 2e-4 and (ret - rret).abs().max().item() < 2e-4
 
 
+def test_ppo_graph_update_equals_eager_update(f16):
+    """The CUDA-graph replay of the optimiser step must reproduce the eager step (same minibatch order)."""
+    cfg = {"dt": 0.01, "tn": 10, "debug_state": False, "determenistic_ref": True, "scenario": "combo"}
+    out = []
+    for use_graph in (True, False):
+        envs = f16.F16VecEnv(cfg, 2048, seed=4)
+        pol = f16.TensorCorePolicy(seed=4, logstd_init=-1.0)
+        tr = f16.PPOTrainer(envs, pol, f16.PPOConfig(num_steps=32, num_minibatches=4, update_epochs=2, learning_rate=1e-3,
+                                                      use_cuda_graph=use_graph))
+        tr.train(num_updates=2)
+        out.append([p.detach().clone() for p in pol.parameters()])
+    for a, b in zip(*out):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), (a - b).abs().max().item()
+
+
 def test_ppo_updates_run_on_device(f16):
     """Two PPO updates (rollout -> GAE -> clipped update) on 4096 envs: finite losses, parameters move,
     the tensor-core weight blob follows the optimiser, and the value function starts explaining returns."""
@@ -139,6 +154,7 @@ def test_ppo_updates_run_on_device(f16):
     hist = trainer.train(num_updates=2)
     assert len(hist) == 2 and all(np.isfinite(h["value_loss"]) and np.isfinite(h["policy_loss"]) for h in hist)
     assert trainer._graph is not None                       # the rollout was replayed from a CUDA graph
+    assert trainer._update_graph not in (None, False)       # ... and so was the optimiser step
     assert any(not torch.equal(a, b) for a, b in zip(before, pol.parameters()))
     assert not torch.equal(blob_before, pol._blob)
     assert hist[-1]["global_step"] == 2 * 64 * 4096 and hist[-1]["rollout_sps"] > 1e6
