@@ -368,7 +368,17 @@ def main():
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": N * world * n_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": 25 * N,
                "steps": n_e2e, "ms_per_step": 1e3 * e2e_s / n_e2e,
-               "path": "f16_env_step_host: pinned host actions -> H2D -> kernel -> D2H obs/reward/done, 3 chunks on 3 streams (PCIe-bound)"}
+               "path": ("f16_env_step_host, zero-copy route: ONE kernel launch reads the pinned (mapped) host actions and bulk-stores "
+                        "obs/reward/done to pinned host memory over PCIe, then a stream sync (PCIe-bound)"
+                        if getattr(env, "last_host_route", "") == "zero_copy" else
+                        "f16_env_step_host, staged route: pinned host actions -> H2D -> kernel -> D2H obs/reward/done, "
+                        "3 chunks on 3 streams (PCIe-bound)")}
+        if os.environ.get("F16B200_BENCH_STAGED_TOO"):   # comparison leg: same call with pageable actions -> staged route
+            a_np = a_host.numpy().copy()
+            t0 = time.perf_counter()
+            for s in range(n_e2e):
+                env.step_host(a_np[s % 4], out=out)
+            e2e["value_staged_route_pageable_actions"] = N * world * n_e2e / max_over_ranks(time.perf_counter() - t0)
 
     # ---- K-substeps sweep (state in registers across K env-steps per launch) -----------------
     sweep = None

@@ -19,7 +19,7 @@ OBS_AOS, OBS_SOA = 0, 1
 ABI_VERSION = 1
 
 EXPORTS = ["f16_abi_version", "f16_last_error", "f16_init", "f16_launch_geometry", "f16_env_reset", "f16_env_step",
-           "f16_env_step_host", "f16_rhs", "f16_model_step", "f16_coeffs", "f16_thrust", "f16_atmosphere",
+           "f16_env_step_host", "f16_host_route", "f16_rhs", "f16_model_step", "f16_coeffs", "f16_thrust", "f16_atmosphere",
            "f16_policy_blob_bytes", "f16_policy_forward", "f16_gae", "f16_trim"]
 
 

@@ -198,6 +198,7 @@ f16::StepArgs<R> make_step_args(const f16_config *cfg, const f16_step_io *io, in
     S.obs_every_step = io->obs_every_step;
     S.K = K;
     S.tma_ok = 0;   // set by step_range once the env buffers are known
+    S.obs_bulk = 0;
     S.i_begin = 0;
     S.i_end = cfg->n_envs;
     return S;
@@ -233,8 +234,10 @@ int tma_aligned(const f16_config *cfg, const f16_env_buffers *env, const f16_ste
     return 1;
 }
 
+// bulk_obs: stage the [N,5] observations in shared memory and write them with bulk stores.  Worth it only when obs
+// lives in mapped host memory (full-line PCIe writes); on device memory plain stores are 1.5-4 % faster (measured).
 int step_range(DeviceCtx *ctx, const f16_config *cfg, const f16_env_buffers *env, const f16_step_io *io, int K, int64_t i0, int64_t i1,
-               cudaStream_t st)
+               cudaStream_t st, bool bulk_obs = false)
 {
     const bool fast = cfg->dtype == F16_F32 && cfg->fast_math != 0;
     const f16::LaunchGeom g = geom(*ctx, cfg->dtype, fast, cfg->autoreset != 0);
@@ -244,6 +247,7 @@ int step_range(DeviceCtx *ctx, const f16_config *cfg, const f16_env_buffers *env
         S.i_begin = i0;
         S.i_end = i1;
         S.tma_ok = tma_aligned(cfg, env, io, i0);
+        S.obs_bulk = bulk_obs && S.tma_ok && io->obs && cfg->obs_layout == F16_OBS_AOS && reinterpret_cast<uintptr_t>(io->obs) % 16 == 0;
         CUDA_TRY(f16::launch_env_step(A, S, fast, g, st));
     } else {
         auto A = make_env_args<double>(cfg, env, ctx->t64);
@@ -254,6 +258,21 @@ int step_range(DeviceCtx *ctx, const f16_config *cfg, const f16_env_buffers *env
         CUDA_TRY(f16::launch_env_step(A, S, false, g, st));
     }
     return F16_OK;
+}
+
+thread_local int t_host_route = F16_HOST_ROUTE_STAGED;
+
+// pinned + mapped host allocation?  -> the device-side alias of the pointer
+bool mapped_host(const void *p, void **dev)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+    *dev = a.devicePointer;
+    return true;
 }
 
 int grow(void **p, size_t *cap, size_t need)
@@ -346,18 +365,45 @@ int f16_env_step_host(const f16_config *cfg, const f16_env_buffers *env, const v
             CUDA_TRY(cudaStreamCreateWithFlags(&P.streams[s], cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&P.done_ev[s], cudaEventDisableTiming));
         }
+    f16_step_io io;
+    std::memset(&io, 0, sizeof io);
+
+    // Zero-copy route: when every host buffer is pinned AND mapped (cudaHostAlloc / cudaHostRegister, e.g. torch's
+    // pin_memory()), the step kernel reads the actions from and writes obs / reward / done to host memory itself --
+    // one launch, no staging copies, transfers overlapped with the arithmetic tile by tile.  It needs the kernel
+    // whose stores are full lines (two-envs-per-thread kernel: bulk-stored [N,5] observations, or the SoA layout);
+    // 20-byte-strided scalar stores over PCIe are 2.5x slower than the staged pipeline (tools/probes/zero_copy_probe.py).
+    {
+        static const int zero_copy = [] {
+            const char *e = std::getenv("F16B200_HOST_ZERO_COPY");
+            return (e && e[0] == '0') ? 0 : 1;
+        }();
+        void *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_done = nullptr;
+        const f16::LaunchGeom g = geom(*ctx, cfg->dtype, cfg->fast_math != 0, cfg->autoreset != 0);
+        const bool wide_stores = cfg->dtype == F16_F32 && g.two_per_thread && cfg->autoreset && !cfg->noise && !env->pos_comp && n >= 512;
+        if (zero_copy && K == 1 && wide_stores && mapped_host(actions_host, &d_act) && mapped_host(reward_host, &d_rew) &&
+            mapped_host(done_host, &d_done) && (!obs_host || mapped_host(obs_host, &d_obs))) {
+            io.actions = d_act;
+            io.obs = d_obs;
+            io.reward = d_rew;
+            io.done = static_cast<uint8_t *>(d_done);
+            if ((rc = step_range(ctx, cfg, env, &io, K, 0, n, P.streams[0], true))) return rc;
+            CUDA_TRY(cudaStreamSynchronize(P.streams[0]));
+            t_host_route = F16_HOST_ROUTE_ZERO_COPY;
+            return F16_OK;
+        }
+    }
+
+    // Staged route (pageable or unmapped host memory, K > 1, other kernels):
+    t_host_route = F16_HOST_ROUTE_STAGED;
     if ((rc = grow(&P.actions, &P.cap_actions, es * K * n))) return rc;
     if ((rc = grow(&P.obs, &P.cap_obs, es * 5 * n))) return rc;
     if ((rc = grow(&P.reward, &P.cap_reward, es * K * n))) return rc;
     if ((rc = grow(reinterpret_cast<void **>(&P.done), &P.cap_done, (size_t)K * n))) return rc;
-
-    f16_step_io io;
-    std::memset(&io, 0, sizeof io);
     io.actions = P.actions;
     io.obs = obs_host ? P.obs : nullptr;
     io.reward = P.reward;
     io.done = P.done;
-
     // chunk the env range so that H2D(c+1), kernel(c) and D2H(c-1) overlap on three streams; the transfer is
     // D2H-bound (25 B per env-step out), so few large copies beat many small ones
     int64_t chunks = n >= (1 << 17) ? 3 : 1;   // measured on B200 / PCIe Gen5 (tools/e2e_probe.py): 3 chunks 1.78e9, 1: 1.72e9, 8: 1.60e9 env-steps/s
@@ -365,9 +411,31 @@ int f16_env_step_host(const f16_config *cfg, const f16_env_buffers *env, const v
         const long v = std::atol(e);
         if (v >= 1 && v <= 64) chunks = v;
     }
-    int64_t per = ((n + chunks - 1) / chunks + 255) / 256 * 256;
-    for (int64_t c = 0, i0 = 0; i0 < n; ++c, i0 += per) {
-        const int64_t i1 = i0 + per < n ? i0 + per : n;
+    // chunk c holds a share proportional to ratio^c: a small first chunk gets the device->host engine going early
+    double ratio = 1.0;
+    if (const char *e = std::getenv("F16B200_HOST_RATIO")) {
+        const double v = std::atof(e);
+        if (v >= 1.0 && v <= 16.0) ratio = v;
+    }
+    int64_t bounds[65];
+    {
+        double total = 0.0, w = 1.0;
+        for (int64_t c = 0; c < chunks; ++c, w *= ratio) total += w;
+        double acc = 0.0;
+        w = 1.0;
+        bounds[0] = 0;
+        for (int64_t c = 0; c < chunks; ++c, w *= ratio) {
+            acc += w;
+            int64_t b = static_cast<int64_t>(static_cast<double>(n) * (acc / total));
+            b = (b + 511) / 512 * 512;
+            if (b > n || c == chunks - 1) b = n;
+            if (b < bounds[c]) b = bounds[c];
+            bounds[c + 1] = b;
+        }
+    }
+    for (int64_t c = 0; c < chunks; ++c) {
+        const int64_t i0 = bounds[c], i1 = bounds[c + 1];
+        if (i1 <= i0) continue;
         const int64_t cnt = i1 - i0;
         cudaStream_t st = P.streams[c % 3];
         for (int k = 0; k < K; ++k)
@@ -398,6 +466,8 @@ int f16_env_step_host(const f16_config *cfg, const f16_env_buffers *env, const v
     for (int s = 0; s < 3; ++s) CUDA_TRY(cudaStreamSynchronize(P.streams[s]));
     return F16_OK;
 }
+
+int f16_host_route(void) { return t_host_route; }
 
 #define DISPATCH_SIMPLE(call32, call64)                 \
     do {                                                \

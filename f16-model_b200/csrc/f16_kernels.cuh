@@ -517,16 +517,43 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
 // ---------------------------------------------------------------------------
 constexpr int kTile2 = 2 * kCtaThreads;
 constexpr int kIn2Rows = 13;   // 9 state rows, action, ep_len, ref_idx, total_return
+#ifndef F16_STAGES2
+#define F16_STAGES2 2
+#endif
+#ifndef F16_PREFETCH2
+#define F16_PREFETCH2 1
+#endif
+constexpr int kStages2 = F16_STAGES2;      // depth of the input ring
+constexpr int kPrefetch2 = F16_PREFETCH2;  // tiles whose rows are prefetched into L2 before the grid dependency resolves
 
 template <typename R>
 struct alignas(16) Step2Smem {
     Tables<R> tbl;
-    R in[2][kIn2Rows][kTile2];
+    R in[kStages2][kIn2Rows][kTile2];
     uint64_t bar_tbl;
-    uint64_t bar_in[2];
-    unsigned drained[2];
+    uint64_t bar_in[kStages2];
+    unsigned drained[kStages2];
     CtaStats stats;
+    alignas(16) R obs_out[kTile2 * 5];   // AoS observations of the tile, written back by per-warp bulk stores
 };
+
+// L2 prefetch of one tile's input rows: legal before griddepcontrol.wait (it moves no data into the SM and L2 is
+// the coherence point, so lines the previous grid is still writing are simply updated in place)
+template <typename R>
+__device__ __forceinline__ void prefetch_tile2(const EnvArgs<R> &A, const StepArgs<R> &S, unsigned i0)
+{
+    const unsigned n = static_cast<unsigned>(A.n);
+    constexpr uint32_t rb = kTile2 * sizeof(R), ib = kTile2 * 4u;
+    auto pf = [&](const void *src, uint32_t bytes) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+    };
+#pragma unroll
+    for (int j = 0; j < 9; ++j) pf(A.state + static_cast<size_t>(j) * n + i0, rb);
+    pf(S.actions + i0, rb);
+    pf(A.ep_len + i0, ib);
+    pf(A.ref_idx + i0, ib);
+    pf(A.total_return + i0, rb);
+}
 
 template <typename R>
 __device__ __forceinline__ void issue_tile2(const EnvArgs<R> &A, const StepArgs<R> &S, Step2Smem<R> *sm, int stage, unsigned i0)
@@ -569,31 +596,41 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
 
     if (t == 0) {
         mbar_init(&sm->bar_tbl, 1);
-        mbar_init(&sm->bar_in[0], 1);
-        mbar_init(&sm->bar_in[1], 1);
-        sm->drained[0] = 0;
-        sm->drained[1] = 0;
+#pragma unroll
+        for (int s = 0; s < kStages2; ++s) {
+            mbar_init(&sm->bar_in[s], 1);
+            sm->drained[s] = 0;
+        }
         sm->stats.count = 0;
         sm->stats.length = 0;
         sm->stats.ret = 0.0;
     }
     __syncthreads();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (t == 0) tma_bulk_g2s(&sm->tbl, A.tables, static_cast<uint32_t>(sizeof(Tables<R>)), &sm->bar_tbl);
+    if (t == 0) {
+        tma_bulk_g2s(&sm->tbl, A.tables, static_cast<uint32_t>(sizeof(Tables<R>)), &sm->bar_tbl);
+#pragma unroll
+        for (int p = 0; p < kPrefetch2; ++p) {
+            const unsigned tp = blockIdx.x + p * gridDim.x;
+            if (tp < n_tiles) prefetch_tile2<R>(A, S, i_begin + tp * kTile2);
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (t == 0 && blockIdx.x < n_tiles) issue_tile2<R>(A, S, sm, 0, i_begin + blockIdx.x * kTile2);
     bool tables_ready = false;
 
-    unsigned it = 0;
+    unsigned it = 0, stage = 0, phase = 0;
     for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int stage = it & 1;
         const unsigned base = i_begin + tile * kTile2;
         R x[2][9], a_in[2], ret[2];
         int ep_len[2], ref_idx[2];
-        mbar_wait(&sm->bar_in[stage], (it >> 1) & 1u);
-        if (it == 0 && t == 0) {
-            const unsigned t1 = tile + gridDim.x;
-            if (t1 < n_tiles) issue_tile2<R>(A, S, sm, 1, i_begin + t1 * kTile2);
+        mbar_wait(&sm->bar_in[stage], phase);
+        if (it == 0 && t == 0) {   // the rest of the opening burst goes out once the first tile has landed
+#pragma unroll
+            for (int s = 1; s < kStages2; ++s) {
+                const unsigned ts = tile + s * gridDim.x;
+                if (ts < n_tiles) issue_tile2<R>(A, S, sm, s, i_begin + ts * kTile2);
+            }
         }
         {
             const R(*in)[kTile2] = sm->in[stage];
@@ -614,13 +651,17 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
             asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(prior) : "r"(smem_u32(&sm->drained[stage])) : "memory");
             if (prior == kCtaThreads / 32 - 1) {
                 sm->drained[stage] = 0;
-                const unsigned next = tile + 2 * gridDim.x;
+                const unsigned next = tile + kStages2 * gridDim.x;
                 if (next < n_tiles) issue_tile2<R>(A, S, sm, stage, i_begin + next * kTile2);
             }
         }
         if (!tables_ready) {
             mbar_wait(&sm->bar_tbl, 0);
             tables_ready = true;
+        }
+        if (++stage == kStages2) {
+            stage = 0;
+            phase ^= 1u;
         }
 
         R pa_in[2] = {x[0][8], x[1][8]};
@@ -716,9 +757,36 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
             }
             A.ep_len[i] = ep_len[e];
             A.total_return[i] = ret[e];
-            if (S.obs) store_obs<R>(S.obs, A.obs_layout, n, i, o[e]);
+            if (S.obs && !S.obs_bulk) store_obs<R>(S.obs, A.obs_layout, n, i, o[e]);
+        }
+        if (S.obs_bulk) {
+            // [N,5] observations: each warp stages its two 32-env runs (2 x 640 B, stride-5 words = conflict-free) and
+            // lane 0 writes them with two bulk stores -- full lines instead of 20-byte-strided scalar stores, which is
+            // what makes the same kernel usable on mapped host memory (PCIe sees large writes)
+            const unsigned lane = t & 31u, w0 = t & ~31u;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // last tile's stores have read the staging area
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                R *dst = sm->obs_out + (t + e * kCtaThreads) * 5u;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) dst[j] = o[e][j];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const unsigned c0 = w0 + e * kCtaThreads;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(S.obs + static_cast<size_t>(base + c0) * 5u),
+                                 "r"(smem_u32(sm->obs_out + c0 * 5u)), "r"(static_cast<uint32_t>(32u * 5u * sizeof(R)))
+                                 : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
         }
     }
+    if (S.obs_bulk && (t & 31u) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (!tables_ready) mbar_wait(&sm->bar_tbl, 0);
     if (S.stats) {
         __syncthreads();

@@ -53,6 +53,7 @@ struct StepArgs {
     int obs_every_step;
     int K;
     int tma_ok;               // every input row of a full tile is 16-byte aligned: TMA-staged loads allowed
+    int obs_bulk;             // AoS obs rows of a full tile are 16-byte aligned: staged in shared memory, written by bulk stores
     int64_t i_begin, i_end;   // env sub-range advanced by this launch (host-buffer path pipelines chunks)
 };
 

@@ -364,8 +364,10 @@ class F16VecEnv:
 
     def step_host(self, actions, out=None):
         """End-to-end step through HOST memory: ``actions`` is a NumPy array / CPU tensor [N] or
-        [K, N]; returns NumPy (obs [N,5], reward [K,N], done [K,N]).  The copies are chunked and
-        overlapped with the kernel inside the library (f16_env_step_host)."""
+        [K, N]; returns (obs [N,5], reward [K,N], done [K,N]) as CPU tensors (``out`` may carry preallocated
+        ones).  With pinned actions and outputs the fp32 gym step takes the library's zero-copy route (the
+        kernel reads / bulk-stores host memory itself); otherwise the copies are chunked and overlapped
+        with the kernel (f16_env_step_host).  ``last_host_route`` says which: "zero_copy" or "staged"."""
         torch = self._torch
         a = torch.as_tensor(actions)
         if a.is_cuda:
@@ -383,6 +385,7 @@ class F16VecEnv:
         torch.cuda.current_stream(self.device).synchronize()   # the library pipelines on its own streams
         _capi.check(self._lib.f16_env_step_host(C.byref(self._cfg), C.byref(self._buf), a.data_ptr(), obs.data_ptr(),
                                                 reward.data_ptr(), done.data_ptr(), K, self.device.index))
+        self.last_host_route = "zero_copy" if self._lib.f16_host_route() == 1 else "staged"
         return self._obs_view(obs), reward, done
 
     # ------------------------------------------------------------------ state access

@@ -126,12 +126,18 @@ int f16_env_reset(const f16_config *cfg, const f16_env_buffers *env, const uint8
  * launch; state stays in registers across the K steps. */
 int f16_env_step(const f16_config *cfg, const f16_env_buffers *env, const f16_step_io *io, int K, void *stream);
 
-/* Same step through HOST buffers (pinned or pageable): H2D of actions, kernel,
- * D2H of obs/reward/done, chunked and double-buffered over internal streams.
- * The env's persistent buffers stay on the device. Blocks until the results are
- * in the host buffers. */
+/* Same step through HOST buffers.  The env's persistent buffers stay on the device; the call blocks until
+ * the results are in the host buffers.  Two routes, both on the GPU:
+ *   F16_HOST_ROUTE_ZERO_COPY  every buffer is pinned AND mapped (cudaHostAlloc / cudaHostRegister), fp32 gym
+ *       step (K = 1, autoreset): the step kernel itself reads the actions from and bulk-stores obs / reward /
+ *       done to host memory -- one launch, transfers overlapped with the arithmetic tile by tile;
+ *   F16_HOST_ROUTE_STAGED     otherwise: H2D of actions, kernel, D2H of obs/reward/done, chunked and
+ *       double-buffered over internal streams.
+ * f16_host_route() names the route the calling thread's last f16_env_step_host took. */
+enum { F16_HOST_ROUTE_STAGED = 0, F16_HOST_ROUTE_ZERO_COPY = 1 };
 int f16_env_step_host(const f16_config *cfg, const f16_env_buffers *env, const void *actions_host, void *obs_host,
                       void *reward_host, uint8_t *done_host, int K, int device);
+int f16_host_route(void);
 
 /* ---- model level ------------------------------------------------------ */
 /* ODE_3DoF.solve (model/ODE_3DoF.py:8-60): dx = f(x, u); x real[9][n], u real[2][n] (stab cmd [rad],

@@ -505,6 +505,29 @@ def test_step_host_equals_device_step(f16):
     assert torch.equal(a_env.state, b_env.state)
 
 
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+def test_step_host_zero_copy_route(f16, layout):
+    """Pinned + mapped host buffers: the kernel reads the actions from and bulk-stores obs/reward/done to host
+    memory itself.  Ragged n, so the two-envs-per-thread kernel and the one-env remainder kernel both write host
+    memory; bit-identical to the device step and to the staged route (pageable actions)."""
+    n = (1 << 17) + 77
+    a_env = f16.F16VecEnv(CFG, n, seed=9, obs_layout=layout)
+    b_env = f16.F16VecEnv(CFG, n, seed=9, obs_layout=layout)
+    c_env = f16.F16VecEnv(CFG, n, seed=9, obs_layout=layout)
+    acts = (torch.rand((4, n)) * 2 - 1).pin_memory()
+    out = (torch.empty((n, 5) if layout == "aos" else (5, n)).pin_memory(), torch.empty((1, n)).pin_memory(),
+           torch.empty((1, n), dtype=torch.uint8).pin_memory())
+    for k in range(4):
+        o, r, d, _, _ = a_env.step(acts[k].cuda())
+        oh, rh, dh = b_env.step_host(acts[k], out=out)
+        assert b_env.last_host_route == "zero_copy"
+        assert torch.equal(o.cpu(), oh) and torch.equal(r.cpu(), rh[0]) and torch.equal(d.cpu().view(torch.uint8), dh[0])
+        oc, rc, dc = c_env.step_host(acts[k].numpy().copy())
+        assert c_env.last_host_route == "staged"
+        assert torch.equal(oc, oh) and torch.equal(rc, rh) and torch.equal(dc, dh)
+    assert torch.equal(a_env.state, b_env.state) and torch.equal(a_env.state, c_env.state)
+
+
 def test_graphed_step_equals_eager_step(f16):
     n = 1 << 16
     a_env = f16.F16VecEnv(CFG, n, seed=9)

@@ -1,3 +1,5 @@
+"""Host-buffer path probe: env-steps/s of F16VecEnv.step_host for the chunk schedule in the environment
+(F16B200_HOST_CHUNKS, F16B200_HOST_RATIO), next to the raw pinned device->host copy rate of the same bytes."""
 import os, sys, time, torch
 sys.path.insert(0, os.getcwd())
 import f16_model_b200 as f16
@@ -10,4 +12,13 @@ for s in range(5): env.step_host(a[s % 4], out=out)
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for s in range(100): env.step_host(a[s % 4], out=out)
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
-print(os.environ.get("F16B200_HOST_CHUNKS"), "chunks:", N * 100 / dt / 1e9, "e9 env-steps/s", dt / 100 * 1e3, "ms/step")
+print("chunks", os.environ.get("F16B200_HOST_CHUNKS"), "ratio", os.environ.get("F16B200_HOST_RATIO"), ":",
+      round(N * 100 / dt / 1e9, 4), "e9 env-steps/s", round(dt / 100 * 1e3, 4), "ms/step")
+if os.environ.get("F16B200_RAW_COPY"):
+    dev = torch.empty(N * 25, dtype=torch.uint8, device="cuda")
+    host = torch.empty(N * 25, dtype=torch.uint8).pin_memory()
+    for _ in range(3): host.copy_(dev, non_blocking=True)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(50): host.copy_(dev, non_blocking=True)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print("raw pinned D2H of 25 B x 2^20:", round(N * 25 * 50 / dt / 1e9, 2), "GB/s", round(dt / 50 * 1e3, 4), "ms per copy")
