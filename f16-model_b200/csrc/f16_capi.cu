@@ -247,7 +247,11 @@ int step_range(DeviceCtx *ctx, const f16_config *cfg, const f16_env_buffers *env
         S.i_begin = i0;
         S.i_end = i1;
         S.tma_ok = tma_aligned(cfg, env, io, i0);
-        S.obs_bulk = bulk_obs && S.tma_ok && io->obs && cfg->obs_layout == F16_OBS_AOS && reinterpret_cast<uintptr_t>(io->obs) % 16 == 0;
+        static const bool force_bulk = [] {   // probing knob: bulk-stored observations on the device route too
+            const char *e = std::getenv("F16B200_BULK_OBS");
+            return e && e[0] == '1';
+        }();
+        S.obs_bulk = (bulk_obs || force_bulk) && S.tma_ok && io->obs && cfg->obs_layout == F16_OBS_AOS && reinterpret_cast<uintptr_t>(io->obs) % 16 == 0;
         CUDA_TRY(f16::launch_env_step(A, S, fast, g, st));
     } else {
         auto A = make_env_args<double>(cfg, env, ctx->t64);

@@ -731,33 +731,67 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
                     make_obs<R, FAST>(x[e][1], x[e][2], x[e][4], A.ref_bank[static_cast<unsigned>(ref_idx[e]) * static_cast<unsigned>(A.ref_len)], o[e]);
                 }
             }
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const unsigned kn = static_cast<unsigned>(k) * n + base + t + e * kCtaThreads;
-                S.reward[kn] = reward[e];
-                S.done[kn] = static_cast<uint8_t>(done[e]);
+            {   // both envs of a thread share one address per array: the second sits kCtaThreads elements further
+                const unsigned kn = static_cast<unsigned>(k) * n + base + t;
+                R *pr = S.reward + kn;
+                uint8_t *pd = S.done + kn;
+                pr[0] = reward[0];
+                pr[kCtaThreads] = reward[1];
+                pd[0] = static_cast<uint8_t>(done[0]);
+                pd[kCtaThreads] = static_cast<uint8_t>(done[1]);
             }
         }
 
         // ---- write back ---------------------------------------------------------------------------------------
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const unsigned i = base + t + e * kCtaThreads;
+        {
+            const unsigned i = base + t;
             R *p = A.state + i;
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
                 if (j == 4) {
-                    if (was_reset[e]) *p = x[e][4];
+                    if (was_reset[0]) p[0] = x[0][4];
+                    if (was_reset[1]) p[kCtaThreads] = x[1][4];
                 } else if (j == 8) {
-                    if (x[e][8] != pa_in[e]) *p = x[e][8];
+                    if (x[0][8] != pa_in[0]) p[0] = x[0][8];
+                    if (x[1][8] != pa_in[1]) p[kCtaThreads] = x[1][8];
                 } else {
-                    *p = x[e][j];
+                    p[0] = x[0][j];
+                    p[kCtaThreads] = x[1][j];
                 }
                 p += n;
             }
-            A.ep_len[i] = ep_len[e];
-            A.total_return[i] = ret[e];
-            if (S.obs && !S.obs_bulk) store_obs<R>(S.obs, A.obs_layout, n, i, o[e]);
+            int32_t *pl = A.ep_len + i;
+            pl[0] = ep_len[0];
+            pl[kCtaThreads] = ep_len[1];
+            R *pt = A.total_return + i;
+            pt[0] = ret[0];
+            pt[kCtaThreads] = ret[1];
+            if (S.obs && !S.obs_bulk) {
+                if (A.obs_layout == 0) {   // F16_OBS_AOS
+                    R *po = S.obs + static_cast<size_t>(i) * 5u;
+#if defined(F16_OBS_INTERLEAVED)
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        po[j] = o[0][j];
+                        po[kCtaThreads * 5 + j] = o[1][j];
+                    }
+#else
+                    // env-major: the five 4-byte stores of one env's row go out back to back (they share sectors)
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) po[j] = o[0][j];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) po[kCtaThreads * 5 + j] = o[1][j];
+#endif
+                } else {
+                    R *po = S.obs + i;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        po[0] = o[0][j];
+                        po[kCtaThreads] = o[1][j];
+                        po += n;
+                    }
+                }
+            }
         }
         if (S.obs_bulk) {
             // [N,5] observations: each warp stages its two 32-env runs (2 x 640 B, stride-5 words = conflict-free) and
