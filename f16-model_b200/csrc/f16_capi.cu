@@ -127,7 +127,9 @@ f16::LaunchGeom geom(const DeviceCtx &c, int dtype, bool fast, bool autoreset)
     }();
     f16::LaunchGeom g{c.n_sm, occ, pdl};
     g.two_per_thread = (dtype == F16_F32) ? x2 : 0;
-    g.ctas2_per_sm = c.occ2[fast ? 1 : 0] > 0 ? c.occ2[fast ? 1 : 0] : 1;
+    const int o2 = c.occ2[fast ? 1 : 0];
+    g.ctas2_per_sm = (o2 & 0xff) > 0 ? (o2 & 0xff) : 1;
+    g.ctas2k_per_sm = ((o2 >> 8) & 0xff) > 0 ? ((o2 >> 8) & 0xff) : 1;
     return g;
 }
 
@@ -431,7 +433,7 @@ int f16_env_step_host(const f16_config *cfg, const f16_env_buffers *env, const v
         for (int64_t c = 0; c < chunks; ++c, w *= ratio) {
             acc += w;
             int64_t b = static_cast<int64_t>(static_cast<double>(n) * (acc / total));
-            b = (b + 511) / 512 * 512;
+            b = (b + 255) / 256 * 256;
             if (b > n || c == chunks - 1) b = n;
             if (b < bounds[c]) b = bounds[c];
             bounds[c + 1] = b;

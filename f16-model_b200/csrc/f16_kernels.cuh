@@ -509,13 +509,27 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
 //
 // The one-env kernel above is bound by dependency stalls (short scoreboard + fixed-latency waits are 37 % of
 // its stall samples, issue slots 64 % busy) and by per-tile bookkeeping.  Here every thread advances envs t and
-// t + 256 of a 512-env tile; the common path of a step is ONE branch-free basic block holding both envs'
+// t + 128 of a 256-env tile (128-thread CTAs, four per SM); the common path of a step is ONE branch-free basic block holding both envs'
 // arithmetic, so the scheduler interleaves two independent dependency chains, and the tile bookkeeping
 // (barrier wait, ring refill, parameter loads) is paid once per two envs.  Rare events -- an altitude outside
 // the troposphere, a termination with its autoreset -- are patched after the common path.  Handles full,
 // 16-byte aligned tiles only; the caller runs the one-env kernel on the remainder.
 // ---------------------------------------------------------------------------
-constexpr int kTile2 = 2 * kCtaThreads;
+#ifndef F16_CTA2_THREADS
+#define F16_CTA2_THREADS 128
+#endif
+#ifndef F16_CTA2K_THREADS
+#define F16_CTA2K_THREADS 256
+#endif
+// CTA size by mode (a tile is two envs per thread).  Gym step (K = 1): 128 threads, 4 CTAs per SM -- measured 2 % faster
+// than 256 x 2 on one stream and 5 % faster with overlapping launches (finer tiles shorten the fill and drain of every
+// launch; 64 x 8 is 15 % slower).  K-step launches are issue-bound and 5 % faster with 256 x 2.
+template <bool SINGLE>
+struct Cta2 {
+    static constexpr int threads = SINGLE ? F16_CTA2_THREADS : F16_CTA2K_THREADS;
+    static constexpr int min_ctas = SINGLE ? 4 : 2;
+    static constexpr int tile = 2 * threads;
+};
 constexpr int kIn2Rows = 13;   // 9 state rows, action, ep_len, ref_idx, total_return
 #ifndef F16_STAGES2
 #define F16_STAGES2 2
@@ -526,24 +540,28 @@ constexpr int kIn2Rows = 13;   // 9 state rows, action, ep_len, ref_idx, total_r
 constexpr int kStages2 = F16_STAGES2;      // depth of the input ring
 constexpr int kPrefetch2 = F16_PREFETCH2;  // tiles whose rows are prefetched into L2 before the grid dependency resolves
 
-template <typename R>
+template <typename R, int CT, bool OBS_STAGING>
 struct alignas(16) Step2Smem {
+    static constexpr int TILE = 2 * CT;
     Tables<R> tbl;
-    R in[kStages2][kIn2Rows][kTile2];
+    R in[kStages2][kIn2Rows][TILE];
     uint64_t bar_tbl;
     uint64_t bar_in[kStages2];
     unsigned drained[kStages2];
     CtaStats stats;
-    alignas(16) R obs_out[kTile2 * 5];   // AoS observations of the tile, written back by per-warp bulk stores
+    // AoS observations of the tile, written back by per-warp bulk stores (gym-step kernel only: in the K-step kernel the
+    // 10 KB would push the shared-memory carve-out up a notch and cost L1, which its reference-row reads live in: -5 %)
+    alignas(16) R obs_out[OBS_STAGING ? TILE * 5 : 4];
 };
 
 // L2 prefetch of one tile's input rows: legal before griddepcontrol.wait (it moves no data into the SM and L2 is
 // the coherence point, so lines the previous grid is still writing are simply updated in place)
-template <typename R>
+template <typename R, int CT>
 __device__ __forceinline__ void prefetch_tile2(const EnvArgs<R> &A, const StepArgs<R> &S, unsigned i0)
 {
+    constexpr int TILE = 2 * CT;
     const unsigned n = static_cast<unsigned>(A.n);
-    constexpr uint32_t rb = kTile2 * sizeof(R), ib = kTile2 * 4u;
+    constexpr uint32_t rb = TILE * sizeof(R), ib = TILE * 4u;
     auto pf = [&](const void *src, uint32_t bytes) {
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
     };
@@ -555,11 +573,12 @@ __device__ __forceinline__ void prefetch_tile2(const EnvArgs<R> &A, const StepAr
     pf(A.total_return + i0, rb);
 }
 
-template <typename R>
-__device__ __forceinline__ void issue_tile2(const EnvArgs<R> &A, const StepArgs<R> &S, Step2Smem<R> *sm, int stage, unsigned i0)
+template <typename R, int CT, bool OBS_STAGING>
+__device__ __forceinline__ void issue_tile2(const EnvArgs<R> &A, const StepArgs<R> &S, Step2Smem<R, CT, OBS_STAGING> *sm, int stage, unsigned i0)
 {
+    constexpr int TILE = 2 * CT;
     const unsigned n = static_cast<unsigned>(A.n);
-    constexpr uint32_t rb = kTile2 * sizeof(R), ib = kTile2 * 4u;
+    constexpr uint32_t rb = TILE * sizeof(R), ib = TILE * 4u;
     constexpr uint32_t total = 11u * rb + 2u * ib;
     uint64_t *bar = &sm->bar_in[stage];
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(total) : "memory");
@@ -568,7 +587,7 @@ __device__ __forceinline__ void issue_tile2(const EnvArgs<R> &A, const StepArgs<
                      "l"(src), "r"(bytes), "r"(smem_u32(bar))
                      : "memory");
     };
-    R(*in)[kTile2] = sm->in[stage];
+    R(*in)[TILE] = sm->in[stage];
 #pragma unroll
     for (int j = 0; j < 9; ++j) cp(in[j], A.state + static_cast<size_t>(j) * n + i0, rb);
     cp(in[9], S.actions + i0, rb);
@@ -577,20 +596,19 @@ __device__ __forceinline__ void issue_tile2(const EnvArgs<R> &A, const StepArgs<
     cp(in[12], A.total_return + i0, rb);
 }
 
-#ifndef F16_MINCTAS2
-#define F16_MINCTAS2 2
-#endif
 template <typename R, bool FAST, bool SINGLE>
-__global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(const EnvArgs<R> A, const StepArgs<R> S)
+__global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas) env_step2_kernel(const EnvArgs<R> A, const StepArgs<R> S)
 {
+    constexpr int CT = Cta2<SINGLE>::threads, TILE = 2 * CT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Step2Smem<R> *sm = reinterpret_cast<Step2Smem<R> *>(smem_raw);
+    using Smem = Step2Smem<R, CT, SINGLE>;
+    Smem *sm = reinterpret_cast<Smem *>(smem_raw);
     const Tables<R> &tbl = sm->tbl;
     using M = Mth<R, FAST>;
 
     const unsigned n = static_cast<unsigned>(A.n);
     const unsigned i_begin = static_cast<unsigned>(S.i_begin);
-    const unsigned n_tiles = static_cast<unsigned>(S.i_end - S.i_begin) / kTile2;   // full tiles only
+    const unsigned n_tiles = static_cast<unsigned>(S.i_end - S.i_begin) / TILE;   // full tiles only
     const R dt = A.dt;
     const unsigned t = threadIdx.x;
 
@@ -612,16 +630,18 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
 #pragma unroll
         for (int p = 0; p < kPrefetch2; ++p) {
             const unsigned tp = blockIdx.x + p * gridDim.x;
-            if (tp < n_tiles) prefetch_tile2<R>(A, S, i_begin + tp * kTile2);
+            if (tp < n_tiles) prefetch_tile2<R, CT>(A, S, i_begin + tp * TILE);
         }
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (t == 0 && blockIdx.x < n_tiles) issue_tile2<R>(A, S, sm, 0, i_begin + blockIdx.x * kTile2);
+    if (t == 0 && blockIdx.x < n_tiles) issue_tile2<R, CT, SINGLE>(A, S, sm, 0, i_begin + blockIdx.x * TILE);
     bool tables_ready = false;
 
-    unsigned it = 0, stage = 0, phase = 0;
+    static_assert(kStages2 == 2 || kStages2 == 4, "ring position is derived from the tile counter");
+    unsigned it = 0;
     for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const unsigned base = i_begin + tile * kTile2;
+        const unsigned stage = it & (kStages2 - 1), phase = (it / kStages2) & 1u;   // nothing ring-related stays live across the K loop
+        const unsigned base = i_begin + tile * TILE;
         R x[2][9], a_in[2], ret[2];
         int ep_len[2], ref_idx[2];
         mbar_wait(&sm->bar_in[stage], phase);
@@ -629,14 +649,14 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
 #pragma unroll
             for (int s = 1; s < kStages2; ++s) {
                 const unsigned ts = tile + s * gridDim.x;
-                if (ts < n_tiles) issue_tile2<R>(A, S, sm, s, i_begin + ts * kTile2);
+                if (ts < n_tiles) issue_tile2<R, CT, SINGLE>(A, S, sm, s, i_begin + ts * TILE);
             }
         }
         {
-            const R(*in)[kTile2] = sm->in[stage];
+            const R(*in)[TILE] = sm->in[stage];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const unsigned c = t + e * kCtaThreads;
+                const unsigned c = t + e * CT;
 #pragma unroll
                 for (int j = 0; j < 9; ++j) x[e][j] = in[j][c];
                 a_in[e] = in[9][c];
@@ -649,19 +669,15 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
         if ((t & 31u) == 0) {
             unsigned prior;
             asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(prior) : "r"(smem_u32(&sm->drained[stage])) : "memory");
-            if (prior == kCtaThreads / 32 - 1) {
+            if (prior == CT / 32 - 1) {
                 sm->drained[stage] = 0;
                 const unsigned next = tile + kStages2 * gridDim.x;
-                if (next < n_tiles) issue_tile2<R>(A, S, sm, stage, i_begin + next * kTile2);
+                if (next < n_tiles) issue_tile2<R, CT, SINGLE>(A, S, sm, stage, i_begin + next * TILE);
             }
         }
         if (!tables_ready) {
             mbar_wait(&sm->bar_tbl, 0);
             tables_ready = true;
-        }
-        if (++stage == kStages2) {
-            stage = 0;
-            phase ^= 1u;
         }
 
         R pa_in[2] = {x[0][8], x[1][8]};
@@ -675,7 +691,7 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 ref[e] = A.ref_bank[static_cast<unsigned>(ref_idx[e]) * static_cast<unsigned>(A.ref_len) + min(ep_len[e], A.ref_len - 1)];
-                if (!SINGLE && k + 1 < K_steps) a_next[e] = S.actions[static_cast<unsigned>(k + 1) * n + base + t + e * kCtaThreads];
+                if (!SINGLE && k + 1 < K_steps) a_next[e] = S.actions[static_cast<unsigned>(k + 1) * n + base + t + e * CT];
                 Hg[e] = isa_geopotential<R, FAST>(x[e][1]);
                 slow[e] = !(Hg[e] >= R(0) && Hg[e] < R(11000));
                 isa_troposphere<R, FAST>(Hg[e], Tk[e], pk[e]);
@@ -716,7 +732,7 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 if (done[e]) {
-                    const unsigned i = base + t + e * kCtaThreads;
+                    const unsigned i = base + t + e * CT;
                     if (S.stats) episode_stats_add(&sm->stats, static_cast<double>(ret[e]), ep_len[e]);
                     if (S.final_obs) store_obs<R>(S.final_obs, A.obs_layout, n, i, o[e]);
                     if (S.final_ep_len) S.final_ep_len[i] = ep_len[e];
@@ -731,14 +747,11 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
                     make_obs<R, FAST>(x[e][1], x[e][2], x[e][4], A.ref_bank[static_cast<unsigned>(ref_idx[e]) * static_cast<unsigned>(A.ref_len)], o[e]);
                 }
             }
-            {   // both envs of a thread share one address per array: the second sits kCtaThreads elements further
-                const unsigned kn = static_cast<unsigned>(k) * n + base + t;
-                R *pr = S.reward + kn;
-                uint8_t *pd = S.done + kn;
-                pr[0] = reward[0];
-                pr[kCtaThreads] = reward[1];
-                pd[0] = static_cast<uint8_t>(done[0]);
-                pd[kCtaThreads] = static_cast<uint8_t>(done[1]);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const unsigned kn = static_cast<unsigned>(k) * n + base + t + e * CT;
+                S.reward[kn] = reward[e];
+                S.done[kn] = static_cast<uint8_t>(done[e]);
             }
         }
 
@@ -750,50 +763,50 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
             for (int j = 0; j < 9; ++j) {
                 if (j == 4) {
                     if (was_reset[0]) p[0] = x[0][4];
-                    if (was_reset[1]) p[kCtaThreads] = x[1][4];
+                    if (was_reset[1]) p[CT] = x[1][4];
                 } else if (j == 8) {
                     if (x[0][8] != pa_in[0]) p[0] = x[0][8];
-                    if (x[1][8] != pa_in[1]) p[kCtaThreads] = x[1][8];
+                    if (x[1][8] != pa_in[1]) p[CT] = x[1][8];
                 } else {
                     p[0] = x[0][j];
-                    p[kCtaThreads] = x[1][j];
+                    p[CT] = x[1][j];
                 }
                 p += n;
             }
             int32_t *pl = A.ep_len + i;
             pl[0] = ep_len[0];
-            pl[kCtaThreads] = ep_len[1];
+            pl[CT] = ep_len[1];
             R *pt = A.total_return + i;
             pt[0] = ret[0];
-            pt[kCtaThreads] = ret[1];
-            if (S.obs && !S.obs_bulk) {
+            pt[CT] = ret[1];
+            if (S.obs && !(SINGLE && S.obs_bulk)) {
                 if (A.obs_layout == 0) {   // F16_OBS_AOS
                     R *po = S.obs + static_cast<size_t>(i) * 5u;
 #if defined(F16_OBS_INTERLEAVED)
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
                         po[j] = o[0][j];
-                        po[kCtaThreads * 5 + j] = o[1][j];
+                        po[CT * 5 + j] = o[1][j];
                     }
 #else
                     // env-major: the five 4-byte stores of one env's row go out back to back (they share sectors)
 #pragma unroll
                     for (int j = 0; j < 5; ++j) po[j] = o[0][j];
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) po[kCtaThreads * 5 + j] = o[1][j];
+                    for (int j = 0; j < 5; ++j) po[CT * 5 + j] = o[1][j];
 #endif
                 } else {
                     R *po = S.obs + i;
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
                         po[0] = o[0][j];
-                        po[kCtaThreads] = o[1][j];
+                        po[CT] = o[1][j];
                         po += n;
                     }
                 }
             }
         }
-        if (S.obs_bulk) {
+        if (SINGLE && S.obs_bulk) {   // the host route is a gym step: compiled out of the K-step kernel
             // [N,5] observations: each warp stages its two 32-env runs (2 x 640 B, stride-5 words = conflict-free) and
             // lane 0 writes them with two bulk stores -- full lines instead of 20-byte-strided scalar stores, which is
             // what makes the same kernel usable on mapped host memory (PCIe sees large writes)
@@ -802,7 +815,7 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
             __syncwarp();
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                R *dst = sm->obs_out + (t + e * kCtaThreads) * 5u;
+                R *dst = sm->obs_out + (t + e * CT) * 5u;
 #pragma unroll
                 for (int j = 0; j < 5; ++j) dst[j] = o[e][j];
             }
@@ -811,7 +824,7 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
             if (lane == 0) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const unsigned c0 = w0 + e * kCtaThreads;
+                    const unsigned c0 = w0 + e * CT;
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(S.obs + static_cast<size_t>(base + c0) * 5u),
                                  "r"(smem_u32(sm->obs_out + c0 * 5u)), "r"(static_cast<uint32_t>(32u * 5u * sizeof(R)))
                                  : "memory");
@@ -820,7 +833,7 @@ __global__ void __launch_bounds__(kCtaThreads, F16_MINCTAS2) env_step2_kernel(co
             }
         }
     }
-    if (S.obs_bulk && (t & 31u) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (SINGLE && S.obs_bulk && (t & 31u) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (!tables_ready) mbar_wait(&sm->bar_tbl, 0);
     if (S.stats) {
         __syncthreads();
@@ -1067,15 +1080,16 @@ cudaError_t launch_env_step_t(const EnvArgs<R> &A, const StepArgs<R> &S, const L
     const bool single = S.K == 1;
     const bool comp = A.pos_comp != nullptr && sizeof(R) == 4;
     if constexpr (sizeof(R) == 4) {
-        // the gym step of the throughput mode: two envs per thread on the full 512-env tiles, one-env kernel on the rest
+        // the gym step of the throughput mode: two envs per thread on the full 256-env tiles, one-env kernel on the rest
         if (g.two_per_thread && A.autoreset && !comp && !A.noise && S.tma_ok && !(S.obs_every_step && !single) &&
-            (S.i_end - S.i_begin) >= kTile2) {
-            const int64_t n2 = (S.i_end - S.i_begin) / kTile2;
-            const int64_t cap2 = static_cast<int64_t>(g.n_sm) * g.ctas2_per_sm;
+            (S.i_end - S.i_begin) >= (single ? Cta2<true>::tile : Cta2<false>::tile)) {
+            const int tile2 = single ? Cta2<true>::tile : Cta2<false>::tile;
+            const int64_t n2 = (S.i_end - S.i_begin) / tile2;
+            const int64_t cap2 = static_cast<int64_t>(g.n_sm) * (single ? g.ctas2_per_sm : g.ctas2k_per_sm);
             cudaLaunchConfig_t lc2 = {};
             lc2.gridDim = dim3(static_cast<unsigned>(n2 < cap2 ? n2 : cap2));
-            lc2.blockDim = dim3(kCtaThreads);
-            lc2.dynamicSmemBytes = sizeof(Step2Smem<R>);
+            lc2.blockDim = dim3(tile2 / 2);
+            lc2.dynamicSmemBytes = single ? sizeof(Step2Smem<R, Cta2<true>::threads, true>) : sizeof(Step2Smem<R, Cta2<false>::threads, false>);
             lc2.stream = st;
             cudaLaunchAttribute at2[1];
             at2[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1086,7 +1100,7 @@ cudaError_t launch_env_step_t(const EnvArgs<R> &A, const StepArgs<R> &S, const L
                                     : cudaLaunchKernelEx(&lc2, env_step2_kernel<R, FAST, false>, A, S);
             if (e2 != cudaSuccess) return e2;
             StepArgs<R> rest = S;
-            rest.i_begin = S.i_begin + n2 * kTile2;
+            rest.i_begin = S.i_begin + n2 * tile2;
             if (rest.i_begin >= rest.i_end) return cudaGetLastError();
             LaunchGeom g1 = g;
             g1.two_per_thread = 0;
@@ -1139,17 +1153,19 @@ int prepare_env_step()
 }
 
 // two-envs-per-thread gym-step kernel: opt into its shared memory, report resident CTAs per SM
+// (returns the gym-step kernel's count in the low byte, the K-step kernel's in the next one)
 template <typename R, bool FAST>
 int prepare_env_step2()
 {
     auto fn1 = env_step2_kernel<R, FAST, true>;
     auto fnk = env_step2_kernel<R, FAST, false>;
-    cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Step2Smem<R>)));
-    cudaFuncSetAttribute(fnk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Step2Smem<R>)));
+    constexpr int s1 = static_cast<int>(sizeof(Step2Smem<R, Cta2<true>::threads, true>)), sk = static_cast<int>(sizeof(Step2Smem<R, Cta2<false>::threads, false>));
+    cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
+    cudaFuncSetAttribute(fnk, cudaFuncAttributeMaxDynamicSharedMemorySize, sk);
     int b1 = 0, bk = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, fn1, kCtaThreads, sizeof(Step2Smem<R>));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bk, fnk, kCtaThreads, sizeof(Step2Smem<R>));
-    return b1 < bk ? b1 : bk;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, fn1, Cta2<true>::threads, s1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bk, fnk, Cta2<false>::threads, sk);
+    return (b1 & 0xff) | ((bk & 0xff) << 8);
 }
 
 }  // namespace f16

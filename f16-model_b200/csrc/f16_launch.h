@@ -14,7 +14,8 @@ struct LaunchGeom {
     int ctas_per_sm;
     int pdl = 1;   // launch the step kernel with programmatic stream serialization (F16B200_PDL=0 disables)
     int two_per_thread = 0;   // fp32 gym step: use the two-envs-per-thread kernel on full tiles
-    int ctas2_per_sm = 2;
+    int ctas2_per_sm = 4;    // resident CTAs of the two-env gym-step kernel (128 threads)
+    int ctas2k_per_sm = 2;   // ... of its K-step variant (256 threads)
 };
 
 // typed view of f16_config + f16_env_buffers (include/f16_b200.h)
