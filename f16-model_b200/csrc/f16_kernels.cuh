@@ -537,17 +537,22 @@ constexpr int kIn2Rows = 13;   // 9 state rows, action, ep_len, ref_idx, total_r
 #ifndef F16_PREFETCH2
 #define F16_PREFETCH2 1
 #endif
-constexpr int kStages2 = F16_STAGES2;      // depth of the input ring
+constexpr int kStages2 = F16_STAGES2;      // depth of the gym-step kernel's input ring
+#ifndef F16_STAGES2K
+#define F16_STAGES2K 2
+#endif
+constexpr int kStages2K = F16_STAGES2K;    // ... of the K-step kernel's (its loads are amortised over K steps)
 constexpr int kPrefetch2 = F16_PREFETCH2;  // tiles whose rows are prefetched into L2 before the grid dependency resolves
 
 template <typename R, int CT, bool OBS_STAGING>
 struct alignas(16) Step2Smem {
     static constexpr int TILE = 2 * CT;
+    static constexpr int STAGES = OBS_STAGING ? kStages2 : kStages2K;   // OBS_STAGING == gym-step kernel
     Tables<R> tbl;
-    R in[kStages2][kIn2Rows][TILE];
+    R in[STAGES][kIn2Rows][TILE];
     uint64_t bar_tbl;
-    uint64_t bar_in[kStages2];
-    unsigned drained[kStages2];
+    uint64_t bar_in[STAGES];
+    unsigned drained[STAGES];
     CtaStats stats;
     // AoS observations of the tile, written back by per-warp bulk stores (gym-step kernel only: in the K-step kernel the
     // 10 KB would push the shared-memory carve-out up a notch and cost L1, which its reference-row reads live in: -5 %)
@@ -615,7 +620,7 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
     if (t == 0) {
         mbar_init(&sm->bar_tbl, 1);
 #pragma unroll
-        for (int s = 0; s < kStages2; ++s) {
+        for (int s = 0; s < Smem::STAGES; ++s) {
             mbar_init(&sm->bar_in[s], 1);
             sm->drained[s] = 0;
         }
@@ -637,17 +642,18 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
     if (t == 0 && blockIdx.x < n_tiles) issue_tile2<R, CT, SINGLE>(A, S, sm, 0, i_begin + blockIdx.x * TILE);
     bool tables_ready = false;
 
-    static_assert(kStages2 == 2 || kStages2 == 4, "ring position is derived from the tile counter");
+    constexpr int NST = Smem::STAGES;
+    static_assert(NST == 1 || NST == 2 || NST == 4, "ring position is derived from the tile counter");
     unsigned it = 0;
     for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const unsigned stage = it & (kStages2 - 1), phase = (it / kStages2) & 1u;   // nothing ring-related stays live across the K loop
+        const unsigned stage = it & (NST - 1), phase = (it / NST) & 1u;   // nothing ring-related stays live across the K loop
         const unsigned base = i_begin + tile * TILE;
         R x[2][9], a_in[2], ret[2];
         int ep_len[2], ref_idx[2];
         mbar_wait(&sm->bar_in[stage], phase);
         if (it == 0 && t == 0) {   // the rest of the opening burst goes out once the first tile has landed
 #pragma unroll
-            for (int s = 1; s < kStages2; ++s) {
+            for (int s = 1; s < NST; ++s) {
                 const unsigned ts = tile + s * gridDim.x;
                 if (ts < n_tiles) issue_tile2<R, CT, SINGLE>(A, S, sm, s, i_begin + ts * TILE);
             }
@@ -671,7 +677,7 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
             asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(prior) : "r"(smem_u32(&sm->drained[stage])) : "memory");
             if (prior == CT / 32 - 1) {
                 sm->drained[stage] = 0;
-                const unsigned next = tile + kStages2 * gridDim.x;
+                const unsigned next = tile + NST * gridDim.x;
                 if (next < n_tiles) issue_tile2<R, CT, SINGLE>(A, S, sm, stage, i_begin + next * TILE);
             }
         }

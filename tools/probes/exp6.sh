@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-for v in f16-model_b200/lib; do
+for v in f16-model_b200/lib f16-model_b200/lib_k1; do
 for rep in 1 2; do
 F16B200_LIB=$PWD/$v/libf16b200.so timeout 300 python bench.py --no-cpu --no-e2e 2>/dev/null | python -c "
 import sys, json
