@@ -133,6 +133,8 @@ int f16_env_step(const f16_config *cfg, const f16_env_buffers *env, const f16_st
  *       done to host memory -- one launch, transfers overlapped with the arithmetic tile by tile;
  *   F16_HOST_ROUTE_STAGED     otherwise: H2D of actions, kernel, D2H of obs/reward/done, chunked and
  *       double-buffered over internal streams.
+ * Both routes run on the library's own streams: work the caller has queued on other streams against the env's
+ * buffers (a reset, a device-side step) must have completed before the call.
  * f16_host_route() names the route the calling thread's last f16_env_step_host took. */
 enum { F16_HOST_ROUTE_STAGED = 0, F16_HOST_ROUTE_ZERO_COPY = 1 };
 int f16_env_step_host(const f16_config *cfg, const f16_env_buffers *env, const void *actions_host, void *obs_host,
