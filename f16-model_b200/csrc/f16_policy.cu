@@ -9,22 +9,17 @@
 //   handles the actor columns, the other the critic columns.
 //   layer 1:  D1[128 x 128] = X[128 x 8] * W1cat^T      one tcgen05.mma (M=128, N=128, K=8, kind::tf32);
 //             W1cat stacks actor (rows 0-63) and critic (rows 64-127), K is 5 padded to 8
-//   layer 2:  D2[:, 0:64]   = H1[:, 0:64]   * W2actor^T  four tcgen05.mma (kind::f16, K=64 in steps of 16)
-//             D2[:, 64:128] = H1[:, 64:128] * W2critic^T four more; D2 reuses D1's TMEM columns
+//   layer 2:  D2[:, 0:64]   = H1[:, 0:64]   * W2actor^T  eight tcgen05.mma (K=64 in steps of 8)
+//             D2[:, 64:128] = H1[:, 64:128] * W2critic^T eight more
 //   layer 3:  64-term dot products in the epilogue (CUDA cores), fused with the Gaussian policy
 //             sample / log-probability.
 //
-// Operands live in shared memory in the canonical K-major no-swizzle layout: the 16-byte K-chunk c of row r sits at
-// c * LBO + (r / 8) * 128 + (r % 8) * 16 bytes, LBO = rows * 16.  X and W1 are fp32 consumed as TF32; H1 (a tanh
-// output, |h| < 1) and W2 are fp16 -- the same 11 significant bits as TF32 at half the bytes.  Thread t writes its own
-// row chunk by chunk (consecutive threads -> consecutive 16 B: conflict-free).  Accumulators are fp32 in TMEM, read
-// back with tcgen05.ld (32 lanes x 32 columns per warp), tanh via MUFU.TANH.
-//
-// Sizing.  The kernel is latency-bound (a chain of load -> MMA -> TMEM read -> tanh -> MMA -> TMEM read per tile), so
-// what matters is tiles in flight per SM: 128 TMEM columns and 54 KB of shared memory per CTA (the X operand aliases the
-// H1 operand, the 22 KB weight blob is staged once per CTA by TMA) put FOUR CTAs on an SM -- the whole 512-column TMEM --
-// and the 512 tiles of a 65,536-env batch are all resident at once.  Launched with programmatic dependent launch: TMEM
-// allocation, barrier init and the weight copy overlap the tail of the env-step kernel that precedes it in a rollout.
+// Operands are fp32 in shared memory, consumed as TF32 (fp32 accumulate in TMEM); both are
+// K-major in the canonical no-swizzle layout: element (row r, 16-byte K-chunk c) lives at
+// c * LBO + (r / 8) * 128 + (r % 8) * 16 bytes, LBO = rows * 16.  Thread t writes its own row
+// chunk by chunk (consecutive threads -> consecutive 16 B: conflict-free).  Accumulators are read
+// back with tcgen05.ld (32 lanes x 32 columns per warp), tanh via MUFU.TANH.  The packed weight
+// blob (38 KB) is staged once per CTA with a TMA bulk copy; the grid is persistent over tiles.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -37,15 +32,12 @@ namespace {
 constexpr int kRows = 128;          // envs per tile == UMMA M
 constexpr int kThreads = 256;       // two threads per env row (actor half / critic half)
 constexpr int kHid = 64;
-constexpr uint32_t kTmemCols = 128;  // D1 = columns [0,128); D2 (actor [0,64) | critic [64,128)) overwrites it
-constexpr int kCtasPerSm = 4;        // 4 x 128 TMEM columns, 4 x 54 KB shared memory, 4 x 256 threads x 64 registers
+constexpr uint32_t kTmemCols = 256;  // D1: columns [0,128), D2: columns [128,256)
 
 struct alignas(16) PolicySmem {
     PolicyBlob w;                    // staged weights (canonical UMMA layouts inside)
-    union {
-        float a1[2][kRows][4];       // X  : 2 K-chunks  x 128 rows x 4 floats (consumed by the layer-1 MMA before H1 is written)
-        __half a2[16][kRows][8];     // H1 : 16 K-chunks x 128 rows x 8 halfs (actor chunks 0-7 | critic 8-15)
-    } op;
+    float a1[2][kRows][4];           // X  : 2 K-chunks  x 128 rows x 4 floats
+    float a2[32][kRows][4];          // H1 : 32 K-chunks x 128 rows x 4 floats (actor 0-15 | critic 16-31)
     uint64_t bar_w;                  // weights landed
     uint64_t bar_mma;                // tcgen05.commit target
     uint32_t tmem_base;
@@ -85,11 +77,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
 {
     return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
-// same with A = B = f16 (format code 0), for kind::f16
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N)
-{
-    return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
-}
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
@@ -97,16 +84,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -156,7 +133,7 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key)
     return ctr;
 }
 
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) policy_forward_kernel(const PolicyArgs P)
+__global__ void __launch_bounds__(kThreads, 2) policy_forward_kernel(const PolicyArgs P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PolicySmem *sm = reinterpret_cast<PolicySmem *>(smem_raw);
@@ -176,21 +153,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) policy_forward_kernel(co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sm->tmem_base;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    if (t == 0) {   // weights: one TMA bulk copy per CTA (they are never written by a kernel: safe ahead of the dependency)
+    if (t == 0) {   // weights: one TMA bulk copy per CTA
         constexpr uint32_t bytes = static_cast<uint32_t>(sizeof(PolicyBlob));
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->bar_w)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&sm->w)),
                      "l"(P.blob), "r"(bytes), "r"(smem_u32(&sm->bar_w))
                      : "memory");
     }
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // the observations (and env counters) come from the previous kernel
     mbar_wait(&sm->bar_w, 0);
 
     constexpr uint32_t idesc1 = umma_idesc_tf32(128, 128);
-    constexpr uint32_t idesc2 = umma_idesc_f16(128, 64);
-    const uint32_t a1 = smem_u32(sm->op.a1), a2 = smem_u32(sm->op.a2);
+    constexpr uint32_t idesc2 = umma_idesc_tf32(128, 64);
+    const uint32_t a1 = smem_u32(sm->a1), a2 = smem_u32(sm->a2);
     const uint32_t w1 = smem_u32(sm->w.w1), w2a = smem_u32(sm->w.w2[0]), w2c = smem_u32(sm->w.w2[1]);
     const uint32_t lane_base = tmem + (((warp & 3u) * 32u) << 16);   // this warp's 32 TMEM lanes (quarter = warp % 4)
     uint32_t phase = 0;
@@ -201,8 +176,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) policy_forward_kernel(co
     const float log_std = P.logstd ? P.logstd[0] : 0.f;
 
     // Two threads per env row: thread (row, half) with half 0 = actor columns, half 1 = critic columns.  That
-    // halves every thread's epilogue and doubles the resident warps; TMEM lanes are reachable from warps w and
-    // w + 4 alike (lane quarter = w % 4).
+    // halves every thread's epilogue and doubles the resident warps (16 per SM), which is what this
+    // latency-bound kernel needs; TMEM lanes are reachable from warps w and w + 4 alike (lane quarter = w % 4).
     const unsigned row = t & (kRows - 1), half = t >> 7;
     for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const unsigned i = tile * kRows + row;
@@ -214,9 +189,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) policy_forward_kernel(co
                 const float *src = P.obs + static_cast<size_t>(i) * 5;
                 c0 = make_float4(src[0], src[1], src[2], src[3]);
             }
-            *reinterpret_cast<float4 *>(sm->op.a1[0][row]) = c0;
+            *reinterpret_cast<float4 *>(sm->a1[0][row]) = c0;
         } else {
-            *reinterpret_cast<float4 *>(sm->op.a1[1][row]) = make_float4(live ? P.obs[static_cast<size_t>(i) * 5 + 4] : 0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4 *>(sm->a1[1][row]) = make_float4(live ? P.obs[static_cast<size_t>(i) * 5 + 4] : 0.f, 0.f, 0.f, 0.f);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -230,37 +205,37 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) policy_forward_kernel(co
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        // ---- hidden layer 1: tanh(D1 + b1) -> fp16 layer-2 operand (overwrites X, which the MMA has consumed) ----
+        // ---- hidden layer 1: tanh(D1 + b1) -> layer-2 operand (same canonical layout) ----------
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
             float v[32];
             const int col0 = half * 64 + blk * 32;
             tmem_ld32(lane_base + col0, v);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {   // 8 columns = one 16-byte K-chunk of halfs
-                const int j = col0 + c * 8;
-                __half2 h[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    h[q] = __floats2half2_rn(fast_tanh(v[c * 8 + 2 * q] + sm->w.b1[j + 2 * q]),
-                                             fast_tanh(v[c * 8 + 2 * q + 1] + sm->w.b1[j + 2 * q + 1]));
-                *reinterpret_cast<uint4 *>(sm->op.a2[j >> 3][row]) = *reinterpret_cast<const uint4 *>(h);
+            for (int c = 0; c < 8; ++c) {
+                const int j = col0 + c * 4;
+                float4 h;
+                h.x = fast_tanh(v[c * 4 + 0] + sm->w.b1[j + 0]);
+                h.y = fast_tanh(v[c * 4 + 1] + sm->w.b1[j + 1]);
+                h.z = fast_tanh(v[c * 4 + 2] + sm->w.b1[j + 2]);
+                h.w = fast_tanh(v[c * 4 + 3] + sm->w.b1[j + 3]);
+                *reinterpret_cast<float4 *>(sm->a2[j >> 2][row]) = h;
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // every thread has read its D1 columns: D2 may overwrite them
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (t == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {   // actor: K-chunks 0..7, two (K = 16) per MMA
-                umma_f16(tmem + 0, umma_desc(a2 + k * 2 * kRows * 16, kRows * 16, 128), umma_desc(w2a + k * 2 * kHid * 16, kHid * 16, 128),
-                         idesc2, k > 0 ? 1u : 0u);
+            for (int k = 0; k < 8; ++k) {   // actor: K-chunks 0..15, two per MMA
+                umma_tf32(tmem + 128, umma_desc(a2 + k * 2 * kRows * 16, kRows * 16, 128),
+                          umma_desc(w2a + k * 2 * kHid * 16, kHid * 16, 128), idesc2, k > 0 ? 1u : 0u);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {   // critic: K-chunks 8..15
-                umma_f16(tmem + 64, umma_desc(a2 + (8 + k * 2) * kRows * 16, kRows * 16, 128),
-                         umma_desc(w2c + k * 2 * kHid * 16, kHid * 16, 128), idesc2, k > 0 ? 1u : 0u);
+            for (int k = 0; k < 8; ++k) {   // critic: K-chunks 16..31
+                umma_tf32(tmem + 192, umma_desc(a2 + (16 + k * 2) * kRows * 16, kRows * 16, 128),
+                          umma_desc(w2c + k * 2 * kHid * 16, kHid * 16, 128), idesc2, k > 0 ? 1u : 0u);
             }
             umma_commit(&sm->bar_mma);
         }
@@ -274,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) policy_forward_kernel(co
         for (int blk = 0; blk < 2; ++blk) {
             float v[32];
             const int col0 = half * 64 + blk * 32;
-            tmem_ld32(lane_base + col0, v);
+            tmem_ld32(lane_base + 128 + col0, v);
             float acc = 0.f;
 #pragma unroll
             for (int c = 0; c < 32; ++c) acc = fmaf(fast_tanh(v[c] + sm->w.b2[col0 + c]), sm->w.w3[col0 + c], acc);
@@ -352,38 +327,21 @@ cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *valu
 
 size_t policy_smem_bytes() { return sizeof(PolicySmem); }
 
-cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, int pdl, cudaStream_t st)
+cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, cudaStream_t st)
 {
     static bool configured[64] = {};
-    static int resident[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (!configured[dev]) {
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(PolicySmem)));
         if (e != cudaSuccess) return e;
-        int b = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, policy_forward_kernel, kThreads, sizeof(PolicySmem));
-        if (e != cudaSuccess) return e;
-        // never more CTAs per SM than TMEM allocations fit (512 columns): an extra CTA would block in tcgen05.alloc
-        resident[dev] = b < 1 ? 1 : (b > kCtasPerSm ? kCtasPerSm : b);
         configured[dev] = true;
     }
     const int64_t tiles = (P.n + kRows - 1) / kRows;
-    const int64_t cap = static_cast<int64_t>(n_sm) * resident[dev];
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(static_cast<unsigned>(tiles < cap ? tiles : cap));
-    lc.blockDim = dim3(kThreads);
-    lc.dynamicSmemBytes = sizeof(PolicySmem);
-    lc.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = attr;
-    lc.numAttrs = pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&lc, policy_forward_kernel, P);
-    if (e != cudaSuccess) return e;
+    const int64_t cap = static_cast<int64_t>(n_sm) * 2;
+    const int grid = static_cast<int>(tiles < cap ? tiles : cap);
+    policy_forward_kernel<<<grid, kThreads, sizeof(PolicySmem), st>>>(P);
     return cudaGetLastError();
 }
 

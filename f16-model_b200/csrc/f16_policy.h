@@ -1,6 +1,5 @@
 // f16_policy.h -- packed weights and launch arguments of the tensor-core policy forward.
 #pragma once
-#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstddef>
@@ -10,12 +9,10 @@ namespace f16 {
 
 // Weights of actor_mean and critic (control/ppo/ppo_model_gsde.py:37-52: Linear(5,64) Tanh
 // Linear(64,64) Tanh Linear(64,1) each), pre-arranged in the tensor core's canonical K-major
-// no-swizzle layout: [16-byte K-chunk][output row][16 bytes].  Layer 1 is TF32 (4 floats per chunk); layer 2 is
-// fp16 (8 halfs per chunk): its A operand is tanh output in (-1, 1), where fp16 carries the same 11 significant
-// bits as TF32, and halving the operand bytes is what lets four CTAs share an SM.  Packed by policy.py.
+// no-swizzle layout: [16-byte K-chunk][output row][4 floats].  Packed by policy.py.
 struct alignas(16) PolicyBlob {
     float w1[2][128][4];      // rows 0-63 actor, 64-127 critic; K = 5 inputs padded to 8
-    __half w2[2][8][64][8];   // [actor|critic][K-chunk][row][8]
+    float w2[2][16][64][4];   // [actor|critic][K-chunk][row][4]
     float b1[128];            // actor | critic
     float b2[128];
     float w3[128];            // output layer weights, actor | critic
@@ -42,6 +39,6 @@ struct PolicyArgs {
 cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *values, const uint8_t *done_after, const float *next_value,
                        float gamma, float lam, float *advantages, float *returns, int n_sm, cudaStream_t st);
 size_t policy_smem_bytes();
-cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, int pdl, cudaStream_t st);
+cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, cudaStream_t st);
 
 }  // namespace f16

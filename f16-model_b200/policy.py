@@ -23,8 +23,7 @@ def _layer_init(layer, std=math.sqrt(2), bias_const=0.0):
 
 def pack_policy_blob(actor, critic, out=None):
     """Arrange the six Linear layers of (actor, critic) in the kernel's layout (csrc/f16_policy.h,
-    ``PolicyBlob``): K-major 16-byte chunks ``[chunk][row][16 B]`` for the two tensor-core layers (layer 1 fp32
-    consumed as TF32, layer 2 fp16)."""
+    ``PolicyBlob``): K-major 16-byte chunks ``[chunk][row][4]`` for the two tensor-core layers."""
     import torch
 
     la = [m for m in actor if isinstance(m, torch.nn.Linear)]
@@ -35,9 +34,8 @@ def pack_policy_blob(actor, critic, out=None):
         w1[:64, :5] = la[0].weight
         w1[64:, :5] = lc[0].weight
         w1p = w1.reshape(128, 2, 4).permute(1, 0, 2).contiguous()                    # [chunk][row][4]
-        w2 = torch.stack([la[1].weight, lc[1].weight]).to(torch.float16)             # [2][64 out][64 in], fp16 operand
-        w2p = w2.reshape(2, 64, 8, 8).permute(0, 2, 1, 3).contiguous()               # [net][chunk][row][8 halfs]
-        w2p = w2p.reshape(-1).view(torch.float32)                                    # the blob is carried as fp32 words
+        w2 = torch.stack([la[1].weight, lc[1].weight])                               # [2][64 out][64 in]
+        w2p = w2.reshape(2, 64, 16, 4).permute(0, 2, 1, 3).contiguous()              # [net][chunk][row][4]
         b1 = torch.cat([la[0].bias, lc[0].bias])
         b2 = torch.cat([la[1].bias, lc[1].bias])
         w3 = torch.cat([la[2].weight.reshape(-1), lc[2].weight.reshape(-1)])
