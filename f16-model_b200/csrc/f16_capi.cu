@@ -599,7 +599,7 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
     P.episode_no = episode_no;
     P.seed = seed;
     P.id_base = env_id_base;
-    CUDA_TRY(f16::launch_policy_forward(P, c->n_sm, static_cast<cudaStream_t>(stream)));
+    CUDA_TRY(f16::launch_policy_forward(P, c->n_sm, geom(*c, F16_F32, true, true).pdl, static_cast<cudaStream_t>(stream)));
     return F16_OK;
 }
 

@@ -153,14 +153,16 @@ __global__ void __launch_bounds__(kThreads, 2) policy_forward_kernel(const Polic
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sm->tmem_base;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    if (t == 0) {   // weights: one TMA bulk copy per CTA
+    if (t == 0) {   // weights: one TMA bulk copy per CTA (no kernel writes them: safe ahead of the grid dependency)
         constexpr uint32_t bytes = static_cast<uint32_t>(sizeof(PolicyBlob));
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->bar_w)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&sm->w)),
                      "l"(P.blob), "r"(bytes), "r"(smem_u32(&sm->bar_w))
                      : "memory");
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the observations and env counters come from the previous kernel
     mbar_wait(&sm->bar_w, 0);
 
     constexpr uint32_t idesc1 = umma_idesc_tf32(128, 128);
@@ -327,7 +329,7 @@ cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *valu
 
 size_t policy_smem_bytes() { return sizeof(PolicySmem); }
 
-cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, cudaStream_t st)
+cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, int pdl, cudaStream_t st)
 {
     static bool configured[64] = {};
     int dev = 0;
@@ -339,9 +341,21 @@ cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, cudaStream_t st
         configured[dev] = true;
     }
     const int64_t tiles = (P.n + kRows - 1) / kRows;
-    const int64_t cap = static_cast<int64_t>(n_sm) * 2;
-    const int grid = static_cast<int>(tiles < cap ? tiles : cap);
-    policy_forward_kernel<<<grid, kThreads, sizeof(PolicySmem), st>>>(P);
+    const int64_t cap = static_cast<int64_t>(n_sm) * 2;   // 2 CTAs per SM: 2 x 256 TMEM columns, 2 x 106 KB shared memory
+    // programmatic dependent launch: TMEM allocation, barrier init and the weight copy overlap the tail of the
+    // env-step kernel that precedes this one in a rollout
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(static_cast<unsigned>(tiles < cap ? tiles : cap));
+    lc.blockDim = dim3(kThreads);
+    lc.dynamicSmemBytes = sizeof(PolicySmem);
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&lc, policy_forward_kernel, P);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

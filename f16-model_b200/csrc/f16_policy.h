@@ -39,6 +39,6 @@ struct PolicyArgs {
 cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *values, const uint8_t *done_after, const float *next_value,
                        float gamma, float lam, float *advantages, float *returns, int n_sm, cudaStream_t st);
 size_t policy_smem_bytes();
-cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, cudaStream_t st);
+cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, int pdl, cudaStream_t st);
 
 }  // namespace f16

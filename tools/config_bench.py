@@ -49,20 +49,32 @@ def main():
                           "minibatches_per_update": cfg.num_minibatches * cfg.update_epochs, "value_loss": h["value_loss"],
                           "approx_kl": h["approx_kl"]}), flush=True)
 
-    # policy forward alone (tensor-core kernel), CUDA events
+    # policy forward alone (tensor-core kernel): CUDA events around replays of a graph of 20 launches (an eager Python
+    # loop is bound by the interpreter + ctypes call, ~20 us per launch, not by the kernel)
     obs = torch.rand((args.envs, 5), device=dev) * 2 - 1
-    for _ in range(5):
+    for _ in range(3):
         pol.act(obs, step=0)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph):
+            for k in range(20):
+                keep = pol.act(obs, step=k)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(2):
+        graph.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
     e0.record()
-    for k in range(50):
-        pol.act(obs, step=k)
+    for _ in range(10):
+        graph.replay()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 50
+    ms = e0.elapsed_time(e1) / 200
     flops = 2 * (8 * 128 + 2 * 64 * 64) * args.envs          # tensor-core MACs actually issued (K padded to 8)
     if rank == 0:
-        print(json.dumps({"kernel": "policy_forward_kernel (tcgen05 tf32)", "envs": args.envs, "us_per_launch": ms * 1e3,
+        print(json.dumps({"kernel": "policy_forward_kernel (tcgen05 tf32), graph of 20 launches", "envs": args.envs, "us_per_launch": ms * 1e3,
                           "envs_per_s": args.envs / (ms * 1e-3), "tensor_tflops": flops / (ms * 1e-3) / 1e12}), flush=True)
 
     # ---- config 5b --------------------------------------------------------------------------
