@@ -21,6 +21,59 @@ def _layer_init(layer, std=math.sqrt(2), bias_const=0.0):
     return layer
 
 
+_split_linear_cls = None
+
+
+def split_k_linear(x, weight, bias, min_rows=8192):
+    """``F.linear(x, weight, bias)`` whose backward computes the weight / bias gradients as a split-K reduction.
+
+    The PPO update multiplies ``[64, B] x [B, 64]`` with B = 262,144 rows per minibatch: cuBLAS runs that skinny
+    product as a 2-CTA SIMT GEMM (280 us, 40 % of the update) and torch's column-sum bias gradient takes 80 us.
+    Splitting the batch into S slices -- ``bmm([S, out, B/S], [S, B/S, in]).sum(0)`` and ``g.view(S, B/S, out).sum(1).sum(0)``
+    -- fills the GPU with S independent products in the same fp32 arithmetic (only the summation order changes)."""
+    global _split_linear_cls
+    import torch
+
+    if _split_linear_cls is None:
+        class _SplitKLinear(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x, weight, bias, slices):
+                ctx.save_for_backward(x, weight)
+                ctx.slices = slices
+                return torch.addmm(bias, x, weight.t())
+
+            @staticmethod
+            def backward(ctx, g):
+                x, weight = ctx.saved_tensors
+                S, B = ctx.slices, x.shape[0]
+                g = g.contiguous()
+                gs = g.view(S, B // S, g.shape[1])
+                gx = g @ weight if ctx.needs_input_grad[0] else None
+                gw = torch.bmm(gs.transpose(1, 2), x.view(S, B // S, x.shape[1])).sum(0)
+                gb = gs.sum(1).sum(0)
+                return gx, gw, gb, None
+
+        _split_linear_cls = _SplitKLinear
+    B = x.shape[0]
+    if x.dim() != 2 or B < min_rows or not x.is_contiguous():
+        return torch.nn.functional.linear(x, weight, bias)
+    slices = 1
+    while slices < 512 and B % (2 * slices) == 0 and B // (2 * slices) >= 256:
+        slices *= 2
+    if slices == 1:
+        return torch.nn.functional.linear(x, weight, bias)
+    return _split_linear_cls.apply(x, weight, bias, slices)
+
+
+def mlp_forward(net, x):
+    """``net(x)`` for a Sequential of Linear / Tanh layers, through ``split_k_linear``."""
+    import torch
+
+    for m in net:
+        x = split_k_linear(x, m.weight, m.bias) if isinstance(m, torch.nn.Linear) else m(x)
+    return x
+
+
 def pack_policy_blob(actor, critic, out=None):
     """Arrange the six Linear layers of (actor, critic) in the kernel's layout (csrc/f16_policy.h,
     ``PolicyBlob``): K-major 16-byte chunks ``[chunk][row][4]`` for the two tensor-core layers."""
@@ -126,9 +179,9 @@ class TensorCorePolicy:
     def evaluate(self, obs, action):
         """(logprob, entropy, value) of given actions, differentiable (ppo_model_gsde.py:81-99)."""
         torch = self._torch
-        mean = self.actor_mean(obs).squeeze(-1)
+        mean = mlp_forward(self.actor_mean, obs).squeeze(-1)
         logstd = self.actor_logstd.expand_as(mean)
         std = torch.exp(logstd)
         logprob = -0.5 * ((action - mean) / std) ** 2 - logstd - 0.5 * math.log(2 * math.pi)
         entropy = 0.5 + 0.5 * math.log(2 * math.pi) + logstd
-        return logprob, entropy, self.critic(obs).squeeze(-1)
+        return logprob, entropy, mlp_forward(self.critic, obs).squeeze(-1)

@@ -35,6 +35,7 @@ class PPOConfig:
     target_kl: float = None
     reset_every_update: bool = True      # the reference re-resets the envs at every update (:210)
     use_cuda_graph: bool = True          # replay the whole rollout (2 kernels per step) from one CUDA graph
+    tf32_update: bool = False            # run the update's matmuls on the TF32 tensor cores (default: torch's fp32)
 
 
 def gae(rewards, values, done_after, next_value, gamma, gae_lambda):
@@ -225,6 +226,15 @@ class PPOTrainer:
         return graph
 
     def update(self, advantages, returns):
+        torch, cfg = self._torch, self.cfg
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(cfg.tf32_update)
+        try:
+            return self._update(advantages, returns)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+
+    def _update(self, advantages, returns):
         torch, cfg = self._torch, self.cfg
         self._prepare_update(advantages, returns)
         use_graph = cfg.use_cuda_graph and self.world == 1

@@ -188,3 +188,24 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in text.lower() or fn == "f16_tables_data.h", f"{fn} mentions the oracle"
+
+
+def test_split_k_linear_gradients_match_plain_linear():
+    """The split-K backward of the PPO update's Linear layers is the same fp32 arithmetic in another summation order."""
+    import torch
+
+    import f16_model_b200.policy as pol   # importing the module needs neither a GPU nor a loaded library
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh(), torch.nn.Linear(64, 1))
+    x = torch.rand(16384, 5) * 2 - 1
+    tgt = torch.randn(16384)
+    loss_a = ((net(x).squeeze(-1) - tgt) ** 2).mean()
+    ga = torch.autograd.grad(loss_a, list(net.parameters()))
+    out_b = pol.mlp_forward(net, x).squeeze(-1)
+    loss_b = ((out_b - tgt) ** 2).mean()
+    gb = torch.autograd.grad(loss_b, list(net.parameters()))
+    assert torch.allclose(loss_a, loss_b, rtol=1e-6)
+    for a, b in zip(ga, gb):
+        assert torch.allclose(a, b, rtol=2e-4, atol=1e-7), (a - b).abs().max().item()
+    # small or ragged batches fall back to F.linear
+    assert pol.split_k_linear(x[:100], net[0].weight, net[0].bias).shape == (100, 64)

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--learn-updates", type=int, default=0)
     ap.add_argument("--envs", type=int, default=65536)
     ap.add_argument("--num-steps", type=int, default=128)
+    ap.add_argument("--tf32-update", type=int, default=0)
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -39,7 +40,7 @@ def main():
     # ---- config 4 -------------------------------------------------------------------------
     envs = make_sharded_env(CFG, args.envs * world, rank, world, dev, seed=1, fast_math=True)
     pol = f16.TensorCorePolicy(device=dev, seed=1, logstd_init=-1.0, env_id_base=shard_range(args.envs * world, rank, world)[0])
-    cfg = f16.PPOConfig(num_steps=args.num_steps, num_minibatches=32, update_epochs=4)
+    cfg = f16.PPOConfig(num_steps=args.num_steps, num_minibatches=32, update_epochs=4, tf32_update=bool(args.tf32_update))
     tr = f16.PPOTrainer(envs, pol, cfg)
     hist = tr.train(num_updates=args.updates)
     if rank == 0:
