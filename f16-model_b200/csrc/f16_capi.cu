@@ -603,6 +603,43 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
     return F16_OK;
 }
 
+int f16_ppo_train_blob_bytes(void) { return static_cast<int>(sizeof(f16::TrainBlob)); }
+int f16_ppo_grad_floats(void) { return static_cast<int>(sizeof(f16::PolicyGrad) / sizeof(float)); }
+
+int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void *actions, const void *logprobs, const void *adv,
+                 const void *ret, const void *val, const int64_t *mb_idx, const void *logstd, const void *adv_stats, void *grad,
+                 double clip_coef, double vf_coef, double ent_coef, int norm_adv, int clip_vloss, void *stream)
+{
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(n, &c, &g);
+    if (rc) return rc;
+    if (!train_blob || !obs || !actions || !logprobs || !adv || !ret || !val || !mb_idx || !logstd || !grad)
+        return fail(F16_EINVAL, "NULL pointer");
+    if (norm_adv && !adv_stats) return fail(F16_EINVAL, "norm_adv needs adv_stats (mean, std of the minibatch advantages)");
+    if (reinterpret_cast<uintptr_t>(train_blob) % 16 != 0) return fail(F16_EINVAL, "train_blob must be 16-byte aligned");
+    f16::PpoGradArgs P;
+    P.blob = static_cast<const f16::TrainBlob *>(train_blob);
+    P.obs = static_cast<const float *>(obs);
+    P.actions = static_cast<const float *>(actions);
+    P.logprobs = static_cast<const float *>(logprobs);
+    P.adv = static_cast<const float *>(adv);
+    P.ret = static_cast<const float *>(ret);
+    P.val = static_cast<const float *>(val);
+    P.mb_idx = mb_idx;
+    P.logstd = static_cast<const float *>(logstd);
+    P.adv_stats = static_cast<const float *>(adv_stats);
+    P.grad = static_cast<f16::PolicyGrad *>(grad);
+    P.n = n;
+    P.clip_coef = static_cast<float>(clip_coef);
+    P.vf_coef = static_cast<float>(vf_coef);
+    P.ent_coef = static_cast<float>(ent_coef);
+    P.norm_adv = norm_adv;
+    P.clip_vloss = clip_vloss;
+    CUDA_TRY(f16::launch_ppo_grad(P, c->n_sm, static_cast<cudaStream_t>(stream)));
+    return F16_OK;
+}
+
 int f16_gae(int T, int64_t n, const void *rewards, const void *values, const uint8_t *done_after, const void *next_value, double gamma,
             double gae_lambda, void *advantages, void *returns, void *stream)
 {

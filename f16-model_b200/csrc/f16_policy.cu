@@ -290,6 +290,382 @@ __global__ void __launch_bounds__(kThreads, 2) policy_forward_kernel(const Polic
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
 }
 
+
+// ---------------------------------------------------------------------------
+// Fused PPO minibatch gradient: one launch = forward of actor_mean and critic on the minibatch rows, the clipped-PPO
+// loss of Agent.train (control/ppo/ppo_model_gsde.py:303-364: ratio clipping, clipped value loss, entropy bonus,
+// advantage normalisation), and the backward pass of both MLPs -- nothing but the 9.3 k gradient floats leaves the SM.
+//
+//   tile = 128 minibatch rows, one CTA of 256 threads: thread (row, half), half 0 = actor, 1 = critic.
+//   tensor cores (tcgen05, TF32, fp32 accumulate in TMEM):
+//       D1 = X  * W1cat^T                 (layer 1, as in the rollout kernel)
+//       D2 = H1 * W2^T       per net      (layer 2)
+//       D3 = dZ2 * W2        per net      (backward data: B operand = W2^T, K-major over the OUTPUT features)
+//   CUDA cores: tanh, heads, loss and its derivative per row, dZ2 = dy w3 (1 - H2^2), dZ1 = D3 (1 - H1^2), and the
+//   weight gradients -- dW2 += dZ2^T H1 as register-tiled outer products (thread = 4 x 8 patch of one net's 64 x 64,
+//   rows streamed from the shared-memory operands the MMAs already use; it runs while D3 is in flight), dW1 likewise,
+//   dW3 / biases as per-thread partial sums reduced through shared memory once per CTA.  Gradients are accumulated over
+//   the CTA's tiles in registers and added to global memory with one atomic per element per CTA.
+//   H1 and dZ2 are kept in fp32 in the canonical K-major layout with a padded chunk stride (LBO = 2048 + 16 bytes), so the
+//   strided reads of the outer-product loop do not collide in the banks.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kLbo2 = kRows * 16 + 16;   // bytes between K-chunks of the H1 / dZ operands
+
+struct alignas(16) TrainSmem {
+    TrainBlob w;
+    float a1[2][kRows][4];            // X, K-major
+    unsigned char a2[32 * kLbo2];     // H1   [chunk j/4][row][4 floats], padded chunk stride
+    unsigned char d2[32 * kLbo2];     // dZ2, later dZ1, same layout; scratch for the final reductions
+    uint64_t bar_w;
+    uint64_t bar_mma;
+    uint32_t tmem_base;
+    float red[16];
+};
+
+__device__ __forceinline__ float *opnd(unsigned char *base, unsigned chunk, unsigned row)
+{
+    return reinterpret_cast<float *>(base + chunk * kLbo2 + row * 16u);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(const PpoGradArgs P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TrainSmem *sm = reinterpret_cast<TrainSmem *>(smem_raw);
+    const unsigned t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+
+    if (t == 0) {
+        mbar_init(&sm->bar_w, 1);
+        mbar_init(&sm->bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (t < 16) sm->red[t] = 0.f;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "n"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = sm->tmem_base;
+    if (t == 0) {
+        constexpr uint32_t bytes = static_cast<uint32_t>(sizeof(TrainBlob));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->bar_w)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&sm->w)),
+                     "l"(P.blob), "r"(bytes), "r"(smem_u32(&sm->bar_w))
+                     : "memory");
+    }
+    mbar_wait(&sm->bar_w, 0);
+
+    const PolicyBlob &W = sm->w.fwd;
+    constexpr uint32_t idesc1 = umma_idesc_tf32(128, 128);
+    constexpr uint32_t idesc2 = umma_idesc_tf32(128, 64);
+    const uint32_t a1 = smem_u32(sm->a1), a2 = smem_u32(sm->a2), d2 = smem_u32(sm->d2);
+    const uint32_t w1 = smem_u32(W.w1), w2a = smem_u32(W.w2[0]), w2c = smem_u32(W.w2[1]);
+    const uint32_t w2ta = smem_u32(sm->w.w2t[0]), w2tc = smem_u32(sm->w.w2t[1]);
+    const uint32_t lane_base = tmem + (((warp & 3u) * 32u) << 16);
+    uint32_t phase = 0;
+
+    const unsigned n = static_cast<unsigned>(P.n);
+    const unsigned n_tiles = (n + kRows - 1) / kRows;
+    const float inv_n = 1.0f / static_cast<float>(n);
+    const float log_std = P.logstd[0], inv_std = __expf(-log_std);
+    const float adv_mean = P.norm_adv ? P.adv_stats[0] : 0.f;
+    const float adv_scale = P.norm_adv ? 1.0f / (P.adv_stats[1] + 1e-8f) : 1.f;
+    const float eps = P.clip_coef;
+    const unsigned row = t & (kRows - 1), half = t >> 7;
+
+    // accumulators that live across the CTA's tiles
+    float acc_w2[4][8];     // patch of dW2[net = half]: rows j = jb*4.., columns i in chunks {ib, ib + 8}
+    float acc_b2[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc_w3[64];       // this thread's rows only; reduced over the CTA at the end
+    float acc_b3 = 0.f, acc_logstd = 0.f;
+    float acc_w1[4] = {0.f, 0.f, 0.f, 0.f}, acc_b1 = 0.f;
+    float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f, st4 = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc_w2[a][b] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc_w3[c] = 0.f;
+    const unsigned jb = (t & 127u) >> 3, ib = t & 7u;      // dW2 patch of this thread
+    const unsigned j1 = t >> 1, kb = t & 1u;               // dW1: output feature j1 (0..127 = actor | critic), obs chunk kb
+
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned i = tile * kRows + row;
+        const bool live = i < n;
+        const int64_t src = live ? P.mb_idx[i] : 0;
+        // ---- gather: observation row -> layer-1 operand; the row's scalars for the loss ----
+        float s_a = 0.f, s_b = 0.f, s_c = 0.f;
+        if (half == 0) {
+            float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                const float *o = P.obs + src * 5;
+                c0 = make_float4(o[0], o[1], o[2], o[3]);
+                s_a = P.actions[src];
+                s_b = P.logprobs[src];
+                s_c = P.adv[src];
+            }
+            *reinterpret_cast<float4 *>(sm->a1[0][row]) = c0;
+        } else {
+            float o4 = 0.f;
+            if (live) {
+                o4 = P.obs[src * 5 + 4];
+                s_a = P.ret[src];
+                s_b = P.val[src];
+            }
+            *reinterpret_cast<float4 *>(sm->a1[1][row]) = make_float4(o4, 0.f, 0.f, 0.f);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (t == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            umma_tf32(tmem + 0, umma_desc(a1, kRows * 16, 128), umma_desc(w1, 128 * 16, 128), idesc1, 0u);
+            umma_commit(&sm->bar_mma);
+        }
+        mbar_wait(&sm->bar_mma, phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- H1 = tanh(D1 + b1) -> a2 ----
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            float v[32];
+            const int col0 = half * 64 + blk * 32;
+            tmem_ld32(lane_base + col0, v);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int j = col0 + c * 4;
+                float4 h;
+                h.x = fast_tanh(v[c * 4 + 0] + W.b1[j + 0]);
+                h.y = fast_tanh(v[c * 4 + 1] + W.b1[j + 1]);
+                h.z = fast_tanh(v[c * 4 + 2] + W.b1[j + 2]);
+                h.w = fast_tanh(v[c * 4 + 3] + W.b1[j + 3]);
+                *reinterpret_cast<float4 *>(opnd(sm->a2, j >> 2, row)) = h;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (t == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                umma_tf32(tmem + 128, umma_desc(a2 + k * 2 * kLbo2, kLbo2, 128), umma_desc(w2a + k * 2 * kHid * 16, kHid * 16, 128), idesc2,
+                          k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                umma_tf32(tmem + 192, umma_desc(a2 + (16 + k * 2) * kLbo2, kLbo2, 128), umma_desc(w2c + k * 2 * kHid * 16, kHid * 16, 128),
+                          idesc2, k > 0 ? 1u : 0u);
+            umma_commit(&sm->bar_mma);
+        }
+        mbar_wait(&sm->bar_mma, phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- H2 (registers), head ----
+        float h2[64];
+        float head = W.b3[half];
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            float v[32];
+            const int col0 = half * 64 + blk * 32;
+            tmem_ld32(lane_base + 128 + col0, v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float h = fast_tanh(v[c] + W.b2[col0 + c]);
+                h2[blk * 32 + c] = h;
+                head = fmaf(h, W.w3[col0 + c], head);
+            }
+        }
+
+        // ---- clipped-PPO loss and d loss / d head for this row ----
+        float dy = 0.f;
+        if (live) {
+            if (half == 0) {
+                const float z = (s_a - head) * inv_std;
+                const float newlp = -0.5f * z * z - log_std - 0.91893853320467274178f;
+                const float logratio = newlp - s_b;
+                const float ratio = __expf(logratio);
+                const float A = (s_c - adv_mean) * adv_scale;
+                const float lo = 1.0f - eps, hi = 1.0f + eps;
+                const float rc = fminf(fmaxf(ratio, lo), hi);
+                const float pg1 = -A * ratio, pg2 = -A * rc;
+                const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+                const float g_ratio = pg1 > pg2 ? -A : (pg2 > pg1 ? -A * in_range : -A * (0.5f + 0.5f * in_range));
+                const float g_lp = g_ratio * ratio * inv_n;
+                dy = g_lp * z * inv_std;
+                acc_logstd += g_lp * (z * z - 1.0f) - P.ent_coef * inv_n;
+                st0 -= logratio;
+                st1 += (ratio - 1.0f) - logratio;
+                st2 += fabsf(ratio - 1.0f) > eps ? 1.f : 0.f;
+                st4 += fmaxf(pg1, pg2);
+            } else {
+                const float du = head - s_a;
+                float g = du, vl = du * du;
+                if (P.clip_vloss) {
+                    const float dv = head - s_b;
+                    const float vc = s_b + fminf(fmaxf(dv, -eps), eps);
+                    const float dc = vc - s_a, vcl = dc * dc;
+                    const float in_range = (dv >= -eps && dv <= eps) ? 1.f : 0.f;
+                    g = vl > vcl ? du : (vcl > vl ? dc * in_range : 0.5f * du + 0.5f * dc * in_range);
+                    vl = fmaxf(vl, vcl);
+                }
+                dy = P.vf_coef * g * inv_n;
+                st3 += 0.5f * vl;
+            }
+        }
+        acc_b3 += dy;
+        // ---- dZ2 = dy * w3 * (1 - H2^2) -> d2; dW3 partial sums ----
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float4 g;
+            const int j = half * 64 + c * 4;
+            acc_w3[c * 4 + 0] = fmaf(dy, h2[c * 4 + 0], acc_w3[c * 4 + 0]);
+            acc_w3[c * 4 + 1] = fmaf(dy, h2[c * 4 + 1], acc_w3[c * 4 + 1]);
+            acc_w3[c * 4 + 2] = fmaf(dy, h2[c * 4 + 2], acc_w3[c * 4 + 2]);
+            acc_w3[c * 4 + 3] = fmaf(dy, h2[c * 4 + 3], acc_w3[c * 4 + 3]);
+            g.x = dy * W.w3[j + 0] * (1.0f - h2[c * 4 + 0] * h2[c * 4 + 0]);
+            g.y = dy * W.w3[j + 1] * (1.0f - h2[c * 4 + 1] * h2[c * 4 + 1]);
+            g.z = dy * W.w3[j + 2] * (1.0f - h2[c * 4 + 2] * h2[c * 4 + 2]);
+            g.w = dy * W.w3[j + 3] * (1.0f - h2[c * 4 + 3] * h2[c * 4 + 3]);
+            *reinterpret_cast<float4 *>(opnd(sm->d2, j >> 2, row)) = g;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // D1 has been read by everyone: D3 may overwrite it
+        __syncthreads();
+        if (t == 0) {   // D3 = dZ2 * W2 (per net), into D1's columns
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                umma_tf32(tmem + 0, umma_desc(d2 + k * 2 * kLbo2, kLbo2, 128), umma_desc(w2ta + k * 2 * kHid * 16, kHid * 16, 128), idesc2,
+                          k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                umma_tf32(tmem + 64, umma_desc(d2 + (16 + k * 2) * kLbo2, kLbo2, 128), umma_desc(w2tc + k * 2 * kHid * 16, kHid * 16, 128),
+                          idesc2, k > 0 ? 1u : 0u);
+            umma_commit(&sm->bar_mma);
+        }
+        // ---- while D3 is in flight: dW2[net][j][i] += sum_r dZ2[r][j] * H1[r][i] (outer products on the CUDA cores) ----
+        {
+            const unsigned cg = half * 16 + jb;                 // dZ2 chunk holding j = jb*4 .. jb*4+3 of this net
+            const unsigned ch0 = half * 16 + ib, ch1 = ch0 + 8;  // H1 chunks: i = ib*4 .. +3 and 32 + ib*4 .. +3
+#pragma unroll 4
+            for (unsigned r = 0; r < kRows; ++r) {
+                const float4 g = *reinterpret_cast<const float4 *>(opnd(sm->d2, cg, r));
+                const float4 ha = *reinterpret_cast<const float4 *>(opnd(sm->a2, ch0, r));
+                const float4 hb = *reinterpret_cast<const float4 *>(opnd(sm->a2, ch1, r));
+                const float gv[4] = {g.x, g.y, g.z, g.w};
+                const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) acc_w2[a][b] = fmaf(gv[a], hv[b], acc_w2[a][b]);
+                }
+                if (ib == 0) {
+                    acc_b2[0] += g.x;
+                    acc_b2[1] += g.y;
+                    acc_b2[2] += g.z;
+                    acc_b2[3] += g.w;
+                }
+            }
+        }
+        mbar_wait(&sm->bar_mma, phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        __syncthreads();   // every thread has finished reading dZ2: d2 may be overwritten with dZ1
+
+        // ---- dZ1 = D3 * (1 - H1^2) -> d2 ----
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            float v[32];
+            const int col0 = half * 64 + blk * 32;
+            tmem_ld32(lane_base + col0, v);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int j = col0 + c * 4;
+                const float4 h = *reinterpret_cast<const float4 *>(opnd(sm->a2, j >> 2, row));
+                float4 g;
+                g.x = v[c * 4 + 0] * (1.0f - h.x * h.x);
+                g.y = v[c * 4 + 1] * (1.0f - h.y * h.y);
+                g.z = v[c * 4 + 2] * (1.0f - h.z * h.z);
+                g.w = v[c * 4 + 3] * (1.0f - h.w * h.w);
+                *reinterpret_cast<float4 *>(opnd(sm->d2, j >> 2, row)) = g;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // ---- dW1[j][k] += sum_r dZ1[r][j] * X[r][k]; db1[j] += sum_r dZ1[r][j] ----
+        {
+            const unsigned cj = j1 >> 2, ej = j1 & 3u;
+#pragma unroll 4
+            for (unsigned r = 0; r < kRows; ++r) {
+                const float dz = opnd(sm->d2, cj, r)[ej];
+                const float4 x = *reinterpret_cast<const float4 *>(sm->a1[kb][r]);
+                acc_w1[0] = fmaf(dz, x.x, acc_w1[0]);
+                acc_w1[1] = fmaf(dz, x.y, acc_w1[1]);
+                acc_w1[2] = fmaf(dz, x.z, acc_w1[2]);
+                acc_w1[3] = fmaf(dz, x.w, acc_w1[3]);
+                if (kb == 0) acc_b1 += dz;
+            }
+        }
+        __syncthreads();   // operands are rewritten by the next tile
+    }
+
+    // ---- flush: register accumulators -> global (atomics), per-thread partials reduced through shared memory ----
+    PolicyGrad *G = P.grad;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const unsigned j = jb * 4 + a;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const unsigned ii = (b < 4 ? ib * 4 + b : 32 + ib * 4 + (b - 4));
+            atomicAdd(&G->w2[half][j][ii], acc_w2[a][b]);
+        }
+        if (ib == 0) atomicAdd(&G->b2[half][j], acc_b2[a]);
+    }
+    {
+        const unsigned net = j1 >> 6, jn = j1 & 63u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned kk = kb * 4 + k;
+            if (kk < 5) atomicAdd(&G->w1[net][jn][kk], acc_w1[k]);
+        }
+        if (kb == 0) atomicAdd(&G->b1[net][jn], acc_b1);
+    }
+    // dW3: [half][row][64] partials -> d2 scratch (64 KB), then 128 threads sum over the 128 rows
+    {
+        float *scr = reinterpret_cast<float *>(sm->d2);
+#pragma unroll
+        for (int c = 0; c < 64; ++c) scr[(half * kRows + row) * 64 + c] = acc_w3[c];
+        __syncthreads();
+        if (t < 128) {
+            const unsigned net = t >> 6, c = t & 63u;
+            float s = 0.f;
+            for (unsigned r = 0; r < kRows; ++r) s += scr[(net * kRows + r) * 64 + c];
+            atomicAdd(&G->w3[net][c], s);
+        }
+    }
+    // scalars: warp shuffle, then shared-memory atomics, then one global atomic each
+    float sc[8] = {st0, st1, st2, st3, st4, acc_logstd, half == 0 ? acc_b3 : 0.f, half == 1 ? acc_b3 : 0.f};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float v = sc[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd(&sm->red[q], v);
+    }
+    __syncthreads();
+    if (t < 5) atomicAdd(&G->stats[t], sm->red[t]);
+    if (t == 5) atomicAdd(&G->logstd, sm->red[5]);
+    if (t == 6) atomicAdd(&G->b3[0], sm->red[6]);
+    if (t == 7) atomicAdd(&G->b3[1], sm->red[7]);
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+}
+
 // Generalised advantage estimation, the reverse scan of ppo_model_gsde.py:244-268 (gae=True):
 //   delta_t = r_t + gamma * V_{t+1} * (1 - d_{t+1}) - V_t ;  A_t = delta_t + gamma * lambda * (1 - d_{t+1}) * A_{t+1}
 // where d_{t+1} = done flag returned BY step t (the reference's dones[t+1] / next_done) = done_after[t],
@@ -328,6 +704,22 @@ cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *valu
 }
 
 size_t policy_smem_bytes() { return sizeof(PolicySmem); }
+
+cudaError_t launch_ppo_grad(const PpoGradArgs &P, int n_sm, cudaStream_t st)
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TrainSmem)));
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int64_t tiles = (P.n + kRows - 1) / kRows;
+    const int grid = static_cast<int>(tiles < n_sm ? tiles : n_sm);   // one CTA per SM (206 KB of shared memory)
+    ppo_grad_kernel<<<grid, kThreads, sizeof(TrainSmem), st>>>(P);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, int pdl, cudaStream_t st)
 {

@@ -36,6 +36,40 @@ struct PolicyArgs {
     int64_t id_base;          // global id of env 0 (sharding-invariant noise)
 };
 
+// ---- fused PPO minibatch gradient (forward + clipped-PPO loss + backward of both MLPs in one kernel) ----
+// weights for the training kernel: the forward blob plus W2^T (the B operand of dH1 = dZ2 * W2), same K-major packing
+struct alignas(16) TrainBlob {
+    PolicyBlob fwd;
+    float w2t[2][16][64][4];   // [actor|critic][K-chunk over OUTPUT features j][row = input feature i][4]
+};
+
+// gradient of the minibatch loss, laid out like the torch parameters (actor | critic), plus the loss statistics
+struct PolicyGrad {
+    float w1[2][64][5];
+    float b1[2][64];
+    float w2[2][64][64];
+    float b2[2][64];
+    float w3[2][64];
+    float b3[2];
+    float logstd;
+    float stats[5];            // sums over the minibatch: -logratio, (ratio-1)-logratio, |ratio-1| > clip, value loss, policy loss
+};
+
+struct PpoGradArgs {
+    const TrainBlob *blob;
+    const float *obs;          // [N][5] rollout buffer (flattened T*n)
+    const float *actions, *logprobs, *adv, *ret, *val;   // [N]
+    const int64_t *mb_idx;     // [n] rows of this minibatch
+    const float *logstd;       // [1]
+    const float *adv_stats;    // [2] mean, std of the minibatch advantages (used when norm_adv)
+    PolicyGrad *grad;          // accumulated with atomics: zero it first
+    int64_t n;
+    float clip_coef, vf_coef, ent_coef;
+    int norm_adv, clip_vloss;
+};
+
+cudaError_t launch_ppo_grad(const PpoGradArgs &P, int n_sm, cudaStream_t st);
+
 cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *values, const uint8_t *done_after, const float *next_value,
                        float gamma, float lam, float *advantages, float *returns, int n_sm, cudaStream_t st);
 size_t policy_smem_bytes();

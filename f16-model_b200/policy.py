@@ -102,6 +102,40 @@ def pack_policy_blob(actor, critic, out=None):
     return out
 
 
+def pack_train_blob(actor, critic, out=None):
+    """The fused PPO-gradient kernel's weights (csrc/f16_policy.h ``TrainBlob``): the forward blob followed by W2^T of
+    both nets in the same K-major packing (the B operand of dH1 = dZ2 * W2)."""
+    import torch
+
+    fwd = pack_policy_blob(actor, critic)
+    with torch.no_grad():
+        w2t = torch.stack([[m for m in net if isinstance(m, torch.nn.Linear)][1].weight.t() for net in (actor, critic)])
+        w2tp = w2t.reshape(2, 64, 16, 4).permute(0, 2, 1, 3).contiguous()            # [net][chunk over j][row i][4]
+        flat = torch.cat([fwd, w2tp.reshape(-1).float()])
+    assert flat.numel() * 4 == _capi.load_library().f16_ppo_train_blob_bytes()
+    if out is None:
+        return flat.contiguous()
+    out.copy_(flat)
+    return out
+
+
+GRAD_FIELDS = (("w1", (2, 64, 5)), ("b1", (2, 64)), ("w2", (2, 64, 64)), ("b2", (2, 64)), ("w3", (2, 64)), ("b3", (2,)),
+               ("logstd", (1,)), ("stats", (5,)))
+
+
+def grad_views(flat):
+    """Named views into the flat gradient buffer written by ``f16_ppo_grad`` (csrc/f16_policy.h ``PolicyGrad``)."""
+    out, off = {}, 0
+    for name, shape in GRAD_FIELDS:
+        n = 1
+        for d in shape:
+            n *= d
+        out[name] = flat[off:off + n].view(shape)
+        off += n
+    assert off == flat.numel(), (off, flat.numel())
+    return out
+
+
 class TensorCorePolicy:
     """actor_mean + critic + log-std, with a tensor-core forward for rollouts."""
 

@@ -9,6 +9,7 @@ deviations: the reference's gSDE noise path is broken as committ
 (``theta_gsde`` is never created in ``train``); here exploration is the standard Gaussian policy
 ``a = mean + exp(logstd) * eps`` with eps drawn by the counter RNG inside the policy kernel."""
 import dataclasses
+import math
 import time
 
 from . import _capi
@@ -36,6 +37,7 @@ class PPOConfig:
     reset_every_update: bool = True      # the reference re-resets the envs at every update (:210)
     use_cuda_graph: bool = True          # replay the whole rollout (2 kernels per step) from one CUDA graph
     tf32_update: bool = False            # run the update's matmuls on the TF32 tensor cores (default: torch's fp32)
+    fused_update: bool = True            # minibatch forward + loss + backward in ONE tcgen05 kernel (f16_ppo_grad); False: torch autograd
 
 
 def gae(rewards, values, done_after, next_value, gamma, gae_lambda):
@@ -90,6 +92,9 @@ class PPOTrainer:
         self._graph = None
         self._update_graph = None
         self._flat = None
+        self._fused = bool(self.cfg.fused_update) and envs.obs_layout == "aos"
+        if self._fused:
+            self._setup_fused()
 
     # ------------------------------------------------------------------ rollout
     def _obs_at(self, t):
@@ -150,10 +155,85 @@ class PPOTrainer:
             p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
             off += p.numel()
 
+    # ---- fused gradient path -------------------------------------------------------------------
+    def _setup_fused(self):
+        """Persistent pieces of the fused path: the flat gradient buffer the kernel accumulates into (the parameters'
+        ``.grad`` are views of it, so clipping and Adam read the kernel's output in place) and the gather that turns the
+        flat parameter vector into the kernel's weight blob in one indexing op."""
+        torch = self._torch
+        from .policy import grad_views, pack_train_blob
+        from torch import nn
+
+        L = _capi.load_library()
+        pol, dev = self.policy, self.device
+        self._g = torch.zeros(L.f16_ppo_grad_floats(), device=dev)
+        V = grad_views(self._g)
+        la = [m for m in pol.actor_mean if isinstance(m, nn.Linear)]
+        lc = [m for m in pol.critic if isinstance(m, nn.Linear)]
+        for net, ls in enumerate((la, lc)):
+            ls[0].weight.grad, ls[0].bias.grad = V["w1"][net], V["b1"][net]
+            ls[1].weight.grad, ls[1].bias.grad = V["w2"][net], V["b2"][net]
+            ls[2].weight.grad, ls[2].bias.grad = V["w3"][net].view(1, 64), V["b3"][net:net + 1]
+        pol.actor_logstd.grad = V["logstd"]
+        self._gstats = V["stats"]
+        self._gparams = self._g[: self._g.numel() - 5]            # everything but the statistics (what NCCL averages)
+        # blob = flat_params[perm]: pack the blob once from modules whose weights hold (their flat index + 1); 0 marks padding
+        params = list(pol.parameters())
+        sizes = [p.numel() for p in params]
+        with torch.no_grad():
+            saved = [p.detach().clone() for p in params]
+            off = 0
+            for p, nel in zip(params, sizes):
+                p.copy_(torch.arange(off + 1, off + nel + 1, device=dev, dtype=torch.float32).view_as(p))
+                off += nel
+            idx_blob = pack_train_blob(pol.actor_mean, pol.critic)
+            for p, sv in zip(params, saved):
+                p.copy_(sv)
+        self._blob_perm = idx_blob.round().long()                  # 0 -> the leading zero of the padded flat vector
+        self._flat_params = torch.zeros(off + 1, device=dev)
+        self._train_blob = torch.zeros_like(idx_blob)
+        self._params = params
+        self._adv_stats = torch.zeros(2, device=dev)
+
+    def _fused_minibatch_step(self, mb):
+        """The same optimiser step with forward, loss and backward in one kernel (csrc/f16_policy.cu ppo_grad_kernel)."""
+        torch, cfg = self._torch, self.cfg
+        b = self._flat
+        L = _capi.load_library()
+        torch.cat([p.detach().reshape(-1) for p in self._params], out=self._flat_params[1:])
+        torch.index_select(self._flat_params, 0, self._blob_perm, out=self._train_blob)
+        if cfg.norm_adv:
+            a = b["adv"][mb]
+            std, mean = torch.std_mean(a)
+            self._adv_stats[0].copy_(mean)
+            self._adv_stats[1].copy_(std)
+        self._g.zero_()
+        with torch.cuda.device(self.device):
+            _capi.check(L.f16_ppo_grad(mb.numel(), self._train_blob.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(),
+                                       b["logprobs"].data_ptr(), b["adv"].data_ptr(), b["ret"].data_ptr(), b["val"].data_ptr(),
+                                       mb.data_ptr(), self.policy.actor_logstd.data_ptr(), self._adv_stats.data_ptr(),
+                                       self._g.data_ptr(), float(cfg.clip_coef), float(cfg.vf_coef), float(cfg.ent_coef),
+                                       int(bool(cfg.norm_adv)), int(bool(cfg.clip_vloss)), _capi.stream_ptr(self.device)))
+        if self.world > 1:
+            torch.distributed.all_reduce(self._g)                  # one NCCL call on the flat buffer (gradients and statistics)
+            self._g /= self.world
+        torch.nn.utils.clip_grad_norm_(self._params, cfg.max_grad_norm)
+        self.optimizer.step()
+        inv_n = 1.0 / mb.numel()
+        st = self._gstats
+        self._diag[0].copy_(st[0] * inv_n)
+        self._diag[1].copy_(st[1] * inv_n)
+        self._diag[2].add_(st[2] * inv_n)
+        self._diag[3].copy_(st[3] * inv_n)
+        self._diag[4].copy_(st[4] * inv_n)
+        self._diag[5].copy_(self.policy.actor_logstd.detach()[0] + (0.5 + 0.5 * math.log(2 * math.pi)))
+
     def _minibatch_step(self, mb):
         """One clipped-PPO optimiser step on the minibatch indices ``mb`` (ppo_model_gsde.py:303-364).
         Writes its diagnostics into persistent scalars so that it can be replayed from a CUDA graph."""
         torch, cfg = self._torch, self.cfg
+        if self._fused:
+            return self._fused_minibatch_step(mb)
         b = self._flat
         newlogprob, entropy, newvalue = self.policy.evaluate(b["obs"][mb], b["actions"][mb])
         logratio = newlogprob - b["logprobs"][mb]

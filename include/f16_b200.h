@@ -181,6 +181,22 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
                        void *action, void *logprob, int sample, uint64_t seed, uint32_t step, const int32_t *ep_len,
                        const uint32_t *episode_no, int64_t env_id_base, void *stream);
 
+/* One clipped-PPO minibatch gradient in ONE kernel (the body of Agent.train's minibatch loop,
+ * control/ppo/ppo_model_gsde.py:303-364, without the optimiser step): forward of actor_mean and critic on the rows
+ * mb_idx[0..n) of the flattened rollout buffers (obs float[N][5]; actions, logprobs, adv, ret, val float[N]), the loss
+ * (ratio clipping with clip_coef, optionally clipped value loss, vf_coef, ent_coef, optional advantage normalisation
+ * with adv_stats = {mean, std} of the minibatch advantages) and the backward pass of both MLPs.  train_blob = the
+ * forward blob followed by W2^T in the same packing (f16_ppo_train_blob_bytes); grad receives, ACCUMULATED with atomics
+ * (zero it first), f16_ppo_grad_floats floats: the parameter gradients in torch order per net
+ * (w1[2][64][5], b1[2][64], w2[2][64][64], b2[2][64], w3[2][64], b3[2], logstd) and five sums over the minibatch
+ * (-logratio, (ratio-1)-logratio, |ratio-1| > clip, value loss, policy loss). */
+int f16_ppo_train_blob_bytes(void);
+int f16_ppo_grad_floats(void);
+int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void *actions, const void *logprobs,
+                 const void *adv, const void *ret, const void *val, const int64_t *mb_idx, const void *logstd,
+                 const void *adv_stats, void *grad, double clip_coef, double vf_coef, double ent_coef, int norm_adv,
+                 int clip_vloss, void *stream);
+
 /* The GAE reverse scan of Agent.train (control/ppo/ppo_model_gsde.py:244-268): float [T][n] rewards, values;
  * done_after u8[T][n] = the done flag returned by step t (the reference's dones[t+1], and next_done for the last
  * step) exactly as f16_env_step writes it; bootstrap next_value float[n] -> advantages, returns float[T][n]. */
