@@ -640,6 +640,40 @@ int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void 
     return F16_OK;
 }
 
+int f16_ppo_adam(int n_params, void *param, const void *grad, void *exp_avg, void *exp_avg_sq, void *max_exp_avg_sq, void *step,
+                 const void *lr, double beta1, double beta2, double eps, double max_grad_norm, const int64_t *fwd_perm, void *fwd_blob,
+                 int n_fwd, const int64_t *train_perm, void *train_blob, int n_train, void *stream)
+{
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(n_params, &c, &g);
+    if (rc) return rc;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !max_exp_avg_sq || !step || !lr) return fail(F16_EINVAL, "NULL pointer");
+    if ((n_fwd > 0 && (!fwd_perm || !fwd_blob)) || (n_train > 0 && (!train_perm || !train_blob)) || n_fwd < 0 || n_train < 0)
+        return fail(F16_EINVAL, "blob permutation / destination missing");
+    f16::PpoAdamArgs A;
+    A.n = n_params;
+    A.param = static_cast<float *>(param);
+    A.grad = static_cast<const float *>(grad);
+    A.exp_avg = static_cast<float *>(exp_avg);
+    A.exp_avg_sq = static_cast<float *>(exp_avg_sq);
+    A.max_exp_avg_sq = static_cast<float *>(max_exp_avg_sq);
+    A.step = static_cast<float *>(step);
+    A.lr = static_cast<const float *>(lr);
+    A.beta1 = static_cast<float>(beta1);
+    A.beta2 = static_cast<float>(beta2);
+    A.eps = static_cast<float>(eps);
+    A.max_grad_norm = static_cast<float>(max_grad_norm);
+    A.fwd_perm = fwd_perm;
+    A.fwd_blob = static_cast<float *>(fwd_blob);
+    A.n_fwd = n_fwd;
+    A.train_perm = train_perm;
+    A.train_blob = static_cast<float *>(train_blob);
+    A.n_train = n_train;
+    CUDA_TRY(f16::launch_ppo_adam(A, static_cast<cudaStream_t>(stream)));
+    return F16_OK;
+}
+
 int f16_gae(int T, int64_t n, const void *rewards, const void *values, const uint8_t *done_after, const void *next_value, double gamma,
             double gae_lambda, void *advantages, void *returns, void *stream)
 {

@@ -666,6 +666,61 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(const PpoGradArgs
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
 }
 
+// torch.nn.utils.clip_grad_norm_ (L2, max_norm) followed by torch.optim.Adam(amsgrad=True) on the flat parameter vector,
+// then both weight blobs are re-packed from the updated parameters: what torch runs as ~60 launches per minibatch.
+__global__ void __launch_bounds__(1024) ppo_adam_kernel(const PpoAdamArgs A)
+{
+    __shared__ float warp_sum[32];
+    __shared__ float s_coef;
+    const unsigned t = threadIdx.x;
+    float ss = 0.f;
+    for (int i = t; i < A.n; i += 1024) {
+        const float g = A.grad[i];
+        ss = fmaf(g, g, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((t & 31u) == 0) warp_sum[t >> 5] = ss;
+    __syncthreads();
+    if (t < 32) {
+        float v = warp_sum[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (t == 0) {
+            const float total = sqrtf(v);
+            const float c = A.max_grad_norm / (total + 1e-6f);      // clip_grad_norm_: clip_coef clamped to 1
+            s_coef = c < 1.0f ? c : 1.0f;
+        }
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    const float step = A.step[0] + 1.0f;
+    const float lr = A.lr[0];
+    const float bc1 = 1.0f - powf(A.beta1, step), bc2 = 1.0f - powf(A.beta2, step);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    for (int i = t; i < A.n; i += 1024) {
+        const float g = A.grad[i] * coef;
+        const float m = A.exp_avg[i] + (g - A.exp_avg[i]) * (1.0f - A.beta1);               // lerp, as torch does
+        const float v = A.exp_avg_sq[i] * A.beta2 + (1.0f - A.beta2) * g * g;
+        const float vmax = fmaxf(A.max_exp_avg_sq[i], v);
+        A.exp_avg[i] = m;
+        A.exp_avg_sq[i] = v;
+        A.max_exp_avg_sq[i] = vmax;
+        const float denom = sqrtf(vmax) * inv_sqrt_bc2 + A.eps;
+        A.param[i] -= step_size * (m / denom);
+    }
+    __syncthreads();   // the CTA's own global writes are visible to it after the barrier
+    if (t == 0) A.step[0] = step;
+    for (int k = t; k < A.n_fwd; k += 1024) {
+        const int64_t q = A.fwd_perm[k];
+        A.fwd_blob[k] = q ? A.param[q - 1] : 0.f;
+    }
+    for (int k = t; k < A.n_train; k += 1024) {
+        const int64_t q = A.train_perm[k];
+        A.train_blob[k] = q ? A.param[q - 1] : 0.f;
+    }
+}
+
 // Generalised advantage estimation, the reverse scan of ppo_model_gsde.py:244-268 (gae=True):
 //   delta_t = r_t + gamma * V_{t+1} * (1 - d_{t+1}) - V_t ;  A_t = delta_t + gamma * lambda * (1 - d_{t+1}) * A_{t+1}
 // where d_{t+1} = done flag returned BY step t (the reference's dones[t+1] / next_done) = done_after[t],
@@ -704,6 +759,12 @@ cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *valu
 }
 
 size_t policy_smem_bytes() { return sizeof(PolicySmem); }
+
+cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st)
+{
+    ppo_adam_kernel<<<1, 1024, 0, st>>>(A);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_ppo_grad(const PpoGradArgs &P, int n_sm, cudaStream_t st)
 {

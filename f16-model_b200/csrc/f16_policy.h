@@ -70,6 +70,24 @@ struct PpoGradArgs {
 
 cudaError_t launch_ppo_grad(const PpoGradArgs &P, int n_sm, cudaStream_t st);
 
+// clip_grad_norm_ + Adam(amsgrad) + re-packing of the two weight blobs, one CTA (the whole model is 9.3 k parameters)
+struct PpoAdamArgs {
+    int n;                      // parameters
+    float *param;               // [n] flat parameters (PolicyGrad field order), updated in place
+    const float *grad;          // [n]
+    float *exp_avg, *exp_avg_sq, *max_exp_avg_sq;   // [n] Adam state
+    float *step;                // [1] step counter (float, as torch keeps it when capturable)
+    const float *lr;            // [1]
+    float beta1, beta2, eps, max_grad_norm;
+    const int64_t *fwd_perm;    // [n_fwd]: blob word k = param[perm[k] - 1], or 0 where perm[k] == 0
+    float *fwd_blob;
+    int n_fwd;
+    const int64_t *train_perm;
+    float *train_blob;
+    int n_train;
+};
+cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st);
+
 cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *values, const uint8_t *done_after, const float *next_value,
                        float gamma, float lam, float *advantages, float *returns, int n_sm, cudaStream_t st);
 size_t policy_smem_bytes();

@@ -157,76 +157,83 @@ class PPOTrainer:
 
     # ---- fused gradient path -------------------------------------------------------------------
     def _setup_fused(self):
-        """Persistent pieces of the fused path: the flat gradient buffer the kernel accumulates into (the parameters'
-        ``.grad`` are views of it, so clipping and Adam read the kernel's output in place) and the gather that turns the
-        flat parameter vector into the kernel's weight blob in one indexing op."""
+        """Persistent pieces of the fused path.  Parameters and gradients become views of two flat vectors in the
+        kernel's field order (``PolicyGrad``): ``f16_ppo_grad`` accumulates into the gradient vector, ``f16_ppo_adam``
+        clips it, applies Adam(amsgrad) to the parameter vector and re-packs both weight blobs (blob = flat[perm])."""
         torch = self._torch
-        from .policy import grad_views, pack_train_blob
+        from .policy import grad_views, pack_policy_blob, pack_train_blob
         from torch import nn
 
         L = _capi.load_library()
         pol, dev = self.policy, self.device
-        self._g = torch.zeros(L.f16_ppo_grad_floats(), device=dev)
-        V = grad_views(self._g)
+        n_all = L.f16_ppo_grad_floats()
+        self._n_params = n_all - 5                                 # the last five floats are loss statistics
+        self._g = torch.zeros(n_all, device=dev)
+        self._pflat = torch.zeros(n_all, device=dev)
+        G, W = grad_views(self._g), grad_views(self._pflat)
         la = [m for m in pol.actor_mean if isinstance(m, nn.Linear)]
         lc = [m for m in pol.critic if isinstance(m, nn.Linear)]
-        for net, ls in enumerate((la, lc)):
-            ls[0].weight.grad, ls[0].bias.grad = V["w1"][net], V["b1"][net]
-            ls[1].weight.grad, ls[1].bias.grad = V["w2"][net], V["b2"][net]
-            ls[2].weight.grad, ls[2].bias.grad = V["w3"][net].view(1, 64), V["b3"][net:net + 1]
-        pol.actor_logstd.grad = V["logstd"]
-        self._gstats = V["stats"]
-        self._gparams = self._g[: self._g.numel() - 5]            # everything but the statistics (what NCCL averages)
-        # blob = flat_params[perm]: pack the blob once from modules whose weights hold (their flat index + 1); 0 marks padding
-        params = list(pol.parameters())
-        sizes = [p.numel() for p in params]
         with torch.no_grad():
-            saved = [p.detach().clone() for p in params]
-            off = 0
-            for p, nel in zip(params, sizes):
-                p.copy_(torch.arange(off + 1, off + nel + 1, device=dev, dtype=torch.float32).view_as(p))
-                off += nel
-            idx_blob = pack_train_blob(pol.actor_mean, pol.critic)
-            for p, sv in zip(params, saved):
-                p.copy_(sv)
-        self._blob_perm = idx_blob.round().long()                  # 0 -> the leading zero of the padded flat vector
-        self._flat_params = torch.zeros(off + 1, device=dev)
-        self._train_blob = torch.zeros_like(idx_blob)
-        self._params = params
+            for net, ls in enumerate((la, lc)):
+                for layer, (wk, bk) in enumerate((("w1", "b1"), ("w2", "b2"), ("w3", "b3"))):
+                    wv = W[wk][net].view_as(ls[layer].weight)
+                    bv = W[bk][net:net + 1].view_as(ls[layer].bias) if bk == "b3" else W[bk][net]
+                    wv.copy_(ls[layer].weight)
+                    bv.copy_(ls[layer].bias)
+                    ls[layer].weight.data, ls[layer].bias.data = wv, bv
+                    ls[layer].weight.grad = G[wk][net].view_as(wv)
+                    ls[layer].bias.grad = G[bk][net:net + 1].view_as(bv) if bk == "b3" else G[bk][net]
+            W["logstd"].copy_(pol.actor_logstd)
+            pol.actor_logstd.data = W["logstd"]
+            pol.actor_logstd.grad = G["logstd"]
+            # blob permutations: pack both blobs once from parameters holding (their flat index + 1); 0 marks padding
+            keep = self._pflat.clone()
+            self._pflat[: self._n_params] = torch.arange(1, self._n_params + 1, device=dev, dtype=torch.float32)
+            self._fwd_perm = pack_policy_blob(pol.actor_mean, pol.critic).round().long()
+            self._train_perm = pack_train_blob(pol.actor_mean, pol.critic).round().long()
+            self._pflat.copy_(keep)
+        self._gstats = G["stats"]
+        self._train_blob = pack_train_blob(pol.actor_mean, pol.critic)
+        self._params = list(pol.parameters())
         self._adv_stats = torch.zeros(2, device=dev)
+        self._adam = [torch.zeros(self._n_params, device=dev) for _ in range(3)] + [torch.zeros(1, device=dev)]   # m, v, vmax, step
 
     def _fused_minibatch_step(self, mb):
-        """The same optimiser step with forward, loss and backward in one kernel (csrc/f16_policy.cu ppo_grad_kernel)."""
+        """The same optimiser step in two kernels: forward + loss + backward (ppo_grad_kernel), then clip + Adam + blob
+        re-packing (ppo_adam_kernel); csrc/f16_policy.cu."""
         torch, cfg = self._torch, self.cfg
         b = self._flat
         L = _capi.load_library()
-        torch.cat([p.detach().reshape(-1) for p in self._params], out=self._flat_params[1:])
-        torch.index_select(self._flat_params, 0, self._blob_perm, out=self._train_blob)
         if cfg.norm_adv:
-            a = b["adv"][mb]
-            std, mean = torch.std_mean(a)
+            std, mean = torch.std_mean(b["adv"][mb])
             self._adv_stats[0].copy_(mean)
             self._adv_stats[1].copy_(std)
         self._g.zero_()
+        m, v, vmax, step = self._adam
         with torch.cuda.device(self.device):
+            st = _capi.stream_ptr(self.device)
             _capi.check(L.f16_ppo_grad(mb.numel(), self._train_blob.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(),
                                        b["logprobs"].data_ptr(), b["adv"].data_ptr(), b["ret"].data_ptr(), b["val"].data_ptr(),
                                        mb.data_ptr(), self.policy.actor_logstd.data_ptr(), self._adv_stats.data_ptr(),
                                        self._g.data_ptr(), float(cfg.clip_coef), float(cfg.vf_coef), float(cfg.ent_coef),
-                                       int(bool(cfg.norm_adv)), int(bool(cfg.clip_vloss)), _capi.stream_ptr(self.device)))
-        if self.world > 1:
-            torch.distributed.all_reduce(self._g)                  # one NCCL call on the flat buffer (gradients and statistics)
-            self._g /= self.world
-        torch.nn.utils.clip_grad_norm_(self._params, cfg.max_grad_norm)
-        self.optimizer.step()
-        inv_n = 1.0 / mb.numel()
-        st = self._gstats
-        self._diag[0].copy_(st[0] * inv_n)
-        self._diag[1].copy_(st[1] * inv_n)
-        self._diag[2].add_(st[2] * inv_n)
-        self._diag[3].copy_(st[3] * inv_n)
-        self._diag[4].copy_(st[4] * inv_n)
+                                       int(bool(cfg.norm_adv)), int(bool(cfg.clip_vloss)), st))
+            if self.world > 1:
+                torch.distributed.all_reduce(self._g)              # one NCCL call on the flat buffer (gradients and statistics)
+                self._g /= self.world
+            _capi.check(L.f16_ppo_adam(self._n_params, self._pflat.data_ptr(), self._g.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                       vmax.data_ptr(), step.data_ptr(), self._lr.data_ptr(), 0.9, 0.999, 1e-8,
+                                       float(cfg.max_grad_norm), self._fwd_perm.data_ptr(), self.policy._blob.data_ptr(),
+                                       self._fwd_perm.numel(), self._train_perm.data_ptr(), self._train_blob.data_ptr(),
+                                       self._train_perm.numel(), st))
+        s5 = self._gstats * (1.0 / mb.numel())
+        self._diag[0:2].copy_(s5[0:2])
+        self._diag[2].add_(s5[2])
+        self._diag[3:5].copy_(s5[3:5])
         self._diag[5].copy_(self.policy.actor_logstd.detach()[0] + (0.5 + 0.5 * math.log(2 * math.pi)))
+
+    def _state_tensors(self):
+        """Everything a fused optimiser step mutates (snapshotted around the CUDA-graph warm-up)."""
+        return [self._pflat, *self._adam, self._train_blob, self.policy._blob]
 
     def _minibatch_step(self, mb):
         """One clipped-PPO optimiser step on the minibatch indices ``mb`` (ppo_model_gsde.py:303-364).
@@ -287,8 +294,12 @@ class PPOTrainer:
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         params = list(self.policy.parameters())
-        saved = [p.detach().clone() for p in params]
-        saved_opt = [{k: v.clone() for k, v in self.optimizer.state.get(p, {}).items() if torch.is_tensor(v)} for p in params]
+        if self._fused:
+            state = self._state_tensors()
+            saved = [t.detach().clone() for t in state]
+        else:                                              # torch creates the Adam state lazily: absent before the first step
+            saved = [p.detach().clone() for p in params]
+            saved_opt = [{k: v.clone() for k, v in self.optimizer.state.get(p, {}).items() if torch.is_tensor(v)} for p in params]
         with torch.cuda.stream(side):                      # warm-up iterations (allocator, autograd, optimiser state)
             for _ in range(3):
                 self._minibatch_step(self._mb_idx)
@@ -297,11 +308,15 @@ class PPOTrainer:
         with torch.cuda.graph(graph):
             self._minibatch_step(self._mb_idx)
         with torch.no_grad():                              # undo the warm-up steps IN PLACE (the graph holds these tensors)
-            for p, q, so in zip(params, saved, saved_opt):
-                p.copy_(q)
-                for k, v in self.optimizer.state[p].items():
-                    if torch.is_tensor(v):
-                        v.copy_(so[k]) if k in so else v.zero_()
+            if self._fused:
+                for t, q in zip(state, saved):
+                    t.copy_(q)
+            else:
+                for p, q, so in zip(params, saved, saved_opt):
+                    p.copy_(q)
+                    for k, v in self.optimizer.state[p].items():
+                        if torch.is_tensor(v):
+                            v.copy_(so[k]) if k in so else v.zero_()
         self._diag.zero_()
         return graph
 
@@ -317,6 +332,9 @@ class PPOTrainer:
     def _update(self, advantages, returns):
         torch, cfg = self._torch, self.cfg
         self._prepare_update(advantages, returns)
+        if self._fused:                                    # parameters may have been changed from outside (load_agent, ...)
+            from .policy import pack_train_blob
+            pack_train_blob(self.policy.actor_mean, self.policy.critic, out=self._train_blob)
         use_graph = cfg.use_cuda_graph and self.world == 1
         if use_graph and self._update_graph is None:
             try:

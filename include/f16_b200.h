@@ -197,6 +197,15 @@ int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void 
                  const void *adv_stats, void *grad, double clip_coef, double vf_coef, double ent_coef, int norm_adv,
                  int clip_vloss, void *stream);
 
+/* The optimiser half of the minibatch step (ppo_model_gsde.py:360-364: clip_grad_norm_(max_grad_norm) then
+ * Adam(amsgrad=True).step()) on the flat parameter vector (same field order as the gradient of f16_ppo_grad), followed
+ * by re-packing the rollout blob and the training blob from the updated parameters: blob word k = param[perm[k] - 1],
+ * 0 where perm[k] == 0.  step and lr are device scalars, so the call can be replayed from a CUDA graph. */
+int f16_ppo_adam(int n_params, void *param, const void *grad, void *exp_avg, void *exp_avg_sq, void *max_exp_avg_sq,
+                 void *step, const void *lr, double beta1, double beta2, double eps, double max_grad_norm,
+                 const int64_t *fwd_perm, void *fwd_blob, int n_fwd, const int64_t *train_perm, void *train_blob,
+                 int n_train, void *stream);
+
 /* The GAE reverse scan of Agent.train (control/ppo/ppo_model_gsde.py:244-268): float [T][n] rewards, values;
  * done_after u8[T][n] = the done flag returned by step t (the reference's dones[t+1], and next_done for the last
  * step) exactly as f16_env_step writes it; bootstrap next_value float[n] -> advantages, returns float[T][n]. */

@@ -250,3 +250,34 @@ def test_fused_ppo_gradient_matches_autograd(f16, n, clip):
         else:
             cos = torch.nn.functional.cosine_similarity(x, r, dim=0).item() if r.numel() > 1 else float(torch.sign(x[0] * r[0]))
             assert cos > 0.95, (k, cos, rel)
+
+
+def test_fused_adam_matches_torch_clip_and_adam(f16):
+    """f16_ppo_adam == clip_grad_norm_(max_norm) + torch.optim.Adam(amsgrad=True) on the same gradients, and the blobs it
+    re-packs equal flat[perm]."""
+    from f16_model_b200 import _capi
+
+    L = _capi.load_library()
+    torch.manual_seed(1)
+    n = 9347
+    p0 = torch.randn(n, device="cuda")
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=3e-4, amsgrad=True)
+    p = p0.clone()
+    m, v, vmax, step = (torch.zeros(n, device="cuda") for _ in range(3)), None, None, torch.zeros(1, device="cuda")
+    m, v, vmax = list(m)
+    lr = torch.tensor(3e-4, device="cuda")
+    perm = torch.randint(0, n + 1, (5000,), device="cuda")
+    blob_a, blob_b = torch.empty(5000, device="cuda"), torch.empty(3000, device="cuda")
+    for it in range(6):
+        g = torch.randn(n, device="cuda") * (0.001 if it % 2 else 1.0)       # below and above the clipping threshold
+        ref.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref], 0.5)
+        opt.step()
+        _capi.check(L.f16_ppo_adam(n, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), vmax.data_ptr(), step.data_ptr(),
+                                   lr.data_ptr(), 0.9, 0.999, 1e-8, 0.5, perm.data_ptr(), blob_a.data_ptr(), 5000,
+                                   perm.data_ptr(), blob_b.data_ptr(), 3000, _capi.stream_ptr(p.device)))
+        assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-7), (it, (p - ref.detach()).abs().max().item())
+    assert step.item() == 6
+    padded = torch.cat([torch.zeros(1, device="cuda"), p])
+    assert torch.equal(blob_a, padded[perm]) and torch.equal(blob_b, padded[perm[:3000]])

@@ -5,7 +5,7 @@ import f16_model_b200 as f16
 CFG = {"dt": 0.01, "tn": 10, "debug_state": False, "determenistic_ref": False, "scenario": "combo"}
 envs = f16.F16VecEnv(CFG, 65536, seed=1, fast_math=True)
 pol = f16.TensorCorePolicy(seed=1, logstd_init=-1.0)
-cfg = f16.PPOConfig(num_steps=128, num_minibatches=32, update_epochs=4, use_cuda_graph=False)
+cfg = f16.PPOConfig(num_steps=128, num_minibatches=32, update_epochs=4, use_cuda_graph=False, fused_update=bool(int(os.environ.get("FUSED", "1"))))
 tr = f16.PPOTrainer(envs, pol, cfg)
 tr.train(num_updates=1)
 adv, ret = tr._adv, tr._ret
