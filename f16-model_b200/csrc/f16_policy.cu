@@ -375,20 +375,20 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(const PpoGradArgs
     const unsigned row = t & (kRows - 1), half = t >> 7;
 
     // accumulators that live across the CTA's tiles
-    float acc_w2[4][8];     // patch of dW2[net = half]: rows j = jb*4.., columns i in chunks {ib, ib + 8}
+    float2 acc_w2[4][4];    // patch of dW2[net = half]: rows j = jb*4.., columns i in chunks {ib, ib + 8}, as FFMA2 pairs
     float acc_b2[4] = {0.f, 0.f, 0.f, 0.f};
     float acc_w3[64];       // this thread's rows only; reduced over the CTA at the end
     float acc_b3 = 0.f, acc_logstd = 0.f;
-    float acc_w1[4] = {0.f, 0.f, 0.f, 0.f}, acc_b1 = 0.f;
+    float acc_w1[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, acc_b1 = 0.f;
     float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f, st4 = 0.f;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) acc_w2[a][b] = 0.f;
+        for (int b = 0; b < 4; ++b) acc_w2[a][b] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < 64; ++c) acc_w3[c] = 0.f;
     const unsigned jb = (t & 127u) >> 3, ib = t & 7u;      // dW2 patch of this thread
-    const unsigned j1 = t >> 1, kb = t & 1u;               // dW1: output feature j1 (0..127 = actor | critic), obs chunk kb
+    const unsigned j1 = t >> 1, kb = t & 1u;               // dW1: output feature j1 (0..127 = actor | critic), row half kb
 
     for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const unsigned i = tile * kRows + row;
@@ -556,18 +556,17 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(const PpoGradArgs
                 const float4 ha = *reinterpret_cast<const float4 *>(opnd(sm->a2, ch0, r));
                 const float4 hb = *reinterpret_cast<const float4 *>(opnd(sm->a2, ch1, r));
                 const float gv[4] = {g.x, g.y, g.z, g.w};
-                const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+                const float2 hp[4] = {make_float2(ha.x, ha.y), make_float2(ha.z, ha.w), make_float2(hb.x, hb.y), make_float2(hb.z, hb.w)};
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
+                    const float2 g2 = make_float2(gv[a], gv[a]);
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) acc_w2[a][b] = fmaf(gv[a], hv[b], acc_w2[a][b]);
+                    for (int b = 0; b < 4; ++b) acc_w2[a][b] = __ffma2_rn(g2, hp[b], acc_w2[a][b]);   // packed FFMA2 (sm_100): half the issue slots
                 }
-                if (ib == 0) {
-                    acc_b2[0] += g.x;
-                    acc_b2[1] += g.y;
-                    acc_b2[2] += g.z;
-                    acc_b2[3] += g.w;
-                }
+                acc_b2[0] += g.x;   // every thread of a jb group keeps the sums; one of them flushes
+                acc_b2[1] += g.y;
+                acc_b2[2] += g.z;
+                acc_b2[3] += g.w;
             }
         }
         mbar_wait(&sm->bar_mma, phase);
@@ -596,17 +595,20 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(const PpoGradArgs
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         // ---- dW1[j][k] += sum_r dZ1[r][j] * X[r][k]; db1[j] += sum_r dZ1[r][j] ----
-        {
+        {   // thread = (output feature j1, half of the rows): one scalar dZ1 and one broadcast X row per step, 5 FMAs
             const unsigned cj = j1 >> 2, ej = j1 & 3u;
-#pragma unroll 4
-            for (unsigned r = 0; r < kRows; ++r) {
+            const unsigned r0 = kb * (kRows / 2);
+#pragma unroll 8
+            for (unsigned r = r0; r < r0 + kRows / 2; ++r) {
                 const float dz = opnd(sm->d2, cj, r)[ej];
-                const float4 x = *reinterpret_cast<const float4 *>(sm->a1[kb][r]);
-                acc_w1[0] = fmaf(dz, x.x, acc_w1[0]);
-                acc_w1[1] = fmaf(dz, x.y, acc_w1[1]);
-                acc_w1[2] = fmaf(dz, x.z, acc_w1[2]);
-                acc_w1[3] = fmaf(dz, x.w, acc_w1[3]);
-                if (kb == 0) acc_b1 += dz;
+                const float4 x0 = *reinterpret_cast<const float4 *>(sm->a1[0][r]);
+                const float x4 = sm->a1[1][r][0];
+                acc_w1[0] = fmaf(dz, x0.x, acc_w1[0]);
+                acc_w1[1] = fmaf(dz, x0.y, acc_w1[1]);
+                acc_w1[2] = fmaf(dz, x0.z, acc_w1[2]);
+                acc_w1[3] = fmaf(dz, x0.w, acc_w1[3]);
+                acc_w1[4] = fmaf(dz, x4, acc_w1[4]);
+                acc_b1 += dz;
             }
         }
         __syncthreads();   // operands are rewritten by the next tile
@@ -620,18 +622,15 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(const PpoGradArgs
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const unsigned ii = (b < 4 ? ib * 4 + b : 32 + ib * 4 + (b - 4));
-            atomicAdd(&G->w2[half][j][ii], acc_w2[a][b]);
+            atomicAdd(&G->w2[half][j][ii], (b & 1) ? acc_w2[a][b >> 1].y : acc_w2[a][b >> 1].x);
         }
         if (ib == 0) atomicAdd(&G->b2[half][j], acc_b2[a]);
     }
     {
         const unsigned net = j1 >> 6, jn = j1 & 63u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned kk = kb * 4 + k;
-            if (kk < 5) atomicAdd(&G->w1[net][jn][kk], acc_w1[k]);
-        }
-        if (kb == 0) atomicAdd(&G->b1[net][jn], acc_b1);
+        for (int k = 0; k < 5; ++k) atomicAdd(&G->w1[net][jn][k], acc_w1[k]);
+        atomicAdd(&G->b1[net][jn], acc_b1);
     }
     // dW3: [half][row][64] partials -> d2 scratch (64 KB), then 128 threads sum over the 128 rows
     {
