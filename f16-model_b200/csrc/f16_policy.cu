@@ -667,10 +667,13 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(const PpoGradArgs
 
 // torch.nn.utils.clip_grad_norm_ (L2, max_norm) followed by torch.optim.Adam(amsgrad=True) on the flat parameter vector,
 // then both weight blobs are re-packed from the updated parameters: what torch runs as ~60 launches per minibatch.
+constexpr int kAdamMaxParams = 10240;   // updated parameters are staged in shared memory for the blob gathers (40 KB)
+
 __global__ void __launch_bounds__(1024) ppo_adam_kernel(const PpoAdamArgs A)
 {
     __shared__ float warp_sum[32];
     __shared__ float s_coef;
+    __shared__ float s_param[kAdamMaxParams];
     const unsigned t = threadIdx.x;
     float ss = 0.f;
     for (int i = t; i < A.n; i += 1024) {
@@ -697,27 +700,59 @@ __global__ void __launch_bounds__(1024) ppo_adam_kernel(const PpoAdamArgs A)
     const float lr = A.lr[0];
     const float bc1 = 1.0f - powf(A.beta1, step), bc2 = 1.0f - powf(A.beta2, step);
     const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
-    for (int i = t; i < A.n; i += 1024) {
-        const float g = A.grad[i] * coef;
-        const float m = A.exp_avg[i] + (g - A.exp_avg[i]) * (1.0f - A.beta1);               // lerp, as torch does
-        const float v = A.exp_avg_sq[i] * A.beta2 + (1.0f - A.beta2) * g * g;
-        const float vmax = fmaxf(A.max_exp_avg_sq[i], v);
-        A.exp_avg[i] = m;
-        A.exp_avg_sq[i] = v;
-        A.max_exp_avg_sq[i] = vmax;
-        const float denom = sqrtf(vmax) * inv_sqrt_bc2 + A.eps;
-        A.param[i] -= step_size * (m / denom);
+    const bool staged = A.n <= kAdamMaxParams;
+    // batches of 4 independent elements per thread: all loads of a batch are issued before its first store (without the
+    // explicit batching the stores serialise the iterations on global-memory latency: 29 us for 9.3 k parameters)
+    for (int i0 = t; i0 < A.n; i0 += 4 * 1024) {
+        float g[4], m[4], v[4], vm[4], p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 1024;
+            const bool ok = i < A.n;
+            g[u] = ok ? A.grad[i] : 0.f;
+            m[u] = ok ? A.exp_avg[i] : 0.f;
+            v[u] = ok ? A.exp_avg_sq[i] : 0.f;
+            vm[u] = ok ? A.max_exp_avg_sq[i] : 0.f;
+            p[u] = ok ? A.param[i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 1024;
+            if (i < A.n) {
+                const float gc = g[u] * coef;
+                const float mn = m[u] + (gc - m[u]) * (1.0f - A.beta1);                     // lerp, as torch does
+                const float vn = v[u] * A.beta2 + (1.0f - A.beta2) * gc * gc;
+                const float vmax = fmaxf(vm[u], vn);
+                const float denom = sqrtf(vmax) * inv_sqrt_bc2 + A.eps;
+                const float pn = p[u] - step_size * (mn / denom);
+                A.exp_avg[i] = mn;
+                A.exp_avg_sq[i] = vn;
+                A.max_exp_avg_sq[i] = vmax;
+                A.param[i] = pn;
+                if (staged) s_param[i] = pn;
+            }
+        }
     }
-    __syncthreads();   // the CTA's own global writes are visible to it after the barrier
+    __syncthreads();   // the CTA's own writes (shared and global) are visible to it after the barrier
     if (t == 0) A.step[0] = step;
-    for (int k = t; k < A.n_fwd; k += 1024) {
-        const int64_t q = A.fwd_perm[k];
-        A.fwd_blob[k] = q ? A.param[q - 1] : 0.f;
-    }
-    for (int k = t; k < A.n_train; k += 1024) {
-        const int64_t q = A.train_perm[k];
-        A.train_blob[k] = q ? A.param[q - 1] : 0.f;
-    }
+    const float *src = staged ? s_param : A.param;
+    auto repack = [&](const int64_t *perm, float *blob, int count) {
+        for (int k0 = t; k0 < count; k0 += 8 * 1024) {
+            int q[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u * 1024;
+                q[u] = k < count ? static_cast<int>(perm[k]) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = k0 + u * 1024;
+                if (q[u] >= 0) blob[k] = q[u] ? src[q[u] - 1] : 0.f;
+            }
+        }
+    };
+    repack(A.fwd_perm, A.fwd_blob, A.n_fwd);
+    repack(A.train_perm, A.train_blob, A.n_train);
 }
 
 // Generalised advantage estimation, the reverse scan of ppo_model_gsde.py:244-268 (gae=True):
