@@ -606,7 +606,7 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
 int f16_ppo_train_blob_bytes(void) { return static_cast<int>(sizeof(f16::TrainBlob)); }
 int f16_ppo_grad_floats(void) { return static_cast<int>(sizeof(f16::PolicyGrad) / sizeof(float)); }
 
-int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void *actions, const void *logprobs, const void *adv,
+static int ppo_grad_impl(bool fp16, int64_t n, const void *train_blob, const void *obs, const void *actions, const void *logprobs, const void *adv,
                  const void *ret, const void *val, const int64_t *mb_idx, const void *logstd, const void *adv_stats, void *grad,
                  double clip_coef, double vf_coef, double ent_coef, int norm_adv, int clip_vloss, void *stream)
 {
@@ -636,13 +636,33 @@ int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void 
     P.ent_coef = static_cast<float>(ent_coef);
     P.norm_adv = norm_adv;
     P.clip_vloss = clip_vloss;
-    CUDA_TRY(f16::launch_ppo_grad(P, c->n_sm, static_cast<cudaStream_t>(stream)));
+    if (fp16) CUDA_TRY(f16::launch_ppo_grad16(P, static_cast<const f16::TrainBlob16 *>(train_blob), c->n_sm, static_cast<cudaStream_t>(stream)));
+    else CUDA_TRY(f16::launch_ppo_grad(P, c->n_sm, static_cast<cudaStream_t>(stream)));
     return F16_OK;
+}
+
+int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void *actions, const void *logprobs, const void *adv,
+                 const void *ret, const void *val, const int64_t *mb_idx, const void *logstd, const void *adv_stats, void *grad,
+                 double clip_coef, double vf_coef, double ent_coef, int norm_adv, int clip_vloss, void *stream)
+{
+    return ppo_grad_impl(false, n, train_blob, obs, actions, logprobs, adv, ret, val, mb_idx, logstd, adv_stats, grad, clip_coef, vf_coef,
+                         ent_coef, norm_adv, clip_vloss, stream);
+}
+
+int f16_ppo_train_blob16_bytes(void) { return static_cast<int>(sizeof(f16::TrainBlob16)); }
+
+int f16_ppo_grad16(int64_t n, const void *train_blob16, const void *obs, const void *actions, const void *logprobs, const void *adv,
+                   const void *ret, const void *val, const int64_t *mb_idx, const void *logstd, const void *adv_stats, void *grad,
+                   double clip_coef, double vf_coef, double ent_coef, int norm_adv, int clip_vloss, void *stream)
+{
+    return ppo_grad_impl(true, n, train_blob16, obs, actions, logprobs, adv, ret, val, mb_idx, logstd, adv_stats, grad, clip_coef, vf_coef,
+                         ent_coef, norm_adv, clip_vloss, stream);
 }
 
 int f16_ppo_adam(int n_params, void *param, const void *grad, void *exp_avg, void *exp_avg_sq, void *max_exp_avg_sq, void *step,
                  const void *lr, double beta1, double beta2, double eps, double max_grad_norm, const int64_t *fwd_perm, void *fwd_blob,
-                 int n_fwd, const int64_t *train_perm, void *train_blob, int n_train, void *stream)
+                 int n_fwd, const int64_t *train_perm, void *train_blob, int n_train, const int64_t *half_perm, void *half_blob, int n_half,
+                 void *stream)
 {
     DeviceCtx *c;
     f16::LaunchGeom g;
@@ -670,6 +690,10 @@ int f16_ppo_adam(int n_params, void *param, const void *grad, void *exp_avg, voi
     A.train_perm = train_perm;
     A.train_blob = static_cast<float *>(train_blob);
     A.n_train = n_train;
+    if (n_half < 0 || (n_half > 0 && (!half_perm || !half_blob))) return fail(F16_EINVAL, "half blob permutation / destination missing");
+    A.half_perm = half_perm;
+    A.half_blob = static_cast<__half *>(half_blob);
+    A.n_half = n_half;
     CUDA_TRY(f16::launch_ppo_adam(A, static_cast<cudaStream_t>(stream)));
     return F16_OK;
 }

@@ -670,6 +670,355 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(const PpoGradArgs
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
 }
 
+
+// ---------------------------------------------------------------------------
+// fp16-operand training kernel: same structure as ppo_grad_kernel, with the weight gradients on the tensor cores.
+//   D1 = X H1 ... as before (kind::f16, K = 16 per MMA);  D3 = dZ2 * W2;
+//   dW2 | .  += dZ2^T * H1      M = 128 (both nets' outputs), N = 128 (both nets' inputs; the cross-net blocks are ignored)
+//   db2      += dZ2^T * [X | 1] N = 16: column 5 of the X operand is 1
+//   dW1 | db1 += dZ1^T * [X | 1]
+// all accumulated in TMEM over the CTA's tiles ([256,384), [400,416), [384,400)) and read back once.  dZ is carried
+// multiplied by the minibatch size so that it sits in fp16's normal range; the accumulators are rescaled at the flush.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kLboH = kRows * 16 + 16;   // bytes between 8-feature chunks of the fp16 H1 / dZ operands
+
+struct alignas(16) TrainSmem16 {
+    TrainBlob16 w;
+    __half a1[2][kRows][8];           // X: chunk 0 = obs[0..4], 1, 0, 0; chunk 1 = 0
+    unsigned char a2[16 * kLboH];     // H1  [chunk j/8][row][8 halfs]
+    unsigned char d2[16 * kLboH];     // dZ2, later dZ1 (a2 | d2 double as the 64 KB scratch of the final dW3 reduction)
+    uint64_t bar_w;
+    uint64_t bar_mma;
+    uint32_t tmem_base;
+    float red[16];
+};
+
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool mn_major)
+{
+    return (1u << 4) | (mn_major ? (1u << 15) | (1u << 16) : 0u) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&v)[8])
+{
+    __half2 h[4] = {__floats2half2_rn(v[0], v[1]), __floats2half2_rn(v[2], v[3]), __floats2half2_rn(v[4], v[5]), __floats2half2_rn(v[6], v[7])};
+    return *reinterpret_cast<const uint4 *>(h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradArgs P, const TrainBlob16 *blob16)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TrainSmem16 *sm = reinterpret_cast<TrainSmem16 *>(smem_raw);
+    const unsigned t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+
+    if (t == 0) {
+        mbar_init(&sm->bar_w, 1);
+        mbar_init(&sm->bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (t < 16) sm->red[t] = 0.f;
+    if (warp == 0) {   // all 512 TMEM columns: D1/D3 [0,128), D2 [128,256), dW2 [256,384), dW1|db1 [384,400), db2 [400,416)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    const unsigned row = t & (kRows - 1), half = t >> 7;
+    if (half == 1) *reinterpret_cast<uint4 *>(sm->a1[1][row]) = make_uint4(0u, 0u, 0u, 0u);   // K padding 8..15, written once
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = sm->tmem_base;
+    if (t == 0) {
+        constexpr uint32_t bytes = static_cast<uint32_t>(sizeof(TrainBlob16));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->bar_w)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&sm->w)),
+                     "l"(blob16), "r"(bytes), "r"(smem_u32(&sm->bar_w))
+                     : "memory");
+    }
+    mbar_wait(&sm->bar_w, 0);
+
+    const TrainBlob16 &W = sm->w;
+    constexpr uint32_t id_l1 = umma_idesc_f16(128, 128, false), id_l2 = umma_idesc_f16(128, 64, false);
+    constexpr uint32_t id_w2 = umma_idesc_f16(128, 128, true), id_w1 = umma_idesc_f16(128, 16, true);
+    const uint32_t a1 = smem_u32(sm->a1), a2 = smem_u32(sm->a2), d2 = smem_u32(sm->d2);
+    const uint32_t w1 = smem_u32(W.w1), w2a = smem_u32(W.w2[0]), w2c = smem_u32(W.w2[1]);
+    const uint32_t w2ta = smem_u32(W.w2t[0]), w2tc = smem_u32(W.w2t[1]);
+    const uint32_t lane_base = tmem + (((warp & 3u) * 32u) << 16);
+    uint32_t phase = 0;
+
+    const unsigned n = static_cast<unsigned>(P.n);
+    const unsigned n_tiles = (n + kRows - 1) / kRows;
+    const float n_f = static_cast<float>(n), inv_n = 1.0f / n_f;
+    const float log_std = P.logstd[0], inv_std = __expf(-log_std);
+    const float adv_mean = P.norm_adv ? P.adv_stats[0] : 0.f;
+    const float adv_scale = P.norm_adv ? 1.0f / (P.adv_stats[1] + 1e-8f) : 1.f;
+    const float eps = P.clip_coef;
+
+    float acc_w3[64];       // this thread's rows only; reduced over the CTA at the end
+    float acc_b3 = 0.f, acc_logstd = 0.f;
+    float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f, st4 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc_w3[c] = 0.f;
+    bool first = true;      // the weight-gradient accumulators in TMEM are initialised by the first tile's MMAs
+
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned i = tile * kRows + row;
+        const bool live = i < n;
+        const int64_t src = live ? P.mb_idx[i] : 0;
+        float s_a = 0.f, s_b = 0.f, s_c = 0.f;
+        if (half == 0) {   // observation row -> X operand, with a 1 in column 5 (bias gradients = that column of dZ^T [X | 1])
+            float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f};
+            if (live) {
+                const float *o = P.obs + src * 5;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) x[k] = o[k];
+                s_a = P.actions[src];
+                s_b = P.logprobs[src];
+                s_c = P.adv[src];
+            }
+            *reinterpret_cast<uint4 *>(sm->a1[0][row]) = pack8(x);
+        } else if (live) {
+            s_a = P.ret[src];
+            s_b = P.val[src];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (t == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            umma_f16(tmem + 0, umma_desc(a1, kRows * 16, 128), umma_desc(w1, 128 * 16, 128), id_l1, 0u);
+            umma_commit(&sm->bar_mma);
+        }
+        mbar_wait(&sm->bar_mma, phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- H1 = tanh(D1 + b1) -> a2 (fp16) ----
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            float v[32];
+            const int col0 = half * 64 + blk * 32;
+            tmem_ld32(lane_base + col0, v);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = col0 + c * 8;
+                float h[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) h[q] = fast_tanh(v[c * 8 + q] + W.b1[j + q]);
+                *reinterpret_cast<uint4 *>(sm->a2 + (j >> 3) * kLboH + row * 16u) = pack8(h);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (t == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_f16(tmem + 128, umma_desc(a2 + k * 2 * kLboH, kLboH, 128), umma_desc(w2a + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
+                         k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_f16(tmem + 192, umma_desc(a2 + (8 + k * 2) * kLboH, kLboH, 128), umma_desc(w2c + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
+                         k > 0 ? 1u : 0u);
+            umma_commit(&sm->bar_mma);
+        }
+        mbar_wait(&sm->bar_mma, phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- H2 (registers), head ----
+        float h2[64];
+        float head = W.b3[half];
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            float v[32];
+            const int col0 = half * 64 + blk * 32;
+            tmem_ld32(lane_base + 128 + col0, v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float h = fast_tanh(v[c] + W.b2[col0 + c]);
+                h2[blk * 32 + c] = h;
+                head = fmaf(h, W.w3[col0 + c], head);
+            }
+        }
+
+        // ---- clipped-PPO loss; g = d(n * loss) / d head for this row ----
+        float g_head = 0.f;
+        if (live) {
+            if (half == 0) {
+                const float z = (s_a - head) * inv_std;
+                const float newlp = -0.5f * z * z - log_std - 0.91893853320467274178f;
+                const float logratio = newlp - s_b;
+                const float ratio = __expf(logratio);
+                const float A = (s_c - adv_mean) * adv_scale;
+                const float lo = 1.0f - eps, hi = 1.0f + eps;
+                const float rc = fminf(fmaxf(ratio, lo), hi);
+                const float pg1 = -A * ratio, pg2 = -A * rc;
+                const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+                const float g_ratio = pg1 > pg2 ? -A : (pg2 > pg1 ? -A * in_range : -A * (0.5f + 0.5f * in_range));
+                const float g_lp = g_ratio * ratio;
+                g_head = g_lp * z * inv_std;
+                acc_logstd += (g_lp * (z * z - 1.0f) - P.ent_coef) * inv_n;
+                st0 -= logratio;
+                st1 += (ratio - 1.0f) - logratio;
+                st2 += fabsf(ratio - 1.0f) > eps ? 1.f : 0.f;
+                st4 += fmaxf(pg1, pg2);
+            } else {
+                const float du = head - s_a;
+                float g = du, vl = du * du;
+                if (P.clip_vloss) {
+                    const float dv = head - s_b;
+                    const float vc = s_b + fminf(fmaxf(dv, -eps), eps);
+                    const float dc = vc - s_a, vcl = dc * dc;
+                    const float in_range = (dv >= -eps && dv <= eps) ? 1.f : 0.f;
+                    g = vl > vcl ? du : (vcl > vl ? dc * in_range : 0.5f * du + 0.5f * dc * in_range);
+                    vl = fmaxf(vl, vcl);
+                }
+                g_head = P.vf_coef * g;
+                st3 += 0.5f * vl;
+            }
+        }
+        const float dy = g_head * inv_n;
+        acc_b3 += dy;
+        // ---- n * dZ2 = g * w3 * (1 - H2^2) -> d2 (fp16); dW3 partial sums in fp32 ----
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int j = half * 64 + c * 8;
+            float g[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float h = h2[c * 8 + q];
+                acc_w3[c * 8 + q] = fmaf(dy, h, acc_w3[c * 8 + q]);
+                g[q] = g_head * W.w3[j + q] * (1.0f - h * h);
+            }
+            *reinterpret_cast<uint4 *>(sm->d2 + (j >> 3) * kLboH + row * 16u) = pack8(g);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // D1 has been read by everyone: D3 may overwrite it
+        __syncthreads();
+        if (t == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // D3 = dZ2 * W2 (per net), into D1's columns: dZ2 read K-major (rows x features)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_f16(tmem + 0, umma_desc(d2 + k * 2 * kLboH, kLboH, 128), umma_desc(w2ta + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
+                         k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_f16(tmem + 64, umma_desc(d2 + (8 + k * 2) * kLboH, kLboH, 128), umma_desc(w2tc + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
+                         k > 0 ? 1u : 0u);
+            // dW2 += dZ2^T * H1, db2 += dZ2^T * [X | 1]: the same buffers read MN-major (features x rows), 16 rows per MMA
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                umma_f16(tmem + 256, umma_desc(d2 + k * 256, 128, kLboH), umma_desc(a2 + k * 256, 128, kLboH), id_w2, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                umma_f16(tmem + 400, umma_desc(d2 + k * 256, 128, kLboH), umma_desc(a1 + k * 256, 128, kRows * 16), id_w1,
+                         (first && k == 0) ? 0u : 1u);
+            umma_commit(&sm->bar_mma);
+        }
+        mbar_wait(&sm->bar_mma, phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        // ---- n * dZ1 = D3 * (1 - H1^2) -> d2 (every MMA that read dZ2 has completed) ----
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            float v[32];
+            const int col0 = half * 64 + blk * 32;
+            tmem_ld32(lane_base + col0, v);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = col0 + c * 8;
+                const uint4 raw = *reinterpret_cast<const uint4 *>(sm->a2 + (j >> 3) * kLboH + row * 16u);
+                const __half2 *hh = reinterpret_cast<const __half2 *>(&raw);
+                float g[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 h = __half22float2(hh[q]);
+                    g[2 * q] = v[c * 8 + 2 * q] * (1.0f - h.x * h.x);
+                    g[2 * q + 1] = v[c * 8 + 2 * q + 1] * (1.0f - h.y * h.y);
+                }
+                *reinterpret_cast<uint4 *>(sm->d2 + (j >> 3) * kLboH + row * 16u) = pack8(g);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (t == 0) {   // dW1 | db1 += dZ1^T * [X | 1]
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                umma_f16(tmem + 384, umma_desc(d2 + k * 256, 128, kLboH), umma_desc(a1 + k * 256, 128, kRows * 16), id_w1,
+                         (first && k == 0) ? 0u : 1u);
+            umma_commit(&sm->bar_mma);
+        }
+        first = false;
+        mbar_wait(&sm->bar_mma, phase);   // the operands are rewritten by the next tile
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+
+    // ---- flush ----
+    PolicyGrad *G = P.grad;
+    {
+        // weight-gradient accumulators: TMEM lane = output feature j (actor 0-63 | critic 64-127), scaled by n.  dW2: the block of
+        // the lane's own net, 64 columns split between the lane's two threads; dW1 (384..388), db1 (389), db2 (405): half 0.
+        const unsigned net = row >> 6, jn = row & 63u;
+        float v[32];
+        tmem_ld32(lane_base + 256 + net * 64 + half * 32, v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) atomicAdd(&G->w2[net][jn][half * 32 + c], v[c] * inv_n);
+        if (half == 0) {
+            tmem_ld32(lane_base + 384, v);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) atomicAdd(&G->w1[net][jn][k], v[k] * inv_n);
+            atomicAdd(&G->b1[net][jn], v[5] * inv_n);
+            atomicAdd(&G->b2[net][jn], v[16 + 5] * inv_n);
+        }
+    }
+    __syncthreads();
+    // dW3: [half][row][64] partials -> scratch (a2 | d2, 64 KB), then 128 threads sum over the 128 rows
+    {
+        float *scr = reinterpret_cast<float *>(sm->a2);
+#pragma unroll
+        for (int c = 0; c < 64; ++c) scr[(half * kRows + row) * 64 + c] = acc_w3[c];
+        __syncthreads();
+        if (t < 128) {
+            const unsigned net = t >> 6, c = t & 63u;
+            float s = 0.f;
+            for (unsigned r = 0; r < kRows; ++r) s += scr[(net * kRows + r) * 64 + c];
+            atomicAdd(&G->w3[net][c], s);
+        }
+    }
+    float sc[8] = {st0, st1, st2, st3, st4, acc_logstd, half == 0 ? acc_b3 : 0.f, half == 1 ? acc_b3 : 0.f};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float v = sc[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd(&sm->red[q], v);
+    }
+    __syncthreads();
+    if (t < 5) atomicAdd(&G->stats[t], sm->red[t]);
+    if (t == 5) atomicAdd(&G->logstd, sm->red[5]);
+    if (t == 6) atomicAdd(&G->b3[0], sm->red[6]);
+    if (t == 7) atomicAdd(&G->b3[1], sm->red[7]);
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
 // torch.nn.utils.clip_grad_norm_ (L2, max_norm) followed by torch.optim.Adam(amsgrad=True) on the flat parameter vector,
 // then both weight blobs are re-packed from the updated parameters: what torch runs as ~60 launches per minibatch.
 constexpr int kAdamMaxParams = 10240;   // updated parameters are staged in shared memory for the blob gathers (40 KB)
@@ -758,6 +1107,19 @@ __global__ void __launch_bounds__(1024) ppo_adam_kernel(const PpoAdamArgs A)
     };
     repack(A.fwd_perm, A.fwd_blob, A.n_fwd);
     repack(A.train_perm, A.train_blob, A.n_train);
+    for (int k0 = t; k0 < A.n_half; k0 += 8 * 1024) {
+        int q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * 1024;
+            q[u] = k < A.n_half ? static_cast<int>(A.half_perm[k]) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k0 + u * 1024;
+            if (q[u] >= 0) A.half_blob[k] = __float2half_rn(q[u] ? src[q[u] - 1] : 0.f);
+        }
+    }
 }
 
 // Generalised advantage estimation, the reverse scan of ppo_model_gsde.py:244-268 (gae=True):
@@ -802,6 +1164,22 @@ size_t policy_smem_bytes() { return sizeof(PolicySmem); }
 cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st)
 {
     ppo_adam_kernel<<<1, 1024, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, int n_sm, cudaStream_t st)
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(ppo_grad16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TrainSmem16)));
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int64_t tiles = (P.n + kRows - 1) / kRows;
+    const int grid = static_cast<int>(tiles < n_sm ? tiles : n_sm);   // one CTA per SM: it owns all 512 TMEM columns
+    ppo_grad16_kernel<<<grid, kThreads, sizeof(TrainSmem16), st>>>(P, blob16);
     return cudaGetLastError();
 }
 

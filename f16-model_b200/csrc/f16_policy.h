@@ -1,5 +1,6 @@
 // f16_policy.h -- packed weights and launch arguments of the tensor-core policy forward.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstddef>
@@ -70,6 +71,18 @@ struct PpoGradArgs {
 
 cudaError_t launch_ppo_grad(const PpoGradArgs &P, int n_sm, cudaStream_t st);
 
+// fp16-operand variant of the training kernel: every tensor-core operand (X, W1, H1, W2, W2^T, dZ2, dZ1) is fp16 -- the
+// same 11 significant bits as TF32 -- because MN-major no-swizzle operands exist for kind::f16 but not for kind::tf32:
+// the [8-feature chunk][row][8 halfs] buffers are then both the (row x feature) operands of the forward / backward-data
+// products and the (feature x row) operands of the weight gradients, which move onto the tensor cores with no copy.
+struct alignas(16) TrainBlob16 {
+    __half w1[2][128][8];      // layer 1, K = 16: k < 5 the observation weights, the rest zero
+    __half w2[2][8][64][8];    // [net][K-chunk over inputs i][row = output j][8]
+    __half w2t[2][8][64][8];   // [net][K-chunk over outputs j][row = input i][8]
+    float b1[128], b2[128], w3[128], b3[4];
+};
+cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, int n_sm, cudaStream_t st);
+
 // clip_grad_norm_ + Adam(amsgrad) + re-packing of the two weight blobs, one CTA (the whole model is 9.3 k parameters)
 struct PpoAdamArgs {
     int n;                      // parameters
@@ -85,6 +98,9 @@ struct PpoAdamArgs {
     const int64_t *train_perm;
     float *train_blob;
     int n_train;
+    const int64_t *half_perm;   // optional third destination, written as fp16 (the tensor-core operands of TrainBlob16)
+    __half *half_blob;
+    int n_half;
 };
 cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st);
 

@@ -119,6 +119,34 @@ def pack_train_blob(actor, critic, out=None):
     return out
 
 
+def pack_train_blob16(actor, critic, logical=False):
+    """The fp16-operand training kernel's weights (csrc/f16_policy.h ``TrainBlob16``): W1 (K padded 5 -> 16), W2 and W2^T as
+    fp16 in K-major 16-byte chunks ``[chunk][row][8 halfs]``, then the fp32 biases and output weights.  Returned as the
+    fp32 words of the blob; ``logical=True`` returns (half region as float32 values, float tail) instead -- what the
+    optimiser kernel's gather permutations are built from."""
+    import torch
+
+    la = [m for m in actor if isinstance(m, torch.nn.Linear)]
+    lc = [m for m in critic if isinstance(m, torch.nn.Linear)]
+    dev = la[0].weight.device
+    with torch.no_grad():
+        w1 = torch.zeros(128, 16, device=dev)
+        w1[:64, :5] = la[0].weight
+        w1[64:, :5] = lc[0].weight
+        w1p = w1.reshape(128, 2, 8).permute(1, 0, 2)                                  # [chunk][row][8]
+        w2 = torch.stack([la[1].weight, lc[1].weight])                                # [net][out j][in i]
+        w2p = w2.reshape(2, 64, 8, 8).permute(0, 2, 1, 3)                             # [net][chunk over i][row j][8]
+        w2tp = w2.transpose(1, 2).reshape(2, 64, 8, 8).permute(0, 2, 1, 3)            # [net][chunk over j][row i][8]
+        halves = torch.cat([w1p.reshape(-1), w2p.reshape(-1), w2tp.reshape(-1)]).float()
+        tail = torch.cat([la[0].bias, lc[0].bias, la[1].bias, lc[1].bias, la[2].weight.reshape(-1), lc[2].weight.reshape(-1),
+                          la[2].bias.reshape(-1), lc[2].bias.reshape(-1), torch.zeros(2, device=dev)]).float()
+        if logical:
+            return halves, tail
+        flat = torch.cat([halves.to(torch.float16).view(torch.float32), tail])
+    assert flat.numel() * 4 == _capi.load_library().f16_ppo_train_blob16_bytes(), flat.numel()
+    return flat.contiguous()
+
+
 GRAD_FIELDS = (("w1", (2, 64, 5)), ("b1", (2, 64)), ("w2", (2, 64, 64)), ("b2", (2, 64)), ("w3", (2, 64)), ("b3", (2,)),
                ("logstd", (1,)), ("stats", (5,)))
 

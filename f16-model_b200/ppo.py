@@ -37,7 +37,8 @@ class PPOConfig:
     reset_every_update: bool = True      # the reference re-resets the envs at every update (:210)
     use_cuda_graph: bool = True          # replay the whole rollout (2 kernels per step) from one CUDA graph
     tf32_update: bool = False            # run the update's matmuls on the TF32 tensor cores (default: torch's fp32)
-    fused_update: bool = True            # minibatch forward + loss + backward in ONE tcgen05 kernel (f16_ppo_grad); False: torch autograd
+    fused_update: bool = True            # minibatch forward + loss + backward in ONE tcgen05 kernel (f16_ppo_grad16); False: torch autograd
+    fused_precision: str = "fp16"        # tensor-core operands of the fused kernel: "fp16" (weight gradients on the tensor cores too) or "tf32"
 
 
 def gae(rewards, values, done_after, next_value, gamma, gae_lambda):
@@ -161,8 +162,12 @@ class PPOTrainer:
         kernel's field order (``PolicyGrad``): ``f16_ppo_grad`` accumulates into the gradient vector, ``f16_ppo_adam``
         clips it, applies Adam(amsgrad) to the parameter vector and re-packs both weight blobs (blob = flat[perm])."""
         torch = self._torch
-        from .policy import grad_views, pack_policy_blob, pack_train_blob
+        from .policy import grad_views, pack_policy_blob, pack_train_blob, pack_train_blob16
         from torch import nn
+
+        if self.cfg.fused_precision not in ("fp16", "tf32"):
+            raise ValueError("fused_precision must be 'fp16' or 'tf32'")
+        self._fp16 = self.cfg.fused_precision == "fp16"
 
         L = _capi.load_library()
         pol, dev = self.policy, self.device
@@ -190,10 +195,17 @@ class PPOTrainer:
             keep = self._pflat.clone()
             self._pflat[: self._n_params] = torch.arange(1, self._n_params + 1, device=dev, dtype=torch.float32)
             self._fwd_perm = pack_policy_blob(pol.actor_mean, pol.critic).round().long()
-            self._train_perm = pack_train_blob(pol.actor_mean, pol.critic).round().long()
+            if self._fp16:
+                halves, tail = pack_train_blob16(pol.actor_mean, pol.critic, logical=True)
+                self._half_perm, self._train_perm = halves.round().long(), tail.round().long()
+            else:
+                self._half_perm = None
+                self._train_perm = pack_train_blob(pol.actor_mean, pol.critic).round().long()
             self._pflat.copy_(keep)
         self._gstats = G["stats"]
-        self._train_blob = pack_train_blob(pol.actor_mean, pol.critic)
+        self._train_blob = (pack_train_blob16 if self._fp16 else pack_train_blob)(pol.actor_mean, pol.critic)
+        # fp16 blob: [fp16 tensor-core operands | fp32 biases and heads]; the optimiser kernel writes the two regions separately
+        self._blob_tail = self._train_blob[self._half_perm.numel() // 2:] if self._fp16 else self._train_blob
         self._params = list(pol.parameters())
         self._adv_stats = torch.zeros(2, device=dev)
         self._adam = [torch.zeros(self._n_params, device=dev) for _ in range(3)] + [torch.zeros(1, device=dev)]   # m, v, vmax, step
@@ -212,7 +224,7 @@ class PPOTrainer:
         m, v, vmax, step = self._adam
         with torch.cuda.device(self.device):
             st = _capi.stream_ptr(self.device)
-            _capi.check(L.f16_ppo_grad(mb.numel(), self._train_blob.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(),
+            _capi.check((L.f16_ppo_grad16 if self._fp16 else L.f16_ppo_grad)(mb.numel(), self._train_blob.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(),
                                        b["logprobs"].data_ptr(), b["adv"].data_ptr(), b["ret"].data_ptr(), b["val"].data_ptr(),
                                        mb.data_ptr(), self.policy.actor_logstd.data_ptr(), self._adv_stats.data_ptr(),
                                        self._g.data_ptr(), float(cfg.clip_coef), float(cfg.vf_coef), float(cfg.ent_coef),
@@ -223,8 +235,10 @@ class PPOTrainer:
             _capi.check(L.f16_ppo_adam(self._n_params, self._pflat.data_ptr(), self._g.data_ptr(), m.data_ptr(), v.data_ptr(),
                                        vmax.data_ptr(), step.data_ptr(), self._lr.data_ptr(), 0.9, 0.999, 1e-8,
                                        float(cfg.max_grad_norm), self._fwd_perm.data_ptr(), self.policy._blob.data_ptr(),
-                                       self._fwd_perm.numel(), self._train_perm.data_ptr(), self._train_blob.data_ptr(),
-                                       self._train_perm.numel(), st))
+                                       self._fwd_perm.numel(), self._train_perm.data_ptr(), self._blob_tail.data_ptr(),
+                                       self._train_perm.numel(), self._half_perm.data_ptr() if self._fp16 else None,
+                                       self._train_blob.data_ptr() if self._fp16 else None,
+                                       self._half_perm.numel() if self._fp16 else 0, st))
         s5 = self._gstats * (1.0 / mb.numel())
         self._diag[0:2].copy_(s5[0:2])
         self._diag[2].add_(s5[2])
@@ -333,8 +347,8 @@ class PPOTrainer:
         torch, cfg = self._torch, self.cfg
         self._prepare_update(advantages, returns)
         if self._fused:                                    # parameters may have been changed from outside (load_agent, ...)
-            from .policy import pack_train_blob
-            pack_train_blob(self.policy.actor_mean, self.policy.critic, out=self._train_blob)
+            from .policy import pack_train_blob, pack_train_blob16
+            self._train_blob.copy_((pack_train_blob16 if self._fp16 else pack_train_blob)(self.policy.actor_mean, self.policy.critic))
         use_graph = cfg.use_cuda_graph and self.world == 1
         if use_graph and self._update_graph is None:
             try:

@@ -191,20 +191,28 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
  * (w1[2][64][5], b1[2][64], w2[2][64][64], b2[2][64], w3[2][64], b3[2], logstd) and five sums over the minibatch
  * (-logratio, (ratio-1)-logratio, |ratio-1| > clip, value loss, policy loss). */
 int f16_ppo_train_blob_bytes(void);
+int f16_ppo_train_blob16_bytes(void);
 int f16_ppo_grad_floats(void);
 int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void *actions, const void *logprobs,
                  const void *adv, const void *ret, const void *val, const int64_t *mb_idx, const void *logstd,
                  const void *adv_stats, void *grad, double clip_coef, double vf_coef, double ent_coef, int norm_adv,
                  int clip_vloss, void *stream);
+/* Same computation with fp16 tensor-core operands (the 11 significant bits of TF32) and the weight gradients on the
+ * tensor cores as well; train_blob16 (f16_ppo_train_blob16_bytes) = W1, W2, W2^T in fp16, then the fp32 biases / heads. */
+int f16_ppo_grad16(int64_t n, const void *train_blob16, const void *obs, const void *actions, const void *logprobs,
+                   const void *adv, const void *ret, const void *val, const int64_t *mb_idx, const void *logstd,
+                   const void *adv_stats, void *grad, double clip_coef, double vf_coef, double ent_coef, int norm_adv,
+                   int clip_vloss, void *stream);
 
 /* The optimiser half of the minibatch step (ppo_model_gsde.py:360-364: clip_grad_norm_(max_grad_norm) then
  * Adam(amsgrad=True).step()) on the flat parameter vector (same field order as the gradient of f16_ppo_grad), followed
  * by re-packing the rollout blob and the training blob from the updated parameters: blob word k = param[perm[k] - 1],
- * 0 where perm[k] == 0.  step and lr are device scalars, so the call can be replayed from a CUDA graph. */
+ * 0 where perm[k] == 0; a third destination (half_perm / half_blob) is written as fp16.  step and lr are device scalars,
+ * so the call can be replayed from a CUDA graph. */
 int f16_ppo_adam(int n_params, void *param, const void *grad, void *exp_avg, void *exp_avg_sq, void *max_exp_avg_sq,
                  void *step, const void *lr, double beta1, double beta2, double eps, double max_grad_norm,
                  const int64_t *fwd_perm, void *fwd_blob, int n_fwd, const int64_t *train_perm, void *train_blob,
-                 int n_train, void *stream);
+                 int n_train, const int64_t *half_perm, void *half_blob, int n_half, void *stream);
 
 /* The GAE reverse scan of Agent.train (control/ppo/ppo_model_gsde.py:244-268): float [T][n] rewards, values;
  * done_after u8[T][n] = the done flag returned by step t (the reference's dones[t+1], and next_done for the last

@@ -186,16 +186,17 @@ def test_ppo_updates_run_on_device(f16):
         assert (m - pol.actor_mean(obs).squeeze(-1)).abs().max().item() < 3e-3     # blob re-packed after the update
 
 
+@pytest.mark.parametrize("precision", ["fp16", "tf32"])
 @pytest.mark.parametrize("n,clip,norm_adv,clip_vloss", [(4096 + 37, 100.0, 1, 1), (128, 100.0, 1, 1), (65536, 0.2, 1, 1),
                                                        (2048 + 5, 100.0, 0, 0)])
-def test_fused_ppo_gradient_matches_autograd(f16, n, clip, norm_adv, clip_vloss):
-    """f16_ppo_grad (forward + clipped-PPO loss + backward of both MLPs in one tcgen05 kernel) against torch autograd on the
-    same minibatch.  With the clip range wide open the loss is smooth and the gradients agree to TF32 / MUFU.TANH level
+def test_fused_ppo_gradient_matches_autograd(f16, n, clip, norm_adv, clip_vloss, precision):
+    """f16_ppo_grad16 / f16_ppo_grad (forward + clipped-PPO loss + backward of both MLPs in one tcgen05 kernel, fp16 or TF32
+    tensor-core operands) against torch autograd on the same minibatch.  With the clip range wide open the loss is smooth and the gradients agree to TF32 / MUFU.TANH level
     (< 2e-2 relative L2 per tensor, measured <= 7e-3); with clip_coef = 0.2 the rows whose ratio sits within the forward's
     ~2e-3 error of a clip boundary flip branch, which is noise of order sqrt(flipped rows) / n on a gradient whose own norm
     is of order 1 / sqrt(n) for this random data: held to cosine > 0.95, and the summed statistics to 1e-2."""
     from f16_model_b200 import _capi
-    from f16_model_b200.policy import grad_views, pack_train_blob
+    from f16_model_b200.policy import grad_views, pack_train_blob, pack_train_blob16
 
     torch.manual_seed(0)
     L = _capi.load_library()
@@ -237,10 +238,10 @@ def test_fused_ppo_gradient_matches_autograd(f16, n, clip, norm_adv, clip_vloss)
            "b3": torch.cat([la[2].bias.grad, lc[2].bias.grad]), "logstd": pol.actor_logstd.grad,
            "stats": torch.stack([(-logratio).sum(), ((ratio - 1) - logratio).sum(), ((ratio - 1).abs() > clip).float().sum(),
                                  vl * n, pg * n]).detach()}
-    blob = pack_train_blob(pol.actor_mean, pol.critic)
+    blob = (pack_train_blob16 if precision == "fp16" else pack_train_blob)(pol.actor_mean, pol.critic)
     g = torch.zeros(L.f16_ppo_grad_floats(), device="cuda")
     stats = torch.stack([adv[mb].mean(), adv[mb].std()])
-    _capi.check(L.f16_ppo_grad(n, blob.data_ptr(), obs.data_ptr(), actions.data_ptr(), logprobs.data_ptr(), adv.data_ptr(),
+    _capi.check((L.f16_ppo_grad16 if precision == "fp16" else L.f16_ppo_grad)(n, blob.data_ptr(), obs.data_ptr(), actions.data_ptr(), logprobs.data_ptr(), adv.data_ptr(),
                                ret.data_ptr(), val.data_ptr(), mb.data_ptr(), pol.actor_logstd.data_ptr(), stats.data_ptr(),
                                g.data_ptr(), clip, vf, ent, norm_adv, clip_vloss, _capi.stream_ptr(obs.device)))
     G = grad_views(g)
@@ -274,6 +275,7 @@ def test_fused_adam_matches_torch_clip_and_adam(f16):
     lr = torch.tensor(3e-4, device="cuda")
     perm = torch.randint(0, n + 1, (5000,), device="cuda")
     blob_a, blob_b = torch.empty(5000, device="cuda"), torch.empty(3000, device="cuda")
+    blob_h = torch.empty(4000, device="cuda", dtype=torch.float16)
     for it in range(6):
         g = torch.randn(n, device="cuda") * (0.001 if it % 2 else 1.0)       # below and above the clipping threshold
         ref.grad = g.clone()
@@ -281,8 +283,10 @@ def test_fused_adam_matches_torch_clip_and_adam(f16):
         opt.step()
         _capi.check(L.f16_ppo_adam(n, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), vmax.data_ptr(), step.data_ptr(),
                                    lr.data_ptr(), 0.9, 0.999, 1e-8, 0.5, perm.data_ptr(), blob_a.data_ptr(), 5000,
-                                   perm.data_ptr(), blob_b.data_ptr(), 3000, _capi.stream_ptr(p.device)))
+                                   perm.data_ptr(), blob_b.data_ptr(), 3000, perm.data_ptr(), blob_h.data_ptr(), 4000,
+                                   _capi.stream_ptr(p.device)))
         assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-7), (it, (p - ref.detach()).abs().max().item())
     assert step.item() == 6
     padded = torch.cat([torch.zeros(1, device="cuda"), p])
     assert torch.equal(blob_a, padded[perm]) and torch.equal(blob_b, padded[perm[:3000]])
+    assert torch.equal(blob_h, padded[perm[:4000]].to(torch.float16))

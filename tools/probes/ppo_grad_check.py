@@ -3,7 +3,7 @@ import os, sys, math, torch
 sys.path.insert(0, os.getcwd())
 import f16_model_b200 as f16
 from f16_model_b200 import _capi
-from f16_model_b200.policy import pack_train_blob, grad_views
+from f16_model_b200.policy import pack_train_blob, pack_train_blob16, grad_views
 
 torch.manual_seed(0)
 L = _capi.load_library()
@@ -49,13 +49,15 @@ ref = {"w1": torch.stack([la[0].weight.grad, lc[0].weight.grad]), "b1": torch.st
        "stats": torch.stack([(-logratio).sum(), ((ratio - 1) - logratio).sum(), ((ratio - 1).abs() > clip).float().sum(), vl * n, pg * n]).detach()}
 
 # ---- fused kernel
-blob = pack_train_blob(pol.actor_mean, pol.critic)
+FP16 = os.environ.get("PPO_GRAD", "fp16") == "fp16"
+blob = pack_train_blob16(pol.actor_mean, pol.critic) if FP16 else pack_train_blob(pol.actor_mean, pol.critic)
+fn = L.f16_ppo_grad16 if FP16 else L.f16_ppo_grad
 g = torch.zeros(L.f16_ppo_grad_floats(), device="cuda")
 am = adv[mb]
 stats = torch.stack([am.mean(), am.std()])
 def run():
     g.zero_()
-    _capi.check(L.f16_ppo_grad(n, blob.data_ptr(), obs.data_ptr(), actions.data_ptr(), logprobs.data_ptr(), adv.data_ptr(), ret.data_ptr(),
+    _capi.check(fn(n, blob.data_ptr(), obs.data_ptr(), actions.data_ptr(), logprobs.data_ptr(), adv.data_ptr(), ret.data_ptr(),
                                val.data_ptr(), mb.data_ptr(), pol.actor_logstd.data_ptr(), stats.data_ptr(), g.data_ptr(), clip, vf, ent, 1, 1,
                                _capi.stream_ptr(obs.device)))
 run()
