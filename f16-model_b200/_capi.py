@@ -89,7 +89,7 @@ def load_library():
     L.f16_ppo_train_blob_bytes.argtypes = []
     L.f16_ppo_grad_floats.argtypes = []
     L.f16_ppo_adam.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp, i32, vp, vp, i32,
-                               vp, vp, i32, vp]
+                               vp, vp, i32, vp, vp, C.c_double, i32, vp]
     L.f16_ppo_train_blob16_bytes.argtypes = []
     L.f16_ppo_grad.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, i32, i32, vp]
     L.f16_ppo_grad16.argtypes = L.f16_ppo_grad.argtypes

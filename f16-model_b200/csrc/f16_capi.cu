@@ -662,7 +662,7 @@ int f16_ppo_grad16(int64_t n, const void *train_blob16, const void *obs, const v
 int f16_ppo_adam(int n_params, void *param, const void *grad, void *exp_avg, void *exp_avg_sq, void *max_exp_avg_sq, void *step,
                  const void *lr, double beta1, double beta2, double eps, double max_grad_norm, const int64_t *fwd_perm, void *fwd_blob,
                  int n_fwd, const int64_t *train_perm, void *train_blob, int n_train, const int64_t *half_perm, void *half_blob, int n_half,
-                 void *stream)
+                 void *diag, const void *logstd, double inv_rows, int zero_grad, void *stream)
 {
     DeviceCtx *c;
     f16::LaunchGeom g;
@@ -694,6 +694,12 @@ int f16_ppo_adam(int n_params, void *param, const void *grad, void *exp_avg, voi
     A.half_perm = half_perm;
     A.half_blob = static_cast<__half *>(half_blob);
     A.n_half = n_half;
+    if (diag && !logstd) return fail(F16_EINVAL, "diag needs logstd");
+    A.diag = static_cast<float *>(diag);
+    A.grad_rw = static_cast<float *>(const_cast<void *>(grad));
+    A.logstd = static_cast<const float *>(logstd);
+    A.inv_rows = static_cast<float>(inv_rows);
+    A.zero_grad = zero_grad;
     CUDA_TRY(f16::launch_ppo_adam(A, static_cast<cudaStream_t>(stream)));
     return F16_OK;
 }

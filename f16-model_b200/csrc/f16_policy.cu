@@ -1120,6 +1120,19 @@ __global__ void __launch_bounds__(1024) ppo_adam_kernel(const PpoAdamArgs A)
             if (q[u] >= 0) A.half_blob[k] = __float2half_rn(q[u] ? src[q[u] - 1] : 0.f);
         }
     }
+    if (A.diag && t == 0) {
+        const float *st = A.grad + A.n;
+        A.diag[0] = st[0] * A.inv_rows;
+        A.diag[1] = st[1] * A.inv_rows;
+        A.diag[2] += st[2] * A.inv_rows;
+        A.diag[3] = st[3] * A.inv_rows;
+        A.diag[4] = st[4] * A.inv_rows;
+        A.diag[5] = A.logstd[0] + 1.4189385332046727f;   // Gaussian entropy 0.5 + 0.5 log(2 pi) + log std (after the step)
+    }
+    if (A.zero_grad) {
+        __syncthreads();   // thread 0 has read the statistics
+        for (int i = t; i < A.n + 5; i += 1024) A.grad_rw[i] = 0.f;
+    }
 }
 
 // Generalised advantage estimation, the reverse scan of ppo_model_gsde.py:244-268 (gae=True):

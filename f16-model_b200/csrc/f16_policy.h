@@ -101,6 +101,13 @@ struct PpoAdamArgs {
     const int64_t *half_perm;   // optional third destination, written as fp16 (the tensor-core operands of TrainBlob16)
     __half *half_blob;
     int n_half;
+    // optional epilogue of the minibatch step: diagnostics from the gradient kernel's five sums (grad[n .. n+5)), then the
+    // gradient buffer is cleared for the next minibatch
+    float *diag;                // [6] old_approx_kl, approx_kl, clip fraction (summed), value loss, policy loss, entropy; or nullptr
+    float *grad_rw;             // the same buffer as grad, writable: zeroed (n + 5 floats) when zero_grad != 0
+    const float *logstd;        // [1]
+    float inv_rows;             // 1 / minibatch rows
+    int zero_grad;
 };
 cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st);
 

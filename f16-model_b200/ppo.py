@@ -220,8 +220,7 @@ class PPOTrainer:
             std, mean = torch.std_mean(b["adv"][mb])
             self._adv_stats[0].copy_(mean)
             self._adv_stats[1].copy_(std)
-        self._g.zero_()
-        m, v, vmax, step = self._adam
+        m, v, vmax, step = self._adam                      # (the gradient buffer is cleared by the previous optimiser kernel)
         with torch.cuda.device(self.device):
             st = _capi.stream_ptr(self.device)
             _capi.check((L.f16_ppo_grad16 if self._fp16 else L.f16_ppo_grad)(mb.numel(), self._train_blob.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(),
@@ -238,12 +237,8 @@ class PPOTrainer:
                                        self._fwd_perm.numel(), self._train_perm.data_ptr(), self._blob_tail.data_ptr(),
                                        self._train_perm.numel(), self._half_perm.data_ptr() if self._fp16 else None,
                                        self._train_blob.data_ptr() if self._fp16 else None,
-                                       self._half_perm.numel() if self._fp16 else 0, st))
-        s5 = self._gstats * (1.0 / mb.numel())
-        self._diag[0:2].copy_(s5[0:2])
-        self._diag[2].add_(s5[2])
-        self._diag[3:5].copy_(s5[3:5])
-        self._diag[5].copy_(self.policy.actor_logstd.detach()[0] + (0.5 + 0.5 * math.log(2 * math.pi)))
+                                       self._half_perm.numel() if self._fp16 else 0, self._diag.data_ptr(),
+                                       self.policy.actor_logstd.data_ptr(), 1.0 / mb.numel(), 1, st))
 
     def _state_tensors(self):
         """Everything a fused optimiser step mutates (snapshotted around the CUDA-graph warm-up)."""
@@ -347,6 +342,7 @@ class PPOTrainer:
         torch, cfg = self._torch, self.cfg
         self._prepare_update(advantages, returns)
         if self._fused:                                    # parameters may have been changed from outside (load_agent, ...)
+            self._g.zero_()
             from .policy import pack_train_blob, pack_train_blob16
             self._train_blob.copy_((pack_train_blob16 if self._fp16 else pack_train_blob)(self.policy.actor_mean, self.policy.critic))
         use_graph = cfg.use_cuda_graph and self.world == 1

@@ -207,12 +207,16 @@ int f16_ppo_grad16(int64_t n, const void *train_blob16, const void *obs, const v
 /* The optimiser half of the minibatch step (ppo_model_gsde.py:360-364: clip_grad_norm_(max_grad_norm) then
  * Adam(amsgrad=True).step()) on the flat parameter vector (same field order as the gradient of f16_ppo_grad), followed
  * by re-packing the rollout blob and the training blob from the updated parameters: blob word k = param[perm[k] - 1],
- * 0 where perm[k] == 0; a third destination (half_perm / half_blob) is written as fp16.  step and lr are device scalars,
- * so the call can be replayed from a CUDA graph. */
+ * 0 where perm[k] == 0; a third destination (half_perm / half_blob) is written as fp16.  Optional epilogue: diag[6]
+ * receives (old_approx_kl, approx_kl, clip fraction ADDED, value loss, policy loss, entropy) from the five sums
+ * f16_ppo_grad left behind the parameter gradients (grad[n_params .. n_params+5)) times inv_rows, and zero_grad clears
+ * the gradient buffer (n_params + 5 floats) for the next minibatch.  step and lr are device scalars, so the call can be
+ * replayed from a CUDA graph. */
 int f16_ppo_adam(int n_params, void *param, const void *grad, void *exp_avg, void *exp_avg_sq, void *max_exp_avg_sq,
                  void *step, const void *lr, double beta1, double beta2, double eps, double max_grad_norm,
                  const int64_t *fwd_perm, void *fwd_blob, int n_fwd, const int64_t *train_perm, void *train_blob,
-                 int n_train, const int64_t *half_perm, void *half_blob, int n_half, void *stream);
+                 int n_train, const int64_t *half_perm, void *half_blob, int n_half, void *diag, const void *logstd,
+                 double inv_rows, int zero_grad, void *stream);
 
 /* The GAE reverse scan of Agent.train (control/ppo/ppo_model_gsde.py:244-268): float [T][n] rewards, values;
  * done_after u8[T][n] = the done flag returned by step t (the reference's dones[t+1], and next_done for the last

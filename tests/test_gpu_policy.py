@@ -284,7 +284,7 @@ def test_fused_adam_matches_torch_clip_and_adam(f16):
         _capi.check(L.f16_ppo_adam(n, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), vmax.data_ptr(), step.data_ptr(),
                                    lr.data_ptr(), 0.9, 0.999, 1e-8, 0.5, perm.data_ptr(), blob_a.data_ptr(), 5000,
                                    perm.data_ptr(), blob_b.data_ptr(), 3000, perm.data_ptr(), blob_h.data_ptr(), 4000,
-                                   _capi.stream_ptr(p.device)))
+                                   None, None, 0.0, 0, _capi.stream_ptr(p.device)))
         assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-7), (it, (p - ref.detach()).abs().max().item())
     assert step.item() == 6
     padded = torch.cat([torch.zeros(1, device="cuda"), p])
