@@ -20,7 +20,7 @@ ABI_VERSION = 1
 
 EXPORTS = ["f16_abi_version", "f16_last_error", "f16_init", "f16_launch_geometry", "f16_env_reset", "f16_env_step",
            "f16_env_step_host", "f16_host_route", "f16_rhs", "f16_model_step", "f16_coeffs", "f16_thrust", "f16_atmosphere",
-           "f16_policy_blob_bytes", "f16_policy_forward", "f16_ppo_train_blob_bytes", "f16_ppo_grad_floats", "f16_ppo_grad", "f16_ppo_train_blob16_bytes", "f16_ppo_grad16", "f16_ppo_adam",
+           "f16_policy_blob_bytes", "f16_policy_forward", "f16_ppo_adv_stats", "f16_ppo_train_blob_bytes", "f16_ppo_grad_floats", "f16_ppo_grad", "f16_ppo_train_blob16_bytes", "f16_ppo_grad16", "f16_ppo_adam",
            "f16_gae", "f16_trim"]
 
 
@@ -86,6 +86,7 @@ def load_library():
     L.f16_thrust.argtypes = [i32, i64, vp, vp, vp, vp, vp]
     L.f16_atmosphere.argtypes = [i32, i64, vp, vp, vp, vp]
     L.f16_policy_blob_bytes.argtypes = []
+    L.f16_ppo_adv_stats.argtypes = [i64, vp, vp, vp, vp, vp]
     L.f16_ppo_train_blob_bytes.argtypes = []
     L.f16_ppo_grad_floats.argtypes = []
     L.f16_ppo_adam.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp, i32, vp, vp, i32,

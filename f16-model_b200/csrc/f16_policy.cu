@@ -1135,6 +1135,57 @@ __global__ void __launch_bounds__(1024) ppo_adam_kernel(const PpoAdamArgs A)
     }
 }
 
+// Advantage normalisation statistics of one minibatch (ppo_model_gsde.py:318-321: mb_advantages.mean(), .std()): gather + sum +
+// sum of squares in one pass (double accumulators), the last CTA to finish turns them into (mean, unbiased std) and re-arms the
+// scratch.  Replaces torch's index + std_mean + two copies.
+__global__ void __launch_bounds__(256) adv_stats_kernel(const float *__restrict__ adv, const int64_t *__restrict__ mb_idx, int64_t n,
+                                                        float *out, double *scratch)
+{
+    double s = 0.0, ss = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = static_cast<double>(adv[mb_idx[i]]);
+        s += a;
+        ss += a * a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    __shared__ double ws[8], wss[8];
+    __shared__ bool last;
+    if ((threadIdx.x & 31u) == 0) {
+        ws[threadIdx.x >> 5] = s;
+        wss[threadIdx.x >> 5] = ss;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            a += ws[w];
+            b += wss[w];
+        }
+        atomicAdd(&scratch[0], a);
+        atomicAdd(&scratch[1], b);
+        __threadfence();
+        const unsigned done = atomicAdd(reinterpret_cast<unsigned *>(&scratch[2]), 1u);
+        last = done == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        const double sum = atomicAdd(&scratch[0], 0.0), sq = atomicAdd(&scratch[1], 0.0);
+        const double mean = sum / static_cast<double>(n);
+        const double var = n > 1 ? (sq - sum * mean) / static_cast<double>(n - 1) : 0.0;
+        out[0] = static_cast<float>(mean);
+        out[1] = static_cast<float>(sqrt(var > 0.0 ? var : 0.0));
+        scratch[0] = 0.0;
+        scratch[1] = 0.0;
+        *reinterpret_cast<unsigned *>(&scratch[2]) = 0u;
+    }
+}
+
 // Generalised advantage estimation, the reverse scan of ppo_model_gsde.py:244-268 (gae=True):
 //   delta_t = r_t + gamma * V_{t+1} * (1 - d_{t+1}) - V_t ;  A_t = delta_t + gamma * lambda * (1 - d_{t+1}) * A_{t+1}
 // where d_{t+1} = done flag returned BY step t (the reference's dones[t+1] / next_done) = done_after[t],
@@ -1173,6 +1224,13 @@ cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *valu
 }
 
 size_t policy_smem_bytes() { return sizeof(PolicySmem); }
+
+cudaError_t launch_adv_stats(const float *adv, const int64_t *mb_idx, int64_t n, float *out, double *scratch, int n_sm, cudaStream_t st)
+{
+    const int64_t blocks = (n + 255) / 256;
+    adv_stats_kernel<<<static_cast<int>(blocks < n_sm ? blocks : n_sm), 256, 0, st>>>(adv, mb_idx, n, out, scratch);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st)
 {

@@ -208,6 +208,7 @@ class PPOTrainer:
         self._blob_tail = self._train_blob[self._half_perm.numel() // 2:] if self._fp16 else self._train_blob
         self._params = list(pol.parameters())
         self._adv_stats = torch.zeros(2, device=dev)
+        self._adv_scratch = torch.zeros(4, device=dev, dtype=torch.float64)
         self._adam = [torch.zeros(self._n_params, device=dev) for _ in range(3)] + [torch.zeros(1, device=dev)]   # m, v, vmax, step
 
     def _fused_minibatch_step(self, mb):
@@ -216,13 +217,12 @@ class PPOTrainer:
         torch, cfg = self._torch, self.cfg
         b = self._flat
         L = _capi.load_library()
-        if cfg.norm_adv:
-            std, mean = torch.std_mean(b["adv"][mb])
-            self._adv_stats[0].copy_(mean)
-            self._adv_stats[1].copy_(std)
         m, v, vmax, step = self._adam                      # (the gradient buffer is cleared by the previous optimiser kernel)
         with torch.cuda.device(self.device):
             st = _capi.stream_ptr(self.device)
+            if cfg.norm_adv:
+                _capi.check(L.f16_ppo_adv_stats(mb.numel(), b["adv"].data_ptr(), mb.data_ptr(), self._adv_stats.data_ptr(),
+                                                self._adv_scratch.data_ptr(), st))
             _capi.check((L.f16_ppo_grad16 if self._fp16 else L.f16_ppo_grad)(mb.numel(), self._train_blob.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(),
                                        b["logprobs"].data_ptr(), b["adv"].data_ptr(), b["ret"].data_ptr(), b["val"].data_ptr(),
                                        mb.data_ptr(), self.policy.actor_logstd.data_ptr(), self._adv_stats.data_ptr(),

@@ -290,3 +290,20 @@ def test_fused_adam_matches_torch_clip_and_adam(f16):
     padded = torch.cat([torch.zeros(1, device="cuda"), p])
     assert torch.equal(blob_a, padded[perm]) and torch.equal(blob_b, padded[perm[:3000]])
     assert torch.equal(blob_h, padded[perm[:4000]].to(torch.float16))
+
+
+def test_adv_stats_kernel_matches_torch(f16):
+    from f16_model_b200 import _capi
+
+    L = _capi.load_library()
+    torch.manual_seed(2)
+    adv = torch.randn(500000, device="cuda") * 3 + 0.7
+    out = torch.zeros(2, device="cuda")
+    scratch = torch.zeros(4, device="cuda", dtype=torch.float64)
+    for n in (1, 2, 1000, 262144):
+        mb = torch.randperm(500000, device="cuda")[:n]
+        _capi.check(L.f16_ppo_adv_stats(n, adv.data_ptr(), mb.data_ptr(), out.data_ptr(), scratch.data_ptr(), _capi.stream_ptr(adv.device)))
+        a = adv[mb]
+        ref = torch.stack([a.mean(), a.std() if n > 1 else torch.zeros((), device="cuda")])
+        assert torch.allclose(out, ref, rtol=2e-6, atol=1e-6), (n, out, ref)
+    assert scratch.abs().sum().item() == 0          # re-armed for the next call
