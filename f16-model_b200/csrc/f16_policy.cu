@@ -111,6 +111,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// same load without the wait: issue several, then tmem_wait_ld() once
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ float fast_tanh(float x)
 {
     float y;
@@ -769,26 +784,43 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
     for (int c = 0; c < 64; ++c) acc_w3[c] = 0.f;
     bool first = true;      // the weight-gradient accumulators in TMEM are initialised by the first tile's MMAs
 
-    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned i = tile * kRows + row;
-        const bool live = i < n;
-        const int64_t src = live ? P.mb_idx[i] : 0;
-        float s_a = 0.f, s_b = 0.f, s_c = 0.f;
-        if (half == 0) {   // observation row -> X operand, with a 1 in column 5 (bias gradients = that column of dZ^T [X | 1])
-            float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f};
-            if (live) {
+    // One row of the minibatch = a random 20-byte row of the rollout buffer plus three scalars: two dependent DRAM round trips
+    // (index, then data).  Exposed per tile they were a third of the kernel (long-scoreboard stalls, ncu r01n), so the next
+    // tile's row is requested while the current tile computes and waits in registers.
+    struct RowIn { float x[5]; float a, b, c; bool live; };
+    auto gather = [&](unsigned tile_) {
+        RowIn g;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) g.x[k] = 0.f;
+        g.a = g.b = g.c = 0.f;
+        const unsigned i_ = tile_ * kRows + row;
+        g.live = tile_ < n_tiles && i_ < n;
+        if (g.live) {
+            const int64_t src = P.mb_idx[i_];
+            if (half == 0) {
                 const float *o = P.obs + src * 5;
 #pragma unroll
-                for (int k = 0; k < 5; ++k) x[k] = o[k];
-                s_a = P.actions[src];
-                s_b = P.logprobs[src];
-                s_c = P.adv[src];
+                for (int k = 0; k < 5; ++k) g.x[k] = o[k];
+                g.a = P.actions[src];
+                g.b = P.logprobs[src];
+                g.c = P.adv[src];
+            } else {
+                g.a = P.ret[src];
+                g.b = P.val[src];
             }
-            *reinterpret_cast<uint4 *>(sm->a1[0][row]) = pack8(x);
-        } else if (live) {
-            s_a = P.ret[src];
-            s_b = P.val[src];
         }
+        return g;
+    };
+    RowIn nxt = gather(blockIdx.x);
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const RowIn cur = nxt;
+        const bool live = cur.live;
+        const float s_a = cur.a, s_b = cur.b, s_c = cur.c;
+        if (half == 0) {   // observation row -> X operand, with a 1 in column 5 (bias gradients = that column of dZ^T [X | 1])
+            const float x[8] = {cur.x[0], cur.x[1], cur.x[2], cur.x[3], cur.x[4], 1.f, 0.f, 0.f};
+            *reinterpret_cast<uint4 *>(sm->a1[0][row]) = pack8(x);
+        }
+        nxt = gather(tile + gridDim.x);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -801,18 +833,20 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        // ---- H1 = tanh(D1 + b1) -> a2 (fp16) ----
+        // ---- H1 = tanh(D1 + b1) -> a2 (fp16); both 32-column TMEM loads are in flight before the one wait ----
+        uint32_t ra[32], rb[32];
+        tmem_ld32_issue(lane_base + half * 64, ra);
+        tmem_ld32_issue(lane_base + half * 64 + 32, rb);
+        tmem_wait_ld();
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
-            float v[32];
             const int col0 = half * 64 + blk * 32;
-            tmem_ld32(lane_base + col0, v);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int j = col0 + c * 8;
                 float h[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) h[q] = fast_tanh(v[c * 8 + q] + W.b1[j + q]);
+                for (int q = 0; q < 8; ++q) h[q] = fast_tanh(__uint_as_float(blk ? rb[c * 8 + q] : ra[c * 8 + q]) + W.b1[j + q]);
                 *reinterpret_cast<uint4 *>(sm->a2 + (j >> 3) * kLboH + row * 16u) = pack8(h);
             }
         }
@@ -838,14 +872,15 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
         // ---- H2 (registers), head ----
         float h2[64];
         float head = W.b3[half];
+        tmem_ld32_issue(lane_base + 128 + half * 64, ra);
+        tmem_ld32_issue(lane_base + 128 + half * 64 + 32, rb);
+        tmem_wait_ld();
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
-            float v[32];
             const int col0 = half * 64 + blk * 32;
-            tmem_ld32(lane_base + 128 + col0, v);
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-                const float h = fast_tanh(v[c] + W.b2[col0 + c]);
+                const float h = fast_tanh(__uint_as_float(blk ? rb[c] : ra[c]) + W.b2[col0 + c]);
                 h2[blk * 32 + c] = h;
                 head = fmaf(h, W.w3[col0 + c], head);
             }
@@ -931,11 +966,12 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
         // ---- n * dZ1 = D3 * (1 - H1^2) -> d2 (every MMA that read dZ2 has completed) ----
+        tmem_ld32_issue(lane_base + half * 64, ra);
+        tmem_ld32_issue(lane_base + half * 64 + 32, rb);
+        tmem_wait_ld();
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
-            float v[32];
             const int col0 = half * 64 + blk * 32;
-            tmem_ld32(lane_base + col0, v);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int j = col0 + c * 8;
@@ -945,8 +981,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float2 h = __half22float2(hh[q]);
-                    g[2 * q] = v[c * 8 + 2 * q] * (1.0f - h.x * h.x);
-                    g[2 * q + 1] = v[c * 8 + 2 * q + 1] * (1.0f - h.y * h.y);
+                    g[2 * q] = __uint_as_float(blk ? rb[c * 8 + 2 * q] : ra[c * 8 + 2 * q]) * (1.0f - h.x * h.x);
+                    g[2 * q + 1] = __uint_as_float(blk ? rb[c * 8 + 2 * q + 1] : ra[c * 8 + 2 * q + 1]) * (1.0f - h.y * h.y);
                 }
                 *reinterpret_cast<uint4 *>(sm->d2 + (j >> 3) * kLboH + row * 16u) = pack8(g);
             }
@@ -976,6 +1012,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
         const unsigned net = row >> 6, jn = row & 63u;
         float v[32];
         tmem_ld32(lane_base + 256 + net * 64 + half * 32, v);
+        // (148 CTAs add into the same 8 k addresses here: 1.2 M atomics cost ~21 us of the kernel whatever the order each
+        // CTA walks its columns in -- measured; per-CTA partials + a reduction kernel would be the next step)
 #pragma unroll
         for (int c = 0; c < 32; ++c) atomicAdd(&G->w2[net][jn][half * 32 + c], v[c] * inv_n);
         if (half == 0) {
