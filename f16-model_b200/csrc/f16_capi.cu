@@ -618,7 +618,7 @@ int f16_ppo_adv_stats(int64_t n, const void *adv, const int64_t *mb_idx, void *o
 int f16_ppo_train_blob_bytes(void) { return static_cast<int>(sizeof(f16::TrainBlob)); }
 int f16_ppo_grad_floats(void) { return static_cast<int>(sizeof(f16::PolicyGrad) / sizeof(float)); }
 
-static int ppo_grad_impl(bool fp16, int64_t n, const void *train_blob, const void *obs, const void *actions, const void *logprobs, const void *adv,
+static int ppo_grad_impl(bool fp16, void *partials, int64_t n, const void *train_blob, const void *obs, const void *actions, const void *logprobs, const void *adv,
                  const void *ret, const void *val, const int64_t *mb_idx, const void *logstd, const void *adv_stats, void *grad,
                  double clip_coef, double vf_coef, double ent_coef, int norm_adv, int clip_vloss, void *stream)
 {
@@ -648,7 +648,7 @@ static int ppo_grad_impl(bool fp16, int64_t n, const void *train_blob, const voi
     P.ent_coef = static_cast<float>(ent_coef);
     P.norm_adv = norm_adv;
     P.clip_vloss = clip_vloss;
-    if (fp16) CUDA_TRY(f16::launch_ppo_grad16(P, static_cast<const f16::TrainBlob16 *>(train_blob), c->n_sm, static_cast<cudaStream_t>(stream)));
+    if (fp16) CUDA_TRY(f16::launch_ppo_grad16(P, static_cast<const f16::TrainBlob16 *>(train_blob), static_cast<float *>(partials), c->n_sm, static_cast<cudaStream_t>(stream)));
     else CUDA_TRY(f16::launch_ppo_grad(P, c->n_sm, static_cast<cudaStream_t>(stream)));
     return F16_OK;
 }
@@ -657,17 +657,24 @@ int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void 
                  const void *ret, const void *val, const int64_t *mb_idx, const void *logstd, const void *adv_stats, void *grad,
                  double clip_coef, double vf_coef, double ent_coef, int norm_adv, int clip_vloss, void *stream)
 {
-    return ppo_grad_impl(false, n, train_blob, obs, actions, logprobs, adv, ret, val, mb_idx, logstd, adv_stats, grad, clip_coef, vf_coef,
+    return ppo_grad_impl(false, nullptr, n, train_blob, obs, actions, logprobs, adv, ret, val, mb_idx, logstd, adv_stats, grad, clip_coef, vf_coef,
                          ent_coef, norm_adv, clip_vloss, stream);
 }
 
 int f16_ppo_train_blob16_bytes(void) { return static_cast<int>(sizeof(f16::TrainBlob16)); }
 
+int f16_ppo_grad16_scratch_floats(int device)
+{
+    DeviceCtx *c;
+    if (ensure_device(device, &c)) return -1;
+    return c->n_sm * static_cast<int>(sizeof(f16::PolicyGrad) / sizeof(float));
+}
+
 int f16_ppo_grad16(int64_t n, const void *train_blob16, const void *obs, const void *actions, const void *logprobs, const void *adv,
                    const void *ret, const void *val, const int64_t *mb_idx, const void *logstd, const void *adv_stats, void *grad,
-                   double clip_coef, double vf_coef, double ent_coef, int norm_adv, int clip_vloss, void *stream)
+                   double clip_coef, double vf_coef, double ent_coef, int norm_adv, int clip_vloss, void *scratch, void *stream)
 {
-    return ppo_grad_impl(true, n, train_blob16, obs, actions, logprobs, adv, ret, val, mb_idx, logstd, adv_stats, grad, clip_coef, vf_coef,
+    return ppo_grad_impl(true, scratch, n, train_blob16, obs, actions, logprobs, adv, ret, val, mb_idx, logstd, adv_stats, grad, clip_coef, vf_coef,
                          ent_coef, norm_adv, clip_vloss, stream);
 }
 

@@ -729,7 +729,7 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8])
     return *reinterpret_cast<const uint4 *>(h);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradArgs P, const TrainBlob16 *blob16)
+__global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradArgs P, const TrainBlob16 *blob16, float *partials)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TrainSmem16 *sm = reinterpret_cast<TrainSmem16 *>(smem_raw);
@@ -1005,7 +1005,13 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
     }
 
     // ---- flush ----
-    PolicyGrad *G = P.grad;
+    // with `partials` every CTA owns a private copy of the gradient and writes each element exactly once; otherwise atomics
+    const bool own = partials != nullptr;
+    PolicyGrad *G = own ? reinterpret_cast<PolicyGrad *>(partials) + blockIdx.x : P.grad;
+    auto put = [&](float *dst, float val) {
+        if (own) *dst = val;
+        else atomicAdd(dst, val);
+    };
     {
         // weight-gradient accumulators: TMEM lane = output feature j (actor 0-63 | critic 64-127), scaled by n.  dW2: the block of
         // the lane's own net, 64 columns split between the lane's two threads; dW1 (384..388), db1 (389), db2 (405): half 0.
@@ -1015,13 +1021,13 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
         // (148 CTAs add into the same 8 k addresses here: 1.2 M atomics cost ~21 us of the kernel whatever the order each
         // CTA walks its columns in -- measured; per-CTA partials + a reduction kernel would be the next step)
 #pragma unroll
-        for (int c = 0; c < 32; ++c) atomicAdd(&G->w2[net][jn][half * 32 + c], v[c] * inv_n);
+        for (int c = 0; c < 32; ++c) put(&G->w2[net][jn][half * 32 + c], v[c] * inv_n);
         if (half == 0) {
             tmem_ld32(lane_base + 384, v);
 #pragma unroll
-            for (int k = 0; k < 5; ++k) atomicAdd(&G->w1[net][jn][k], v[k] * inv_n);
-            atomicAdd(&G->b1[net][jn], v[5] * inv_n);
-            atomicAdd(&G->b2[net][jn], v[16 + 5] * inv_n);
+            for (int k = 0; k < 5; ++k) put(&G->w1[net][jn][k], v[k] * inv_n);
+            put(&G->b1[net][jn], v[5] * inv_n);
+            put(&G->b2[net][jn], v[16 + 5] * inv_n);
         }
     }
     __syncthreads();
@@ -1035,7 +1041,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
             const unsigned net = t >> 6, c = t & 63u;
             float s = 0.f;
             for (unsigned r = 0; r < kRows; ++r) s += scr[(net * kRows + r) * 64 + c];
-            atomicAdd(&G->w3[net][c], s);
+            put(&G->w3[net][c], s);
         }
     }
     float sc[8] = {st0, st1, st2, st3, st4, acc_logstd, half == 0 ? acc_b3 : 0.f, half == 1 ? acc_b3 : 0.f};
@@ -1047,14 +1053,33 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
         if (lane == 0) atomicAdd(&sm->red[q], v);
     }
     __syncthreads();
-    if (t < 5) atomicAdd(&G->stats[t], sm->red[t]);
-    if (t == 5) atomicAdd(&G->logstd, sm->red[5]);
-    if (t == 6) atomicAdd(&G->b3[0], sm->red[6]);
-    if (t == 7) atomicAdd(&G->b3[1], sm->red[7]);
+    if (t < 5) put(&G->stats[t], sm->red[t]);
+    if (t == 5) put(&G->logstd, sm->red[5]);
+    if (t == 6) put(&G->b3[0], sm->red[6]);
+    if (t == 7) put(&G->b3[1], sm->red[7]);
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+// sum the CTAs' private gradients: thread (output p, group g of 8) adds every 8th row, the 8 groups meet in shared memory
+__global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const float *__restrict__ partials, int n_rows, int n_out, float *__restrict__ out)
+{
+    __shared__ float part[8][32];
+    const unsigned lane = threadIdx.x & 31u, g = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + lane;
+    float s = 0.f;
+    if (p < n_out)
+        for (int b = g; b < n_rows; b += 8) s += partials[static_cast<size_t>(b) * n_out + p];
+    part[g][lane] = s;
+    __syncthreads();
+    if (g == 0 && p < n_out) {
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot += part[k][lane];
+        out[p] = tot;
+    }
 }
 
 // torch.nn.utils.clip_grad_norm_ (L2, max_norm) followed by torch.optim.Adam(amsgrad=True) on the flat parameter vector,
@@ -1276,7 +1301,7 @@ cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, int n_sm, cudaStream_t st)
+cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials, int n_sm, cudaStream_t st)
 {
     static bool configured[64] = {};
     int dev = 0;
@@ -1288,7 +1313,11 @@ cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, i
     }
     const int64_t tiles = (P.n + kRows - 1) / kRows;
     const int grid = static_cast<int>(tiles < n_sm ? tiles : n_sm);   // one CTA per SM: it owns all 512 TMEM columns
-    ppo_grad16_kernel<<<grid, kThreads, sizeof(TrainSmem16), st>>>(P, blob16);
+    ppo_grad16_kernel<<<grid, kThreads, sizeof(TrainSmem16), st>>>(P, blob16, partials);
+    if (partials) {
+        constexpr int n_out = static_cast<int>(sizeof(PolicyGrad) / sizeof(float));
+        ppo_grad_reduce_kernel<<<(n_out + 31) / 32, 256, 0, st>>>(partials, grid, n_out, reinterpret_cast<float *>(P.grad));
+    }
     return cudaGetLastError();
 }
 

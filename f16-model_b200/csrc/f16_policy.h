@@ -81,7 +81,9 @@ struct alignas(16) TrainBlob16 {
     __half w2t[2][8][64][8];   // [net][K-chunk over outputs j][row = input i][8]
     float b1[128], b2[128], w3[128], b3[4];
 };
-cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, int n_sm, cudaStream_t st);
+// partials: optional [n_sm][sizeof(PolicyGrad)/4] floats.  With it every CTA stores its own gradient (no atomics: 148 CTAs adding
+// into the same 9 k addresses cost a fifth of the kernel) and a second small kernel sums the CTAs' rows into P.grad (overwritten).
+cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials, int n_sm, cudaStream_t st);
 
 // clip_grad_norm_ + Adam(amsgrad) + re-packing of the two weight blobs, one CTA (the whole model is 9.3 k parameters)
 struct PpoAdamArgs {

@@ -209,6 +209,7 @@ class PPOTrainer:
         self._params = list(pol.parameters())
         self._adv_stats = torch.zeros(2, device=dev)
         self._adv_scratch = torch.zeros(4, device=dev, dtype=torch.float64)
+        self._grad_scratch = torch.empty(max(1, L.f16_ppo_grad16_scratch_floats(dev.index)), device=dev) if self._fp16 else None
         self._adam = [torch.zeros(self._n_params, device=dev) for _ in range(3)] + [torch.zeros(1, device=dev)]   # m, v, vmax, step
 
     def _fused_minibatch_step(self, mb):
@@ -223,11 +224,15 @@ class PPOTrainer:
             if cfg.norm_adv:
                 _capi.check(L.f16_ppo_adv_stats(mb.numel(), b["adv"].data_ptr(), mb.data_ptr(), self._adv_stats.data_ptr(),
                                                 self._adv_scratch.data_ptr(), st))
-            _capi.check((L.f16_ppo_grad16 if self._fp16 else L.f16_ppo_grad)(mb.numel(), self._train_blob.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(),
-                                       b["logprobs"].data_ptr(), b["adv"].data_ptr(), b["ret"].data_ptr(), b["val"].data_ptr(),
-                                       mb.data_ptr(), self.policy.actor_logstd.data_ptr(), self._adv_stats.data_ptr(),
-                                       self._g.data_ptr(), float(cfg.clip_coef), float(cfg.vf_coef), float(cfg.ent_coef),
-                                       int(bool(cfg.norm_adv)), int(bool(cfg.clip_vloss)), st))
+            args = (mb.numel(), self._train_blob.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(),
+                    b["logprobs"].data_ptr(), b["adv"].data_ptr(), b["ret"].data_ptr(), b["val"].data_ptr(),
+                    mb.data_ptr(), self.policy.actor_logstd.data_ptr(), self._adv_stats.data_ptr(),
+                    self._g.data_ptr(), float(cfg.clip_coef), float(cfg.vf_coef), float(cfg.ent_coef),
+                    int(bool(cfg.norm_adv)), int(bool(cfg.clip_vloss)))
+            if self._fp16:   # per-CTA partial gradients + a reduction kernel instead of 1.4 M atomics
+                _capi.check(L.f16_ppo_grad16(*args, self._grad_scratch.data_ptr(), st))
+            else:
+                _capi.check(L.f16_ppo_grad(*args, st))
             if self.world > 1:
                 torch.distributed.all_reduce(self._g)              # one NCCL call on the flat buffer (gradients and statistics)
                 self._g /= self.world

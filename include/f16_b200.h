@@ -201,11 +201,14 @@ int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void 
                  const void *adv_stats, void *grad, double clip_coef, double vf_coef, double ent_coef, int norm_adv,
                  int clip_vloss, void *stream);
 /* Same computation with fp16 tensor-core operands (the 11 significant bits of TF32) and the weight gradients on the
- * tensor cores as well; train_blob16 (f16_ppo_train_blob16_bytes) = W1, W2, W2^T in fp16, then the fp32 biases / heads. */
+ * tensor cores as well; train_blob16 (f16_ppo_train_blob16_bytes) = W1, W2, W2^T in fp16, then the fp32 biases / heads.
+ * scratch: optional f16_ppo_grad16_scratch_floats(device) floats.  With it every CTA stores a private gradient and a second
+ * small kernel sums them into grad, which is then OVERWRITTEN (no zeroing needed); without it grad is accumulated with atomics. */
+int f16_ppo_grad16_scratch_floats(int device);
 int f16_ppo_grad16(int64_t n, const void *train_blob16, const void *obs, const void *actions, const void *logprobs,
                    const void *adv, const void *ret, const void *val, const int64_t *mb_idx, const void *logstd,
                    const void *adv_stats, void *grad, double clip_coef, double vf_coef, double ent_coef, int norm_adv,
-                   int clip_vloss, void *stream);
+                   int clip_vloss, void *scratch, void *stream);
 
 /* The optimiser half of the minibatch step (ppo_model_gsde.py:360-364: clip_grad_norm_(max_grad_norm) then
  * Adam(amsgrad=True).step()) on the flat parameter vector (same field order as the gradient of f16_ppo_grad), followed

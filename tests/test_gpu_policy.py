@@ -241,9 +241,18 @@ def test_fused_ppo_gradient_matches_autograd(f16, n, clip, norm_adv, clip_vloss,
     blob = (pack_train_blob16 if precision == "fp16" else pack_train_blob)(pol.actor_mean, pol.critic)
     g = torch.zeros(L.f16_ppo_grad_floats(), device="cuda")
     stats = torch.stack([adv[mb].mean(), adv[mb].std()])
-    _capi.check((L.f16_ppo_grad16 if precision == "fp16" else L.f16_ppo_grad)(n, blob.data_ptr(), obs.data_ptr(), actions.data_ptr(), logprobs.data_ptr(), adv.data_ptr(),
-                               ret.data_ptr(), val.data_ptr(), mb.data_ptr(), pol.actor_logstd.data_ptr(), stats.data_ptr(),
-                               g.data_ptr(), clip, vf, ent, norm_adv, clip_vloss, _capi.stream_ptr(obs.device)))
+    args = (n, blob.data_ptr(), obs.data_ptr(), actions.data_ptr(), logprobs.data_ptr(), adv.data_ptr(), ret.data_ptr(), val.data_ptr(),
+            mb.data_ptr(), pol.actor_logstd.data_ptr(), stats.data_ptr(), g.data_ptr(), clip, vf, ent, norm_adv, clip_vloss)
+    if precision == "fp16":
+        # with scratch (per-CTA partials + reduction kernel: grad is overwritten) and without (atomics into the zeroed grad)
+        g_atomic = torch.zeros_like(g)
+        _capi.check(L.f16_ppo_grad16(*args[:11], g_atomic.data_ptr(), *args[12:], None, _capi.stream_ptr(obs.device)))
+        scratch = torch.empty(L.f16_ppo_grad16_scratch_floats(0), device="cuda")
+        g.fill_(123.0)
+        _capi.check(L.f16_ppo_grad16(*args, scratch.data_ptr(), _capi.stream_ptr(obs.device)))
+        assert torch.allclose(g, g_atomic, rtol=1e-4, atol=1e-7)
+    else:
+        _capi.check(L.f16_ppo_grad(*args, _capi.stream_ptr(obs.device)))
     G = grad_views(g)
     for k, r in ref.items():
         r, x = r.float().reshape(-1), G[k].reshape(-1)

@@ -53,13 +53,15 @@ FP16 = os.environ.get("PPO_GRAD", "fp16") == "fp16"
 blob = pack_train_blob16(pol.actor_mean, pol.critic) if FP16 else pack_train_blob(pol.actor_mean, pol.critic)
 fn = L.f16_ppo_grad16 if FP16 else L.f16_ppo_grad
 g = torch.zeros(L.f16_ppo_grad_floats(), device="cuda")
+scratch = torch.empty(L.f16_ppo_grad16_scratch_floats(0), device="cuda")
 am = adv[mb]
 stats = torch.stack([am.mean(), am.std()])
 def run():
     g.zero_()
+    extra = (scratch.data_ptr(),) if FP16 else ()
     _capi.check(fn(n, blob.data_ptr(), obs.data_ptr(), actions.data_ptr(), logprobs.data_ptr(), adv.data_ptr(), ret.data_ptr(),
                                val.data_ptr(), mb.data_ptr(), pol.actor_logstd.data_ptr(), stats.data_ptr(), g.data_ptr(), clip, vf, ent, 1, 1,
-                               _capi.stream_ptr(obs.device)))
+                               *extra, _capi.stream_ptr(obs.device)))
 run()
 torch.cuda.synchronize()
 G = grad_views(g)
