@@ -297,6 +297,7 @@ class PPOTrainer:
                 "adv": self._adv.reshape(-1), "ret": self._ret.reshape(-1), "val": self.values.reshape(-1)}
             self._diag = torch.zeros(6, device=self.device)
             self._mb_idx = torch.zeros(self.minibatch_size, dtype=torch.long, device=self.device)
+            self._perm_buf = torch.arange(self.batch_size, dtype=torch.long, device=self.device)
         self._adv.copy_(advantages)
         self._ret.copy_(returns)
         self._diag.zero_()
@@ -320,7 +321,13 @@ class PPOTrainer:
         torch.cuda.current_stream(self.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self._minibatch_step(self._mb_idx)
+            if self._fused:
+                # a whole epoch in one graph: every minibatch reads its slice of the persistent permutation buffer, so an epoch
+                # costs one randperm and one graph launch (4 kernels per minibatch)
+                for start in range(0, self.batch_size - self.minibatch_size + 1, self.minibatch_size):
+                    self._minibatch_step(self._perm_buf[start:start + self.minibatch_size])
+            else:
+                self._minibatch_step(self._mb_idx)
         with torch.no_grad():                              # undo the warm-up steps IN PLACE (the graph holds these tensors)
             if self._fused:
                 for t, q in zip(state, saved):
@@ -358,7 +365,15 @@ class PPOTrainer:
                 print(f"[ppo] update graph capture failed ({exc}); running eagerly")
                 self._update_graph = False
         n_steps = 0
+        per_epoch = len(range(0, self.batch_size - self.minibatch_size + 1, self.minibatch_size))
         for epoch in range(cfg.update_epochs):
+            if use_graph and self._update_graph and self._fused:
+                torch.randperm(self.batch_size, device=self.device, generator=self._gen, out=self._perm_buf)
+                self._update_graph.replay()
+                n_steps += per_epoch
+                if cfg.target_kl is not None and self._diag[1].item() > cfg.target_kl:
+                    break
+                continue
             perm = torch.randperm(self.batch_size, device=self.device, generator=self._gen)
             for start in range(0, self.batch_size - self.minibatch_size + 1, self.minibatch_size):
                 mb = perm[start:start + self.minibatch_size]
