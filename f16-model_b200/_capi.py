@@ -86,7 +86,7 @@ def load_library():
     L.f16_thrust.argtypes = [i32, i64, vp, vp, vp, vp, vp]
     L.f16_atmosphere.argtypes = [i32, i64, vp, vp, vp, vp]
     L.f16_policy_blob_bytes.argtypes = []
-    L.f16_ppo_adv_stats.argtypes = [i64, vp, vp, vp, vp, vp]
+    L.f16_ppo_adv_stats.argtypes = [i64, i32, vp, vp, vp, vp, vp]
     L.f16_ppo_train_blob_bytes.argtypes = []
     L.f16_ppo_grad_floats.argtypes = []
     L.f16_ppo_adam.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp, i32, vp, vp, i32,

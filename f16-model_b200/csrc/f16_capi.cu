@@ -603,14 +603,15 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
     return F16_OK;
 }
 
-int f16_ppo_adv_stats(int64_t n, const void *adv, const int64_t *mb_idx, void *out, void *scratch, void *stream)
+int f16_ppo_adv_stats(int64_t n, int n_minibatches, const void *adv, const int64_t *mb_idx, void *out, void *scratch, void *stream)
 {
     DeviceCtx *c;
     f16::LaunchGeom g;
     int rc = prep(n, &c, &g);
     if (rc) return rc;
     if (!adv || !mb_idx || !out || !scratch) return fail(F16_EINVAL, "NULL pointer");
-    CUDA_TRY(f16::launch_adv_stats(static_cast<const float *>(adv), mb_idx, n, static_cast<float *>(out), static_cast<double *>(scratch),
+    if (n_minibatches < 1 || n_minibatches > 65535) return fail(F16_EINVAL, "n_minibatches must be in 1..65535");
+    CUDA_TRY(f16::launch_adv_stats(static_cast<const float *>(adv), mb_idx, n, n_minibatches, static_cast<float *>(out), static_cast<double *>(scratch),
                                    c->n_sm, static_cast<cudaStream_t>(stream)));
     return F16_OK;
 }

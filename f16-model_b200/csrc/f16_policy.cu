@@ -1204,6 +1204,10 @@ __global__ void __launch_bounds__(1024) ppo_adam_kernel(const PpoAdamArgs A)
 __global__ void __launch_bounds__(256) adv_stats_kernel(const float *__restrict__ adv, const int64_t *__restrict__ mb_idx, int64_t n,
                                                         float *out, double *scratch)
 {
+    // blockIdx.y = minibatch: rows [y * n, (y + 1) * n) of mb_idx, out[y][2], scratch[y][4] (a whole epoch in one launch)
+    mb_idx += static_cast<int64_t>(blockIdx.y) * n;
+    out += blockIdx.y * 2;
+    scratch += blockIdx.y * 4;
     double s = 0.0, ss = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double a = static_cast<double>(adv[mb_idx[i]]);
@@ -1288,10 +1292,14 @@ cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *valu
 
 size_t policy_smem_bytes() { return sizeof(PolicySmem); }
 
-cudaError_t launch_adv_stats(const float *adv, const int64_t *mb_idx, int64_t n, float *out, double *scratch, int n_sm, cudaStream_t st)
+cudaError_t launch_adv_stats(const float *adv, const int64_t *mb_idx, int64_t n, int n_minibatches, float *out, double *scratch, int n_sm,
+                             cudaStream_t st)
 {
     const int64_t blocks = (n + 255) / 256;
-    adv_stats_kernel<<<static_cast<int>(blocks < n_sm ? blocks : n_sm), 256, 0, st>>>(adv, mb_idx, n, out, scratch);
+    int per_mb = (2 * n_sm + n_minibatches - 1) / n_minibatches;   // about two waves in total
+    if (per_mb < 1) per_mb = 1;
+    const dim3 grid(static_cast<unsigned>(blocks < per_mb ? blocks : per_mb), static_cast<unsigned>(n_minibatches));
+    adv_stats_kernel<<<grid, 256, 0, st>>>(adv, mb_idx, n, out, scratch);
     return cudaGetLastError();
 }
 

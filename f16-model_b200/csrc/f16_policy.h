@@ -112,8 +112,10 @@ struct PpoAdamArgs {
     int zero_grad;
 };
 cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st);
-// mean and unbiased std of adv[mb_idx[0..n)] -> out[2]; scratch = 4 doubles, zero before the first call (the kernel re-zeroes it)
-cudaError_t launch_adv_stats(const float *adv, const int64_t *mb_idx, int64_t n, float *out, double *scratch, int n_sm, cudaStream_t st);
+// mean and unbiased std of adv[mb_idx[y*n .. (y+1)*n)] -> out[y][2] for y < n_minibatches; scratch = n_minibatches x 4 doubles,
+// zero before the first call (the kernel re-zeroes it)
+cudaError_t launch_adv_stats(const float *adv, const int64_t *mb_idx, int64_t n, int n_minibatches, float *out, double *scratch, int n_sm,
+                             cudaStream_t st);
 
 cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *values, const uint8_t *done_after, const float *next_value,
                        float gamma, float lam, float *advantages, float *returns, int n_sm, cudaStream_t st);

@@ -212,7 +212,7 @@ class PPOTrainer:
         self._grad_scratch = torch.empty(max(1, L.f16_ppo_grad16_scratch_floats(dev.index)), device=dev) if self._fp16 else None
         self._adam = [torch.zeros(self._n_params, device=dev) for _ in range(3)] + [torch.zeros(1, device=dev)]   # m, v, vmax, step
 
-    def _fused_minibatch_step(self, mb):
+    def _fused_minibatch_step(self, mb, adv_stats=None):
         """The same optimiser step in two kernels: forward + loss + backward (ppo_grad_kernel), then clip + Adam + blob
         re-packing (ppo_adam_kernel); csrc/f16_policy.cu."""
         torch, cfg = self._torch, self.cfg
@@ -221,12 +221,14 @@ class PPOTrainer:
         m, v, vmax, step = self._adam                      # (the gradient buffer is cleared by the previous optimiser kernel)
         with torch.cuda.device(self.device):
             st = _capi.stream_ptr(self.device)
-            if cfg.norm_adv:
-                _capi.check(L.f16_ppo_adv_stats(mb.numel(), b["adv"].data_ptr(), mb.data_ptr(), self._adv_stats.data_ptr(),
-                                                self._adv_scratch.data_ptr(), st))
+            if adv_stats is None:
+                adv_stats = self._adv_stats
+                if cfg.norm_adv:
+                    _capi.check(L.f16_ppo_adv_stats(mb.numel(), 1, b["adv"].data_ptr(), mb.data_ptr(), adv_stats.data_ptr(),
+                                                    self._adv_scratch.data_ptr(), st))
             args = (mb.numel(), self._train_blob.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(),
                     b["logprobs"].data_ptr(), b["adv"].data_ptr(), b["ret"].data_ptr(), b["val"].data_ptr(),
-                    mb.data_ptr(), self.policy.actor_logstd.data_ptr(), self._adv_stats.data_ptr(),
+                    mb.data_ptr(), self.policy.actor_logstd.data_ptr(), adv_stats.data_ptr(),
                     self._g.data_ptr(), float(cfg.clip_coef), float(cfg.vf_coef), float(cfg.ent_coef),
                     int(bool(cfg.norm_adv)), int(bool(cfg.clip_vloss)))
             if self._fp16:   # per-CTA partial gradients + a reduction kernel instead of 1.4 M atomics
@@ -298,6 +300,9 @@ class PPOTrainer:
             self._diag = torch.zeros(6, device=self.device)
             self._mb_idx = torch.zeros(self.minibatch_size, dtype=torch.long, device=self.device)
             self._perm_buf = torch.arange(self.batch_size, dtype=torch.long, device=self.device)
+            n_mb = max(1, self.batch_size // self.minibatch_size)
+            self._adv_stats_epoch = torch.zeros((n_mb, 2), device=self.device)
+            self._adv_scratch_epoch = torch.zeros((n_mb, 4), device=self.device, dtype=torch.float64)
         self._adv.copy_(advantages)
         self._ret.copy_(returns)
         self._diag.zero_()
@@ -324,8 +329,14 @@ class PPOTrainer:
             if self._fused:
                 # a whole epoch in one graph: every minibatch reads its slice of the persistent permutation buffer, so an epoch
                 # costs one randperm and one graph launch (4 kernels per minibatch)
-                for start in range(0, self.batch_size - self.minibatch_size + 1, self.minibatch_size):
-                    self._minibatch_step(self._perm_buf[start:start + self.minibatch_size])
+                starts = range(0, self.batch_size - self.minibatch_size + 1, self.minibatch_size)
+                if self.cfg.norm_adv:                      # the advantage statistics of all the epoch's minibatches in one launch
+                    with torch.cuda.device(self.device):
+                        _capi.check(_capi.load_library().f16_ppo_adv_stats(
+                            self.minibatch_size, len(starts), self._flat["adv"].data_ptr(), self._perm_buf.data_ptr(),
+                            self._adv_stats_epoch.data_ptr(), self._adv_scratch_epoch.data_ptr(), _capi.stream_ptr(self.device)))
+                for k, start in enumerate(starts):
+                    self._fused_minibatch_step(self._perm_buf[start:start + self.minibatch_size], adv_stats=self._adv_stats_epoch[k])
             else:
                 self._minibatch_step(self._mb_idx)
         with torch.no_grad():                              # undo the warm-up steps IN PLACE (the graph holds these tensors)

@@ -190,9 +190,10 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
  * (zero it first), f16_ppo_grad_floats floats: the parameter gradients in torch order per net
  * (w1[2][64][5], b1[2][64], w2[2][64][64], b2[2][64], w3[2][64], b3[2], logstd) and five sums over the minibatch
  * (-logratio, (ratio-1)-logratio, |ratio-1| > clip, value loss, policy loss). */
-/* mean and unbiased std of adv[mb_idx[0..n)] -> out float[2] (the advantage normalisation of ppo_model_gsde.py:318-321);
- * scratch = 4 doubles, zeroed once by the caller (the kernel re-arms it). */
-int f16_ppo_adv_stats(int64_t n, const void *adv, const int64_t *mb_idx, void *out, void *scratch, void *stream);
+/* mean and unbiased std of the advantages of n_minibatches consecutive minibatches of n rows each (the advantage normalisation
+ * of ppo_model_gsde.py:318-321): minibatch y = adv[mb_idx[y*n .. (y+1)*n)] -> out float[y][2]; scratch = n_minibatches x 4
+ * doubles, zeroed once by the caller (the kernel re-arms it).  One launch can serve a whole epoch. */
+int f16_ppo_adv_stats(int64_t n, int n_minibatches, const void *adv, const int64_t *mb_idx, void *out, void *scratch, void *stream);
 int f16_ppo_train_blob_bytes(void);
 int f16_ppo_train_blob16_bytes(void);
 int f16_ppo_grad_floats(void);

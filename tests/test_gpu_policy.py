@@ -311,8 +311,15 @@ def test_adv_stats_kernel_matches_torch(f16):
     scratch = torch.zeros(4, device="cuda", dtype=torch.float64)
     for n in (1, 2, 1000, 262144):
         mb = torch.randperm(500000, device="cuda")[:n]
-        _capi.check(L.f16_ppo_adv_stats(n, adv.data_ptr(), mb.data_ptr(), out.data_ptr(), scratch.data_ptr(), _capi.stream_ptr(adv.device)))
+        _capi.check(L.f16_ppo_adv_stats(n, 1, adv.data_ptr(), mb.data_ptr(), out.data_ptr(), scratch.data_ptr(), _capi.stream_ptr(adv.device)))
         a = adv[mb]
         ref = torch.stack([a.mean(), a.std() if n > 1 else torch.zeros((), device="cuda")])
         assert torch.allclose(out, ref, rtol=2e-6, atol=1e-6), (n, out, ref)
     assert scratch.abs().sum().item() == 0          # re-armed for the next call
+    # a whole epoch in one launch: 7 minibatches of 5000 rows
+    perm = torch.randperm(500000, device="cuda")[:35000]
+    out7 = torch.zeros((7, 2), device="cuda")
+    scratch7 = torch.zeros((7, 4), device="cuda", dtype=torch.float64)
+    _capi.check(L.f16_ppo_adv_stats(5000, 7, adv.data_ptr(), perm.data_ptr(), out7.data_ptr(), scratch7.data_ptr(), _capi.stream_ptr(adv.device)))
+    a7 = adv[perm].view(7, 5000)
+    assert torch.allclose(out7, torch.stack([a7.mean(1), a7.std(1)], 1), rtol=2e-6, atol=1e-6)
