@@ -751,6 +751,10 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sm->tmem_base;
+    // programmatic dependent launch: everything above overlapped the previous kernel's tail; the weights, log-std and
+    // statistics read below are that kernel's (the optimiser's) output
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (t == 0) {
         constexpr uint32_t bytes = static_cast<uint32_t>(sizeof(TrainBlob16));
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->bar_w)), "r"(bytes) : "memory");
@@ -1067,6 +1071,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
 __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const float *__restrict__ partials, int n_rows, int n_out, float *__restrict__ out)
 {
     __shared__ float part[8][32];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const unsigned lane = threadIdx.x & 31u, g = threadIdx.x >> 5;
     const int p = blockIdx.x * 32 + lane;
     float s = 0.f;
@@ -1092,6 +1098,8 @@ __global__ void __launch_bounds__(1024) ppo_adam_kernel(const PpoAdamArgs A)
     __shared__ float s_coef;
     __shared__ float s_param[kAdamMaxParams];
     const unsigned t = threadIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     float ss = 0.f;
     for (int i = t; i < A.n; i += 1024) {
         const float g = A.grad[i];
@@ -1305,7 +1313,17 @@ cudaError_t launch_adv_stats(const float *adv, const int64_t *mb_idx, int64_t n,
 
 cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st)
 {
-    ppo_adam_kernel<<<1, 1024, 0, st>>>(A);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(1);
+    lc.blockDim = dim3(1024);
+    lc.stream = st;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&lc, ppo_adam_kernel, A);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
@@ -1321,10 +1339,25 @@ cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, f
     }
     const int64_t tiles = (P.n + kRows - 1) / kRows;
     const int grid = static_cast<int>(tiles < n_sm ? tiles : n_sm);   // one CTA per SM: it owns all 512 TMEM columns
-    ppo_grad16_kernel<<<grid, kThreads, sizeof(TrainSmem16), st>>>(P, blob16, partials);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // the minibatch chain gradient -> reduction -> optimiser -> gradient ...
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kThreads);
+    lc.dynamicSmemBytes = sizeof(TrainSmem16);
+    lc.stream = st;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&lc, ppo_grad16_kernel, P, blob16, partials);
+    if (e != cudaSuccess) return e;
     if (partials) {
         constexpr int n_out = static_cast<int>(sizeof(PolicyGrad) / sizeof(float));
-        ppo_grad_reduce_kernel<<<(n_out + 31) / 32, 256, 0, st>>>(partials, grid, n_out, reinterpret_cast<float *>(P.grad));
+        lc.gridDim = dim3((n_out + 31) / 32);
+        lc.blockDim = dim3(256);
+        lc.dynamicSmemBytes = 0;
+        e = cudaLaunchKernelEx(&lc, ppo_grad_reduce_kernel, static_cast<const float *>(partials), grid, n_out, reinterpret_cast<float *>(P.grad));
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }
