@@ -715,7 +715,12 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
                 isa_finish<R, FAST>(Tk[e], pk[e], rho, asnd);
                 const R a = clampr(a_in[e], R(-1), R(1));
                 const R u_stab = R(K::act_lo) + R(0.5) * (a + R(1.0)) * R(K::act_span);
+#ifdef F16_PROBE_NOMATH   // probe build: the memory pipeline alone (inputs -> outputs with a trivial right-hand side)
+#pragma unroll
+                for (int j = 0; j < 9; ++j) dx[j] = x[e][j] * R(1e-6) + u_stab * rho * asnd * R(1e-9);
+#else
                 rhs_atm<R, FAST, false>(tbl, x[e], u_stab, R(0), rho, asnd, dx);
+#endif
 #pragma unroll
                 for (int j = 0; j < 9; ++j)
                     if (j != 4) x[e][j] = dx[j] * dt + x[e][j];
