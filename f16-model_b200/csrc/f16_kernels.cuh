@@ -518,6 +518,9 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
 #ifndef F16_CTA2_THREADS
 #define F16_CTA2_THREADS 128
 #endif
+#ifndef F16_MINCTAS2S
+#define F16_MINCTAS2S 4
+#endif
 #ifndef F16_CTA2K_THREADS
 #define F16_CTA2K_THREADS 256
 #endif
@@ -527,7 +530,7 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
 template <bool SINGLE>
 struct Cta2 {
     static constexpr int threads = SINGLE ? F16_CTA2_THREADS : F16_CTA2K_THREADS;
-    static constexpr int min_ctas = SINGLE ? 4 : 2;
+    static constexpr int min_ctas = SINGLE ? F16_MINCTAS2S : 2;
     static constexpr int tile = 2 * threads;
 };
 constexpr int kIn2Rows = 13;   // 9 state rows, action, ep_len, ref_idx, total_return
