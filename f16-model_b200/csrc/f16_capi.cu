@@ -201,6 +201,7 @@ f16::StepArgs<R> make_step_args(const f16_config *cfg, const f16_step_io *io, in
     S.K = K;
     S.tma_ok = 0;   // set by step_range once the env buffers are known
     S.obs_bulk = 0;
+    S.pdl_mode = 0;
     S.i_begin = 0;
     S.i_end = cfg->n_envs;
     return S;

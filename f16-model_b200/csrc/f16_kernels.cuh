@@ -319,7 +319,10 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
     if (threadIdx.x == 0) tma_bulk_g2s(&sm->tbl, A.tables, static_cast<uint32_t>(sizeof(Tables<R>)), &sm->bar_tbl);
     // ... and do not touch anything the PREVIOUS launch may still be writing (state, counters, actions)
     // until it has completed.  (No-op when the launch carries no programmatic dependency.)
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // pdl_mode 2 = this launch is the ragged tail of a step whose full tiles run in the two-env kernel just before it: that kernel
+    // released us only after ITS wait (everything older is complete) and touches other envs, so the tail runs alongside it and
+    // waits at its end instead -- its completion then still implies the completion of everything before it.
+    if (S.pdl_mode != 2) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) {
         if (tma) {   // prologue: only the FIRST tile of every CTA -- the opening burst is half as deep, so it lands sooner
             const unsigned t0 = blockIdx.x;
@@ -502,6 +505,7 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
             atomicAdd(S.stats + 2, static_cast<double>(sm->stats.length));
         }
     }
+    if (S.pdl_mode == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------
@@ -632,7 +636,8 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
         sm->stats.ret = 0.0;
     }
     __syncthreads();
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // (pdl_mode 1: a ragged-tail launch follows and must not start before everything older than this grid is complete)
+    if (S.pdl_mode != 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (t == 0) {
         tma_bulk_g2s(&sm->tbl, A.tables, static_cast<uint32_t>(sizeof(Tables<R>)), &sm->bar_tbl);
 #pragma unroll
@@ -642,6 +647,7 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
         }
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (S.pdl_mode == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (t == 0 && blockIdx.x < n_tiles) issue_tile2<R, CT, SINGLE>(A, S, sm, 0, i_begin + blockIdx.x * TILE);
     bool tables_ready = false;
 
@@ -1110,11 +1116,16 @@ cudaError_t launch_env_step_t(const EnvArgs<R> &A, const StepArgs<R> &S, const L
             at2[0].val.programmaticStreamSerializationAllowed = 1;
             lc2.attrs = at2;
             lc2.numAttrs = g.pdl ? 1 : 0;
-            cudaError_t e2 = single ? cudaLaunchKernelEx(&lc2, env_step2_kernel<R, FAST, true>, A, S)
-                                    : cudaLaunchKernelEx(&lc2, env_step2_kernel<R, FAST, false>, A, S);
-            if (e2 != cudaSuccess) return e2;
-            StepArgs<R> rest = S;
+            StepArgs<R> head = S, rest = S;
             rest.i_begin = S.i_begin + n2 * tile2;
+            const bool split = rest.i_begin < rest.i_end && g.pdl && S.pdl_mode == 0;
+            if (split) {   // the ragged tail runs alongside the full tiles instead of after them
+                head.pdl_mode = 1;
+                rest.pdl_mode = 2;
+            }
+            cudaError_t e2 = single ? cudaLaunchKernelEx(&lc2, env_step2_kernel<R, FAST, true>, A, head)
+                                    : cudaLaunchKernelEx(&lc2, env_step2_kernel<R, FAST, false>, A, head);
+            if (e2 != cudaSuccess) return e2;
             if (rest.i_begin >= rest.i_end) return cudaGetLastError();
             LaunchGeom g1 = g;
             g1.two_per_thread = 0;

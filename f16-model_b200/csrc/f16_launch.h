@@ -55,6 +55,7 @@ struct StepArgs {
     int K;
     int tma_ok;               // every input row of a full tile is 16-byte aligned: TMA-staged loads allowed
     int obs_bulk;             // AoS obs rows of a full tile are 16-byte aligned: staged in shared memory, written by bulk stores
+    int pdl_mode;             // 0: normal; 1: head of a split step (dependents released after the own wait); 2: tail (waits at its END)
     int64_t i_begin, i_end;   // env sub-range advanced by this launch (host-buffer path pipelines chunks)
 };
 
