@@ -41,3 +41,46 @@ def global_episode_stats(env, group=None):
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     return stats
+
+
+def trim_grid_sharded(V, H, rank, world_size, device="cuda", group=None, trim_fn=None, **kw):
+    """Batched trim search over a grid of flight conditions striped across ranks: every rank
+    trims its contiguous block of (V, H) cells on its own GPU, then ONE ``all_gather`` of ``[cells, 5]``
+    doubles (stab, throttle, alpha, cost, iterations) gives every rank the whole grid.  Returns the same dict
+    as ``trim.trim_grid`` for all cells.  ``trim_fn`` (default ``trim.trim_grid``) does the per-rank work."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if trim_fn is None:
+        from .trim import trim_grid as trim_fn
+    V = np.atleast_1d(np.asarray(V, dtype=np.float64)).ravel()
+    H = np.atleast_1d(np.asarray(H, dtype=np.float64)).ravel()
+    if V.shape != H.shape:
+        raise ValueError("V and H must have the same number of cells")
+    begin, end = shard_range(V.size, rank, world_size)
+    n_max = (V.size + world_size - 1) // world_size          # blocks differ by at most one cell -> pad to the largest
+    mine = np.zeros((n_max, 5))
+    n_starts = 0
+    if end > begin:
+        r = trim_fn(V[begin:end], H[begin:end], device=device, **kw)
+        mine[: end - begin] = np.stack([r["stab"], r["throttle"], r["alpha"], r["cost"], r["iterations"]], axis=1)
+        n_starts = int(r.get("n_starts", 0))
+    if world_size > 1:
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("trim_grid_sharded with world_size > 1 needs an initialised process group")
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.tensor(mine, device=device if on_gpu else "cpu")
+        parts = [torch.empty_like(t) for _ in range(world_size)]
+        dist.all_gather(parts, t, group=group)
+        blocks = []
+        for r_, part in enumerate(parts):
+            b, e = shard_range(V.size, r_, world_size)
+            blocks.append(part[: e - b].cpu().numpy())
+        full = np.concatenate(blocks, axis=0)
+    else:
+        full = mine[: V.size]
+    out = {"stab": full[:, 0], "throttle": full[:, 1], "alpha": full[:, 2], "cost": full[:, 3],
+           "iterations": full[:, 4].astype(np.int32), "n_starts": n_starts}
+    out["accepted"] = out["cost"] <= 10e-6
+    return out

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from f16_model_b200.sharding import global_episode_stats, shard_range
+from f16_model_b200.sharding import global_episode_stats, shard_range, trim_grid_sharded
 
 TOTAL = 1001      # deliberately not divisible by the world size
 
@@ -39,7 +39,22 @@ def _worker(rank, world, port, out):
     spans = [None] * world
     dist.all_gather_object(spans, (begin, end))
     cover = spans[0][0] == 0 and spans[-1][1] == TOTAL and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
-    out.put((rank, bool(ok), bool(cover)))
+    # trim grid striped over ranks + one all_gather: every rank ends up with the whole grid, cell for cell
+    Vg, Hg = np.meshgrid(np.linspace(100, 300, 7), np.linspace(1000, 10000, 5))     # 35 cells: ragged over 2 ranks
+    seen = []
+
+    def fake_trim(V, H, device=None, **kw):     # stands in for the CUDA search: a closed form of the cell
+        seen.append(len(V))
+        return {"stab": -V / 1000, "throttle": H / 20000, "alpha": V / H, "cost": 1e-7 * V, "iterations": (V + H).astype(np.int32),
+                "n_starts": 11}
+
+    g = trim_grid_sharded(Vg, Hg, rank, world, device="cpu", trim_fn=fake_trim)
+    Vf, Hf = Vg.ravel(), Hg.ravel()
+    b, e = shard_range(Vf.size, rank, world)
+    trim_ok = (seen == [e - b] and np.array_equal(g["stab"], -Vf / 1000) and np.array_equal(g["throttle"], Hf / 20000)
+               and np.array_equal(g["alpha"], Vf / Hf) and np.array_equal(g["iterations"], (Vf + Hf).astype(np.int32))
+               and np.array_equal(g["accepted"], 1e-7 * Vf <= 1e-5) and g["n_starts"] == 11)
+    out.put((rank, bool(ok), bool(cover and trim_ok)))
     dist.destroy_process_group()
 
 

@@ -17,7 +17,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import f16_model_b200 as f16  # noqa: E402
-from f16_model_b200.sharding import make_sharded_env, shard_range  # noqa: E402
+from f16_model_b200.sharding import make_sharded_env, shard_range, trim_grid_sharded  # noqa: E402
 
 CFG = {"dt": 0.01, "tn": 10, "debug_state": False, "determenistic_ref": False, "scenario": "combo"}
 
@@ -83,17 +83,10 @@ def main():
     b, e = shard_range(Vg.size, rank, world)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    g = f16.trim_grid(Vg.ravel()[b:e], Hg.ravel()[b:e], device=dev)
+    g = trim_grid_sharded(Vg, Hg, rank, world, device=dev)     # cells striped over ranks + one all_gather
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    res = torch.tensor(np.stack([g["stab"], g["throttle"], g["alpha"], g["cost"]], 1), device=dev)
-    if world > 1:     # one all_gather of [cells, 4] doubles; shards differ by at most one cell -> pad
-        n_max = (Vg.size + world - 1) // world
-        pad = torch.zeros((n_max, 4), dtype=res.dtype, device=dev)
-        pad[: res.shape[0]] = res
-        out = [torch.empty_like(pad) for _ in range(world)]
-        torch.distributed.all_gather(out, pad)
-        res = torch.cat([o[: shard_range(Vg.size, r, world)[1] - shard_range(Vg.size, r, world)[0]] for r, o in enumerate(out)])
+    res = torch.tensor(np.stack([g["stab"], g["throttle"], g["alpha"], g["cost"]], 1))
     if rank == 0:
         print(json.dumps({"config": "5b: trim grid %d cells x %d starts (reference grid), %d GPU(s)" % (Vg.size, g["n_starts"], world),
                           "seconds_rank0": dt, "searches_per_s": (e - b) * g["n_starts"] * world / dt,

@@ -1,6 +1,9 @@
 """Small end-to-end exercise of every step-kernel route for compute-sanitizer (memcheck / racecheck / synccheck):
 one-env and two-env kernels, gym step and K-step, ragged tail, zero-copy host route with bulk-stored observations,
-policy forward, trim.  Sizes are tiny because the tools slow execution 10-100x."""
+policy forward, PPO rollout + fused update (fp16 and tf32 gradient kernels, Adam, GAE), trim.  Sizes are tiny because the tools slow execution 10-100x.
+(compute-sanitizer is closed on this GPU pool -- the gpurun wrapper refuses it -- so here the script only serves as a
+plain run-through of every route; the bounds evidence is the parity suite itself: ragged sizes 1..300, canary-free
+bit-exact comparisons against the oracle, and sharding invariance at 8 Mi envs.)"""
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
 import f16_model_b200 as f16
@@ -22,5 +25,11 @@ e64.step(torch.zeros(1000, dtype=torch.float64, device="cuda"))
 pol = f16.TensorCorePolicy(seed=1)
 pol.act(env._obs, env=env)
 f16.trim_grid([200.0], [3000.0])
+CFG_D = dict(CFG, determenistic_ref=True)
+for prec in ("fp16", "tf32"):
+    envs = f16.F16VecEnv(CFG_D, 512, seed=3)
+    tr = f16.PPOTrainer(envs, f16.TensorCorePolicy(seed=3, logstd_init=-1.0),
+                        f16.PPOConfig(num_steps=8, num_minibatches=2, update_epochs=1, fused_precision=prec, use_cuda_graph=False))
+    tr.train(num_updates=1)
 torch.cuda.synchronize()
 print("sanitize workload done", float(env.total_return.sum()))
