@@ -274,7 +274,7 @@ __device__ __forceinline__ R thrust(const Tables<R> &T, R H, R Mach, R Pa)
     const R p = Pa - R(50) * R(ip);
     const R h = H - R(K::thrust_dH) * R(ih);
     const R m = Mach - R(K::thrust_dM) * R(im);
-    const R *t = T.thrust[ip][ih][im];
+    const R *t = T.thrust[ip][ih] + 8 * im;
     const Vec4<R> lo = Vec4<R>::ld(t), hi = Vec4<R>::ld(t + 4);
     return ((lo.x + lo.y * m) + h * (lo.z + lo.w * m)) + p * ((hi.x + hi.y * m) + h * (hi.z + hi.w * m));
 }

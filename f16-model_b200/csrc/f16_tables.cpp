@@ -72,7 +72,7 @@ void build_tables(Tables<double> &T)
                 const double(*P1)[6] = F16T_THRUST[ip + 1];
                 bilinear_poly(P0[ih][im], P0[ih + 1][im], P0[ih][im + 1], P0[ih + 1][im + 1], dm, dh, lo);
                 bilinear_poly(P1[ih][im], P1[ih + 1][im], P1[ih][im + 1], P1[ih + 1][im + 1], dm, dh, hi);
-                double *t = T.thrust[ip][ih][im];
+                double *t = T.thrust[ip][ih] + 8 * im;
                 for (int k = 0; k < 4; ++k) {
                     t[k] = lo[k];                       // t0 + t1*m + h*(t2 + t3*m)
                     t[4 + k] = (hi[k] - lo[k]) / dp;    // + p*(t4 + t5*m + h*(t6 + t7*m))
