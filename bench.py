@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fast-math", type=int, default=1)
+    ap.add_argument("--pool", type=int, default=64, help="rows of the cycled stick tensor per batch (period of each env's stick, in steps)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -228,7 +229,7 @@ def main():
     # R_SETS x 77 MB (state + actions + outputs) = 308 MB >> 126 MB of L2, so every step's inputs come
     # from HBM and its dirty lines are written back while the next batches run -- the steady state of a
     # streaming workload, with no flush kernel inside the timed region.
-    R_SETS, POOL = 4, 8
+    R_SETS, POOL = 4, max(1, args.pool)
     envs = [make_sharded_env(CFG, N * world, rank, world, device, dtype=torch.float32, autoreset=True, seed=1 + j,
                              fast_math=fast, bank_size=256) for j in range(R_SETS)]
     env = envs[0]
@@ -247,7 +248,7 @@ def main():
 
     # The K = 1 gym step is launch-bound from Python (~30 us of interpreter + ctypes per call vs a
     # ~25 us kernel), so the timed loop replays a CUDA graph of G consecutive steps.
-    G = min(48, args.steps)
+    G = min(max(48, R_SETS * POOL), args.steps)   # one graph covers a whole cycle of the stick pool
     graphs = {}
 
     def graph_of(n_steps):
@@ -466,6 +467,7 @@ def main():
                    "envs_per_gpu": N, "substeps_per_launch": 1, "fast_math": fast, "parallelism": f"env-shard x{world}, no collective",
                    "l2": "inputs larger than L2: 4 resident batches of 2^20 envs stepped round-robin (308 MB per cycle vs 126 MB L2), "
                          "no flush kernel in the timed region",
+                   "stick": f"U(-1,1) rows cycled from a pool of {POOL} per batch (each env's stick repeats every {POOL} steps)",
                    "launch": f"CUDA graph of {G} consecutive steps, replayed"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu,
         "value_eager_python_loop": N * world * n_sec / eager_s,

@@ -25,7 +25,9 @@ def sample_states(n=8192, T=400, seed=3):
     x0 = np.zeros((n, 9))
     x0[:, 1], x0[:, 2], x0[:, 3] = rng.uniform(2000, 4000, n), rng.uniform(-d5, d5, n), al
     x0[:, 4], x0[:, 5] = rng.uniform(90, 250, n), al
-    acts = rng.uniform(-1, 1, (T, n))
+    # bench.py cycles a pool of 8 action rows per batch: every env sees a PERIODIC 8-step stick (DC offset + 12.5 Hz
+    # harmonics), which spreads stab and alpha much wider than an i.i.d. stick would
+    acts = np.tile(rng.uniform(-1, 1, (8, n)), (T // 8 + 1, 1))[:T]
     bank = f16.build_reference_bank(0.01, 10, "combo", True)
     r = orc.rollout(x0, acts, bank, np.zeros(n, dtype=np.int32), want_obs=False)
     return r["states"], r["ep_len"]
@@ -82,8 +84,9 @@ def layout_cost(ia, i1, i3, ip, ih, im, L, verbose=False):
     return tot
 
 
-CURRENT = dict(cell3_base=0, cell3_f=NA * 3, cell3_a=3, arow_base=228, arow_a=4, dmzds_base=304, dmzds_a=6,
-               eta_base=418, thrust_base=422, thrust_c=2)
+ORIGINAL = dict(cell3_base=0, cell3_f=NA * 3, cell3_a=3, arow_base=228, arow_a=4, dmzds_base=304, dmzds_a=6,
+                eta_base=418, thrust_base=422, thrust_c=2)
+CURRENT = ORIGINAL
 
 if __name__ == "__main__":
     states, ep_len = sample_states()
@@ -115,3 +118,7 @@ if __name__ == "__main__":
     res = {(s, hs): wavefronts((ip * 5 + ih) * (800 + hs) + im * s) for s in (2, 3, 5, 7) for hs in range(8)}
     for k in sorted(res, key=res.get)[:6]:
         print("  thrust m-stride %d, h-stride = %d mod 8: %.3f" % (k[0], k[1], res[k]))
+    print("\nall residues, stationary sample")
+    print("  cell3 (a-stride 3) by f-stride mod 8:", {f: round(sum(wavefronts(i1 * (800 + f) + ia * 3 + c) for c in range(3)) / 3, 3) for f in range(8)})
+    print("  dmzds (f-stride 1) by a-stride mod 8:", {a: round(wavefronts(ia * (800 + a) + i3), 3) for a in range(8)})
+    print("  arow by a-stride:", {a: round(wavefronts(ia * a), 3) for a in (4, 5, 6, 7, 9, 11, 13)})
