@@ -18,19 +18,30 @@ import f16_model_b200 as f16  # noqa: E402
 NA, NF1, NF3 = 19, 4, 6
 
 
-def sample_states(n=8192, T=400, seed=3):
+def sample_states(n=8192, T=400, seed=3, stick_period=None):
+    """States of n envs over T steps under a U(-1,1) stick: i.i.d. per step, or (stick_period = P) a P-step random
+    pattern repeated -- what a bench that cycles a pool of P action rows feeds every env."""
     rng = np.random.default_rng(seed)
     d5 = np.radians(5)
     al = rng.uniform(-d5, d5, n)
     x0 = np.zeros((n, 9))
     x0[:, 1], x0[:, 2], x0[:, 3] = rng.uniform(2000, 4000, n), rng.uniform(-d5, d5, n), al
     x0[:, 4], x0[:, 5] = rng.uniform(90, 250, n), al
-    # bench.py cycles a pool of 8 action rows per batch: every env sees a PERIODIC 8-step stick (DC offset + 12.5 Hz
-    # harmonics), which spreads stab and alpha much wider than an i.i.d. stick would
-    acts = np.tile(rng.uniform(-1, 1, (8, n)), (T // 8 + 1, 1))[:T]
+    if stick_period:
+        acts = np.tile(rng.uniform(-1, 1, (stick_period, n)), (T // stick_period + 1, 1))[:T]
+    else:
+        acts = rng.uniform(-1, 1, (T, n))
     bank = f16.build_reference_bank(0.01, 10, "combo", True)
     r = orc.rollout(x0, acts, bank, np.zeros(n, dtype=np.int32), want_obs=False)
     return r["states"], r["ep_len"]
+
+
+def stationary_cells(states, ep_len, lo=100, hi=None, seed=0):
+    """cell indices of the env-steps lo..hi of still-running episodes, shuffled (lanes of a warp are independent envs)."""
+    hi = hi or states.shape[0]
+    xs = np.concatenate([states[t][ep_len > t] for t in range(lo, hi, 7)])
+    xs = xs[np.random.default_rng(seed).permutation(xs.shape[0])]
+    return cells(xs)
 
 
 def cells(x):
@@ -66,59 +77,62 @@ def wavefronts(chunk):
 
 
 def layout_cost(ia, i1, i3, ip, ih, im, L, verbose=False):
-    """L: dict of base / strides (in chunks).  Returns total mean wavefronts per quarter-warp over the 12 loads."""
-    tot = 0.0
+    """L: strides of the table image in 16-byte fp32 chunks.  Mean wavefronts per quarter-warp summed over the 11
+    loads of one env-step (11.0 = conflict-free)."""
     parts = {}
-    for c in range(3):   # cell3: px, py, pm
+    for c in range(3):   # cell3: Cx, Cy, mz polynomials
         parts[f"cell3.{c}"] = wavefronts(L["cell3_base"] + i1 * L["cell3_f"] + ia * L["cell3_a"] + c)
-    for c in range(4):   # arow: kx, ky, km, r3
+    for c in range(4):   # arow: Cxwz, Cywz, mzwz cubics, dmz1 line
         parts[f"arow.{c}"] = wavefronts(L["arow_base"] + ia * L["arow_a"] + c)
     parts["dmzds"] = wavefronts(L["dmzds_base"] + ia * L["dmzds_a"] + i3)
     parts["eta"] = wavefronts(L["eta_base"] + i1)
-    cell = (ip * 5 + ih) * 5 + im
     for c in range(2):
-        parts[f"thrust.{c}"] = wavefronts(L["thrust_base"] + cell * L["thrust_c"] + c)
-    tot = sum(parts.values())
+        parts[f"thrust.{c}"] = wavefronts(L["thrust_base"] + (ip * 5 + ih) * L["thrust_h"] + im * 2 + c)
     if verbose:
         print("  " + "  ".join(f"{k} {v:.2f}" for k, v in parts.items()))
-    return tot
+    return sum(parts.values())
 
 
-ORIGINAL = dict(cell3_base=0, cell3_f=NA * 3, cell3_a=3, arow_base=228, arow_a=4, dmzds_base=304, dmzds_a=6,
-                eta_base=418, thrust_base=422, thrust_c=2)
-CURRENT = ORIGINAL
+# the image the first round-1 builds used: rows of 16 / cells of 12 / 8 floats back to back
+ORIGINAL = dict(cell3_base=0, cell3_f=NA * 3, cell3_a=3, arow_base=228, arow_a=4, dmzds_base=304, dmzds_a=NF3,
+                eta_base=418, thrust_base=422, thrust_h=10)
+
+
+def layout_from_header(path=None):
+    """Strides of the image csrc/f16_tables.h declares (parsed from its constants and array bounds)."""
+    import re
+
+    path = path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "f16-model_b200", "csrc", "f16_tables.h")
+    src = open(path).read()
+    const = {k: int(eval(v, {}, {})) for k, v in re.findall(r"constexpr int (k\w+) = ([^;]+);", src)}   # noqa: S307 (integer expressions)
+
+    def dims(name):
+        m = re.search(r"R %s((?:\[[^\]]+\])+);" % name, src)
+        return [int(eval(d, {}, dict(const))) for d in re.findall(r"\[([^\]]+)\]", m.group(1))]
+
+    c3, ar, dz, et, th = dims("cell3"), dims("arow"), dims("dmzds"), dims("eta"), dims("thrust")
+    L = dict(cell3_base=0, cell3_f=c3[1] * c3[2] // 4, cell3_a=c3[2] // 4)
+    L["arow_base"] = c3[0] * c3[1] * c3[2] // 4
+    L["arow_a"] = ar[1] // 4
+    L["dmzds_base"] = L["arow_base"] + ar[0] * ar[1] // 4
+    L["dmzds_a"] = dz[1] * dz[2] // 4
+    L["eta_base"] = L["dmzds_base"] + dz[0] * dz[1] * dz[2] // 4
+    L["thrust_base"] = L["eta_base"] + et[0] * et[1] // 4
+    L["thrust_h"] = th[2] // 4
+    return L
+
 
 if __name__ == "__main__":
-    states, ep_len = sample_states()
-    for lo, hi in ((0, 20), (100, 400)):
-        xs = np.concatenate([states[t][ep_len > t] for t in range(lo, hi, 7)])
-        rng = np.random.default_rng(0)
-        xs = xs[rng.permutation(xs.shape[0])]          # lanes of a warp are independent envs
-        idx = cells(xs)
-        print(f"steps {lo}..{hi}: {xs.shape[0]} samples; distinct ia per quarter-warp "
-              f"{np.mean([len(set(q)) for q in idx[0][: 8000].reshape(-1, 8)]):.2f}, ideal total = 12 wavefronts")
-        print(" current layout:", f"{layout_cost(*idx, CURRENT, verbose=True):.2f}")
-        for arow_a in (5, 6, 7):
-            L = dict(CURRENT, arow_a=arow_a)
-            print(f" arow stride {arow_a} chunks:", f"{layout_cost(*idx, L, verbose=True):.2f}")
-
-    # ---- search: strides only matter mod 8 (and must be >= the cell size) ----------------------------
-    print("\nsearch on the stationary sample")
-    ia, i1, i3, ip, ih, im = idx
-    best = {}
-    res = {(a, f): sum(wavefronts(i1 * (800 + f) + ia * a + c) for c in range(3)) for a in (3, 5, 7) for f in range(8)}   # 800 = 0 mod 8: distinct cells stay distinct
-    for k in sorted(res, key=res.get)[:5]:
-        print("  cell3 a-stride %d, f-stride = %d mod 8: %.3f" % (k[0], k[1], res[k] / 3))
-    res = {a: wavefronts(ia * a) for a in (5, 7)}
-    print("  arow:", res)
-    res = {(a, b): wavefronts(ia * (800 + a) + i3 * b) for a in range(8) for b in (1, 3, 5, 7)}
-    for k in sorted(res, key=res.get)[:5]:
-        print("  dmzds a-stride = %d mod 8, f-stride %d: %.3f" % (k[0], k[1], res[k]))
-    cell = (ip * 5 + ih) * 5 + im
-    res = {(s, hs): wavefronts((ip * 5 + ih) * (800 + hs) + im * s) for s in (2, 3, 5, 7) for hs in range(8)}
-    for k in sorted(res, key=res.get)[:6]:
-        print("  thrust m-stride %d, h-stride = %d mod 8: %.3f" % (k[0], k[1], res[k]))
-    print("\nall residues, stationary sample")
-    print("  cell3 (a-stride 3) by f-stride mod 8:", {f: round(sum(wavefronts(i1 * (800 + f) + ia * 3 + c) for c in range(3)) / 3, 3) for f in range(8)})
-    print("  dmzds (f-stride 1) by a-stride mod 8:", {a: round(wavefronts(ia * (800 + a) + i3), 3) for a in range(8)})
-    print("  arow by a-stride:", {a: round(wavefronts(ia * a), 3) for a in (4, 5, 6, 7, 9, 11, 13)})
+    CURRENT = layout_from_header()
+    print("layout in f16_tables.h:", CURRENT)
+    for name, period in (("i.i.d. stick", None), ("stick repeating every 8 steps (bench --pool 8)", 8), ("every 64 steps (bench default)", 64)):
+        states, ep_len = sample_states(stick_period=period)
+        idx = stationary_cells(states, ep_len)
+        ia = idx[0]
+        print(f"\n{name}: {ia.size} env-steps, {np.mean([len(set(q)) for q in ia[:8000].reshape(-1, 8)]):.2f} distinct alpha cells per quarter-warp")
+        print(" original image :", f"{layout_cost(*idx, ORIGINAL, verbose=True):.2f}")
+        print(" f16_tables.h   :", f"{layout_cost(*idx, CURRENT, verbose=True):.2f}")
+        i1, i3 = idx[1], idx[2]
+        print("  cell3 by plane stride mod 8:", {f: round(sum(wavefronts(i1 * (800 + f) + ia * 3 + c) for c in range(3)) / 3, 2) for f in range(8)})
+        print("  dmzds by row stride mod 8  :", {a: round(wavefronts(ia * (800 + a) + i3), 2) for a in range(8)})
+        print("  arow by row stride         :", {a: round(wavefronts(ia * a), 2) for a in (4, 5, 6, 7)})
