@@ -623,6 +623,19 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
     const unsigned n_tiles = static_cast<unsigned>(S.i_end - S.i_begin) / TILE;   // full tiles only
     const R dt = A.dt;
     const unsigned t = threadIdx.x;
+    // A warp owns 64 CONSECUTIVE envs of the tile: lane l advances envs 64 w + l and 64 w + 32 + l.  Every global store of the
+    // warp still covers 32 consecutive envs, and the warp's [64, 5] block of AoS observations (1280 B) as well as its 64
+    // rewards / done flags are contiguous -- one bulk store each on the host route (full-size PCIe writes).
+#ifndef F16_X2_WARP64
+#define F16_X2_WARP64 1
+#endif
+#if F16_X2_WARP64
+    constexpr unsigned E2 = 32;
+    const unsigned tl = ((t & ~31u) << 1) | (t & 31u);
+#else
+    constexpr unsigned E2 = CT;
+    const unsigned tl = t;
+#endif
 
     if (t == 0) {
         mbar_init(&sm->bar_tbl, 1);
@@ -671,7 +684,7 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
             const R(*in)[TILE] = sm->in[stage];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const unsigned c = t + e * CT;
+                const unsigned c = tl + e * E2;
 #pragma unroll
                 for (int j = 0; j < 9; ++j) x[e][j] = in[j][c];
                 a_in[e] = in[9][c];
@@ -706,7 +719,7 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 ref[e] = A.ref_bank[static_cast<unsigned>(ref_idx[e]) * static_cast<unsigned>(A.ref_len) + min(ep_len[e], A.ref_len - 1)];
-                if (!SINGLE && k + 1 < K_steps) a_next[e] = S.actions[static_cast<unsigned>(k + 1) * n + base + t + e * CT];
+                if (!SINGLE && k + 1 < K_steps) a_next[e] = S.actions[static_cast<unsigned>(k + 1) * n + base + tl + e * E2];
                 Hg[e] = isa_geopotential<R, FAST>(x[e][1]);
                 slow[e] = !(Hg[e] >= R(0) && Hg[e] < R(11000));
                 isa_troposphere<R, FAST>(Hg[e], Tk[e], pk[e]);
@@ -752,7 +765,7 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 if (done[e]) {
-                    const unsigned i = base + t + e * CT;
+                    const unsigned i = base + tl + e * E2;
                     if (S.stats) episode_stats_add(&sm->stats, static_cast<double>(ret[e]), ep_len[e]);
                     if (S.final_obs) store_obs<R>(S.final_obs, A.obs_layout, n, i, o[e]);
                     if (S.final_ep_len) S.final_ep_len[i] = ep_len[e];
@@ -769,7 +782,7 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
             }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const unsigned kn = static_cast<unsigned>(k) * n + base + t + e * CT;
+                const unsigned kn = static_cast<unsigned>(k) * n + base + tl + e * E2;
                 S.reward[kn] = reward[e];
                 S.done[kn] = static_cast<uint8_t>(done[e]);
             }
@@ -777,28 +790,28 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
 
         // ---- write back ---------------------------------------------------------------------------------------
         {
-            const unsigned i = base + t;
+            const unsigned i = base + tl;
             R *p = A.state + i;
 #pragma unroll
             for (int j = 0; j < 9; ++j) {
                 if (j == 4) {
                     if (was_reset[0]) p[0] = x[0][4];
-                    if (was_reset[1]) p[CT] = x[1][4];
+                    if (was_reset[1]) p[E2] = x[1][4];
                 } else if (j == 8) {
                     if (x[0][8] != pa_in[0]) p[0] = x[0][8];
-                    if (x[1][8] != pa_in[1]) p[CT] = x[1][8];
+                    if (x[1][8] != pa_in[1]) p[E2] = x[1][8];
                 } else {
                     p[0] = x[0][j];
-                    p[CT] = x[1][j];
+                    p[E2] = x[1][j];
                 }
                 p += n;
             }
             int32_t *pl = A.ep_len + i;
             pl[0] = ep_len[0];
-            pl[CT] = ep_len[1];
+            pl[E2] = ep_len[1];
             R *pt = A.total_return + i;
             pt[0] = ret[0];
-            pt[CT] = ret[1];
+            pt[E2] = ret[1];
             if (S.obs && !(SINGLE && S.obs_bulk)) {
                 if (A.obs_layout == 0) {   // F16_OBS_AOS
                     R *po = S.obs + static_cast<size_t>(i) * 5u;
@@ -806,21 +819,21 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
                         po[j] = o[0][j];
-                        po[CT * 5 + j] = o[1][j];
+                        po[E2 * 5 + j] = o[1][j];
                     }
 #else
                     // env-major: the five 4-byte stores of one env's row go out back to back (they share sectors)
 #pragma unroll
                     for (int j = 0; j < 5; ++j) po[j] = o[0][j];
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) po[CT * 5 + j] = o[1][j];
+                    for (int j = 0; j < 5; ++j) po[E2 * 5 + j] = o[1][j];
 #endif
                 } else {
                     R *po = S.obs + i;
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
                         po[0] = o[0][j];
-                        po[CT] = o[1][j];
+                        po[E2] = o[1][j];
                         po += n;
                     }
                 }
@@ -830,23 +843,25 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
             // [N,5] observations: each warp stages its two 32-env runs (2 x 640 B, stride-5 words = conflict-free) and
             // lane 0 writes them with two bulk stores -- full lines instead of 20-byte-strided scalar stores, which is
             // what makes the same kernel usable on mapped host memory (PCIe sees large writes)
-            const unsigned lane = t & 31u, w0 = t & ~31u;
+            const unsigned lane = t & 31u, w0 = tl & ~31u;   // first env of this warp's first run
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // last tile's stores have read the staging area
             __syncwarp();
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                R *dst = sm->obs_out + (t + e * CT) * 5u;
+                R *dst = sm->obs_out + (tl + e * E2) * 5u;
 #pragma unroll
                 for (int j = 0; j < 5; ++j) dst[j] = o[e][j];
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
+                constexpr int RUNS = (E2 == 32) ? 1 : 2;           // one [64, 5] block, or two [32, 5] runs CT envs apart
+                constexpr uint32_t run_bytes = (2 / RUNS) * 32u * 5u * sizeof(R);
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const unsigned c0 = w0 + e * CT;
+                for (int e = 0; e < RUNS; ++e) {
+                    const unsigned c0 = w0 + e * E2;
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(S.obs + static_cast<size_t>(base + c0) * 5u),
-                                 "r"(smem_u32(sm->obs_out + c0 * 5u)), "r"(static_cast<uint32_t>(32u * 5u * sizeof(R)))
+                                 "r"(smem_u32(sm->obs_out + c0 * 5u)), "r"(run_bytes)
                                  : "memory");
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
