@@ -444,7 +444,7 @@ def main():
                 "frac_single_launch_write_flushed_l2": BYTES_PER_ENV_STEP_F32 * N / (flushed_ms * 1e-3 / n_sec) / 1e9 / peaks["hbm_gbs"]}
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # the CPU baseline leg belongs to the N = 1 run (the other ranks' processes would share its cores)
         probe_steps, probe_dt, cores = cpu_oracle_run(1 << 13, 16)
         rate = probe_steps / probe_dt
         n_envs, n_steps = 1 << 17, 500
