@@ -27,7 +27,7 @@ constexpr int kNF3 = 6;   // fi3 intervals (7 nodes)
 // mod 8) or coincide (broadcast).  Neighbouring cells are what a quarter-warp of similar envs reads, so the strides (in
 // fp32 chunks) are padded to spread neighbours over the groups: alpha rows 5 chunks apart (was 4: every second row
 // collided), fi planes of the 3-D tables 60 = 4 (mod 8) chunks apart, thrust altitude rows 11 chunks apart.  Measured
-// with the stationary state distribution of the bench (tools/probes/bank_conflict_model.py): 17.3 -> 11.3 wavefronts
+// with the stationary state distribution of the bench (tests/studies/bank_conflict_model.py): 17.3 -> 11.3 wavefronts
 // per quarter-warp for the 11 loads (11 = conflict-free).
 constexpr int kArowStride = 20;     // 16 used + 4 pad
 constexpr int kThrustRow = 5 * 8 + 4;   // five Mach cells of 8 + 4 pad

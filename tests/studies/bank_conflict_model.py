@@ -5,7 +5,7 @@ same 16-byte chunk are broadcast, lanes that read DIFFERENT chunks of the same 1
 serialise.  The cells a lane reads depend on its env's state, so the cost depends on the state distribution: this
 script rolls the CPU oracle under the bench's stick distribution (i.i.d. U(-1,1)), takes states from the stationary
 part of the episodes, and counts wavefronts per lookup for a given table layout (strides / bases in 16-byte chunks).
-Test infrastructure (uses oracle/); run here on the CPU:  python tools/probes/bank_conflict_model.py"""
+Test infrastructure (it uses oracle/, hence it lives under tests/); run on the CPU:  python tests/studies/bank_conflict_model.py"""
 import os
 import sys
 

@@ -1,6 +1,6 @@
 """The packed table image is laid out for the shared-memory banks (csrc/f16_tables.h): the lookups are LDS.128 at
 lane-dependent addresses, and neighbouring cells must fall into different 16-byte bank groups.  This CPU test keeps
-the header's strides honest with the offline wavefront model (tools/probes/bank_conflict_model.py), which rolls the
+the header's strides honest with the offline wavefront model (tests/studies/bank_conflict_model.py), which rolls the
 oracle to get a realistic state distribution -- test infrastructure only, no GPU."""
 import importlib.util
 import os
@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _model():
-    spec = importlib.util.spec_from_file_location("bank_conflict_model", os.path.join(ROOT, "tools", "probes", "bank_conflict_model.py"))
+    spec = importlib.util.spec_from_file_location("bank_conflict_model", os.path.join(ROOT, "tests", "studies", "bank_conflict_model.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
