@@ -31,6 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "env-steps/sec (F-16 long., batched)"
+WORKLOAD = ("BASELINE configs[2]: 2^20 envs per GPU, fp32, random init + random combo refs + uniform stick, "
+            "gym step K=1 with autoreset, obs [N,5] + reward + done emitted every step")
 UNIT = "env-steps/s"
 ENVS_PER_GPU = 1 << 20
 BYTES_PER_ENV_STEP_F32 = 113      # 48 B read + 65 B written per env-step, fp32, K = 1
@@ -169,8 +171,8 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tsum / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "F-16 longitudinal env-step, 2^20 envs/GPU, fp32, K=1 (reference arm: bounded CPU sample)",
-                   "envs_per_gpu": ENVS_PER_GPU, "substeps_per_launch": 1},
+        "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs, "substeps_per_launch": 1,
+                   "reference_arm": "bounded CPU sample of that workload in fp64 (the reference's arithmetic): " + sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -462,9 +464,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[2]: 2^20 envs per GPU, fp32, random init + random combo refs + uniform stick, "
-                               "gym step K=1 with autoreset, obs [N,5] + reward + done emitted every step",
-                   "envs_per_gpu": N, "substeps_per_launch": 1, "fast_math": fast, "parallelism": f"env-shard x{world}, no collective",
+        "config": {"workload": WORKLOAD, "envs_per_gpu": N, "substeps_per_launch": 1, "fast_math": fast, "parallelism": f"env-shard x{world}, no collective",
                    "l2": "inputs larger than L2: 4 resident batches of 2^20 envs stepped round-robin (308 MB per cycle vs 126 MB L2), "
                          "no flush kernel in the timed region",
                    "stick": f"U(-1,1) rows cycled from a pool of {POOL} per batch (each env's stick repeats every {POOL} steps)",
