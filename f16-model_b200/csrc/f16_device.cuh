@@ -179,7 +179,20 @@ __device__ __forceinline__ void isa_layer(R H, R &T, R &p)
 template <typename R, bool FAST>
 __device__ __forceinline__ R isa_geopotential(R h)
 {
-    return Mth<R, FAST>::div(R(K::isa_r) * h, R(K::isa_r) + h);
+    if constexpr (FAST) return __fdividef(h, h * R(1.0 / K::isa_r) + R(1));   // h / (1 + h/r): one FMA, one MUFU.RCP, one FMUL
+    else return Mth<R, FAST>::div(R(K::isa_r) * h, R(K::isa_r) + h);
+}
+
+// FAST fp32, troposphere: density and speed of sound straight from u = T/Tb = 1 + (beta/Tb) H, without forming T and p:
+//   rho = p / (R T) = pb/(R Tb) * u^(expo - 1),   a = sqrt(kappa R Tb) * u^(1/2)
+// -- one MUFU.LG2 shared by two MUFU.EX2 (3 FMA/FMUL + 3 MUFU instead of 8 + 4).  Both exponents stay O(1), so the
+// approximate lg2/ex2 keep their ~2^-22 relative accuracy.  expo = g0 / (-beta R) = 5.2558798...
+template <typename R>
+__device__ __forceinline__ void isa_troposphere_direct(R H, R &rho, R &a)
+{
+    const R L = __log2f(H * R(-6.5e-3 / 288.15) + R(1));
+    rho = exp2f(L * R(4.255879812716676) + R(0.29278177057300514));   // lg2(pb / (R Tb)) = lg2(1.2250)
+    a = R(340.29398803459594) * exp2f(R(0.5) * L);                    // sqrt(kappa R Tb)
 }
 
 template <typename R, bool FAST>
@@ -195,8 +208,16 @@ __device__ __forceinline__ void isa(R h, R &rho, R &a)
 {
     const R H = isa_geopotential<R, FAST>(h);
     R T, p;
-    if (H >= R(0) && H < R(11000)) isa_troposphere<R, FAST>(H, T, p);   // warp-uniform in practice
-    else isa_layer<R, FAST>(H, T, p);
+    if constexpr (FAST) {
+        if (H >= R(0) && H < R(11000)) {   // warp-uniform in practice
+            isa_troposphere_direct<R>(H, rho, a);
+            return;
+        }
+        isa_layer<R, FAST>(H, T, p);
+    } else {
+        if (H >= R(0) && H < R(11000)) isa_troposphere<R, FAST>(H, T, p);
+        else isa_layer<R, FAST>(H, T, p);
+    }
     isa_finish<R, FAST>(T, p, rho, a);
 }
 
@@ -296,9 +317,14 @@ __device__ __forceinline__ R power_level(R Pa, R thr)
 // WANT_VDOT: also compute V_dot (the integrator discards it; trim search needs it).
 // ---------------------------------------------------------------------------
 // rhs_atm: the right-hand side with the atmosphere (rho, speed of sound at x[1]) supplied by the caller.
-template <typename R, bool FAST, bool WANT_VDOT>
+// U_CLAMPED: the caller's stab command is already inside +-maxabsstab (the env's rescaled action in fp32, where
+// float(act_lo) == -float(maxabsstab) and act_lo + act_span == float(maxabsstab)): the clip of ODE_3DoF.py:37 is a no-op.
+// fp32 only: constant factors are folded (0.5 S into q S, 1/Jz and ba into the moment, ba/2 into qhat) -- the fp64
+// parity mode keeps the reference's operation order.
+template <typename R, bool FAST, bool WANT_VDOT, bool U_CLAMPED = false>
 __device__ __forceinline__ void rhs_atm(const Tables<R> &T, const R (&x)[9], R u_stab, R u_thr, R rho, R asnd, R (&dx)[9])
 {
+    constexpr bool F32 = sizeof(R) == 4;
     using M = Mth<R, FAST>;
     const R Oy = x[1], wz = x[2], theta = x[3], V = x[4], alpha = x[5], stab = x[6], dstab = x[7], Pa = x[8];
     R sa, ca, st, ct;
@@ -308,26 +334,27 @@ __device__ __forceinline__ void rhs_atm(const Tables<R> &T, const R (&x)[9], R u
     const R Vy = -V * sa;
 
     const R Mach = M::div(V, asnd);
-    const R q = (rho * (V * V)) * R(0.5);
 
     dx[0] = ct * Vx - st * Vy;
     dx[1] = st * Vx + ct * Vy;
     dx[3] = wz;
 
-    const R qhat = M::div(wz * R(K::ba), R(2) * V);
+    R qhat;
+    if constexpr (F32) qhat = M::div(wz * R(0.5 * K::ba), V);
+    else qhat = M::div(wz * R(K::ba), R(2) * V);
     R cx, cy, mz;
     aero_coeffs<R, FAST>(T, alpha, stab, qhat, cx, cy, mz);
 
-    const R qS = q * R(K::S);
+    R qS;
+    if constexpr (F32) qS = (rho * (V * V)) * R(0.5 * K::S);
+    else qS = ((rho * (V * V)) * R(0.5)) * R(K::S);
     const R X = -qS * cx;
     const R Y = qS * cy;
     const R Px = thrust<R, FAST>(T, Oy, Mach, Pa);
-    const R Mz = qS * R(K::ba) * mz;
     const R Rx = X + Px;
     const R Ry = Y;
-    const R MRz = Mz + R(K::rcgx) * Ry;
 
-    const R cs = M::fmin(M::fmax(u_stab, R(-K::maxabsstab)), R(K::maxabsstab));
+    const R cs = (U_CLAMPED && F32) ? u_stab : M::fmin(M::fmax(u_stab, R(-K::maxabsstab)), R(K::maxabsstab));
     const R cth = M::fmin(M::fmax(u_thr, R(0)), R(1));
 
     const R Vx_dot = (wz * Vy - R(K::g) * st) + M::divc(Rx, R(K::m), R(1.0 / K::m));
@@ -335,30 +362,36 @@ __device__ __forceinline__ void rhs_atm(const Tables<R> &T, const R (&x)[9], R u
 
     dx[4] = WANT_VDOT ? M::div(Vx * Vx_dot - Vy * Vy_dot, V) : R(0);
     dx[5] = M::div(-Vx * Vy_dot + Vy * Vx_dot, Vx * Vx + Vy * Vy);
-    dx[2] = M::divc(MRz, R(K::Jz), R(1.0 / K::Jz));
+    if constexpr (F32) {
+        dx[2] = (qS * R(1.0 / K::Jz)) * (R(K::ba) * mz + R(K::rcgx) * cy);   // (Mz + rcgx Ry) / Jz with q S factored out
+    } else {
+        const R Mz = qS * R(K::ba) * mz;
+        const R MRz = Mz + R(K::rcgx) * Ry;
+        dx[2] = M::divc(MRz, R(K::Jz), R(1.0 / K::Jz));
+    }
     dx[6] = M::fmin(M::fmax(dstab, R(-K::maxabsdstab)), R(K::maxabsdstab));
     dx[7] = M::divc(R(-2 * K::Tstab) * R(K::Xistab) * dstab - stab + cs, R(K::Tstab * K::Tstab),
                     R(1.0 / (K::Tstab * K::Tstab)));
     dx[8] = power_level<R>(Pa, cth);
 }
 
-template <typename R, bool FAST, bool WANT_VDOT>
+template <typename R, bool FAST, bool WANT_VDOT, bool U_CLAMPED = false>
 __device__ __forceinline__ void rhs(const Tables<R> &T, const R (&x)[9], R u_stab, R u_thr, R (&dx)[9])
 {
     R rho, asnd;
     isa<R, FAST>(x[1], rho, asnd);
-    rhs_atm<R, FAST, WANT_VDOT>(T, x, u_stab, u_thr, rho, asnd, dx);
+    rhs_atm<R, FAST, WANT_VDOT, U_CLAMPED>(T, x, u_stab, u_thr, rho, asnd, dx);
 }
 
 // F16model.step: explicit Euler, clip wz, V frozen (dx[4] ignored).
 // comp: Kahan-compensated accumulation of the two position integrals (fp32 mode): Ox, Oy are pure
 // accumulators of ~1e-4-relative increments, where plain fp32 drifts by up to 1 ulp per step; the
 // carries (ox_lo, oy_lo) persist across steps and launches.
-template <typename R, bool FAST>
+template <typename R, bool FAST, bool U_CLAMPED = false>
 __device__ __forceinline__ void euler_step(const Tables<R> &T, R (&x)[9], R u_stab, R u_thr, R dt, bool comp, R &ox_lo, R &oy_lo)
 {
     R dx[9];
-    rhs<R, FAST, false>(T, x, u_stab, u_thr, dx);
+    rhs<R, FAST, false, U_CLAMPED>(T, x, u_stab, u_thr, dx);
     if (comp) {
         R y = dx[0] * dt + ox_lo;
         R t = x[0] + y;

@@ -115,11 +115,19 @@ template <typename R, bool FAST>
 __device__ __forceinline__ void make_obs(R Oy, R wz_obs, R V, R ref, R (&o)[5])
 {
     using M = Mth<R, FAST>;
-    o[0] = M::divc(Oy - R(0), R(35000.0), R(1.0 / 35000.0));
-    o[1] = M::divc(wz_obs - R(-K::wz_bound), R(K::wz_bound - (-K::wz_bound)), R(1.0 / (2.0 * K::wz_bound)));
-    o[2] = M::divc(V - R(0), R(500.0), R(1.0 / 500.0));
-    o[3] = ref;
-    o[4] = R(0.5) * (ref - wz_obs);
+    if constexpr (sizeof(R) == 4) {   // same affine maps, one FMA / FMUL each
+        o[0] = Oy * R(1.0 / 35000.0);
+        o[1] = wz_obs * R(1.0 / (2.0 * K::wz_bound)) + R(0.5);
+        o[2] = V * R(1.0 / 500.0);
+        o[3] = ref;
+        o[4] = R(0.5) * ref - R(0.5) * wz_obs;
+    } else {
+        o[0] = M::divc(Oy - R(0), R(35000.0), R(1.0 / 35000.0));
+        o[1] = M::divc(wz_obs - R(-K::wz_bound), R(K::wz_bound - (-K::wz_bound)), R(1.0 / (2.0 * K::wz_bound)));
+        o[2] = M::divc(V - R(0), R(500.0), R(1.0 / 500.0));
+        o[3] = ref;
+        o[4] = R(0.5) * (ref - wz_obs);
+    }
 }
 
 template <typename R>
@@ -142,9 +150,16 @@ __device__ __forceinline__ R tracking_reward(R ref, R wz)
     using M = Mth<R, FAST>;
     const R e = (ref - wz) * R(K::rad2deg);
     const R ae = M::fabs(e);
-    const R asym = clampr(R(1) - M::div(ae, R(1) + ae), R(0), R(1));
-    const R lin = clampr(R(1) - e * e, R(0), R(1));
-    return asym + R(0.04) * lin;
+    if constexpr (sizeof(R) == 4) {
+        // 1 - |e|/(1+|e|) == 1/(1+|e|) in (0, 1]; 1 - e^2 <= 1: only the lower clip of the second term can act
+        const R asym = M::div(R(1), R(1) + ae);
+        const R lin = M::fmax(R(1) - e * e, R(0));
+        return asym + R(0.04) * lin;
+    } else {
+        const R asym = clampr(R(1) - M::div(ae, R(1) + ae), R(0), R(1));
+        const R lin = clampr(R(1) - e * e, R(0), R(1));
+        return asym + R(0.04) * lin;
+    }
 }
 
 // Episode statistics with warp primitives, called from the rare termination branch only: the lanes that
@@ -419,7 +434,7 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
                 // F16.rescale_action (env.py:200-211): clip to [-1,1], float32-cast bounds
                 const R a = clampr(a_k, R(-1), R(1));
                 const R u_stab = R(K::act_lo) + R(0.5) * (a + R(1.0)) * R(K::act_span);
-                euler_step<R, FAST>(tbl, x, u_stab, R(0), dt, comp, ox_lo, oy_lo);   // Control(action, 0), env.py:49
+                euler_step<R, FAST, true>(tbl, x, u_stab, R(0), dt, comp, ox_lo, oy_lo);   // Control(action, 0), env.py:49
                 // check_state (env.py:103-117) on the post-step state, pre-increment counter
                 R pen = R(0);
                 if (!(x[1] > R(300))) { pen += R(-1000); done_now = 1; }
@@ -714,7 +729,7 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
         const int K_steps = SINGLE ? 1 : S.K;
         for (int k = 0; k < K_steps; ++k) {
             // ---- common path: both envs in one basic block ------------------------------------------------
-            R ref[2], Hg[2], Tk[2], pk[2], a_next[2] = {R(0), R(0)};
+            R ref[2], Hg[2], Tk[2], pk[2], rho[2], asnd[2], a_next[2] = {R(0), R(0)};
             bool slow[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -722,40 +737,41 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
                 if (!SINGLE && k + 1 < K_steps) a_next[e] = S.actions[static_cast<unsigned>(k + 1) * n + base + tl + e * E2];
                 Hg[e] = isa_geopotential<R, FAST>(x[e][1]);
                 slow[e] = !(Hg[e] >= R(0) && Hg[e] < R(11000));
-                isa_troposphere<R, FAST>(Hg[e], Tk[e], pk[e]);
+                if constexpr (FAST) isa_troposphere_direct<R>(Hg[e], rho[e], asnd[e]);
+                else isa_troposphere<R, FAST>(Hg[e], Tk[e], pk[e]);
             }
             if (slow[0] | slow[1]) {   // rare: some other layer of the standard atmosphere
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
-                    if (slow[e]) isa_layer<R, FAST>(Hg[e], Tk[e], pk[e]);
+                    if (slow[e]) {
+                        isa_layer<R, FAST>(Hg[e], Tk[e], pk[e]);
+                        if constexpr (FAST) isa_finish<R, FAST>(Tk[e], pk[e], rho[e], asnd[e]);
+                    }
             }
-            R reward[2];
+            R reward[2], ret_in[2];
             bool done[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                R rho, asnd, dx[9];
-                isa_finish<R, FAST>(Tk[e], pk[e], rho, asnd);
+                R dx[9];
+                if constexpr (!FAST) isa_finish<R, FAST>(Tk[e], pk[e], rho[e], asnd[e]);
                 const R a = clampr(a_in[e], R(-1), R(1));
                 const R u_stab = R(K::act_lo) + R(0.5) * (a + R(1.0)) * R(K::act_span);
 #ifdef F16_PROBE_NOMATH   // probe build: the memory pipeline alone (inputs -> outputs with a trivial right-hand side)
 #pragma unroll
-                for (int j = 0; j < 9; ++j) dx[j] = x[e][j] * R(1e-6) + u_stab * rho * asnd * R(1e-9);
+                for (int j = 0; j < 9; ++j) dx[j] = x[e][j] * R(1e-6) + u_stab * rho[e] * asnd[e] * R(1e-9);
 #else
-                rhs_atm<R, FAST, false>(tbl, x[e], u_stab, R(0), rho, asnd, dx);
+                rhs_atm<R, FAST, false, true>(tbl, x[e], u_stab, R(0), rho[e], asnd[e], dx);
 #endif
 #pragma unroll
                 for (int j = 0; j < 9; ++j)
                     if (j != 4) x[e][j] = dx[j] * dt + x[e][j];
                 x[e][2] = clampr(x[e][2], R(-K::wz_clip), R(K::wz_clip));
-                R pen = R(0);
-                bool d = false;
-                if (!(x[e][1] > R(300))) { pen += R(-1000); d = true; }
-                if (x[e][1] >= R(30000)) { pen += R(-1000); d = true; }
-                if (!(M::fabs(x[e][2]) < R(K::wz_term))) { pen += R(-1000); d = true; }
-                d = d || (ep_len[e] == A.horizon);
-                reward[e] = pen + tracking_reward<R, FAST>(ref[e], x[e][2]);
+                // check_state (env.py:103-117): the flags here, the -1000 penalties in the rare branch below (0 + r == r)
+                const bool d = !(x[e][1] > R(300)) | (x[e][1] >= R(30000)) | !(M::fabs(x[e][2]) < R(K::wz_term)) | (ep_len[e] == A.horizon);
+                reward[e] = tracking_reward<R, FAST>(ref[e], x[e][2]);
                 make_obs<R, FAST>(x[e][1], x[e][2], x[e][4], ref[e], o[e]);
                 ep_len[e] += 1;
+                ret_in[e] = ret[e];
                 ret[e] += reward[e];
                 done[e] = d;
                 a_in[e] = a_next[e];
@@ -766,6 +782,14 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
             for (int e = 0; e < 2; ++e) {
                 if (done[e]) {
                     const unsigned i = base + tl + e * E2;
+                    R pen = R(0);   // penalties stack (env.py:106-114); evaluated on the post-step state, like the flags above
+                    if (!(x[e][1] > R(300))) pen += R(-1000);
+                    if (x[e][1] >= R(30000)) pen += R(-1000);
+                    if (!(M::fabs(x[e][2]) < R(K::wz_term))) pen += R(-1000);
+                    if (pen != R(0)) {
+                        reward[e] = pen + reward[e];
+                        ret[e] = ret_in[e] + reward[e];
+                    }
                     if (S.stats) episode_stats_add(&sm->stats, static_cast<double>(ret[e]), ep_len[e]);
                     if (S.final_obs) store_obs<R>(S.final_obs, A.obs_layout, n, i, o[e]);
                     if (S.final_ep_len) S.final_ep_len[i] = ep_len[e];
