@@ -11,7 +11,6 @@ CUDA kernel launch and observations, rewards and termination flags stay on the d
 ``F16`` is the single-env facade with the reference's NumPy in / NumPy out signature.
 There is no CPU fallback: without the CUDA library or a B200 the constructors raise."""
 import ctypes as C
-import math
 
 import numpy as np
 

@@ -3,7 +3,6 @@
 
 ``States`` / ``Control`` keep the reference's field names and arithmetic
 (model/_interface.py:6-90) but each field may be a scalar or a tensor of N values."""
-import ctypes as C
 
 import numpy as np
 

@@ -7,7 +7,6 @@ state-independent log-std.
 evaluates them for the rollout with the hand-written tcgen05 kernel (csrc/f16_policy.cu) through
 the C ABI: one launch gives mean, value, a sampled action and its log-probability for all envs.
 No CPU path: the forward raises without the CUDA library / a B200."""
-import ctypes as C
 import math
 
 from . import _capi

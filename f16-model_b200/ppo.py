@@ -9,7 +9,6 @@ deviations: the reference's gSDE noise path is broken as committ
 (``theta_gsde`` is never created in ``train``); here exploration is the standard Gaussian policy
 ``a = mean + exp(logstd) * eps`` with eps drawn by the counter RNG inside the policy kernel."""
 import dataclasses
-import math
 import time
 
 from . import _capi

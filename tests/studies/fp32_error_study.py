@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import f16_model_b200 as f16  # noqa: E402
 from oracle import f16_oracle as orc  # noqa: E402
-from workloads import FIELD_SCALE, FP32_FIELD_SCALE, config2_inputs, rel_err  # noqa: E402
+from workloads import FP32_FIELD_SCALE, config2_inputs, rel_err  # noqa: E402
 
 CFG = {"dt": 0.01, "tn": 10, "debug_state": False, "determenistic_ref": True, "scenario": "combo"}
 NAMES = ["Ox", "Oy", "wz", "theta", "V", "alpha", "stab", "dstab", "Pa"]
