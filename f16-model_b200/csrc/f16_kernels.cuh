@@ -527,8 +527,8 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
 // Two aircraft per thread: the gym step (K = 1, autoreset, fp32) with instruction-level parallelism.
 //
 // The one-env kernel above is bound by dependency stalls (short scoreboard + fixed-latency waits are 37 % of
-// its stall samples, issue slots 64 % busy) and by per-tile bookkeeping.  Here every thread advances envs t and
-// t + 128 of a 256-env tile (128-thread CTAs, four per SM); the common path of a step is ONE branch-free basic block holding both envs'
+// its stall samples, issue slots 64 % busy) and by per-tile bookkeeping.  Here every thread advances two envs of a
+// 256-env tile (128-thread CTAs, four per SM; a warp owns 64 consecutive envs, see the kernel); the common path of a step is ONE branch-free basic block holding both envs'
 // arithmetic, so the scheduler interleaves two independent dependency chains, and the tile bookkeeping
 // (barrier wait, ring refill, parameter loads) is paid once per two envs.  Rare events -- an altitude outside
 // the troposphere, a termination with its autoreset -- are patched after the common path.  Handles full,
@@ -864,9 +864,9 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
             }
         }
         if (SINGLE && S.obs_bulk) {   // the host route is a gym step: compiled out of the K-step kernel
-            // [N,5] observations: each warp stages its two 32-env runs (2 x 640 B, stride-5 words = conflict-free) and
-            // lane 0 writes them with two bulk stores -- full lines instead of 20-byte-strided scalar stores, which is
-            // what makes the same kernel usable on mapped host memory (PCIe sees large writes)
+            // [N,5] observations: each warp stages its 64 envs' rows (1280 B, stride-5 words = conflict-free) and lane 0
+            // writes them with one bulk store -- full lines instead of 20-byte-strided scalar stores, which is what
+            // makes the same kernel usable on mapped host memory (PCIe sees large writes)
             const unsigned lane = t & 31u, w0 = tl & ~31u;   // first env of this warp's first run
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // last tile's stores have read the staging area
             __syncwarp();
