@@ -142,6 +142,42 @@ def test_shard_range_covers_batch():
         assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_range_properties():
+    """Any (total, world): blocks are contiguous, ordered, cover [0, total) exactly and differ by at most one env."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 1 << 24), st.integers(1, 64))
+    def check(total, world):
+        spans = [shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(b <= e for b, e in spans) and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        sizes = [e - b for b, e in spans]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+    check()
+    with pytest.raises(ValueError):
+        shard_range(10, 3, 3)
+
+
+def test_trim_grid_sharded_single_rank_needs_no_process_group():
+    from f16_model_b200.sharding import trim_grid_sharded
+
+    V, H = np.meshgrid(np.linspace(100, 300, 5), np.linspace(1000, 9000, 3))
+
+    def fake_trim(V, H, device=None, **kw):
+        return {"stab": -V, "throttle": H, "alpha": V + H, "cost": np.where(V > 200, 1e-3, 1e-7), "iterations": np.full(V.size, 7, np.int32),
+                "n_starts": 3}
+
+    g = trim_grid_sharded(V, H, 0, 1, device="cpu", trim_fn=fake_trim)
+    assert np.array_equal(g["stab"], -V.ravel()) and np.array_equal(g["alpha"], (V + H).ravel()) and g["n_starts"] == 3
+    assert np.array_equal(g["accepted"], V.ravel() <= 200) and g["iterations"].dtype == np.int32
+    with pytest.raises(ValueError):
+        trim_grid_sharded(V, H[:2], 0, 1, device="cpu", trim_fn=fake_trim)
+    with pytest.raises(RuntimeError):                      # more than one rank without an initialised process group
+        trim_grid_sharded(V, H, 0, 2, device="cpu", trim_fn=fake_trim)
+
+
 # ---------------------------------------------------------------- C ABI surface
 def _header_functions():
     hdr = open(os.path.join(ROOT, "include", "f16_b200.h")).read()
