@@ -204,6 +204,18 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_capi.StepIO) == 7 * 8 + 8 + 8
 
 
+def test_integration_md_struct_mirrors_match_the_binding():
+    """The ctypes snippets a maintainer would copy from INTEGRATION.md lay the structs out like _capi.py (and the header)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = text[text.index("class Config(C.Structure)"):text.index("N, dev = 1 << 20")]
+    ns = {"C": ctypes}
+    exec(code, ns)   # noqa: S102 (our own documentation snippet)
+    for name in ("Config", "EnvBuffers", "StepIO"):
+        doc, ref = ns[name], getattr(_capi, name)
+        assert ctypes.sizeof(doc) == ctypes.sizeof(ref), name
+        assert [(f[0], ctypes.sizeof(f[1])) for f in doc._fields_] == [(f[0], ctypes.sizeof(f[1])) for f in ref._fields_], name
+
+
 def test_no_cpu_fallback_without_a_gpu():
     import torch
 
