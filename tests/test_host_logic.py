@@ -204,6 +204,21 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_capi.StepIO) == 7 * 8 + 8 + 8
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as strict C99 on its own (no C++, no CUDA, no torch types)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "f16_b200.h"\nint main(void) { f16_config c; f16_env_buffers b; f16_step_io io; (void)c; (void)b; (void)io;'
+                   ' return F16_ABI_VERSION == 0; }\n')
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                          "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
 def test_integration_md_struct_mirrors_match_the_binding():
     """The ctypes snippets a maintainer would copy from INTEGRATION.md lay the structs out like _capi.py (and the header)."""
     text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
