@@ -11,7 +11,7 @@ fallback and importing the compute entry points without it raises.
 from . import plane                                           # noqa: F401
 from .task import ReferenceSignal, build_reference_bank        # noqa: F401
 from .model import States, Control, F16model, rhs, model_step  # noqa: F401
-from .env import (F16, F16VecEnv, get_trimmed_state_control, get_random_state,  # noqa: F401
+from .env import (F16, F16VecEnv, get_trimmed_state_control, get_random_state, get_action,  # noqa: F401
                   find_correct_thrust_position)
 from .policy import TensorCorePolicy, pack_policy_blob         # noqa: F401
 from .ppo import PPOConfig, PPOTrainer, gae                     # noqa: F401
@@ -21,5 +21,5 @@ from . import artifacts                                         # noqa: F401
 from ._capi import build, load_library, library_path, F16Error   # noqa: F401
 
 __all__ = ["F16", "F16VecEnv", "ReferenceSignal", "build_reference_bank", "States", "Control", "F16model", "rhs",
-           "model_step", "get_trimmed_state_control", "get_random_state", "find_correct_thrust_position", "plane",
+           "model_step", "get_trimmed_state_control", "get_random_state", "get_action", "find_correct_thrust_position", "plane",
            "TensorCorePolicy", "pack_policy_blob", "PPOConfig", "PPOTrainer", "gae", "trim_grid", "reference_starts", "find_trim_position", "artifacts", "build", "load_library", "library_path", "F16Error"]

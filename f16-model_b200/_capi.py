@@ -16,7 +16,8 @@ _lib = None
 F16_F32, F16_F64 = 0, 1
 INIT_RANDOM, INIT_FIXED, INIT_PER_ENV = 0, 1, 2
 OBS_AOS, OBS_SOA = 0, 1
-ABI_VERSION = 1
+FLAG_ONE_ENV_PER_THREAD, FLAG_NO_PDL, FLAG_HOST_STAGED = 1, 2, 4
+ABI_VERSION = 2
 
 EXPORTS = ["f16_abi_version", "f16_last_error", "f16_init", "f16_launch_geometry", "f16_env_reset", "f16_env_step",
            "f16_env_step_host", "f16_host_route", "f16_rhs", "f16_model_step", "f16_coeffs", "f16_thrust", "f16_atmosphere",
@@ -31,14 +32,14 @@ class F16Error(RuntimeError):
 class Config(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("fast_math", C.c_int32), ("n_envs", C.c_int64), ("dt", C.c_double),
                 ("horizon", C.c_int32), ("ref_len", C.c_int32), ("n_ref", C.c_int32), ("autoreset", C.c_int32),
-                ("init_mode", C.c_int32), ("obs_layout", C.c_int32), ("noise", C.c_int32), ("reserved", C.c_int32),
+                ("init_mode", C.c_int32), ("obs_layout", C.c_int32), ("noise", C.c_int32), ("flags", C.c_int32),
                 ("seed", C.c_uint64), ("env_id_base", C.c_int64), ("x0", C.c_double * 9)]
 
 
 class EnvBuffers(C.Structure):
     _fields_ = [("state", C.c_void_p), ("ep_len", C.c_void_p), ("total_return", C.c_void_p), ("ref_idx", C.c_void_p),
                 ("done", C.c_void_p), ("episode_no", C.c_void_p), ("ref_bank", C.c_void_p), ("init_state", C.c_void_p),
-                ("pos_comp", C.c_void_p)]
+                ("pos_comp", C.c_void_p), ("seed_dev", C.c_void_p)]
 
 
 class StepIO(C.Structure):

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 
@@ -35,7 +36,29 @@ int fail(int code, const char *fmt, ...)
 
 constexpr int kMaxDev = 64;
 
-struct HostPipe {   // scratch of f16_env_step_host
+// Makes `device` current for the scope and restores the caller's device on every exit path.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) {
+            err = cudaSetDevice(device);
+            switched = err == cudaSuccess;
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
+struct HostPipe {   // scratch of f16_env_step_host, one per device; `mu` serialises the host threads that share it
+    std::mutex mu;
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t done_ev[3] = {nullptr, nullptr, nullptr};
     void *actions = nullptr, *obs = nullptr, *reward = nullptr;
@@ -68,26 +91,23 @@ int ensure_device(int device, DeviceCtx **out)
             return fail(F16_ENODEV, "no CUDA device visible: the F-16 simulator has no CPU fallback");
         }
         if (device >= count) return fail(F16_ENODEV, "device %d not present (%d visible)", device, count);
-        int prev = 0;
-        CUDA_TRY(cudaGetDevice(&prev));
-        CUDA_TRY(cudaSetDevice(device));
+        DeviceGuard guard(device);   // the caller's current device is restored on every return below
+        CUDA_TRY(guard.err);
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, device));
         if (prop.major != 10)
             return fail(F16_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
                         prop.minor);
         c.n_sm = prop.multiProcessorCount;
-        auto *h32 = new (std::nothrow) f16::Tables<float>;
-        auto *h64 = new (std::nothrow) f16::Tables<double>;
+        std::unique_ptr<f16::Tables<float>> h32(new (std::nothrow) f16::Tables<float>);
+        std::unique_ptr<f16::Tables<double>> h64(new (std::nothrow) f16::Tables<double>);
         if (!h32 || !h64) return fail(F16_EINVAL, "out of host memory");
         f16::build_tables(*h32);
         f16::build_tables(*h64);
         CUDA_TRY(cudaMalloc(&c.t32, sizeof *h32));
         CUDA_TRY(cudaMalloc(&c.t64, sizeof *h64));
-        CUDA_TRY(cudaMemcpy(c.t32, h32, sizeof *h32, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(c.t64, h64, sizeof *h64, cudaMemcpyHostToDevice));
-        delete h32;
-        delete h64;
+        CUDA_TRY(cudaMemcpy(c.t32, h32.get(), sizeof *h32, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(c.t64, h64.get(), sizeof *h64, cudaMemcpyHostToDevice));
         for (int f = 0; f < 2; ++f)
             for (int a = 0; a < 2; ++a) {
                 c.occ[F16_F32][f][a] = f16::env_step_occupancy_f32(f != 0, a != 0);
@@ -96,7 +116,6 @@ int ensure_device(int device, DeviceCtx **out)
         c.occ2[0] = f16::env_step2_occupancy_f32(false);
         c.occ2[1] = f16::env_step2_occupancy_f32(true);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaSetDevice(prev));
         c.ready = true;
     }
     *out = &c;
@@ -113,20 +132,13 @@ int current_device(int *dev)
     return F16_OK;
 }
 
-f16::LaunchGeom geom(const DeviceCtx &c, int dtype, bool fast, bool autoreset)
+// flags = f16_config.flags: kernel selection is a per-call property of the config, not process state
+f16::LaunchGeom geom(const DeviceCtx &c, int dtype, bool fast, bool autoreset, int flags)
 {
     int occ = c.occ[dtype][fast ? 1 : 0][autoreset ? 1 : 0];
     if (occ < 1) occ = 1;
-    static const int pdl = [] {
-        const char *e = std::getenv("F16B200_PDL");
-        return (e && e[0] == '0') ? 0 : 1;
-    }();
-    static const int x2 = [] {
-        const char *e = std::getenv("F16B200_TWO_PER_THREAD");
-        return (e && e[0] == '0') ? 0 : 1;
-    }();
-    f16::LaunchGeom g{c.n_sm, occ, pdl};
-    g.two_per_thread = (dtype == F16_F32) ? x2 : 0;
+    f16::LaunchGeom g{c.n_sm, occ, (flags & F16_FLAG_NO_PDL) ? 0 : 1};
+    g.two_per_thread = (dtype == F16_F32 && !(flags & F16_FLAG_ONE_ENV_PER_THREAD)) ? 1 : 0;
     const int o2 = c.occ2[fast ? 1 : 0];
     g.ctas2_per_sm = (o2 & 0xff) > 0 ? (o2 & 0xff) : 1;
     g.ctas2k_per_sm = ((o2 >> 8) & 0xff) > 0 ? ((o2 >> 8) & 0xff) : 1;
@@ -142,6 +154,7 @@ int check_cfg(const f16_config *cfg)
     if (cfg->ref_len <= 0 || cfg->n_ref <= 0) return fail(F16_EINVAL, "reference bank must hold >= 1 signal of >= 1 sample");
     if (cfg->init_mode < 0 || cfg->init_mode > 2) return fail(F16_EINVAL, "bad init_mode");
     if (cfg->obs_layout != F16_OBS_AOS && cfg->obs_layout != F16_OBS_SOA) return fail(F16_EINVAL, "bad obs_layout");
+    if (cfg->flags & ~(F16_FLAG_ONE_ENV_PER_THREAD | F16_FLAG_NO_PDL | F16_FLAG_HOST_STAGED)) return fail(F16_EINVAL, "unknown bits in flags");
     return F16_OK;
 }
 
@@ -171,6 +184,7 @@ f16::EnvArgs<R> make_env_args(const f16_config *cfg, const f16_env_buffers *env,
     A.obs_layout = cfg->obs_layout;
     A.noise = cfg->noise;
     A.seed = cfg->seed;
+    A.seed_dev = env->seed_dev;
     A.id_base = cfg->env_id_base;
     for (int j = 0; j < 9; ++j) A.x0[j] = static_cast<R>(cfg->x0[j]);
     A.state = static_cast<R *>(env->state);
@@ -243,7 +257,7 @@ int step_range(DeviceCtx *ctx, const f16_config *cfg, const f16_env_buffers *env
                cudaStream_t st, bool bulk_obs = false)
 {
     const bool fast = cfg->dtype == F16_F32 && cfg->fast_math != 0;
-    const f16::LaunchGeom g = geom(*ctx, cfg->dtype, fast, cfg->autoreset != 0);
+    const f16::LaunchGeom g = geom(*ctx, cfg->dtype, fast, cfg->autoreset != 0, cfg->flags);
     if (cfg->dtype == F16_F32) {
         auto A = make_env_args<float>(cfg, env, ctx->t32);
         auto S = make_step_args<float>(cfg, io, K);
@@ -361,10 +375,20 @@ int f16_env_step_host(const f16_config *cfg, const f16_env_buffers *env, const v
     if ((rc = check_env(cfg, env))) return rc;
     if (K <= 0) return fail(F16_EINVAL, "K must be >= 1");
     if (!actions_host || !reward_host || !done_host) return fail(F16_EINVAL, "actions_host, reward_host and done_host are required");
+    {   // the same 32-bit index limits as the device route (check_step)
+        f16_step_io probe;
+        std::memset(&probe, 0, sizeof probe);
+        probe.actions = actions_host;
+        probe.reward = reward_host;
+        probe.done = done_host;
+        if ((rc = check_step(cfg, &probe, K))) return rc;
+    }
     DeviceCtx *ctx;
     if ((rc = ensure_device(device, &ctx))) return rc;
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);   // restores the caller's current device when the call returns
+    CUDA_TRY(guard.err);
     HostPipe &P = ctx->pipe;
+    std::lock_guard<std::mutex> pipe_lock(P.mu);   // staging buffers and streams are per device: one host step at a time
     const int64_t n = cfg->n_envs;
     const size_t es = cfg->dtype == F16_F32 ? 4 : 8;
     if (!P.streams[0])
@@ -381,12 +405,9 @@ int f16_env_step_host(const f16_config *cfg, const f16_env_buffers *env, const v
     // whose stores are full lines (two-envs-per-thread kernel: bulk-stored [N,5] observations, or the SoA layout);
     // 20-byte-strided scalar stores over PCIe are 2.5x slower than the staged pipeline (tools/probes/zero_copy_probe.py).
     {
-        static const int zero_copy = [] {
-            const char *e = std::getenv("F16B200_HOST_ZERO_COPY");
-            return (e && e[0] == '0') ? 0 : 1;
-        }();
+        const bool zero_copy = !(cfg->flags & F16_FLAG_HOST_STAGED);
         void *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_done = nullptr;
-        const f16::LaunchGeom g = geom(*ctx, cfg->dtype, cfg->fast_math != 0, cfg->autoreset != 0);
+        const f16::LaunchGeom g = geom(*ctx, cfg->dtype, cfg->fast_math != 0, cfg->autoreset != 0, cfg->flags);
         const bool wide_stores = cfg->dtype == F16_F32 && g.two_per_thread && cfg->autoreset && !cfg->noise && !env->pos_comp && n >= 512;
         if (zero_copy && K == 1 && wide_stores && mapped_host(actions_host, &d_act) && mapped_host(reward_host, &d_rew) &&
             mapped_host(done_host, &d_done) && (!obs_host || mapped_host(obs_host, &d_obs))) {
@@ -600,7 +621,7 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
     P.episode_no = episode_no;
     P.seed = seed;
     P.id_base = env_id_base;
-    CUDA_TRY(f16::launch_policy_forward(P, c->n_sm, geom(*c, F16_F32, true, true).pdl, static_cast<cudaStream_t>(stream)));
+    CUDA_TRY(f16::launch_policy_forward(P, c->n_sm, geom(*c, F16_F32, true, true, 0).pdl, static_cast<cudaStream_t>(stream)));
     return F16_OK;
 }
 

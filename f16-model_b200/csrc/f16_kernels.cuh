@@ -194,7 +194,8 @@ template <typename R>
 __device__ __forceinline__ void init_episode(const EnvArgs<R> &A, int64_t i, uint32_t episode, bool keep_ref, R (&x)[9],
                                              int &ref_idx)
 {
-    const uint2 key = make_uint2(static_cast<uint32_t>(A.seed), static_cast<uint32_t>(A.seed >> 32));
+    const uint64_t seed = A.seed_dev ? *A.seed_dev : A.seed;
+    const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     const int64_t gid = A.id_base + i;   // global env id: sharding-invariant streams
     const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), episode, 0u), key);
     if (A.init_mode == 0) {
@@ -229,7 +230,8 @@ __device__ __forceinline__ void init_episode(const EnvArgs<R> &A, int64_t i, uin
 template <typename R>
 __device__ __forceinline__ R obs_noise(const EnvArgs<R> &A, int64_t i, uint32_t episode, int k)
 {
-    const uint2 key = make_uint2(static_cast<uint32_t>(A.seed), static_cast<uint32_t>(A.seed >> 32));
+    const uint64_t seed = A.seed_dev ? *A.seed_dev : A.seed;
+    const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     const int64_t gid = A.id_base + i;
     const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), episode,
                                           2u + static_cast<uint32_t>(k)), key);

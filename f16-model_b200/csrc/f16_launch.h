@@ -12,7 +12,7 @@ namespace f16 {
 struct LaunchGeom {
     int n_sm;
     int ctas_per_sm;
-    int pdl = 1;   // launch the step kernel with programmatic stream serialization (F16B200_PDL=0 disables)
+    int pdl = 1;   // launch the step kernel with programmatic stream serialization (F16_FLAG_NO_PDL disables)
     int two_per_thread = 0;   // fp32 gym step: use the two-envs-per-thread kernel on full tiles
     int ctas2_per_sm = 4;    // resident CTAs of the two-env gym-step kernel (128 threads)
     int ctas2k_per_sm = 2;   // ... of its K-step variant (256 threads)
@@ -27,6 +27,7 @@ struct EnvArgs {
     int horizon, ref_len, n_ref;
     int autoreset, init_mode, obs_layout, noise;
     uint64_t seed;
+    const uint64_t *seed_dev;   // optional device copy of the seed (read on the rare reset / noise paths): re-keying reaches captured CUDA graphs
     int64_t id_base;
     R x0[9];
     R *state;

@@ -34,6 +34,12 @@ def get_trimmed_state_control():
     return x0.to_array(), u.to_array()
 
 
+def get_action():
+    """A random control (env/env.py:217-218): stabilator U(-25, 25) deg in radians, throttle U(0, 1),
+    drawn from the process-global ``np.random`` in the reference's order."""
+    return Control(np.radians(np.random.uniform(-25, 25)), np.random.uniform(0, 1))
+
+
 def get_random_state():
     """One draw of the reference's random initial state on the HOST with ``np.random``
     (env/env.py:221-243), same draw order: alpha(=theta), Oy, wz, V."""
@@ -102,12 +108,20 @@ class F16VecEnv:
         keyed by global env id, so a sharded run reproduces the single-GPU run env for env.
     obs_layout : "aos" -> obs [N, 5] contiguous (reference layout); "soa" -> stored [5, N],
         returned as the transposed view [N, 5].
+    bank_size : rows of the device reference bank for random scenarios.  None (default) = the reference's
+        whole distribution where it is finite (``combo``: all 6480 signals, 26 MB in fp32), 256 draws
+        otherwise; see ``task.build_reference_bank``.
+    two_per_thread, pdl, host_zero_copy : per-env kernel / route selection (``f16_config.flags``): the
+        one-env-per-thread step kernel instead of the two-envs-per-thread one, launches without programmatic
+        dependent launch, the staged host route instead of zero-copy.  All variants are bit-identical
+        (tests/test_gpu_parity.py); the switches exist for tests and profiling.
     """
 
     metadata = {}
 
     def __init__(self, config, num_envs, device="cuda", dtype=None, autoreset=True, seed=0, fast_math=False,
-                 obs_layout="aos", bank_size=256, reference_bank=None, env_id_base=0, compensated_position=None):
+                 obs_layout="aos", bank_size=None, reference_bank=None, env_id_base=0, compensated_position=None,
+                 two_per_thread=True, pdl=True, host_zero_copy=True):
         import torch
 
         self._torch = torch
@@ -169,6 +183,9 @@ class F16VecEnv:
         self.ref_idx = torch.zeros(N, dtype=torch.int32, device=dev)
         self.done = torch.zeros(N, dtype=torch.uint8, device=dev)
         self.episode_no = torch.zeros(N, dtype=torch.int32, device=dev)
+        # the RNG key lives on the device too: kernels captured in a CUDA graph see a later reset(seed=...)
+        self._seed_dev = torch.full((1,), (int(seed) & 0xFFFFFFFFFFFFFFFF) - (1 << 64 if int(seed) & (1 << 63) else 0),
+                                    dtype=torch.int64, device=dev)
         compensated_position = bool(compensated_position) and dt_ == torch.float32
         self.pos_comp = torch.zeros((2, N), dtype=dt_, device=dev) if compensated_position else None
         obs_shape = (N, 5) if obs_layout == "aos" else (5, N)
@@ -194,6 +211,8 @@ class F16VecEnv:
         cfg.init_mode = init_mode
         cfg.obs_layout = _capi.OBS_AOS if obs_layout == "aos" else _capi.OBS_SOA
         cfg.noise = int(bool(config.get("noise", False)))
+        cfg.flags = ((0 if two_per_thread else _capi.FLAG_ONE_ENV_PER_THREAD) | (0 if pdl else _capi.FLAG_NO_PDL)
+                     | (0 if host_zero_copy else _capi.FLAG_HOST_STAGED))
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.env_id_base = int(env_id_base)
         for j in range(9):
@@ -220,6 +239,7 @@ class F16VecEnv:
         b.ref_bank = self.ref_bank.data_ptr()
         b.init_state = self.init_state_tensor.data_ptr() if self.init_state_tensor is not None else None
         b.pos_comp = self.pos_comp.data_ptr() if self.pos_comp is not None else None
+        b.seed_dev = self._seed_dev.data_ptr()
         self._buf = b
         io = _capi.StepIO()
         io.obs = self._obs.data_ptr()
@@ -279,7 +299,9 @@ class F16VecEnv:
         counters and computes the reset observation on the device."""
         torch = self._torch
         if seed is not None:
-            self._cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+            key = int(seed) & 0xFFFFFFFFFFFFFFFF
+            self._cfg.seed = key
+            self._seed_dev.fill_(key - (1 << 64) if key & (1 << 63) else key)   # stream-ordered: later graph replays see it
         mptr = None
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
@@ -392,7 +414,10 @@ class F16VecEnv:
         """Load explicit states [9, N] (or [N, 9]) and clear the done flags / returns."""
         torch = self._torch
         t = torch.as_tensor(state)
-        if t.shape != (9, self.num_envs):
+        N = self.num_envs
+        if t.dim() != 2 or (tuple(t.shape) != (9, N) and tuple(t.shape) != (N, 9)):
+            raise ValueError(f"state must have shape [9, {N}] (or [{N}, 9]), got {tuple(t.shape)}")
+        if tuple(t.shape) != (9, N):     # N == 9 is read as [9, N] = field-major, the storage layout
             t = t.t()
         self.state.copy_(t.to(device=self.device, dtype=self.dtype))
         self.done.zero_()
@@ -461,7 +486,11 @@ class _BankSignal:
 class F16:
     """Single-env facade with the reference's exact call signature (env/env.py:13-70):
     ``step(np.ndarray[1]) -> (obs ndarray[5], reward float, done bool, False, info)``.
-    Runs the same CUDA kernel with N = 1 in fp64 (the parity mode)."""
+    Runs the same CUDA kernel with N = 1 in fp64 (the parity mode).
+
+    One deliberate difference: after ``done`` the reference keeps integrating if ``step`` is called again (every
+    caller in the reference resets instead); here a finished episode is frozen -- reward 0, state unchanged,
+    ``done`` stays True -- until ``reset``."""
 
     def __init__(self, config, device="cuda", dtype=None, seed=0):
         import torch
@@ -478,6 +507,11 @@ class F16:
                               reference_bank=ref)
         self.action_space = Box(-1, 1, (1,), np.float32)
         self.observation_space = Box(-1, 1, (5,), np.float64)
+        if self._vec._cfg.init_mode == _capi.INIT_RANDOM:
+            # like the reference's constructor (env/env.py:27 -> :172-195), the first initial state comes from the
+            # process-global np.random, so np.random.seed(s); F16(cfg) reproduces the reference's first episode
+            self._vec.set_state(torch.tensor(get_random_state().to_array().reshape(9, 1)))
+            self._vec.reset(keep_state=True, keep_reference=True)
         self._sync_init()
 
     def _sync_init(self):
@@ -527,6 +561,20 @@ class F16:
 
     def render(self):
         raise UserWarning("TODO: Implement this function")
+
+    def state_transform(self, state):
+        """Observation of a ``States`` at the current step (env/env.py:83-101): normalised [Oy, wz, V], the
+        reference sample ``wz_ref[episode_length]`` and the tracking error ``0.5 * (wz_ref - wz)``.
+        Host-side helper (NumPy, fp64); ``step`` gets the same five numbers from the kernel."""
+        short = _normalize([vars(state)[k] for k in plane.state_bound if k in vars(state)])
+        ref = self.ref_signal.wz_ref[self.episode_length]
+        short.append(ref)
+        short.append(0.5 * (ref - state.wz))
+        return np.array(short)
+
+    def _state_size(self):
+        """env/env.py:212-213."""
+        return self.state_transform(self.init_state).size
 
     normalize = staticmethod(_normalize)
     denormalize = staticmethod(_denormalize)

@@ -14,29 +14,24 @@ def _deg_range(lo, hi):
 
 
 # mass / geometry (SI units)
-_AIRFRAME = {
-    "m": 9295.44,       # mass [kg]
-    "l": 9.144,         # span [m] (lateral model only)
-    "S": 27.87,         # wing area [m^2]
-    "b_a": 3.45,        # mean aerodynamic chord [m]
-    "Jz": 75673.6,      # pitch inertia [kg m^2]
-}
-# stabilator actuator (second-order lag with rate limit) and throttle limits
-_ACTUATOR = {
-    "Tstab": 0.03,
-    "Xistab": 0.707,
-    "maxabsstab": 25 * _DEG,
-    "maxabsdstab": 60 * _DEG,
-    "minthrottle": 0,
-    "maxthrottle": 1,
-}
-# configuration held fixed by the longitudinal model: leading-edge flap and speed brake retracted
-_CONFIG = {"lef": 0, "sb": 0}
+m = 9295.44         # mass [kg]
+l = 9.144           # span [m] (lateral model only)  # noqa: E741 (the reference's name)
+S = 27.87           # wing area [m^2]
+b_a = 3.45          # mean aerodynamic chord [m]
+Jz = 75673.6        # pitch inertia [kg m^2]
+rcgx = -0.05 * b_a  # centre-of-gravity offset [m]
 
-globals().update(_AIRFRAME)
-globals().update(_ACTUATOR)
-globals().update(_CONFIG)
-rcgx = -0.05 * _AIRFRAME["b_a"]    # centre-of-gravity offset [m]
+# stabilator actuator (second-order lag with rate limit) and throttle limits
+Tstab = 0.03
+Xistab = 0.707
+maxabsstab = 25 * _DEG
+maxabsdstab = 60 * _DEG
+minthrottle = 0
+maxthrottle = 1
+
+# configuration held fixed by the longitudinal model: leading-edge flap and speed brake retracted
+lef = 0
+sb = 0
 
 # Observation normalisation ranges.  The ORDER of the keys is the order of the first three observation
 # entries (env/env.py:93-97): altitude, pitch rate, airspeed.

@@ -104,8 +104,16 @@ class ReferenceSignal:
         return sig
 
 
-def build_reference_bank(dt, tn, scenario, determenistic, bank_size=256, seed=0):
+_FULL_COMBO_CACHE = {}
+
+
+def build_reference_bank(dt, tn, scenario, determenistic, bank_size=None, seed=0):
     """Bank of ``wz_ref`` rows for a batch of envs, shape [R, T] (fp64).
+
+    ``bank_size=None`` (the default) serves the reference's own distribution wherever its parameter space is
+    finite: every member of it, equally weighted -- for the random ``combo`` scenario of a 10 s episode that is
+    ``bank_size="full"`` (6480 rows); only multi-block combo episodes (tn >= 20 s, 97,200 distinct signals) fall
+    back to 256 draws.  An integer asks for that many draws where the space is larger than it.
 
     Deterministic configs give one row (three when ``scenario`` is None, which the
     reference still draws at random).  Random configs enumerate the reference's whole
@@ -116,6 +124,8 @@ def build_reference_bank(dt, tn, scenario, determenistic, bank_size=256, seed=0)
     A reset picks a row uniformly, so resets are distributed like the reference's.
     """
     rows = []
+    if bank_size is None:
+        bank_size = "full" if (scenario == "combo" and not determenistic and int(tn / 10) == 1) else 256
     if determenistic:
         for sc in ([scenario] if scenario is not None else ["step", "cos", "pure_step"]):
             rows.append(ReferenceSignal(dt, tn, True, sc).wz_ref)
@@ -123,7 +133,7 @@ def build_reference_bank(dt, tn, scenario, determenistic, bank_size=256, seed=0)
     scen = [scenario] if scenario is not None else ["step", "cos", "pure_step"]
     proto = ReferenceSignal(dt, tn, True, "pure_step")
     enumerable = {"step": 6, "cos": 16, "pure_step": 24}
-    if all(s in enumerable for s in scen) and (bank_size == "full" or max(enumerable[s] for s in scen) * len(scen) <= max(bank_size, 24 * 3)):
+    if all(s in enumerable for s in scen):   # at most 3 x 48 rows: always enumerated in full
         # equal weight per scenario: replicate to the lcm so that uniform row choice == choice of
         # scenario followed by uniform choice of parameters
         per = int(np.lcm.reduce([enumerable[s] for s in scen]))
@@ -148,6 +158,9 @@ def build_reference_bank(dt, tn, scenario, determenistic, bank_size=256, seed=0)
             rows += sigs * (per // len(sigs))
         return np.ascontiguousarray(np.stack(rows))
     if bank_size == "full":
+        key = (float(dt), float(tn))
+        if key in _FULL_COMBO_CACHE:          # 0.6 s to enumerate: built once per (dt, tn), handed out read-only
+            return _FULL_COMBO_CACHE[key]
         # the whole discrete space of the random `combo` scenario: 6 x 6 x 5 x 6 parameter sets x 3! segment orders
         # = 6480 rows (26 MB in fp32).  Exact distribution equivalence, at the price of a bank that no longer stays
         # hot in L2 when several large batches stream through it.
@@ -156,7 +169,10 @@ def build_reference_bank(dt, tn, scenario, determenistic, bank_size=256, seed=0)
         for a_s, a_n, f, a_c in itertools.product(_AMPS6, _AMPS6, [0.125, 0.25, 0.45, 0.5, 0.75], _AMPS6):
             for order in itertools.permutations(range(3)):
                 rows.append(proto._combo_from(np.radians(a_s), np.radians(a_n), f, np.radians(a_c), order) / 2)
-        return np.ascontiguousarray(np.stack(rows))
+        bank = np.ascontiguousarray(np.stack(rows))
+        bank.setflags(write=False)
+        _FULL_COMBO_CACHE[key] = bank
+        return bank
     rng = _random.Random(seed)
     for _ in range(bank_size):
         rows.append(ReferenceSignal(dt, tn, False, scenario, rng=rng).wz_ref)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define F16_ABI_VERSION 1
+#define F16_ABI_VERSION 2
 
 enum { F16_F32 = 0, F16_F64 = 1 };
 
@@ -46,6 +46,15 @@ enum {
 
 enum { F16_OBS_AOS = 0 /* obs[n][5], the reference's layout */, F16_OBS_SOA = 1 /* obs[5][n] */ };
 
+/* f16_config.flags: which kernel / route a call takes.  All variants compute the same numbers bit for bit
+ * (tested); the flags exist so that a caller -- and the parity tests -- can pin one per call. */
+enum {
+    F16_FLAG_ONE_ENV_PER_THREAD = 1, /* fp32 autoreset step: run the one-env-per-thread kernel on every tile instead of
+                                        the two-envs-per-thread kernel (the default on full 256/512-env tiles) */
+    F16_FLAG_NO_PDL = 2,             /* launch without programmatic dependent launch */
+    F16_FLAG_HOST_STAGED = 4         /* f16_env_step_host: never take the zero-copy route */
+};
+
 /* Scalar configuration of a batch of envs (reference: the config dict of
  * F16.__init__, env/env.py:18-35, plus what SyncVectorEnv adds). */
 typedef struct f16_config {
@@ -60,7 +69,7 @@ typedef struct f16_config {
     int32_t init_mode;    /* F16_INIT_* */
     int32_t obs_layout;   /* F16_OBS_* */
     int32_t noise;        /* config["noise"] truthy: wz_obs += radians(N(0, 0.5)) (env/env.py:139-152) */
-    int32_t reserved;
+    int32_t flags;        /* F16_FLAG_* bits, 0 = defaults: per-call kernel / route selection (was `reserved`) */
     uint64_t seed;        /* key of the counter-based RNG (reset + noise) */
     int64_t env_id_base;  /* global id of env 0 of this shard: RNG streams are keyed by the GLOBAL env id, so
                              results do not depend on how the batch is sharded over GPUs */
@@ -81,6 +90,10 @@ typedef struct f16_env_buffers {
     void *pos_comp;          /* real[2][n]   r/w  Kahan carry of the Ox, Oy position integrals, or NULL: keeps the
                                 fp32 mode's positions within ~1e-7 of the fp64 reference over an episode (plain fp32
                                 accumulation drifts up to 1 ulp per step). Leave NULL in fp64 parity mode. */
+    const uint64_t *seed_dev; /* [1] optional DEVICE copy of the RNG key, or NULL.  When set, resets and observation noise read
+                                the key from here instead of f16_config.seed (kernel arguments are frozen into a captured CUDA
+                                graph; a device scalar is not), so re-seeding (F16.reset(seed), env/env.py:155-158) also reaches
+                                autoresets replayed from a graph. */
 } f16_env_buffers;
 
 /* Per-call tensors of f16_env_step. */

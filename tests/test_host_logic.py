@@ -194,13 +194,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/f16_b200.h but not exported"
     assert sorted(_capi.EXPORTS) == names
     lib.f16_abi_version.restype = ctypes.c_int
-    assert lib.f16_abi_version() == 1
+    assert lib.f16_abi_version() == _capi.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header():
     """ctypes mirrors of the ABI structs: sizes as the C compiler lays them out."""
     assert ctypes.sizeof(_capi.Config) == 4 + 4 + 8 + 8 + 8 * 4 + 8 + 8 + 9 * 8   # 144 bytes
-    assert ctypes.sizeof(_capi.EnvBuffers) == 9 * 8
+    assert ctypes.sizeof(_capi.EnvBuffers) == 10 * 8
     assert ctypes.sizeof(_capi.StepIO) == 7 * 8 + 8 + 8
 
 
