@@ -131,7 +131,7 @@ def test_k_step_two_env_kernel_bitwise_and_vs_oracle_through_resets(f16, workloa
         assert torch.equal(o2, o1) and torch.equal(r2, r1) and torch.equal(d2, d1), c
         _same(two, one, "state", "episode_length", "total_return", "ref_idx", "episode_no", "_final_obs", "_final_len", "_final_ret")
         d = d2.cpu().numpy().astype(bool)
-        hit = d.any(axis=0) & (first < 0)
+        hit = d.any(axis=0) & (first == -1)
         if hit.any():
             kk = d.argmax(axis=0)
             once = hit & (d.sum(axis=0) == 1)                         # final_* hold the LAST episode that ended in the call
