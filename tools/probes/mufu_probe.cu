@@ -69,7 +69,7 @@ int main()
     cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
     const double ops = 148.0 * 8 * 256 * 8.0 * iters;   // PTX-level tanh instructions per launch
     const float t0 = run<0>(d, iters), t1 = run<1>(d, iters), t2 = run<2>(d, iters), t3 = run<3>(d, iters), t4 = run<4>(d, iters);
-    const double per = 1e-3 / 148.0 / (clk_khz * 1e3);  // -> per clock per SM at the nominal max clock
+    const double per = 1e3 / 148.0 / (clk_khz * 1e3);  // -> per clock per SM at the nominal max clock
     printf("max clock %.0f MHz (rates below assume it; the real clock under load is lower)\n", clk_khz * 1e-3);
     printf("tanh.approx.f32   : %.3f ms  %.2f results/clk/SM\n", t0, ops / t0 * per);
     printf("tanh.approx.f16   : %.3f ms  %.2f results/clk/SM\n", t1, ops / t1 * per);
