@@ -11,13 +11,21 @@ semantics.  One bench "step" = one F16VecEnv.step() = ONE kernel launch that adv
 env by one env-step and emits obs / reward / done (K = 1, the closed-loop gym step).  Envs
 are sharded over GPUs with no data-path collective (weak scaling).
 
-Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB write)
-before each timed step and excluded from the timing, summed over the K steps, max over
-ranks.  `e2e` repeats the measurement through the host-buffer entry point
-(f16_env_step_host: pinned host actions in, host obs/reward/done out, copies inside the
-timed region).  `cpu_baseline` / `--impl reference` time the CPU oracle (oracle/f16_oracle.c,
-a C port of the reference's NumPy path -- the reference itself is Python and cannot travel
-to the GPU box) on all host cores.
+Timing: the timed region is a CUDA graph of consecutive steps replayed on one stream, one
+CUDA-event pair around the whole region, max over ranks; four resident batches are stepped
+round-robin so that every step's inputs come from HBM (308 MB per cycle vs 126 MB of L2).
+The region is measured in the STATIONARY state of the workload, whatever --steps / --warmup
+are: before the first timed step every batch has flown >= 128 env-steps (untimed K-step
+launches) and the graph has been replayed for >= 0.3 s so that the board sits at the clocks
+it sustains; `roofline.frac_early` is the same measurement on freshly reset envs.
+`kernels` carries a roofline object for every other kernel of the library (policy, PPO
+gradient / optimiser, GAE, trim search, reset), each against the peak that bounds it, with
+pipe peaks measured in the same run (f16_peak_probe).
+`e2e` repeats the measurement through the host-buffer entry point (f16_env_step_host).
+`cpu_baseline` / `--impl reference` time the reference's CPU path on the box's host cores:
+the C restatement (oracle/f16_oracle.c, OpenMP, all threads) on the GPU arm's own step shape
+(2^20 envs x 1 env-step per bench step), and -- when baseline/_ref is present -- the
+reference's unmodified Python `F16.step` in one process per core.
 """
 import argparse
 import json
@@ -38,6 +46,8 @@ ENVS_PER_GPU = 1 << 20
 BYTES_PER_ENV_STEP_F32 = 113      # 48 B read + 65 B written per env-step, fp32, K = 1
 # (the kernel really moves 117 B: + total_return r/w 8, - the V row write 4)
 CFG = {"dt": 0.01, "tn": 10, "debug_state": False, "determenistic_ref": False, "scenario": "combo"}
+PREROLL_ENV_STEPS = 128           # env-steps every batch has flown before the timed region starts
+SUSTAIN_S = 0.3                   # untimed graph replays before the timed region (sustained clocks)
 
 
 def measured_peaks():
@@ -47,7 +57,16 @@ def measured_peaks():
             return json.load(open(p)), "measured"
         except Exception:
             pass
-    return {"hbm_gbs": 6650.0}, "fallback"      # B200_PROFILING.md fallback
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"      # B200_PROFILING.md fallback
+
+
+def profile_constants():
+    """Per-launch constants that only ncu can give (DRAM bytes, FP64 instructions per trim search), captured once per
+    change and committed under profiles/ (tools/ncu_summary.py writes the file)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -82,7 +101,11 @@ class ClockSampler(threading.Thread):
             except Exception:
                 self.proc.kill()
         self.join(timeout=5)
-        rows = [p for t, p in self.samples if (t0 is None or t >= t0) and (t1 is None or t <= t1)] or [p for _, p in self.samples]
+        rows = [p for t, p in self.samples if (t0 is None or t >= t0) and (t1 is None or t <= t1)]
+        window = "timed region"
+        if not rows:      # a region shorter than the sampling period: the samples of the sustain phase right before it
+            rows = [p for t, p in self.samples if t0 is None or (t0 - 0.25 <= t <= (t1 or t0) + 0.05)] or [p for _, p in self.samples]
+            window = "last 0.25 s before and during the timed region (region shorter than the sampling period)"
 
         def num(v):
             try:
@@ -98,7 +121,7 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(rows), "power_w_max": max(pw) if pw else None}
+                "samples": len(rows), "power_w_max": max(pw) if pw else None, "window": window}
 
 
 # ------------------------------------------------------------------------------------ CPU arm
@@ -110,74 +133,155 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-_CPU_INPUTS = {}
+class CpuPort:
+    """The C restatement of the reference's path (oracle/f16_oracle.c, OpenMP) stepping ONE resident batch the way the GPU
+    arm does: every bench step advances all n_envs aircraft by one env-step with a fresh stick row and emits
+    obs / reward / done; finished episodes are re-initialised from the workload's initial-state distribution between
+    steps (the port freezes an env at `done`; its caller resets it, as the reference's SyncVectorEnv would)."""
 
+    def __init__(self, n_envs, threads=None, seed=12345):
+        import numpy as np
 
-def cpu_oracle_run(n_envs, n_steps, threads=None, seed=0):
-    """Time the CPU oracle on a bounded sample of the same workload: n_envs aircraft from the
-    same initial-state distribution, uniform random stick, n_steps env-steps each."""
-    import numpy as np
+        from oracle import f16_oracle as orc
+        import f16_model_b200 as f16
 
-    from oracle import f16_oracle as orc
-    import f16_model_b200 as f16
+        self.np, self.orc = np, orc
+        self.n, self.threads = int(n_envs), threads or host_threads()
+        self.rng = np.random.default_rng(seed)
+        self.bank = f16.build_reference_bank(0.01, 10, "combo", False, bank_size=64, seed=0)
+        self.x = self._draw(self.n)
+        self.idx = self.rng.integers(0, self.bank.shape[0], self.n).astype(np.int32)
+        self.sticks = self.rng.uniform(-1, 1, (16, self.n))
+        self.k = 0
 
-    key = (n_envs, n_steps)
-    if key not in _CPU_INPUTS:       # drawn once per sample shape; every call rotates them by `seed` (untimed either way)
-        rng = np.random.default_rng(12345)
+    def _draw(self, n):
+        np, rng = self.np, self.rng
         d5 = np.radians(5)
-        al = rng.uniform(-d5, d5, n_envs)
-        x0 = np.zeros((n_envs, 9))
-        x0[:, 1], x0[:, 2], x0[:, 3] = rng.uniform(2000, 4000, n_envs), rng.uniform(-d5, d5, n_envs), al
-        x0[:, 4], x0[:, 5] = rng.uniform(90, 250, n_envs), al
-        acts = rng.uniform(-1, 1, (n_steps, n_envs))
-        bank = f16.build_reference_bank(0.01, 10, "combo", False, bank_size=64, seed=0)
-        idx = rng.integers(0, bank.shape[0], n_envs).astype(np.int32)
-        _CPU_INPUTS.clear()
-        _CPU_INPUTS[key] = (x0, acts, bank, idx)
-    x0, acts, bank, idx = _CPU_INPUTS[key]
-    if seed:
-        shift = (int(seed) * 7919) % n_envs
-        x0, acts, idx = np.roll(x0, shift, axis=0), np.roll(acts, shift, axis=1), np.roll(idx, shift)
-    threads = threads or host_threads()
+        al = rng.uniform(-d5, d5, n)
+        x0 = np.zeros((n, 9))
+        x0[:, 1], x0[:, 2], x0[:, 3] = rng.uniform(2000, 4000, n), rng.uniform(-d5, d5, n), al
+        x0[:, 4], x0[:, 5] = rng.uniform(90, 250, n), al
+        return x0
+
+    def step(self, n_steps=1):
+        """-> (env-steps done, seconds inside the oracle call)."""
+        acts = self.sticks[[(self.k + j) % 16 for j in range(n_steps)]]
+        self.k += n_steps
+        t0 = time.perf_counter()
+        out = self.orc.rollout(self.x, acts, self.bank, self.idx, want_states=False, want_obs=True, nthreads=self.threads)
+        dt = time.perf_counter() - t0
+        self.x = out["final_state"]
+        done = out["done"][-1].astype(bool)
+        if done.any():                                    # untimed: the caller-side reset of the episodes that ended
+            self.x[done] = self._draw(int(done.sum()))
+        return out["env_steps"], dt
+
+
+_PYREF_WORKER = r'''
+import os, sys, time, random, warnings
+warnings.simplefilter("ignore")
+sys.path[:0] = [os.environ["F16_PYREF_SHIMS"], os.environ["F16_PYREF_ROOT"]]
+import numpy as np
+from F16model.env import F16
+budget, seed = float(sys.argv[1]), int(sys.argv[2])
+random.seed(seed); np.random.seed(seed)
+cfg = {"dt": 0.01, "tn": 10, "debug_state": False, "determenistic_ref": True, "scenario": "combo"}
+env = F16(cfg); env.reset()
+rng = np.random.default_rng(seed)
+for _ in range(20):                                   # warm-up: imports, SciPy caches
+    env.step(np.array([0.0]))
+env.reset()
+steps, a = 0, 0.0
+t0 = time.perf_counter()
+while True:
+    if steps % 25 == 0:
+        a = float(rng.uniform(-0.3, 0.1))             # piecewise-constant stick, as in BASELINE.md section 3
+        if time.perf_counter() - t0 >= budget:
+            break
+    _, _, done, _, _ = env.step(np.array([a]))
+    steps += 1
+    if done:
+        env.reset()
+print(steps, time.perf_counter() - t0, flush=True)
+'''
+
+
+def python_reference_leg(budget_s=6.0, workers=None):
+    """The reference's OWN `F16model.env.F16.step` (unmodified, from baseline/_ref, with the stand-ins of oracle/shims for
+    its four absent third-party imports), one process per host core, config-1-style episodes (random initial state,
+    deterministic combo reference, piecewise-constant stick) for `budget_s` seconds each (BASELINE.md section 3)."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    shims = os.path.join(ROOT, "oracle", "shims")
+    if not os.path.isdir(os.path.join(ref_root, "F16model")):
+        return {"unavailable": "baseline/_ref/F16model is not installed (python -m pip install --no-index --no-deps --target baseline/_ref <reference>)"}
+    workers = workers or host_threads()
+    env = dict(os.environ, F16_PYREF_ROOT=ref_root, F16_PYREF_SHIMS=shims, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1",
+               MKL_NUM_THREADS="1")
     t0 = time.perf_counter()
-    out = orc.rollout(x0, acts, bank, idx, want_states=False, want_obs=True, nthreads=threads)
-    dt = time.perf_counter() - t0
-    return out["env_steps"], dt, threads
+    procs = [subprocess.Popen([sys.executable, "-c", _PYREF_WORKER, str(budget_s), str(1000 + w)], env=env, stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for w in range(workers)]
+    steps, secs, errs = [], [], []
+    for p in procs:
+        try:
+            out, err = p.communicate(timeout=budget_s * 6 + 120)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, err = "", "timeout"
+        try:
+            s, d = out.split()[-2:]
+            steps.append(int(s))
+            secs.append(float(d))
+        except Exception:
+            errs.append((err or out).strip().splitlines()[-1:] or ["no output"])
+    wall = time.perf_counter() - t0
+    if not steps:
+        return {"unavailable": f"the reference did not run: {errs[0][0][:200] if errs else 'unknown'}"}
+    import numpy
+    import scipy
+
+    rate = sum(s / d for s, d in zip(steps, secs))
+    return {"value": rate, "unit": UNIT, "cores": len(steps), "per_core": rate / len(steps), "kind": "reference",
+            "sample": f"{len(steps)} processes x {budget_s:.0f} s of the unmodified F16model.env.F16.step (baseline/_ref + oracle/shims), "
+                      f"{sum(steps)} env-steps, wall {wall:.1f} s incl. imports; numpy {numpy.__version__}, scipy {scipy.__version__}",
+            "failed_workers": len(errs)}
 
 
 def reference_arm(args, rank, world):
-    """`--impl reference`: the reference's CPU implementation of the path -- here the C oracle port,
-    all host threads.  Rank 0 only."""
+    """`--impl reference`: the reference's CPU implementation of the path, all host threads.  Rank 0 only."""
     if rank != 0:
         return
-    # one bench step = a bounded sample of the 2^20-env gym step: 16 consecutive env-steps of n_envs aircraft, n_envs sized from
-    # a probe so that the K timed steps take about 45 s of CPU work whatever K is (2^16 envs = one full 2^20-env-step batch)
-    n_steps = 16
-    probe_steps, probe_dt, _ = cpu_oracle_run(1 << 14, n_steps)
-    per_env_step = probe_dt / max(probe_steps, 1)
-    n_envs = 1 << 16
-    while n_envs > 1024 and args.steps * n_envs * n_steps * per_env_step > 45.0:
+    n_envs = args.envs
+    port = CpuPort(n_envs)
+    # the reference arm runs the GPU arm's own step shape (n_envs aircraft x 1 env-step per bench step) unless K timed
+    # steps of it would take more than ~60 s of CPU; then the batch is halved until they fit (and the line says so)
+    steps0, dt0 = port.step()
+    while n_envs > 4096 and args.steps * dt0 * (n_envs / port.n) > 60.0:
         n_envs //= 2
-    for _ in range(args.warmup):
-        cpu_oracle_run(n_envs, n_steps)
-    total, tsum, cores = 0, 0.0, 1
-    for s in range(args.steps):
-        steps, dt, cores = cpu_oracle_run(n_envs, n_steps, seed=s)
-        total += steps
-        tsum += dt
+    if n_envs != port.n:
+        port = CpuPort(n_envs)
+    for _ in range(max(args.warmup, 1)):
+        port.step()
+    total, tsum = 0, 0.0
+    for _ in range(args.steps):
+        s, d = port.step()
+        total += s
+        tsum += d
     value = total / tsum
-    sample = f"{n_envs} envs x {n_steps} env-steps per bench step, config-3 distributions, C oracle port (OpenMP)"
+    same = n_envs == args.envs
+    sample = (f"{n_envs} envs x 1 env-step per bench step (one resident batch stepped {args.steps} times), config-3 distributions, "
+              "C restatement of the reference's path in fp64 (oracle/f16_oracle.c, gcc -O2, OpenMP)")
+    pyref = python_reference_leg() if not args.no_pyref else None
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tsum / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * tsum / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs, "substeps_per_launch": 1,
-                   "reference_arm": "bounded CPU sample of that workload in fp64 (the reference's arithmetic): " + sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs, "substeps_per_launch": 1, "same_config": same,
+                   "reference_arm": "the same gym step on the host cores, in the reference's fp64 arithmetic: " + sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": port.threads, "kind": "port", "sample": sample, "python_reference": pyref},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference is pure Python (SciPy interpolators rebuilt every step, ~156 env-steps/s/core measured in the "
-                "build container, BASELINE.md section 2) and cannot travel to the GPU box; this arm times its C restatement",
+        "note": "value = the C port (the conservative comparator: ~1e4 x faster per core than the reference's Python); "
+                "cpu_baseline.python_reference = the reference's own unmodified F16.step timed on the same cores",
     }
     print(json.dumps(line), flush=True)
 
@@ -192,9 +296,13 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--no-sweep", action="store_true", help="skip the K-substeps sweep")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-pyref", action="store_true", help="skip the Python-reference sub-leg of the CPU baseline")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline list")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (eager loop, 4 streams, L2-resident, flushed)")
     ap.add_argument("--fast-math", type=int, default=1)
     ap.add_argument("--pool", type=int, default=64, help="rows of the cycled stick tensor per batch (period of each env's stick, in steps)")
+    ap.add_argument("--bank", default="default", help="'default' = the library default (all 6480 random combo signals), or a row count")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -209,9 +317,10 @@ def main():
     import torch.distributed as dist
 
     import f16_model_b200 as f16
+    from f16_model_b200 import _capi
     from f16_model_b200.sharding import make_sharded_env
 
-    f16.load_library()                       # fails loudly if the CUDA library is missing
+    L = f16.load_library()                   # fails loudly if the CUDA library is missing
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -225,6 +334,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     N = args.envs
     fast = bool(args.fast_math)
     # R_SETS independent batches of N envs resident in HBM, stepped round-robin: the cycle touches
@@ -232,8 +348,9 @@ def main():
     # from HBM and its dirty lines are written back while the next batches run -- the steady state of a
     # streaming workload, with no flush kernel inside the timed region.
     R_SETS, POOL = 4, max(1, args.pool)
+    bank_kw = {} if args.bank == "default" else {"bank_size": int(args.bank)}
     envs = [make_sharded_env(CFG, N * world, rank, world, device, dtype=torch.float32, autoreset=True, seed=1 + j,
-                             fast_math=fast, bank_size=256) for j in range(R_SETS)]
+                             fast_math=fast, **bank_kw) for j in range(R_SETS)]
     env = envs[0]
     g = torch.Generator(device=device).manual_seed(1000 + rank)
     pools = [torch.rand((POOL, N), device=device, generator=g) * 2 - 1 for _ in range(R_SETS)]   # stick tensors, cycled
@@ -244,12 +361,22 @@ def main():
         for s in range(first, first + n_steps):
             envs[s % R_SETS].step(pools[s % R_SETS][(s // R_SETS) % POOL])
 
+    def preroll(env_steps):
+        """Advance every batch by `env_steps` env-steps, untimed, in K-step launches over the batch's own stick pool
+        (K launches of one step and one launch of K steps are bit-identical: tests/test_gpu_parity.py)."""
+        left = env_steps
+        while left > 0:
+            k = min(left, POOL)
+            for j in range(R_SETS):
+                envs[j].step_k(pools[j][:k])
+            left -= k
+
     for _ in range(max(args.warmup, 3)):
         enqueue_steps(R_SETS)
     torch.cuda.synchronize()
 
     # The K = 1 gym step is launch-bound from Python (~30 us of interpreter + ctypes per call vs a
-    # ~25 us kernel), so the timed loop replays a CUDA graph of G consecutive steps.
+    # ~22 us kernel), so the timed loop replays a CUDA graph of G consecutive steps.
     G = min(max(48, R_SETS * POOL), args.steps)   # one graph covers a whole cycle of the stick pool
     graphs = {}
 
@@ -266,6 +393,18 @@ def main():
             graphs[n_steps] = gr
         return graphs[n_steps]
 
+    def time_replays(gr, n_replays, warm=3):
+        for _ in range(warm):
+            gr.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_replays):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
     def timed_concurrent(n_steps):
         """Extra (not the headline): the R_SETS batches are independent, so their steps may overlap -- one capture
         stream per batch inside the graph hides each kernel's ramp-up / ramp-down behind its neighbours."""
@@ -281,16 +420,7 @@ def main():
                     envs[s % R_SETS].step(pools[s % R_SETS][(s // R_SETS) % POOL])
             for st_ in side:
                 cur.wait_stream(st_)
-        for _ in range(3):
-            gr.replay()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n_steps // G):
-            gr.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1), n_steps
+        return time_replays(gr, n_steps // G), n_steps
 
     def timed_resident(n_steps):
         """Extra (not the headline, breaks the L2 rule on purpose): ONE batch stepped repeatedly, as a PPO loop
@@ -300,16 +430,7 @@ def main():
         with torch.cuda.graph(gr):
             for s in range(G):
                 envs[0].step(pools[0][s % POOL])
-        for _ in range(3):
-            gr.replay()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n_steps // G):
-            gr.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1), n_steps
+        return time_replays(gr, n_steps // G), n_steps
 
     def timed_graph_steps(n_steps):
         plan = [G] * (n_steps // G) + ([n_steps % G] if n_steps % G else [])
@@ -337,38 +458,68 @@ def main():
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in ev)
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    # ---- bring the workload to its stationary state, untimed -------------------------------------------------
+    # (1) every env flies PREROLL_ENV_STEPS env-steps: alpha / stab have spread over the table cells (the step kernel's
+    #     shared-memory lookups depend on that: a launch on fresh envs is ~10 % faster than a stationary one);
+    # (2) the timed graph itself is replayed for >= SUSTAIN_S so that the board settles at the clocks it sustains;
+    # (3) the replays stop when the envs are ~mid-episode (age 300..700 of 1000), away from the synchronised time-out
+    #     resets that put every env back into the early state for ~35 steps.
+    preroll(PREROLL_ENV_STEPS)
     timed_graph_steps(min(args.steps, 4 * G))                                  # warm the graphs themselves
+    torch.cuda.synchronize()
+    flown = lambda: int(env.episode_length.float().median().item())          # noqa: E731  (typical env age of batch 0)
+    gr_full = graph_of(G)
+    t_s = time.perf_counter()
+    sustain_replays = 0
+    while time.perf_counter() - t_s < SUSTAIN_S or not (300 <= flown() <= 700):
+        gr_full.replay()
+        sustain_replays += 1
+        if sustain_replays % 4 == 0:
+            torch.cuda.synchronize()
+        if sustain_replays > 4000:
+            break
+    torch.cuda.synchronize()
+    age_at_start = flown()
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.1)
+        for _ in range(8):                                                     # keep the board busy while the sampler comes up
+            gr_full.replay()
+        torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     dev_ms = timed_graph_steps(args.steps)
     t_wall1 = time.perf_counter()
     wall_s = t_wall1 - t_wall0
-    n_sec = min(args.steps, 500)
-    flushed_ms = timed_steps(n_sec, do_flush=True)
-    eager_t0 = time.perf_counter()
-    enqueue_steps(n_sec)
-    torch.cuda.synchronize()
-    eager_s = time.perf_counter() - eager_t0
-    conc_ms, conc_steps = timed_concurrent(min(args.steps, 960))
-    res_ms, res_steps = timed_resident(min(args.steps, 960))
-    barrier()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    barrier()
+
+    # ---- the same measurement on freshly reset envs (the "early" state a short cold benchmark would see) -----
+    n_early = min(args.steps, 20 * R_SETS) // R_SETS * R_SETS or R_SETS
+    for j in range(R_SETS):
+        envs[j].reset(seed=101 + j)
+    enqueue_steps(3 * R_SETS)                                                  # W >= 3 warm-up steps per batch
+    early_ms = max_over_ranks(timed_graph_steps(n_early))
+    preroll(PREROLL_ENV_STEPS)                                                 # back to the stationary state for everything below
+
+    n_sec = min(args.steps, 500)
+    extras = {}
+    if not args.no_extras:
+        flushed_ms = max_over_ranks(timed_steps(n_sec, do_flush=True))
+        eager_t0 = time.perf_counter()
+        enqueue_steps(n_sec)
+        torch.cuda.synchronize()
+        eager_s = max_over_ranks(time.perf_counter() - eager_t0)
+        conc_ms, conc_steps = timed_concurrent(min(args.steps, 960))
+        res_ms, res_steps = timed_resident(min(args.steps, 960))
+        conc_ms, res_ms = max_over_ranks(conc_ms), max_over_ranks(res_ms)
+        extras = {"value_eager_python_loop": N * world * n_sec / eager_s,
+                  "value_4_batches_on_4_streams": N * world * conc_steps / (conc_ms * 1e-3),
+                  "value_one_batch_l2_resident": N * world * res_steps / (res_ms * 1e-3),
+                  "value_single_launch_events_write_flushed_l2": N * world * n_sec / (flushed_ms * 1e-3)}
+        barrier()
 
     dev_ms = max_over_ranks(dev_ms)
-    flushed_ms = max_over_ranks(flushed_ms)
-    eager_s = max_over_ranks(eager_s)
-    conc_ms = max_over_ranks(conc_ms)
-    res_ms = max_over_ranks(res_ms)
     total_env_steps = N * world * args.steps
     value = total_env_steps / (dev_ms * 1e-3)
 
@@ -389,11 +540,27 @@ def main():
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": N * world * n_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": 25 * N,
                "steps": n_e2e, "ms_per_step": 1e3 * e2e_s / n_e2e,
+               "d2h_gbs_per_gpu": 25 * N * n_e2e / e2e_s / 1e9,
                "path": ("f16_env_step_host, zero-copy route: ONE kernel launch reads the pinned (mapped) host actions and bulk-stores "
                         "obs/reward/done to pinned host memory over PCIe, then a stream sync (PCIe-bound)"
                         if getattr(env, "last_host_route", "") == "zero_copy" else
                         "f16_env_step_host, staged route: pinned host actions -> H2D -> kernel -> D2H obs/reward/done, "
                         "3 chunks on 3 streams (PCIe-bound)")}
+        # the link ceiling the e2e number is to be read against: plain pinned D2H copies of the same 25 B x N, all ranks at once
+        dsrc = torch.empty(25 * N, dtype=torch.uint8, device=device)
+        hdst = torch.empty(25 * N, dtype=torch.uint8).pin_memory()
+        for _ in range(2):
+            hdst.copy_(dsrc, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            hdst.copy_(dsrc, non_blocking=True)
+        torch.cuda.synchronize()
+        copy_s = max_over_ranks(time.perf_counter() - t0)
+        e2e["d2h_copy_ceiling_gbs_per_gpu"] = 25 * N * 20 / copy_s / 1e9
+        e2e["frac_of_concurrent_d2h_ceiling"] = e2e["d2h_gbs_per_gpu"] / e2e["d2h_copy_ceiling_gbs_per_gpu"]
+        e2e["d2h_ceiling_note"] = f"cudaMemcpyAsync D2H of the same 25 B x N from pinned memory, {world} rank(s) concurrently, 20 copies back to back"
+        del dsrc, hdst
         if os.environ.get("F16B200_BENCH_STAGED_TOO"):   # comparison leg: same call with pageable actions -> staged route
             a_np = a_host.numpy().copy()
             t0 = time.perf_counter()
@@ -423,42 +590,52 @@ def main():
             sweep[str(K)] = N * world * K * reps / (max_over_ranks(tot) * 1e-3)
             del acts, outb
 
+    peaks, peak_kind = measured_peaks()
+    consts = profile_constants()
+
+    # ---- every other kernel of the library against the peak that bounds it ---------------------
+    kernels = None
+    if not args.no_kernels:
+        del flush
+        kernels = kernel_rooflines(torch, f16, _capi, L, device, rank, world, peaks, peak_kind, consts, sweep, N, clocks)
+    barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks, peak_kind = measured_peaks()
     per_launch_s = dev_ms * 1e-3 / args.steps
     achieved = BYTES_PER_ENV_STEP_F32 * N / per_launch_s / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("env_step_f32_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    early_s = early_ms * 1e-3 / n_early
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic, "peak_kind": f"of {peak_kind}", "kernel": "env_step2_kernel<float,fast,single> (two envs per thread)",
+                "traffic": consts.get("env_step_f32_dram_bytes_per_launch"), "peak_kind": f"of {peak_kind}",
+                "kernel": "env_step2_kernel<float,fast,single> (two envs per thread)",
                 "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP_F32, "units_per_launch": N,
                 "avg_launch_us": per_launch_s * 1e6,
-                "timing": "CUDA events around the whole timed region (graph replays of consecutive steps) / steps: includes inter-kernel gaps",
-                "frac_single_launch_write_flushed_l2": BYTES_PER_ENV_STEP_F32 * N / (flushed_ms * 1e-3 / n_sec) / 1e9 / peaks["hbm_gbs"]}
+                "state": f"stationary: every env had flown >= {PREROLL_ENV_STEPS} env-steps and the graph had been replayed for >= {SUSTAIN_S} s "
+                         f"before the first timed step (median env age at the start of the region: {age_at_start} steps)",
+                "frac_early": BYTES_PER_ENV_STEP_F32 * N / early_s / 1e9 / peaks["hbm_gbs"],
+                "early_launch_us": early_s * 1e6,
+                "early_state": f"{n_early} steps on freshly reset envs (3 warm-up steps per batch): alpha within +-5 deg, stab = 0",
+                "timing": "CUDA events around the whole timed region (graph replays of consecutive steps) / steps: includes inter-kernel gaps"}
+    if "value_single_launch_events_write_flushed_l2" in extras:
+        roofline["frac_single_launch_write_flushed_l2"] = (BYTES_PER_ENV_STEP_F32 * extras["value_single_launch_events_write_flushed_l2"]
+                                                           / world / 1e9 / peaks["hbm_gbs"])
 
     cpu = None
     if not args.no_cpu and world == 1:   # the CPU baseline leg belongs to the N = 1 run (the other ranks' processes would share its cores)
-        probe_steps, probe_dt, cores = cpu_oracle_run(1 << 13, 16)
-        rate = probe_steps / probe_dt
-        n_envs, n_steps = 1 << 17, 500
-        reps = int(min(64, max(1, round(rate * 12 / (n_envs * n_steps)))))    # ~12 s of CPU work
+        port = CpuPort(N)
+        port.step()                                                            # warm-up (page faults, thread pool)
         steps_done = dt = 0
-        for r in range(reps):
-            s_, d_, cores = cpu_oracle_run(n_envs, n_steps, seed=r)
+        while dt < 10.0 and steps_done < 64 * N:                               # ~10 s of CPU work on the GPU arm's own step shape
+            s_, d_ = port.step()
             steps_done += s_
             dt += d_
-        cpu = {"value": steps_done / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{reps} x ({n_envs} envs x {n_steps} env-steps) = {steps_done:.3g} env-steps in {dt:.1f} s, same "
-                         "distributions as the GPU workload, C oracle port (gcc -O2, OpenMP)"}
+        cpu = {"value": steps_done / dt, "unit": UNIT, "cores": port.threads, "kind": "port",
+               "sample": f"{steps_done // N} bench steps of {N} envs x 1 env-step = {steps_done:.3g} env-steps in {dt:.1f} s, same "
+                         "distributions and step shape as the GPU workload, C restatement of the reference (gcc -O2, OpenMP)",
+               "python_reference": None if args.no_pyref else python_reference_leg()}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -468,18 +645,174 @@ def main():
                    "l2": "inputs larger than L2: 4 resident batches of 2^20 envs stepped round-robin (308 MB per cycle vs 126 MB L2), "
                          "no flush kernel in the timed region",
                    "stick": f"U(-1,1) rows cycled from a pool of {POOL} per batch (each env's stick repeats every {POOL} steps)",
-                   "launch": f"CUDA graph of {G} consecutive steps, replayed"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu,
-        "value_eager_python_loop": N * world * n_sec / eager_s,
-        "value_4_batches_on_4_streams": N * world * conc_steps / (conc_ms * 1e-3),
-        "value_one_batch_l2_resident": N * world * res_steps / (res_ms * 1e-3),
-        "value_single_launch_events_write_flushed_l2": N * world * n_sec / (flushed_ms * 1e-3),
+                   "reference_bank_rows": int(env.ref_bank.shape[0]),
+                   "launch": f"CUDA graph of {G} consecutive steps, replayed",
+                   "untimed_preroll": f"{max(args.warmup, 3)} warm-up cycles, {PREROLL_ENV_STEPS} env-steps per env in K-step launches, "
+                                      f"{sustain_replays} graph replays ({SUSTAIN_S} s) to sustained clocks"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
         "wall_s_timed_region": wall_s,
         "substeps_sweep_env_steps_per_s": sweep,
     }
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def kernel_rooflines(torch, f16, _capi, L, device, rank, world, peaks, peak_kind, consts, sweep, N, clocks):
+    """One roofline object per kernel of the library that is not the headline step kernel.  Every duration is the
+    average of a CUDA graph of back-to-back launches timed with one CUDA-event pair (cold-launch effects excluded, the
+    working set of one launch may stay in L2 -- said per entry); pipe peaks come from f16_peak_probe in this run."""
+    import ctypes as C
+
+    import numpy as np
+
+    out = []
+    st = lambda: _capi.stream_ptr(device)     # noqa: E731
+
+    def graph_us(fn, reps=20, replays=5):
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream(device).wait_stream(side)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for _ in range(reps):
+                fn()
+        gr.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(replays):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / (reps * replays)
+
+    # ---- measured pipe peaks (this board, this run's clocks) ----
+    scratch = torch.zeros(16, device=device)
+    pipe = {}
+    for name, kind, iters in (("fp32_fma", 0, 4000), ("fp64_fma", 1, 600), ("mufu_tanh", 2, 1500)):
+        ops = C.c_double(0.0)
+        us = graph_us(lambda: _capi.check(L.f16_peak_probe(kind, iters, C.byref(ops), scratch.data_ptr(), st())), reps=2, replays=3)
+        pipe[name] = ops.value / (us * 1e-6)
+    hbm = peaks["hbm_gbs"]
+    how = "graph of back-to-back launches, CUDA events"
+
+    def entry(kernel, bound, achieved, peak, unit, us, units, **kw):
+        e = {"kernel": kernel, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak if peak else None,
+             "avg_launch_us": us, "units_per_launch": units, "timing": how}
+        e.update(kw)
+        out.append(e)
+
+    cfg = dict(CFG)
+    # ---- K-step env kernel (issue-bound): warp-instructions per second against 4 schedulers x n_sm x clock ----
+    if sweep and "64" in sweep and clocks and clocks.get("sm_mhz"):
+        instr = consts.get("env_step2_k_sass_instr_per_env_step", 248)
+        ach = sweep["64"] / world * instr / 32.0
+        n_sm = torch.cuda.get_device_properties(device).multi_processor_count
+        peak = 4.0 * n_sm * clocks["sm_mhz"] * 1e6
+        entry("env_step2_kernel<float,fast,K-step> (K = 64, state in registers)", "issue", ach / 1e9, peak / 1e9, "G warp-instr/s",
+              64 * N / (sweep["64"] / world) * 1e6, 64 * N, peak_kind=f"4 warp schedulers x {n_sm} SMs x {clocks['sm_mhz']} MHz (sampled in this run)",
+              algorithmic_per_unit=f"{instr} SASS instructions per env-step on the K-loop's common path (cuobjdump; two envs per thread)",
+              env_steps_per_s=sweep["64"] / world, fp32_fma_peak_tflops=2 * pipe["fp32_fma"] / 1e12)
+
+    # ---- env_reset_kernel (HBM: 85 B per env: 9 state rows + counters + obs written, ref_idx / episode_no / bank read) ----
+    renv = f16.F16VecEnv(cfg, N, device=device, dtype=torch.float32, seed=5, fast_math=True, bank_size=256)
+    us = graph_us(lambda: renv.reset(), reps=10)
+    entry("env_reset_kernel<float>", "hbm", 85 * N / (us * 1e-6) / 1e9, hbm, "GB/s", us, N, peak_kind=f"of {peak_kind}",
+          algorithmic_per_unit="85 B per env (36 state + 13 counters/flags + 4 ref row + 20 obs written; 12 read)",
+          l2="one batch (89 MB) re-written per launch: write-back overlaps the next launch")
+
+    # ---- policy_forward_kernel (MUFU.TANH: 256 tanh per env) ----
+    pol = f16.TensorCorePolicy(device=device, seed=1, logstd_init=-1.0)
+    obs = renv.reset()[0]
+    act_out = (torch.empty(N, device=device), torch.empty(N, device=device), torch.empty(N, device=device))
+    for n_pol in sorted({N, min(N, 65536)}, reverse=True):
+        o = obs[:n_pol]
+        oo = tuple(t[:n_pol] for t in act_out)
+        us = graph_us(lambda: pol.act(o, step=0, out=oo))
+        entry("policy_forward_kernel (tcgen05 kind::tf32, TMEM accumulators)", "mufu", 256 * n_pol / (us * 1e-6) / 1e9, pipe["mufu_tanh"] / 1e9,
+              "G tanh/s", us, n_pol, peak_kind="MUFU.TANH results/s of f16_peak_probe in this run (16 per clock per SM)",
+              algorithmic_per_unit="256 tanh per env (two 5-64-64-1 MLPs)",
+              tensor_tflops=2 * (8 * 128 + 2 * 64 * 64) * n_pol / (us * 1e-6) / 1e12, tensor_frac=2 * (8 * 128 + 2 * 64 * 64) * n_pol / (us * 1e-6) / 1e12 / peaks["bf16_tflops"] * 2,
+              tensor_note="TF32 MACs issued (K padded 5 -> 8) against HALF the measured bf16 rate; irrelevant for a 5-64-64-1 MLP")
+    del renv
+
+    # ---- PPO: config 4 (65,536 envs x 128 steps): rollout, GAE, gradient, optimiser ----
+    n4, T4 = 65536, 128
+    envs4 = f16.F16VecEnv(cfg, n4, device=device, dtype=torch.float32, seed=1, fast_math=True)
+    pol4 = f16.TensorCorePolicy(device=device, seed=1, logstd_init=-1.0)
+    pcfg = f16.PPOConfig(num_steps=T4, num_minibatches=32, update_epochs=4)
+    tr = f16.PPOTrainer(envs4, pol4, pcfg)
+    hist = tr.train(num_updates=3) if world == 1 else None     # multi-rank PPO is measured by tools/config_bench.py under torchrun
+    if hist:
+        h = hist[-1]
+        # rollout: 128 x (policy + env) replayed from one graph; bounded by the policy's tanh stream
+        ach = 256 * n4 * T4 / h["rollout_s"] / 1e9
+        entry("PPO rollout: 128 x (policy_forward_kernel -> env_step2_kernel), one CUDA graph", "mufu", ach, pipe["mufu_tanh"] / 1e9, "G tanh/s",
+              h["rollout_s"] * 1e6, n4 * T4, peak_kind="MUFU.TANH results/s of f16_peak_probe in this run", timing="wall clock around the graph replay + GAE + sync",
+              env_steps_per_s=h["rollout_sps"], update_s=h["update_s"], minibatches_per_update=pcfg.num_minibatches * pcfg.update_epochs)
+        b = tr._flat
+        mb = tr._perm_buf[: tr.minibatch_size]
+        adv, ret = f16.gae(tr.rewards, tr.values, tr.done_after, tr.values[-1].clone(), 0.99, 0.95)
+        us = graph_us(lambda: f16.gae(tr.rewards, tr.values, tr.done_after, tr.values[-1], 0.99, 0.95), reps=5)
+        entry("gae_kernel (reverse scan, one thread per env)", "hbm", 17 * n4 * T4 / (us * 1e-6) / 1e9, hbm, "GB/s", us, n4 * T4,
+              peak_kind=f"of {peak_kind}", algorithmic_per_unit="17 B per (step, env): reward, value, done read; advantage, return written",
+              l2="151 MB per launch, larger than L2")
+        args16 = (mb.numel(), tr._train_blob.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(), b["logprobs"].data_ptr(),
+                  b["adv"].data_ptr(), b["ret"].data_ptr(), b["val"].data_ptr(), mb.data_ptr(), pol4.actor_logstd.data_ptr(),
+                  tr._adv_stats.data_ptr(), tr._g.data_ptr(), 0.5, 0.5, 0.0, 1, 1)
+        rows = mb.numel()
+        us = graph_us(lambda: _capi.check(L.f16_ppo_grad16(*args16, tr._grad_scratch.data_ptr(), st())), reps=10)
+        flops = 2.0 * rows * (16 * 128 + 2 * 64 * 64 + 2 * 64 * 64 + 128 * 128 + 16 * 128 + 16 * 128)   # MACs issued per row: fwd L1, L2; dZ2 W2; dW2 (both nets in one M=N=128 product); db2|dW1
+        entry("ppo_grad16_kernel + ppo_grad_reduce (forward + clipped-PPO loss + backward of both MLPs, tcgen05 kind::f16)", "mufu",
+              256 * rows / (us * 1e-6) / 1e9, pipe["mufu_tanh"] / 1e9, "G tanh/s", us, rows,
+              peak_kind="MUFU.TANH results/s of f16_peak_probe in this run",
+              algorithmic_per_unit="256 tanh per minibatch row (the forward); the backward reuses H1, H2",
+              tensor_tflops=flops / (us * 1e-6) / 1e12, tensor_frac=flops / (us * 1e-6) / 1e12 / peaks["bf16_tflops"],
+              tensor_note="fp16 MACs issued against the measured bf16 burst rate: the tensor cores are not the bound of a 64-wide MLP",
+              gather_gbs=rows * (20 + 5 * 4 + 8) / (us * 1e-6) / 1e9)
+        m, v, vmax, step = tr._adam
+        us = graph_us(lambda: _capi.check(L.f16_ppo_adam(
+            tr._n_params, tr._pflat.data_ptr(), tr._g.data_ptr(), m.data_ptr(), v.data_ptr(), vmax.data_ptr(), step.data_ptr(), tr._lr.data_ptr(),
+            0.9, 0.999, 1e-8, 0.5, tr._fwd_perm.data_ptr(), pol4._blob.data_ptr(), tr._fwd_perm.numel(), tr._train_perm.data_ptr(),
+            tr._blob_tail.data_ptr(), tr._train_perm.numel(), tr._half_perm.data_ptr(), tr._train_blob.data_ptr(), tr._half_perm.numel(),
+            tr._diag.data_ptr(), pol4.actor_logstd.data_ptr(), 1.0 / rows, 1, st())), reps=10)
+        nbytes = tr._n_params * 4 * 9 + (tr._fwd_perm.numel() + tr._train_perm.numel()) * 12 + tr._half_perm.numel() * 10
+        entry("ppo_adam_kernel (clip_grad_norm + Adam(amsgrad) + re-packing of three weight blobs, ONE CTA)", "latency",
+              nbytes / (us * 1e-6) / 1e9, hbm, "GB/s", us, tr._n_params, peak_kind=f"of {peak_kind}",
+              algorithmic_per_unit="9.3 k parameters: ~0.9 MB touched per launch, all L2-resident",
+              note="a 9.3 k-parameter model has no throughput roofline: the launch is a chain of three CTA-wide reductions / barriers; "
+                   "its cost is latency (us), which the PDL chain of the update graph overlaps with the next gradient kernel's prologue")
+    del tr, envs4, pol4
+
+    # ---- trim search (FP64 pipe) ----
+    Vg, Hg = np.meshgrid(np.linspace(100, 300, 21), np.linspace(1000, 10000, 19))
+    starts = f16.reference_starts()[::4]
+    f16.trim_grid(Vg[:2], Hg[:2], starts=starts, device=device)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = f16.trim_grid(Vg, Hg, starts=starts, device=device, return_all=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    searches = Vg.size * starts.shape[0]
+    iters = float(np.sum(r["all_iterations"]))
+    per_iter = consts.get("trim_fp64_thread_instr_per_iteration")
+    ach = iters * per_iter / dt if per_iter else None
+    e = {"kernel": "trim_kernel<double> (one Nelder-Mead search per thread, scipy.optimize.fmin rules)", "bound": "fp64",
+         "achieved": ach / 1e9 if ach else None, "peak": pipe["fp64_fma"] / 1e9, "unit": "G fp64-instr/s",
+         "frac": ach / pipe["fp64_fma"] if ach else None, "avg_launch_us": dt * 1e6, "units_per_launch": searches,
+         "timing": "wall clock around one trim_grid call (upload, kernel, arg-min, download)",
+         "peak_kind": "DFMA/s of f16_peak_probe in this run", "searches_per_s": searches / dt, "nelder_mead_iterations": iters,
+         "algorithmic_per_unit": ("%s FP64-pipe thread-instructions per Nelder-Mead iteration (ncu, profiles/traffic.json)" % per_iter) if per_iter
+         else "FP64 instructions per iteration not captured yet (profiles/traffic.json)"}
+    out.append(e)
+    out.append({"pipe_peaks_measured_in_this_run": {"fp32_tflops": 2 * pipe["fp32_fma"] / 1e12, "fp64_tflops": 2 * pipe["fp64_fma"] / 1e12,
+                                                    "mufu_tanh_per_s": pipe["mufu_tanh"]}})
+    return out
 
 
 if __name__ == "__main__":

@@ -19,7 +19,7 @@ OBS_AOS, OBS_SOA = 0, 1
 FLAG_ONE_ENV_PER_THREAD, FLAG_NO_PDL, FLAG_HOST_STAGED = 1, 2, 4
 ABI_VERSION = 2
 
-EXPORTS = ["f16_abi_version", "f16_last_error", "f16_init", "f16_launch_geometry", "f16_env_reset", "f16_env_step",
+EXPORTS = ["f16_abi_version", "f16_last_error", "f16_init", "f16_launch_geometry", "f16_peak_probe", "f16_env_reset", "f16_env_step",
            "f16_env_step_host", "f16_host_route", "f16_rhs", "f16_model_step", "f16_coeffs", "f16_thrust", "f16_atmosphere",
            "f16_policy_blob_bytes", "f16_policy_forward", "f16_ppo_adv_stats", "f16_ppo_train_blob_bytes", "f16_ppo_grad_floats", "f16_ppo_grad", "f16_ppo_train_blob16_bytes", "f16_ppo_grad16_scratch_floats", "f16_ppo_grad16", "f16_ppo_adam",
            "f16_gae", "f16_trim"]
@@ -78,6 +78,7 @@ def load_library():
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
     L.f16_init.argtypes = [i32]
     L.f16_launch_geometry.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.f16_peak_probe.argtypes = [i32, i32, C.POINTER(C.c_double), vp, vp]
     L.f16_env_reset.argtypes = [C.POINTER(Config), C.POINTER(EnvBuffers), vp, i32, vp, vp]
     L.f16_env_step.argtypes = [C.POINTER(Config), C.POINTER(EnvBuffers), C.POINTER(StepIO), i32, vp]
     L.f16_env_step_host.argtypes = [C.POINTER(Config), C.POINTER(EnvBuffers), vp, vp, vp, vp, i32, i32]

@@ -333,6 +333,17 @@ int f16_launch_geometry(int device, int dtype, int *n_sm, int *cta_threads, int 
     return F16_OK;
 }
 
+int f16_peak_probe(int kind, int iters, double *ops_per_launch, void *scratch, void *stream)
+{
+    if (kind < F16_PEAK_FP32_FMA || kind > F16_PEAK_MUFU_TANH || iters <= 0 || !scratch) return fail(F16_EINVAL, "bad kind / iters / scratch");
+    int dev, rc;
+    if ((rc = current_device(&dev))) return rc;
+    DeviceCtx *ctx;
+    if ((rc = ensure_device(dev, &ctx))) return rc;
+    CUDA_TRY(f16::launch_peak_probe(kind, iters, ctx->n_sm, static_cast<float *>(scratch), ops_per_launch, static_cast<cudaStream_t>(stream)));
+    return F16_OK;
+}
+
 int f16_env_reset(const f16_config *cfg, const f16_env_buffers *env, const uint8_t *mask, int keep_ref, void *obs, void *stream)
 {
     int rc = check_cfg(cfg);

@@ -83,4 +83,7 @@ int env_step_occupancy_f64(bool autoreset);
 cudaError_t launch_trim(const Tables<double> *, int n_cells, int n_starts, const double *V, const double *H, const double *starts,
                         double *out_x, double *out_cost, int *out_iters, const LaunchGeom &, cudaStream_t);
 
+// f16_peaks.cu: kind 0 = FP32 FMA, 1 = FP64 FMA, 2 = MUFU.TANH; *ops = operations one launch performs
+cudaError_t launch_peak_probe(int kind, int iters, int n_sm, float *sink, double *ops, cudaStream_t);
+
 }  // namespace f16

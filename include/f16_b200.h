@@ -123,6 +123,13 @@ int f16_init(int device);
 /* SMs of `device`, CTA size and the resident-CTA count the step kernel is launched with. */
 int f16_launch_geometry(int device, int dtype, int *n_sm, int *cta_threads, int *ctas_per_sm);
 
+/* Pipe-rate probe: one launch of a persistent grid that does nothing but `iters` x 32 independent operations per thread
+ * of one kind -- the MEASURED denominator of the rooflines MEASURED_PEAKS.json has no entry for (bench.py times it with
+ * CUDA events beside the kernel it reports on).  *ops_per_launch receives the operations one launch performs (an FMA
+ * counts once).  scratch: >= 4 bytes of device memory. */
+enum { F16_PEAK_FP32_FMA = 0, F16_PEAK_FP64_FMA = 1, F16_PEAK_MUFU_TANH = 2 };
+int f16_peak_probe(int kind, int iters, double *ops_per_launch, void *scratch, void *stream);
+
 /* ---- env level -------------------------------------------------------- */
 /* F16.reset (env/env.py:154-170) for every env whose mask byte is non-zero
  * (mask == NULL: all).  Draws/copies the initial state, zeroes the counters,
