@@ -302,7 +302,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (eager loop, 4 streams, L2-resident, flushed)")
     ap.add_argument("--fast-math", type=int, default=1)
     ap.add_argument("--pool", type=int, default=64, help="rows of the cycled stick tensor per batch (period of each env's stick, in steps)")
-    ap.add_argument("--bank", default="default", help="'default' = the library default (all 6480 random combo signals), or a row count")
+    ap.add_argument("--bank", default="default", help="'default' = the library default (all 6480 random combo signals, segment bank), "
+                                                      "a row count, or 'full' (all 6480 as whole rows)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -348,7 +349,7 @@ def main():
     # from HBM and its dirty lines are written back while the next batches run -- the steady state of a
     # streaming workload, with no flush kernel inside the timed region.
     R_SETS, POOL = 4, max(1, args.pool)
-    bank_kw = {} if args.bank == "default" else {"bank_size": int(args.bank)}
+    bank_kw = {} if args.bank == "default" else {"bank_size": args.bank if args.bank == "full" else int(args.bank)}
     envs = [make_sharded_env(CFG, N * world, rank, world, device, dtype=torch.float32, autoreset=True, seed=1 + j,
                              fast_math=fast, **bank_kw) for j in range(R_SETS)]
     env = envs[0]
@@ -432,13 +433,19 @@ def main():
                 envs[0].step(pools[0][s % POOL])
         return time_replays(gr, n_steps // G), n_steps
 
-    def timed_graph_steps(n_steps):
+    def timed_graph_steps(n_steps, runway=2):
+        """Device time [ms] of exactly n_steps steps.  Barrier + synchronize on both sides; between the opening barrier and
+        the first event, `runway` untimed replays of the same graph are queued so that the timed steps start on a busy
+        GPU (an event recorded on an idle stream would charge the region with the graph-launch latency and with a first
+        kernel that has no predecessor to overlap its prologue with: +5 % on a 20-step region, nothing on a long one)."""
         plan = [G] * (n_steps // G) + ([n_steps % G] if n_steps % G else [])
         for k in set(plan):
             graph_of(k)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        for _ in range(runway):
+            graphs[plan[0]].replay()
         e0.record()
         for k in plan:
             graphs[k].replay()
@@ -464,6 +471,9 @@ def main():
     # (2) the timed graph itself is replayed for >= SUSTAIN_S so that the board settles at the clocks it sustains;
     # (3) the replays stop when the envs are ~mid-episode (age 300..700 of 1000), away from the synchronised time-out
     #     resets that put every env back into the early state for ~35 steps.
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()                                                        # nvidia-smi needs ~0.5 s before its first sample
     preroll(PREROLL_ENV_STEPS)
     timed_graph_steps(min(args.steps, 4 * G))                                  # warm the graphs themselves
     torch.cuda.synchronize()
@@ -481,12 +491,6 @@ def main():
     torch.cuda.synchronize()
     age_at_start = flown()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        for _ in range(8):                                                     # keep the board busy while the sampler comes up
-            gr_full.replay()
-        torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     dev_ms = timed_graph_steps(args.steps)
     t_wall1 = time.perf_counter()
@@ -645,8 +649,8 @@ def main():
                    "l2": "inputs larger than L2: 4 resident batches of 2^20 envs stepped round-robin (308 MB per cycle vs 126 MB L2), "
                          "no flush kernel in the timed region",
                    "stick": f"U(-1,1) rows cycled from a pool of {POOL} per batch (each env's stick repeats every {POOL} steps)",
-                   "reference_bank_rows": int(env.ref_bank.shape[0]),
-                   "launch": f"CUDA graph of {G} consecutive steps, replayed",
+                   "reference_signals": f"{env._cfg.n_ref} ({env.ref_mode})",
+                   "launch": f"CUDA graph of {G} consecutive steps, replayed; 2 untimed replays queued ahead of the first event (busy GPU at the start)",
                    "untimed_preroll": f"{max(args.warmup, 3)} warm-up cycles, {PREROLL_ENV_STEPS} env-steps per env in K-step launches, "
                                       f"{sustain_replays} graph replays ({SUSTAIN_S} s) to sustained clocks"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,

@@ -33,13 +33,14 @@ class Config(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("fast_math", C.c_int32), ("n_envs", C.c_int64), ("dt", C.c_double),
                 ("horizon", C.c_int32), ("ref_len", C.c_int32), ("n_ref", C.c_int32), ("autoreset", C.c_int32),
                 ("init_mode", C.c_int32), ("obs_layout", C.c_int32), ("noise", C.c_int32), ("flags", C.c_int32),
-                ("seed", C.c_uint64), ("env_id_base", C.c_int64), ("x0", C.c_double * 9)]
+                ("seed", C.c_uint64), ("env_id_base", C.c_int64), ("x0", C.c_double * 9),
+                ("seg_len", C.c_int32), ("seg_stride", C.c_int32)]
 
 
 class EnvBuffers(C.Structure):
     _fields_ = [("state", C.c_void_p), ("ep_len", C.c_void_p), ("total_return", C.c_void_p), ("ref_idx", C.c_void_p),
                 ("done", C.c_void_p), ("episode_no", C.c_void_p), ("ref_bank", C.c_void_p), ("init_state", C.c_void_p),
-                ("pos_comp", C.c_void_p), ("seed_dev", C.c_void_p)]
+                ("pos_comp", C.c_void_p), ("seed_dev", C.c_void_p), ("ref_codes", C.c_void_p)]
 
 
 class StepIO(C.Structure):

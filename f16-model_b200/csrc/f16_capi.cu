@@ -154,6 +154,8 @@ int check_cfg(const f16_config *cfg)
     if (cfg->ref_len <= 0 || cfg->n_ref <= 0) return fail(F16_EINVAL, "reference bank must hold >= 1 signal of >= 1 sample");
     if (cfg->init_mode < 0 || cfg->init_mode > 2) return fail(F16_EINVAL, "bad init_mode");
     if (cfg->obs_layout != F16_OBS_AOS && cfg->obs_layout != F16_OBS_SOA) return fail(F16_EINVAL, "bad obs_layout");
+    if (cfg->seg_len < 0 || (cfg->seg_len > 0 && (cfg->seg_stride < 1 || cfg->seg_stride > 256 || cfg->ref_len > 4 * cfg->seg_len)))
+        return fail(F16_EINVAL, "segment mode needs 1 <= seg_stride <= 256 and ref_len <= 4 * seg_len");
     if (cfg->flags & ~(F16_FLAG_ONE_ENV_PER_THREAD | F16_FLAG_NO_PDL | F16_FLAG_HOST_STAGED)) return fail(F16_EINVAL, "unknown bits in flags");
     return F16_OK;
 }
@@ -164,6 +166,7 @@ int check_env(const f16_config *cfg, const f16_env_buffers *env)
     if (!env->state || !env->ep_len || !env->total_return || !env->ref_idx || !env->done || !env->episode_no || !env->ref_bank)
         return fail(F16_EINVAL, "state, ep_len, total_return, ref_idx, done, episode_no and ref_bank are required");
     if (env->pos_comp && cfg->dtype != F16_F32) return fail(F16_EINVAL, "pos_comp is an fp32-mode feature; leave it NULL in fp64");
+    if ((cfg->seg_len > 0) != (env->ref_codes != nullptr)) return fail(F16_EINVAL, "ref_codes goes with segment mode (seg_len > 0), and only with it");
     if (cfg->init_mode == F16_INIT_PER_ENV && !env->init_state)
         return fail(F16_EINVAL, "init_mode F16_INIT_PER_ENV needs env->init_state");
     return F16_OK;
@@ -179,6 +182,9 @@ f16::EnvArgs<R> make_env_args(const f16_config *cfg, const f16_env_buffers *env,
     A.horizon = cfg->horizon;
     A.ref_len = cfg->ref_len;
     A.n_ref = cfg->n_ref;
+    A.seg_len = cfg->seg_len;
+    A.seg_stride = cfg->seg_stride;
+    A.ref_codes = env->ref_codes;
     A.autoreset = cfg->autoreset;
     A.init_mode = cfg->init_mode;
     A.obs_layout = cfg->obs_layout;
@@ -229,7 +235,7 @@ int check_step(const f16_config *cfg, const f16_step_io *io, int K)
     const double lim = 4294967296.0;
     const double n = static_cast<double>(cfg->n_envs);
     if (9.0 * n >= lim || static_cast<double>(K) * n * (io->obs_every_step ? 5.0 : 1.0) >= lim || 5.0 * n >= lim ||
-        static_cast<double>(cfg->n_ref) * cfg->ref_len >= lim)
+        (cfg->seg_len > 0 ? 0.0 : static_cast<double>(cfg->n_ref) * cfg->ref_len) >= lim)
         return fail(F16_EINVAL, "batch too large for 32-bit indexing (n_envs * max(9, K, 5K with obs_every_step) must be < 2^32): "
                                 "shard the envs or lower K");
     if (!io->actions || !io->reward || !io->done) return fail(F16_EINVAL, "actions, reward and done are required");

@@ -189,6 +189,27 @@ static __device__ __noinline__ void episode_stats_add(CtaStats *cta, double ret,
     }
 }
 
+// Reference sample wz_ref[t] of one env (env/task.py: ReferenceSignal.wz_ref[episode_length]).
+//   row mode      ref_bank is real[n_ref][ref_len] and ref_idx a row of it;
+//   segment mode  (seg_len > 0) the signal is a concatenation of up to four equal-length segments followed by zeros -- the
+//                 reference's random `combo` scenario: a rectangular pulse, three seconds of sine and a raised-cosine bump in
+//                 shuffled order (env/task.py:65-103).  ref_bank is then the SEGMENT bank real[seg_len][seg_stride], stored
+//                 sample-major, and ref_idx packs four 8-bit rows of it (segment s in bits [8s, 8s+8)).  The 6480 distinct combo
+//                 signals (26 MB as rows) become 43 rows of 300 samples (52 KB, L1-resident), and the 32 envs of a warp, which
+//                 sit at the same sample of different signals, read ONE 172-byte run instead of 32 different sectors.
+template <typename R>
+__device__ __forceinline__ R ref_sample(const EnvArgs<R> &A, int ref_idx, int t)
+{
+    t = min(t, A.ref_len - 1);
+    if (A.seg_len > 0) {
+        const int L = A.seg_len;
+        const int seg = (t >= L) + (t >= 2 * L) + (t >= 3 * L);
+        const unsigned row = (static_cast<unsigned>(ref_idx) >> (8 * seg)) & 0xffu;
+        return A.ref_bank[static_cast<unsigned>(t - seg * L) * static_cast<unsigned>(A.seg_stride) + row];
+    }
+    return A.ref_bank[static_cast<unsigned>(ref_idx) * static_cast<unsigned>(A.ref_len) + static_cast<unsigned>(t)];
+}
+
 // Draw / copy an episode's initial state (env.py:172-195,221-243) and pick its reference signal.
 template <typename R>
 __device__ __forceinline__ void init_episode(const EnvArgs<R> &A, int64_t i, uint32_t episode, bool keep_ref, R (&x)[9],
@@ -220,9 +241,10 @@ __device__ __forceinline__ void init_episode(const EnvArgs<R> &A, int64_t i, uin
     }
     if (!keep_ref && A.n_ref > 1) {
         const uint4 q = philox4x32(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32), episode, 1u), key);
-        ref_idx = static_cast<int>(__umulhi(q.x, static_cast<uint32_t>(A.n_ref)));
+        const uint32_t r = __umulhi(q.x, static_cast<uint32_t>(A.n_ref));
+        ref_idx = A.ref_codes ? static_cast<int>(A.ref_codes[r]) : static_cast<int>(r);
     } else if (A.n_ref <= 1) {
-        ref_idx = 0;
+        ref_idx = A.ref_codes ? static_cast<int>(A.ref_codes[0]) : 0;
     }
 }
 
@@ -417,7 +439,6 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
         }
         if (!live) continue;
 
-        const R *ref_row = A.ref_bank + static_cast<unsigned>(ref_idx) * static_cast<unsigned>(A.ref_len);
         R o[5];
         bool have_obs = false;
         R a_k = a0;
@@ -427,7 +448,7 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
             const unsigned kn = static_cast<unsigned>(k) * n + i;
             // issue next step's loads before this step's arithmetic: the reference sample (a gather
             // that depends on ref_idx / ep_len) and the next action row
-            const R ref = ref_row[min(ep_len, A.ref_len - 1)];
+            const R ref = ref_sample<R>(A, ref_idx, ep_len);
             R a_next = R(0);
             if (!SINGLE && k + 1 < K_steps) a_next = S.actions[kn + n];
             R reward = R(0);
@@ -463,13 +484,12 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
                         A.episode_no[i] = episode;
                         init_episode<R>(A, i, episode, false, x, ref_idx);
                         A.ref_idx[i] = ref_idx;
-                        ref_row = A.ref_bank + static_cast<unsigned>(ref_idx) * static_cast<unsigned>(A.ref_len);
                         was_reset = true;
                         ep_len = 0;
                         ret = R(0);
                         ox_lo = R(0);
                         oy_lo = R(0);
-                        make_obs<R, FAST>(x[1], x[2], x[4], ref_row[0], o);
+                        make_obs<R, FAST>(x[1], x[2], x[4], ref_sample<R>(A, ref_idx, 0), o);
                     } else {
                         done_sticky = 1;
                     }
@@ -480,7 +500,7 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
             F16_ST(S.done + kn, static_cast<uint8_t>(done_now));
             if (every) {
                 if (!have_obs) {   // env was already done when the launch started
-                    make_obs<R, FAST>(x[1], x[2], x[4], ref_row[min(max(ep_len - 1, 0), A.ref_len - 1)], o);
+                    make_obs<R, FAST>(x[1], x[2], x[4], ref_sample<R>(A, ref_idx, max(ep_len - 1, 0)), o);
                     have_obs = true;
                 }
                 store_obs<R>(S.obs + static_cast<size_t>(k) * n * 5, A.obs_layout, n, i, o);
@@ -509,7 +529,7 @@ __global__ void __launch_bounds__(kCtaThreads, MinCtas<R>::v) env_step_kernel(co
         }
         if (!AUTORESET) A.done[i] = static_cast<uint8_t>(done_sticky);
         if (!every && S.obs) {
-            if (!have_obs) make_obs<R, FAST>(x[1], x[2], x[4], ref_row[min(max(ep_len - 1, 0), A.ref_len - 1)], o);
+            if (!have_obs) make_obs<R, FAST>(x[1], x[2], x[4], ref_sample<R>(A, ref_idx, max(ep_len - 1, 0)), o);
             store_obs<R>(S.obs, A.obs_layout, n, i, o);
         }
     }
@@ -735,7 +755,7 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
             bool slow[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                ref[e] = A.ref_bank[static_cast<unsigned>(ref_idx[e]) * static_cast<unsigned>(A.ref_len) + min(ep_len[e], A.ref_len - 1)];
+                ref[e] = ref_sample<R>(A, ref_idx[e], ep_len[e]);
                 if (!SINGLE && k + 1 < K_steps) a_next[e] = S.actions[static_cast<unsigned>(k + 1) * n + base + tl + e * E2];
                 Hg[e] = isa_geopotential<R, FAST>(x[e][1]);
                 slow[e] = !(Hg[e] >= R(0) && Hg[e] < R(11000));
@@ -803,7 +823,7 @@ __global__ void __launch_bounds__(Cta2<SINGLE>::threads, Cta2<SINGLE>::min_ctas)
                     was_reset[e] = true;
                     ep_len[e] = 0;
                     ret[e] = R(0);
-                    make_obs<R, FAST>(x[e][1], x[e][2], x[e][4], A.ref_bank[static_cast<unsigned>(ref_idx[e]) * static_cast<unsigned>(A.ref_len)], o[e]);
+                    make_obs<R, FAST>(x[e][1], x[e][2], x[e][4], ref_sample<R>(A, ref_idx[e], 0), o[e]);
                 }
             }
 #pragma unroll
@@ -936,7 +956,7 @@ __global__ void __launch_bounds__(kCtaThreads) env_reset_kernel(const EnvArgs<R>
         A.episode_no[i] = episode;
         if (obs) {
             R o[5];
-            make_obs<R, false>(x[1], x[2], x[4], A.ref_bank[(int64_t)ref_idx * A.ref_len], o);
+            make_obs<R, false>(x[1], x[2], x[4], ref_sample<R>(A, ref_idx, 0), o);
             store_obs<R>(obs, A.obs_layout, A.n, i, o);
         }
     }

@@ -25,6 +25,7 @@ struct EnvArgs {
     int64_t n;
     R dt;
     int horizon, ref_len, n_ref;
+    int seg_len, seg_stride;    // segment mode of the reference bank (seg_len > 0), see ref_sample() / include/f16_b200.h
     int autoreset, init_mode, obs_layout, noise;
     uint64_t seed;
     const uint64_t *seed_dev;   // optional device copy of the seed (read on the rare reset / noise paths): re-keying reaches captured CUDA graphs
@@ -37,6 +38,7 @@ struct EnvArgs {
     uint8_t *done;
     uint32_t *episode_no;
     const R *ref_bank;
+    const uint32_t *ref_codes;  // segment mode: packed segment rows of each of the n_ref signals (read by resets only)
     const R *init_state;
     R *pos_comp;   // [2][n] Kahan carry of Ox, Oy (fp32 mode), or nullptr
 };

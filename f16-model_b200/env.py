@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _capi, plane
 from .model import States, Control
-from .task import ReferenceSignal, build_reference_bank
+from .task import ReferenceSignal, build_combo_segments, build_reference_bank, signals_from_codes
 
 
 def find_correct_thrust_position(control_throttle):
@@ -108,9 +108,11 @@ class F16VecEnv:
         keyed by global env id, so a sharded run reproduces the single-GPU run env for env.
     obs_layout : "aos" -> obs [N, 5] contiguous (reference layout); "soa" -> stored [5, N],
         returned as the transposed view [N, 5].
-    bank_size : rows of the device reference bank for random scenarios.  None (default) = the reference's
-        whole distribution where it is finite (``combo``: all 6480 signals, 26 MB in fp32), 256 draws
-        otherwise; see ``task.build_reference_bank``.
+    bank_size : rows of the device reference bank for random scenarios.  None (default) = the reference's own
+        distribution: random ``combo`` episodes are served from the 52 KB segment bank that holds all 6480 signals
+        (``ref_mode == "segments"``: ``ref_idx`` then carries packed segment codes, ``reference_signals()`` rebuilds
+        rows); the other random scenarios are enumerated in full.  An integer (or "full") asks for a bank of
+        whole rows instead, see ``task.build_reference_bank``.
     two_per_thread, pdl, host_zero_copy : per-env kernel / route selection (``f16_config.flags``): the
         one-env-per-thread step kernel instead of the two-envs-per-thread one, launches without programmatic
         dependent launch, the staged host route instead of zero-copy.  All variants are bit-identical
@@ -142,13 +144,34 @@ class F16VecEnv:
         _capi.check(self._lib.f16_init(self.device.index))
 
         # ---- reference signals (env/task.py) --------------------------------
-        if reference_bank is None:
-            reference_bank = build_reference_bank(self.dt, self.tn, config["scenario"], config["determenistic_ref"],
-                                                  bank_size=bank_size, seed=seed)
-        bank = np.ascontiguousarray(np.atleast_2d(np.asarray(reference_bank, dtype=np.float64)))
-        self.ref_bank_host = bank
-        self.ref_bank = torch.tensor(bank, dtype=dt_, device=dev)
-        ref_len = bank.shape[1]
+        # Random `combo` episodes (the reference's training scenario) are served from the SEGMENT bank: all 6480 signals of
+        # the reference's distribution in 52 KB (task.build_combo_segments).  Everything else -- deterministic scenarios, the
+        # small enumerable scenarios, a caller-supplied bank, an explicit bank_size -- is a bank of whole rows [R, T].
+        segments = None
+        if reference_bank is None and bank_size is None and config["scenario"] == "combo" and not config["determenistic_ref"]:
+            segments = build_combo_segments(self.dt, self.tn)
+        self.ref_codes = None
+        if segments is not None:
+            seg_bank, codes, seg_len = segments
+            ref_len = int(np.arange(0, self.tn, self.dt).size)
+            self.ref_mode = "segments"
+            self._seg_bank_host, self._codes_host = seg_bank, codes
+            self._seg_stride = (seg_bank.shape[0] + 7) // 8 * 8            # rows of one sample padded to whole 32-byte sectors
+            padded = np.zeros((seg_len, self._seg_stride))
+            padded[:, : seg_bank.shape[0]] = seg_bank.T                     # sample-major: the envs of a warp share the sample index
+            self.ref_bank = torch.tensor(padded, dtype=dt_, device=dev)
+            self.ref_codes = torch.tensor(codes.astype(np.int64), dtype=torch.int64, device=dev).to(torch.int32)
+            n_ref = int(codes.size)
+        else:
+            if reference_bank is None:
+                reference_bank = build_reference_bank(self.dt, self.tn, config["scenario"], config["determenistic_ref"],
+                                                      bank_size=bank_size, seed=seed)
+            bank = np.ascontiguousarray(np.atleast_2d(np.asarray(reference_bank, dtype=np.float64)))
+            self.ref_mode = "rows"
+            self.ref_bank_host = bank
+            self.ref_bank = torch.tensor(bank, dtype=dt_, device=dev)
+            ref_len, n_ref, seg_len = bank.shape[1], bank.shape[0], 0
+            self._seg_stride = 0
         horizon = self.tn / self.dt - 1          # env.py:115 compares the step counter with this float
         self.horizon = int(horizon) if float(horizon).is_integer() else ref_len - 1
 
@@ -206,7 +229,9 @@ class F16VecEnv:
         cfg.dt = self.dt
         cfg.horizon = self.horizon
         cfg.ref_len = ref_len
-        cfg.n_ref = bank.shape[0]
+        cfg.n_ref = n_ref
+        cfg.seg_len = seg_len
+        cfg.seg_stride = self._seg_stride
         cfg.autoreset = int(self.autoreset)
         cfg.init_mode = init_mode
         cfg.obs_layout = _capi.OBS_AOS if obs_layout == "aos" else _capi.OBS_SOA
@@ -240,6 +265,7 @@ class F16VecEnv:
         b.init_state = self.init_state_tensor.data_ptr() if self.init_state_tensor is not None else None
         b.pos_comp = self.pos_comp.data_ptr() if self.pos_comp is not None else None
         b.seed_dev = self._seed_dev.data_ptr()
+        b.ref_codes = self.ref_codes.data_ptr() if self.ref_codes is not None else None
         self._buf = b
         io = _capi.StepIO()
         io.obs = self._obs.data_ptr()
@@ -432,6 +458,14 @@ class F16VecEnv:
             self.ref_idx.copy_(torch.as_tensor(ref_idx, dtype=torch.int32))
         self.init_state = self.state.clone()
 
+    def reference_signals(self, ref_idx=None):
+        """``wz_ref`` rows [n, T] (NumPy, fp64) followed by the given envs' ``ref_idx`` values (default: every env's current
+        one) -- the rows of the bank, or, in segment mode, the signals rebuilt from the packed segment codes."""
+        idx = self.ref_idx.cpu().numpy() if ref_idx is None else np.atleast_1d(np.asarray(ref_idx))
+        if self.ref_mode == "segments":
+            return signals_from_codes(self._seg_bank_host, idx.astype(np.int64).astype(np.uint32), self._cfg.ref_len)
+        return self.ref_bank_host[idx]
+
     def pop_episode_stats(self):
         """(episodes finished, mean return, mean length) since the last call -- the counters the kernel keeps
         with warp-level reductions (replaces the per-env Python loop of control/ppo/utils.py:197-235)."""
@@ -457,8 +491,7 @@ class F16VecEnv:
             arr = self.init_state.double().cpu().numpy()
             return tuple(States.from_array(arr[:, i]) for i in range(self.num_envs))
         if name == "ref_signal":
-            idx = self.ref_idx.cpu().numpy()
-            return tuple(_BankSignal(self.ref_bank_host[j], self.dt, self.tn) for j in idx)
+            return tuple(_BankSignal(row, self.dt, self.tn) for row in self.reference_signals())
         if name == "episode_length":
             return tuple(self.episode_length.cpu().tolist())
         if name == "total_return":

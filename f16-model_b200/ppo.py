@@ -62,6 +62,22 @@ def gae(rewards, values, done_after, next_value, gamma, gae_lambda):
     return adv, ret
 
 
+def kl_early_stop(approx_kl, target_kl, world=1, group=None):
+    """The early-stop test of the update loop (ppo_model_gsde.py:367-369), made rank-consistent: with more than one
+    rank the approximate KL of the last minibatch is averaged over ranks before it is compared with ``target_kl``, so
+    every rank leaves the epoch loop at the same epoch (a rank-local decision would leave the gradient all-reduce of
+    the next epoch with mismatched participants -- NCCL would hang)."""
+    if target_kl is None:
+        return False
+    import torch
+
+    kl = approx_kl.detach().reshape(1).clone()
+    if world > 1:
+        torch.distributed.all_reduce(kl, group=group)
+        kl /= world
+    return bool(kl.item() > target_kl)
+
+
 class PPOTrainer:
     def __init__(self, envs, policy, config=None):
         import torch
@@ -381,7 +397,7 @@ class PPOTrainer:
                 torch.randperm(self.batch_size, device=self.device, generator=self._gen, out=self._perm_buf)
                 self._update_graph.replay()
                 n_steps += per_epoch
-                if cfg.target_kl is not None and self._diag[1].item() > cfg.target_kl:
+                if kl_early_stop(self._diag[1], cfg.target_kl, self.world):
                     break
                 continue
             perm = torch.randperm(self.batch_size, device=self.device, generator=self._gen)
@@ -393,7 +409,7 @@ class PPOTrainer:
                 else:
                     self._minibatch_step(mb)
                 n_steps += 1
-            if cfg.target_kl is not None and self._diag[1].item() > cfg.target_kl:
+            if kl_early_stop(self._diag[1], cfg.target_kl, self.world):
                 break
         self.policy.sync_weights()                                  # refresh the tensor-core weight blob
         d = self._diag.tolist()

@@ -105,6 +105,65 @@ class ReferenceSignal:
 
 
 _FULL_COMBO_CACHE = {}
+_COMBO_PARAMS = (_AMPS6, _AMPS6, (0.125, 0.25, 0.45, 0.5, 0.75), _AMPS6)   # step amplitude, sine amplitude, sine frequency, bump amplitude
+
+
+def combo_parameter_sets():
+    """The reference's discrete space of random ``combo`` signals (env/task.py:73-76, :100-101) in the order both device
+    banks enumerate it: (step amplitude [deg], sine amplitude [deg], frequency [Hz], bump amplitude [deg], segment order)
+    -- 6 x 6 x 5 x 6 parameter sets x 3! orders of the (pulse, sine, bump) segments = 6480 equally likely signals."""
+    for a_s, a_n, f, a_c in itertools.product(*_COMBO_PARAMS):
+        for order in itertools.permutations(range(3)):
+            yield a_s, a_n, f, a_c, order
+
+
+def build_combo_segments(dt, tn):
+    """The random ``combo`` scenario as a SEGMENT bank (the device's segment mode, include/f16_b200.h ``seg_len``).
+
+    Every combo signal of a 10 s episode is three 3 s segments in shuffled order followed by zeros, and each segment
+    depends on one parameter group only: 6 pulses, 6 x 5 sines, 6 bumps.  So the 6480 signals (26 MB as fp32 rows) are
+    43 rows of ``L = 3 / dt`` samples -- rows 0-5 pulses, 6-35 sines, 36-41 bumps, 42 zeros -- plus one packed code per
+    signal: row of segment s in bits [8s, 8s+8), the zero row in the top byte.  Values are the very numbers
+    ``ReferenceSignal`` computes (the segments are slices of its arrays, halved exactly), so a signal rebuilt from its
+    code is bit-identical to the reference's.  Returns (bank [43, L] float64, codes uint32 [6480], L), or None when
+    the scenario does not factor this way (multi-block episodes, a dt for which the three segments differ in length).
+    """
+    if int(tn / 10) != 1:
+        return None
+    proto = ReferenceSignal(dt, tn, True, "pure_step")
+    T = proto.t.size
+    rows, index = [], {}
+    for a in _AMPS6:
+        rect, _, _ = proto._combo_segments(np.radians(a), 0.0, 0.25, 0.0)
+        index["rect", a] = len(rows)
+        rows.append(np.asarray(rect, dtype=np.float64) / 2)
+    for a, f in itertools.product(_AMPS6, _COMBO_PARAMS[2]):
+        _, sine, _ = proto._combo_segments(0.0, np.radians(a), f, 0.0)
+        index["sine", a, f] = len(rows)
+        rows.append(np.asarray(sine, dtype=np.float64) / 2)
+    for a in _AMPS6:
+        _, _, bump = proto._combo_segments(0.0, 0.0, 0.25, np.radians(a))
+        index["bump", a] = len(rows)
+        rows.append(np.asarray(bump, dtype=np.float64) / 2)
+    L = rows[0].size
+    if any(r.size != L for r in rows) or not (3 * L <= T <= 4 * L) or len(rows) + 1 > 256:
+        return None
+    zero = len(rows)
+    rows.append(np.zeros(L))
+    codes = []
+    for a_s, a_n, f, a_c, order in combo_parameter_sets():
+        seg = (index["rect", a_s], index["sine", a_n, f], index["bump", a_c])
+        codes.append(seg[order[0]] | seg[order[1]] << 8 | seg[order[2]] << 16 | zero << 24)
+    return np.ascontiguousarray(np.stack(rows)), np.array(codes, dtype=np.uint32), L
+
+
+def signals_from_codes(bank, codes, T):
+    """Whole ``wz_ref`` rows [len(codes), T] rebuilt from packed segment codes (host side; tests, ``call('ref_signal')``)."""
+    codes = np.atleast_1d(np.asarray(codes)).astype(np.uint32)
+    L = bank.shape[1]
+    out = np.concatenate([bank[(codes >> np.uint32(8 * s)) & np.uint32(0xFF)] for s in range(4)], axis=1)
+    assert out.shape[1] == 4 * L
+    return np.ascontiguousarray(out[:, :T])
 
 
 def build_reference_bank(dt, tn, scenario, determenistic, bank_size=None, seed=0):
@@ -166,9 +225,8 @@ def build_reference_bank(dt, tn, scenario, determenistic, bank_size=None, seed=0
         # hot in L2 when several large batches stream through it.
         if scenario != "combo" or int(tn / 10) != 1:
             raise ValueError('bank_size="full" enumerates the single-block combo scenario only')
-        for a_s, a_n, f, a_c in itertools.product(_AMPS6, _AMPS6, [0.125, 0.25, 0.45, 0.5, 0.75], _AMPS6):
-            for order in itertools.permutations(range(3)):
-                rows.append(proto._combo_from(np.radians(a_s), np.radians(a_n), f, np.radians(a_c), order) / 2)
+        for a_s, a_n, f, a_c, order in combo_parameter_sets():
+            rows.append(proto._combo_from(np.radians(a_s), np.radians(a_n), f, np.radians(a_c), order) / 2)
         bank = np.ascontiguousarray(np.stack(rows))
         bank.setflags(write=False)
         _FULL_COMBO_CACHE[key] = bank

@@ -74,6 +74,12 @@ typedef struct f16_config {
     int64_t env_id_base;  /* global id of env 0 of this shard: RNG streams are keyed by the GLOBAL env id, so
                              results do not depend on how the batch is sharded over GPUs */
     double x0[9];         /* F16_INIT_FIXED: the initial state */
+    int32_t seg_len;      /* 0: ref_bank holds whole signals, real[n_ref][ref_len].  > 0: SEGMENT mode -- every signal is a
+                             concatenation of up to four segments of seg_len samples, then zeros (the random `combo` scenario,
+                             env/task.py:65-103); ref_bank is the segment bank real[seg_len][seg_stride] (sample-major: row r of
+                             segment sample t at [t * seg_stride + r]), an env's ref_idx packs four 8-bit rows of it (segment s in
+                             bits [8s, 8s+8)), and a reset copies ref_codes[uniform draw < n_ref].  Needs ref_len <= 4 * seg_len. */
+    int32_t seg_stride;   /* segment mode: rows per sample of the segment bank (>= number of rows, <= 256) */
 } f16_config;
 
 /* Persistent per-env buffers (device).  What the reference keeps in the F16
@@ -85,7 +91,7 @@ typedef struct f16_env_buffers {
     int32_t *ref_idx;        /* [n]          r/w  row of ref_bank followed by each env */
     uint8_t *done;           /* [n]          r/w  F16.done (sticky until reset; always 0 after an autoreset) */
     uint32_t *episode_no;    /* [n]          r/w  episodes started so far (RNG counter) */
-    const void *ref_bank;    /* real[n_ref][ref_len]  wz_ref = theta_ref/2 (env/task.py:25-26) */
+    const void *ref_bank;    /* real[n_ref][ref_len]  wz_ref = theta_ref/2 (env/task.py:25-26); segment mode: real[seg_len][seg_stride] */
     const void *init_state;  /* real[9][n]   F16_INIT_PER_ENV only, else NULL */
     void *pos_comp;          /* real[2][n]   r/w  Kahan carry of the Ox, Oy position integrals, or NULL: keeps the
                                 fp32 mode's positions within ~1e-7 of the fp64 reference over an episode (plain fp32
@@ -94,6 +100,7 @@ typedef struct f16_env_buffers {
                                 the key from here instead of f16_config.seed (kernel arguments are frozen into a captured CUDA
                                 graph; a device scalar is not), so re-seeding (F16.reset(seed), env/env.py:155-158) also reaches
                                 autoresets replayed from a graph. */
+    const uint32_t *ref_codes; /* [n_ref] segment mode only (else NULL): the packed segment rows of every signal of the scenario */
 } f16_env_buffers;
 
 /* Per-call tensors of f16_env_step. */

@@ -182,3 +182,34 @@ def test_reseed_reaches_a_captured_graph(f16):
     other = f16.F16VecEnv(CFG, n, seed=5, fast_math=True)
     other.reset(seed=124)
     assert not torch.equal(other.state, eager.init_state)
+
+
+@pytest.mark.parametrize("two_per_thread", [True, False])
+def test_segment_bank_equals_full_row_bank_bitwise(f16, two_per_thread):
+    """The default reference bank for random `combo` episodes is the 52 KB segment bank (ref_idx = packed segment rows).
+    Against a bank of the 6480 whole rows (26 MB) with the same seed: resets draw the same signal number, so observations
+    (which carry wz_ref), rewards, terminations and states are bit-identical, step for step, through resets."""
+    cfg = dict(CFG, determenistic_ref=False)
+    n = 8192 + 37
+    seg = f16.F16VecEnv(cfg, n, seed=31, fast_math=True, two_per_thread=two_per_thread)
+    row = f16.F16VecEnv(cfg, n, seed=31, fast_math=True, two_per_thread=two_per_thread, bank_size="full")
+    assert seg.ref_mode == "segments" and row.ref_mode == "rows" and seg._cfg.n_ref == row._cfg.n_ref == 6480
+    assert tuple(seg.ref_bank.shape) == (300, 48) and tuple(row.ref_bank.shape) == (6480, 1000)
+    assert torch.equal(seg.state, row.state)
+    assert np.array_equal(seg.reference_signals(), row.reference_signals())
+    g = torch.Generator(device="cuda").manual_seed(9)
+    acts = torch.rand((1100, n), device="cuda", generator=g) * 2 - 1
+    acts[:, ::4] = 1.0                                   # a quarter of the fleet keeps terminating (~45 steps) and drawing new signals
+    n_done = 0
+    for k in range(1100):                                # past the 1000-step time-out: everybody resets at least once
+        os_, rs, ds, _, _ = seg.step(acts[k])
+        orow, rr, dr, _, _ = row.step(acts[k])
+        assert torch.equal(os_, orow) and torch.equal(rs, rr) and torch.equal(ds, dr), k
+        n_done += int(ds.sum()) if k % 100 == 99 else 0
+    assert torch.equal(seg.state, row.state) and torch.equal(seg.episode_no, row.episode_no)
+    assert int(seg.episode_no.min()) >= 2 and n_done > 0
+    assert np.array_equal(seg.reference_signals(), row.reference_signals())
+    # K-step launches read the segment bank the same way
+    o1, r1, d1 = seg.step_k(acts[:64])
+    o2, r2, d2 = row.step_k(acts[:64])
+    assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)

@@ -94,6 +94,16 @@ def test_atmosphere_against_published_table(f16):
         assert np.max(np.abs(out[1] / np.array([r[2] for r in ISA_TABLE]) - 1)) < 3e-5
 
 
+def test_atmosphere_layer_table_consistent_on_device(f16):
+    """The device ISA's layer table (above 11 km: tabulated base pressures) against the primary constants:
+    pressure continuous across every layer boundary to the table's six digits (tests/test_oracle_golden.py)."""
+    from f16_model_b200.model import atmosphere
+    from test_oracle_golden import isa_pressure_jumps
+
+    jumps = isa_pressure_jumps(lambda h: atmosphere(dev(h)).cpu().numpy())
+    assert np.max(np.abs(jumps)) < 1e-5, jumps
+
+
 # ------------------------------------------------------------------ model level
 def test_rhs_fp64_vs_reference(f16, golden, orc):
     x, u, ref = golden["rhs_x"], golden["rhs_u"], golden["rhs_dx"]

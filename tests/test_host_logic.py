@@ -178,6 +178,44 @@ def test_trim_grid_sharded_single_rank_needs_no_process_group():
         trim_grid_sharded(V, H, 0, 2, device="cpu", trim_fn=fake_trim)
 
 
+def test_combo_segment_bank_is_the_reference_distribution():
+    """f3: the default device bank for random `combo` episodes (segment mode) holds EXACTLY the reference's distribution
+    (env/task.py:65-103): 6480 distinct, equally weighted signals; every signal rebuilt from its packed code is
+    bit-identical to the enumerated whole row, and every draw the reference's own procedure makes (random.choice x 4 +
+    random.shuffle, any seed) is one of them."""
+    import random
+
+    from f16_model_b200 import task
+
+    bank, codes, L = task.build_combo_segments(0.01, 10)
+    assert bank.shape == (43, 300) and L == 300 and codes.dtype == np.uint32
+    assert codes.size == 6480 == len(set(codes.tolist())) and int(codes.max()) < 2 ** 31
+    assert np.all(bank[42] == 0) and np.all((codes >> 24) == 42)
+    rows = task.signals_from_codes(bank, codes, 1000)
+    full = task.build_reference_bank(0.01, 10, "combo", False, bank_size="full")
+    assert np.array_equal(rows, full)
+    assert len({r.tobytes() for r in rows}) == 6480                       # all distinct: uniform over codes == uniform over signals
+    where = {r.tobytes(): i for i, r in enumerate(rows)}
+    seen = set()
+    for seed in range(300):
+        sig = task.ReferenceSignal(0.01, 10, False, "combo", rng=random.Random(seed)).wz_ref
+        assert sig.tobytes() in where, seed
+        seen.add(where[sig.tobytes()])
+    assert len(seen) > 280                                                # draws spread over the space (300 of 6480: ~7 collisions expected)
+    # the parameter marginals of the enumeration are uniform, as random.choice makes them
+    params = list(task.combo_parameter_sets())
+    for k, n_values in ((0, 6), (1, 6), (2, 5), (3, 6), (4, 6)):
+        counts = {}
+        for p_ in params:
+            counts[p_[k]] = counts.get(p_[k], 0) + 1
+        assert len(counts) == n_values and len(set(counts.values())) == 1
+    # other step sizes factor the same way; multi-block episodes do not (they keep the row bank)
+    b2, c2, L2 = task.build_combo_segments(0.02, 10)
+    assert L2 == 150 and np.array_equal(task.signals_from_codes(b2, c2, 500), task.build_reference_bank(0.02, 10, "combo", False, bank_size="full"))
+    assert task.build_combo_segments(0.01, 20) is None
+    assert task.build_reference_bank(0.01, 20, "combo", False).shape == (256, 2000)
+
+
 # ---------------------------------------------------------------- C ABI surface
 def _header_functions():
     hdr = open(os.path.join(ROOT, "include", "f16_b200.h")).read()
@@ -199,8 +237,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     """ctypes mirrors of the ABI structs: sizes as the C compiler lays them out."""
-    assert ctypes.sizeof(_capi.Config) == 4 + 4 + 8 + 8 + 8 * 4 + 8 + 8 + 9 * 8   # 144 bytes
-    assert ctypes.sizeof(_capi.EnvBuffers) == 10 * 8
+    assert ctypes.sizeof(_capi.Config) == 4 + 4 + 8 + 8 + 8 * 4 + 8 + 8 + 9 * 8 + 8   # 152 bytes
+    assert ctypes.sizeof(_capi.EnvBuffers) == 11 * 8
     assert ctypes.sizeof(_capi.StepIO) == 7 * 8 + 8 + 8
 
 
