@@ -378,7 +378,10 @@ def main():
 
     # The K = 1 gym step is launch-bound from Python (~30 us of interpreter + ctypes per call vs a
     # ~22 us kernel), so the timed loop replays a CUDA graph of G consecutive steps.
-    G = min(max(48, R_SETS * POOL), args.steps)   # one graph covers a whole cycle of the stick pool
+    # One graph covers a whole cycle of the stick pool, whatever --steps is: a shorter graph would replay only the first
+    # rows of every pool, i.e. give every env a stick of a few steps' period -- a different (and slower: the periodic stick
+    # spreads alpha over more table cells per quarter-warp) workload than the one the long run measures.
+    G = R_SETS * POOL
     graphs = {}
 
     def graph_of(n_steps):
@@ -435,7 +438,7 @@ def main():
 
     def timed_graph_steps(n_steps, runway=2):
         """Device time [ms] of exactly n_steps steps.  Barrier + synchronize on both sides; between the opening barrier and
-        the first event, `runway` untimed replays of the same graph are queued so that the timed steps start on a busy
+        the first event, `runway` untimed replays of the full-cycle graph are queued so that the timed steps start on a busy
         GPU (an event recorded on an idle stream would charge the region with the graph-launch latency and with a first
         kernel that has no predecessor to overlap its prologue with: +5 % on a 20-step region, nothing on a long one)."""
         plan = [G] * (n_steps // G) + ([n_steps % G] if n_steps % G else [])
@@ -443,9 +446,11 @@ def main():
             graph_of(k)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if runway:
+            graph_of(G)
         barrier()
         for _ in range(runway):
-            graphs[plan[0]].replay()
+            graphs[G].replay()
         e0.record()
         for k in plan:
             graphs[k].replay()
@@ -475,7 +480,7 @@ def main():
     if sampler:
         sampler.start()                                                        # nvidia-smi needs ~0.5 s before its first sample
     preroll(PREROLL_ENV_STEPS)
-    timed_graph_steps(min(args.steps, 4 * G))                                  # warm the graphs themselves
+    timed_graph_steps(args.steps if args.steps < G else G)                     # build and warm the graphs themselves
     torch.cuda.synchronize()
     flown = lambda: int(env.episode_length.float().median().item())          # noqa: E731  (typical env age of batch 0)
     gr_full = graph_of(G)
@@ -499,11 +504,11 @@ def main():
     barrier()
 
     # ---- the same measurement on freshly reset envs (the "early" state a short cold benchmark would see) -----
-    n_early = min(args.steps, 20 * R_SETS) // R_SETS * R_SETS or R_SETS
+    n_early = 20 * R_SETS
     for j in range(R_SETS):
         envs[j].reset(seed=101 + j)
     enqueue_steps(3 * R_SETS)                                                  # W >= 3 warm-up steps per batch
-    early_ms = max_over_ranks(timed_graph_steps(n_early))
+    early_ms = max_over_ranks(timed_graph_steps(n_early, runway=0))            # (no runway: it would age the envs)
     preroll(PREROLL_ENV_STEPS)                                                 # back to the stationary state for everything below
 
     n_sec = min(args.steps, 500)
@@ -650,7 +655,8 @@ def main():
                          "no flush kernel in the timed region",
                    "stick": f"U(-1,1) rows cycled from a pool of {POOL} per batch (each env's stick repeats every {POOL} steps)",
                    "reference_signals": f"{env._cfg.n_ref} ({env.ref_mode})",
-                   "launch": f"CUDA graph of {G} consecutive steps, replayed; 2 untimed replays queued ahead of the first event (busy GPU at the start)",
+                   "launch": f"CUDA graphs of consecutive steps ({G} = one cycle of the stick pool, plus one for the remainder), replayed; "
+                             "2 untimed replays of the cycle graph are queued ahead of the first event (busy GPU at the start)",
                    "untimed_preroll": f"{max(args.warmup, 3)} warm-up cycles, {PREROLL_ENV_STEPS} env-steps per env in K-step launches, "
                                       f"{sustain_replays} graph replays ({SUSTAIN_S} s) to sustained clocks"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
