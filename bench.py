@@ -753,18 +753,40 @@ def kernel_rooflines(torch, f16, _capi, L, device, rank, world, peaks, peak_kind
 
     # ---- PPO: config 4 (65,536 envs x 128 steps): rollout, GAE, gradient, optimiser ----
     n4, T4 = 65536, 128
-    envs4 = f16.F16VecEnv(cfg, n4, device=device, dtype=torch.float32, seed=1, fast_math=True)
-    pol4 = f16.TensorCorePolicy(device=device, seed=1, logstd_init=-1.0)
-    pcfg = f16.PPOConfig(num_steps=T4, num_minibatches=32, update_epochs=4)
-    tr = f16.PPOTrainer(envs4, pol4, pcfg)
-    hist = tr.train(num_updates=3) if world == 1 else None     # multi-rank PPO is measured by tools/config_bench.py under torchrun
-    if hist:
+    hist = None
+    for fused in ((False, True) if world == 1 else ()):     # multi-rank PPO is measured by tools/config_bench.py under torchrun
+        envs4 = f16.F16VecEnv(cfg, n4, device=device, dtype=torch.float32, seed=1, fast_math=True)
+        pol4 = f16.TensorCorePolicy(device=device, seed=1, logstd_init=-1.0)
+        pcfg = f16.PPOConfig(num_steps=T4, num_minibatches=32, update_epochs=4, fused_rollout=fused)
+        tr = f16.PPOTrainer(envs4, pol4, pcfg)
+        hist = tr.train(num_updates=3)
         h = hist[-1]
-        # rollout: 128 x (policy + env) replayed from one graph; bounded by the policy's tanh stream
-        ach = 256 * n4 * T4 / h["rollout_s"] / 1e9
-        entry("PPO rollout: 128 x (policy_forward_kernel -> env_step2_kernel), one CUDA graph", "mufu", ach, pipe["mufu_tanh"] / 1e9, "G tanh/s",
-              h["rollout_s"] * 1e6, n4 * T4, peak_kind="MUFU.TANH results/s of f16_peak_probe in this run", timing="wall clock around the graph replay + GAE + sync",
+        ach = 268 * n4 * T4 / h["rollout_s"] / 1e9
+        entry(("rollout_kernel: 128 closed-loop steps of policy (tcgen05 kind::f16) -> Gaussian head -> F16.step in ONE persistent launch"
+               if fused else "PPO rollout, two-kernel path: 128 x (policy_forward_kernel -> env_step2_kernel), one CUDA graph"),
+              "mufu", ach, pipe["mufu_tanh"] / 1e9, "G MUFU/s", h["rollout_s"] * 1e6, n4 * T4,
+              peak_kind="MUFU.TANH results/s of f16_peak_probe in this run (every MUFU op has that rate)",
+              algorithmic_per_unit="268 MUFU per env-step: 256 tanh of the two MLPs + 12 in the env step (sin/cos, lg2/ex2, rcp)",
+              timing="wall clock around reset + rollout + GAE + sync (PPOTrainer.rollout)",
               env_steps_per_s=h["rollout_sps"], update_s=h["update_s"], minibatches_per_update=pcfg.num_minibatches * pcfg.update_epochs)
+    if hist:
+        # the same fused kernel at the bench's batch size: 2^20 envs, K = 16 closed-loop steps per launch
+        envs_big = f16.F16VecEnv(cfg, N, device=device, dtype=torch.float32, seed=2, fast_math=True)
+        Kb = 16
+        bufs = dict(obs_next=torch.zeros((Kb, N, 5), device=device), actions=torch.zeros((Kb, N), device=device),
+                    logprobs=torch.zeros((Kb, N), device=device), values=torch.zeros((Kb, N), device=device),
+                    rewards=torch.zeros((Kb, N), device=device), dones=torch.zeros((Kb, N), dtype=torch.uint8, device=device),
+                    next_value=torch.zeros(N, device=device))
+        obs0 = envs_big.reset()[0].clone()
+        blob16 = f16.pack_train_blob16(pol4.actor_mean, pol4.critic)
+        us = graph_us(lambda: f16.fused_rollout(envs_big, blob16, pol4.actor_logstd.detach(), obs0, **bufs, policy_seed=1), reps=2, replays=3)
+        entry("rollout_kernel at the bench's batch size: 2^20 envs x 16 closed-loop steps per launch", "mufu",
+              268 * N * Kb / (us * 1e-6) / 1e9, pipe["mufu_tanh"] / 1e9, "G MUFU/s", us, N * Kb,
+              peak_kind="MUFU.TANH results/s of f16_peak_probe in this run",
+              algorithmic_per_unit="268 MUFU per env-step", us_per_closed_loop_step_of_all_envs=us / Kb,
+              env_steps_per_s=N * Kb / (us * 1e-6), hbm_gbs=37.0 * N * Kb / (us * 1e-6) / 1e9,
+              note="the two-kernel path needs policy_forward_kernel + env_step2_kernel per step (see their entries)")
+        del envs_big, bufs
         b = tr._flat
         mb = tr._perm_buf[: tr.minibatch_size]
         adv, ret = f16.gae(tr.rewards, tr.values, tr.done_after, tr.values[-1].clone(), 0.99, 0.95)
@@ -797,7 +819,7 @@ def kernel_rooflines(torch, f16, _capi, L, device, rank, world, peaks, peak_kind
               algorithmic_per_unit="9.3 k parameters: ~0.9 MB touched per launch, all L2-resident",
               note="a 9.3 k-parameter model has no throughput roofline: the launch is a chain of three CTA-wide reductions / barriers; "
                    "its cost is latency (us), which the PDL chain of the update graph overlaps with the next gradient kernel's prologue")
-    del tr, envs4, pol4
+        del tr, envs4, pol4
 
     # ---- trim search (FP64 pipe) ----
     Vg, Hg = np.meshgrid(np.linspace(100, 300, 21), np.linspace(1000, 10000, 19))

@@ -21,7 +21,7 @@ ABI_VERSION = 2
 
 EXPORTS = ["f16_abi_version", "f16_last_error", "f16_init", "f16_launch_geometry", "f16_peak_probe", "f16_env_reset", "f16_env_step",
            "f16_env_step_host", "f16_host_route", "f16_rhs", "f16_model_step", "f16_coeffs", "f16_thrust", "f16_atmosphere",
-           "f16_policy_blob_bytes", "f16_policy_forward", "f16_ppo_adv_stats", "f16_ppo_train_blob_bytes", "f16_ppo_grad_floats", "f16_ppo_grad", "f16_ppo_train_blob16_bytes", "f16_ppo_grad16_scratch_floats", "f16_ppo_grad16", "f16_ppo_adam",
+           "f16_policy_blob_bytes", "f16_policy_forward", "f16_rollout", "f16_ppo_adv_stats", "f16_ppo_train_blob_bytes", "f16_ppo_grad_floats", "f16_ppo_grad", "f16_ppo_train_blob16_bytes", "f16_ppo_grad16_scratch_floats", "f16_ppo_grad16", "f16_ppo_adam",
            "f16_gae", "f16_trim"]
 
 
@@ -47,6 +47,14 @@ class StepIO(C.Structure):
     _fields_ = [("actions", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
                 ("final_obs", C.c_void_p), ("final_ep_len", C.c_void_p), ("final_return", C.c_void_p),
                 ("obs_every_step", C.c_int32), ("reserved", C.c_int32), ("stats", C.c_void_p)]
+
+
+class RolloutIO(C.Structure):
+    _fields_ = [("train_blob16", C.c_void_p), ("logstd", C.c_void_p), ("obs0", C.c_void_p), ("obs_next", C.c_void_p),
+                ("actions", C.c_void_p), ("logprobs", C.c_void_p), ("values", C.c_void_p), ("rewards", C.c_void_p),
+                ("dones", C.c_void_p), ("next_value", C.c_void_p), ("final_obs", C.c_void_p), ("final_ep_len", C.c_void_p),
+                ("final_return", C.c_void_p), ("stats", C.c_void_p), ("sample", C.c_int32), ("reserved", C.c_int32),
+                ("policy_seed", C.c_uint64)]
 
 
 def library_path():
@@ -83,6 +91,7 @@ def load_library():
     L.f16_env_reset.argtypes = [C.POINTER(Config), C.POINTER(EnvBuffers), vp, i32, vp, vp]
     L.f16_env_step.argtypes = [C.POINTER(Config), C.POINTER(EnvBuffers), C.POINTER(StepIO), i32, vp]
     L.f16_env_step_host.argtypes = [C.POINTER(Config), C.POINTER(EnvBuffers), vp, vp, vp, vp, i32, i32]
+    L.f16_rollout.argtypes = [C.POINTER(Config), C.POINTER(EnvBuffers), C.POINTER(RolloutIO), i32, vp]
     L.f16_rhs.argtypes = [i32, i64, vp, vp, vp, vp]
     L.f16_model_step.argtypes = [i32, i64, vp, vp, C.c_double, i32, vp]
     L.f16_coeffs.argtypes = [i32, i64, vp, vp, vp, vp, vp, vp]

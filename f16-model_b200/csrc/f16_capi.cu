@@ -642,6 +642,47 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
     return F16_OK;
 }
 
+int f16_rollout(const f16_config *cfg, const f16_env_buffers *env, const f16_rollout_io *io, int K, void *stream)
+{
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    if ((rc = check_env(cfg, env))) return rc;
+    if (!io) return fail(F16_EINVAL, "io is NULL");
+    if (K <= 0) return fail(F16_EINVAL, "K must be >= 1");
+    if (cfg->dtype != F16_F32 || !cfg->autoreset || cfg->obs_layout != F16_OBS_AOS || cfg->noise || env->pos_comp)
+        return fail(F16_EINVAL, "f16_rollout runs the fp32 autoreset env with [n][5] observations, without observation noise or position carries");
+    if (!io->train_blob16 || !io->logstd || !io->obs0 || !io->obs_next || !io->actions || !io->logprobs || !io->values || !io->rewards || !io->dones)
+        return fail(F16_EINVAL, "train_blob16, logstd, obs0, obs_next, actions, logprobs, values, rewards and dones are required");
+    if (reinterpret_cast<uintptr_t>(io->train_blob16) % 16 != 0) return fail(F16_EINVAL, "train_blob16 must be 16-byte aligned");
+    if (5.0 * static_cast<double>(K) * static_cast<double>(cfg->n_envs) >= 4294967296.0 || 9.0 * static_cast<double>(cfg->n_envs) >= 4294967296.0)
+        return fail(F16_EINVAL, "batch too large for 32-bit indexing (5 * K * n_envs must be < 2^32): shard the envs or lower K");
+    int dev;
+    if ((rc = current_device(&dev))) return rc;
+    DeviceCtx *ctx;
+    if ((rc = ensure_device(dev, &ctx))) return rc;
+    auto A = make_env_args<float>(cfg, env, ctx->t32);
+    f16::RolloutArgs R;
+    R.blob = static_cast<const f16::TrainBlob16 *>(io->train_blob16);
+    R.logstd = static_cast<const float *>(io->logstd);
+    R.obs0 = static_cast<const float *>(io->obs0);
+    R.obs_next = static_cast<float *>(io->obs_next);
+    R.actions = static_cast<float *>(io->actions);
+    R.logprobs = static_cast<float *>(io->logprobs);
+    R.values = static_cast<float *>(io->values);
+    R.rewards = static_cast<float *>(io->rewards);
+    R.dones = io->dones;
+    R.next_value = static_cast<float *>(io->next_value);
+    R.final_obs = static_cast<float *>(io->final_obs);
+    R.final_ep_len = io->final_ep_len;
+    R.final_return = static_cast<float *>(io->final_return);
+    R.stats = io->stats;
+    R.K = K;
+    R.sample = io->sample;
+    R.policy_seed = io->policy_seed;
+    CUDA_TRY(f16::launch_rollout(A, R, cfg->fast_math != 0, ctx->n_sm, (cfg->flags & F16_FLAG_NO_PDL) ? 0 : 1, static_cast<cudaStream_t>(stream)));
+    return F16_OK;
+}
+
 int f16_ppo_adv_stats(int64_t n, int n_minibatches, const void *adv, const int64_t *mb_idx, void *out, void *scratch, void *stream)
 {
     DeviceCtx *c;

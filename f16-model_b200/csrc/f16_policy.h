@@ -119,6 +119,27 @@ cudaError_t launch_adv_stats(const float *adv, const int64_t *mb_idx, int64_t n,
 
 cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *values, const uint8_t *done_after, const float *next_value,
                        float gamma, float lam, float *advantages, float *returns, int n_sm, cudaStream_t st);
+// ---- closed-loop rollout: K x (policy forward -> Gaussian head -> F16.step) in one persistent kernel (f16_rollout.cu) ----
+template <typename R>
+struct EnvArgs;
+struct RolloutArgs {
+    const TrainBlob16 *blob;      // fp16 tensor-core operands W1, W2 and the fp32 biases / heads (the W2^T block is skipped)
+    const float *logstd;          // [1]
+    const float *obs0;            // [n][5]   the observation the first step acts on
+    float *obs_next;              // [K][n][5] observation returned by step k (the reset observation where an episode ended)
+    float *actions, *logprobs, *values, *rewards;   // [K][n]
+    uint8_t *dones;               // [K][n]
+    float *next_value;            // [n] critic value of the observation after the last step (GAE bootstrap), or nullptr
+    float *final_obs;             // gymnasium final_observation / final_info of the most recent episode that ended, or nullptr
+    int32_t *final_ep_len;
+    float *final_return;
+    double *stats;                // [4] episode statistics accumulators, or nullptr
+    int K;
+    int sample;                   // 0: deterministic actions (eps = 0)
+    uint64_t policy_seed;         // key of the exploration-noise stream (the counter is the env's own: id, episode, step)
+};
+cudaError_t launch_rollout(const EnvArgs<float> &A, const RolloutArgs &R, bool fast, int n_sm, int pdl, cudaStream_t st);
+
 size_t policy_smem_bytes();
 cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, int pdl, cudaStream_t st);
 

@@ -38,6 +38,7 @@ class PPOConfig:
     tf32_update: bool = False            # run the update's matmuls on the TF32 tensor cores (default: torch's fp32)
     fused_update: bool = True            # minibatch forward + loss + backward in ONE tcgen05 kernel (f16_ppo_grad16); False: torch autograd
     fused_precision: str = "fp16"        # tensor-core operands of the fused kernel: "fp16" (weight gradients on the tensor cores too) or "tf32"
+    fused_rollout: bool = True           # the whole closed-loop rollout in ONE persistent kernel (f16_rollout): policy -> head -> env step, K times
 
 
 def gae(rewards, values, done_after, next_value, gamma, gae_lambda):
@@ -60,6 +61,41 @@ def gae(rewards, values, done_after, next_value, gamma, gae_lambda):
         _capi.check(L.f16_gae(T, N, rewards.data_ptr(), values.data_ptr(), done_after.data_ptr(), next_value.data_ptr(),
                               float(gamma), float(gae_lambda), adv.data_ptr(), ret.data_ptr(), _capi.stream_ptr(rewards.device)))
     return adv, ret
+
+
+def fused_rollout(envs, blob16, logstd, obs0, obs_next, actions, logprobs, values, rewards, dones, next_value=None,
+                  sample=True, policy_seed=0):
+    """K closed-loop steps of ``policy -> Gaussian head -> F16.step`` for every env of ``envs`` in ONE kernel launch
+    (csrc/f16_rollout.cu; the loop of ppo_model_gsde.py:216-230).  ``blob16`` = ``policy.pack_train_blob16(actor, critic)``
+    (the PPO trainer's fp16 weight blob); ``obs0`` [N,5] is the observation the first step acts on; the [K,N(,5)] rollout
+    rows and the bootstrap value of the last observation are written into the caller's tensors.  The env's episode
+    statistics and ``final_*`` buffers are updated as by ``step``."""
+    import ctypes as C
+    import torch
+
+    K, N = actions.shape
+    if N != envs.num_envs or obs_next.shape != (K, N, 5) or obs0.shape != (N, 5):
+        raise ValueError("rollout buffers must be [K, N] / [K, N, 5] with N = envs.num_envs, obs0 [N, 5]")
+    for name, t in (("obs0", obs0), ("obs_next", obs_next), ("actions", actions), ("logprobs", logprobs), ("values", values),
+                    ("rewards", rewards), ("blob16", blob16), ("logstd", logstd)):
+        _capi.require_cuda(t, name)
+        if t.dtype != torch.float32:
+            raise ValueError(f"{name} must be float32")
+    _capi.require_cuda(dones, "dones")
+    if dones.dtype not in (torch.uint8, torch.bool) or dones.shape != (K, N):
+        raise ValueError("dones must be uint8 [K, N]")
+    io = _capi.RolloutIO()
+    io.train_blob16, io.logstd, io.obs0, io.obs_next = blob16.data_ptr(), logstd.data_ptr(), obs0.data_ptr(), obs_next.data_ptr()
+    io.actions, io.logprobs, io.values, io.rewards = actions.data_ptr(), logprobs.data_ptr(), values.data_ptr(), rewards.data_ptr()
+    io.dones = dones.data_ptr()
+    io.next_value = _capi.require_cuda(next_value, "next_value").data_ptr() if next_value is not None else None
+    io.final_obs, io.final_ep_len, io.final_return = envs._final_obs.data_ptr(), envs._final_len.data_ptr(), envs._final_ret.data_ptr()
+    io.stats = envs.episode_stats.data_ptr()
+    io.sample = int(bool(sample))
+    io.policy_seed = int(policy_seed) & 0xFFFFFFFFFFFFFFFF
+    with torch.cuda.device(envs.device):
+        _capi.check(_capi.load_library().f16_rollout(C.byref(envs._cfg), C.byref(envs._buf), C.byref(io), K, _capi.stream_ptr(envs.device)))
+    envs._obs.copy_(obs_next[K - 1])          # the env's own "last observation" buffer stays current for step() users
 
 
 def kl_early_stop(approx_kl, target_kl, world=1, group=None):
@@ -111,6 +147,11 @@ class PPOTrainer:
         self._fused = bool(self.cfg.fused_update) and envs.obs_layout == "aos"
         if self._fused:
             self._setup_fused()
+        self._next_value = torch.zeros(N, device=dev)
+        c = envs._cfg
+        self._fused_rollout = (bool(self.cfg.fused_rollout) and aos and envs.dtype == torch.float32 and envs.autoreset
+                               and not c.noise and envs.pos_comp is None)
+        self._rollout_blob = None
 
     # ------------------------------------------------------------------ rollout
     def _obs_at(self, t):
@@ -125,15 +166,39 @@ class PPOTrainer:
                             out=(self.actions[t], self.logprobs[t], self.values[t]))
             self.envs.step_k(self.actions[t:t + 1], out=(self.obs[t + 1], self.rewards[t:t + 1], self.done_after[t:t + 1]))
 
+    def _blob16(self):
+        """The fp16 weight blob the rollout kernel reads: the fused update's own training blob (kept current by the
+        optimiser kernel), otherwise packed from the torch parameters."""
+        if self._fused and getattr(self, "_fp16", False):
+            return self._train_blob
+        from .policy import pack_train_blob16
+
+        blob = pack_train_blob16(self.policy.actor_mean, self.policy.critic)
+        if self._rollout_blob is None:
+            self._rollout_blob = blob
+        else:
+            self._rollout_blob.copy_(blob)
+        return self._rollout_blob
+
     def rollout(self):
-        """num_steps closed-loop steps for all envs, everything device-resident; replayed from a CUDA
-        graph (one launch per rollout) unless ``use_cuda_graph=False``."""
+        """num_steps closed-loop steps for all envs, everything device-resident: ONE persistent kernel
+        (``fused_rollout``, the default), or 2 kernels per step replayed from a CUDA graph."""
         torch, cfg = self._torch, self.cfg
         if cfg.reset_every_update or self.update_idx == 0:
             obs0, _ = self.envs.reset(seed=cfg.seed + self.update_idx + 1)
             self._obs_at(0).copy_(obs0)
         else:
             self.obs[0].copy_(self.obs[cfg.num_steps])
+        if self._fused_rollout:
+            T = cfg.num_steps
+            fused_rollout(self.envs, self._blob16(), self.policy.actor_logstd.detach(), self.obs[0], self.obs[1:], self.actions,
+                          self.logprobs, self.values, self.rewards, self.done_after, next_value=self._next_value,
+                          sample=True, policy_seed=self.policy.seed)
+            self.global_step += self.N * T
+            adv, ret = gae(self.rewards, self.values, self.done_after, self._next_value, cfg.gamma, cfg.gae_lambda)
+            s = self.envs.episode_stats.clone()
+            self.envs.episode_stats.zero_()
+            return adv, ret, s[1], s[0]
         if not cfg.use_cuda_graph:
             self._enqueue_rollout()
         else:

@@ -208,6 +208,35 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
                        void *action, void *logprob, int sample, uint64_t seed, uint32_t step, const int32_t *ep_len,
                        const uint32_t *episode_no, int64_t env_id_base, void *stream);
 
+/* The closed-loop rollout of Agent.train (control/ppo/ppo_model_gsde.py:216-230) in ONE persistent kernel launch:
+ *     for k in range(K):  action, logprob, value = policy(obs);  obs, reward, done = F16.step(action)   (autoreset)
+ * for all n envs, with the state and the observation held on the SM between the steps: the two MLPs run on the tensor
+ * cores (tcgen05, fp16 operands, fp32 accumulate in TMEM), the Gaussian head draws its noise from the counter RNG keyed
+ * by (policy_seed, global env id, episode_no, ep_len) exactly like f16_policy_forward does with the env's counters, and
+ * the env step is the arithmetic of f16_env_step (fp32, bit-identical given the same actions).  Only the rollout rows
+ * are written.  Requirements: dtype F16_F32, autoreset 1, obs_layout F16_OBS_AOS, noise 0, pos_comp NULL.
+ * train_blob16 = the fp16 weight blob of f16_ppo_grad16 (f16_ppo_train_blob16_bytes), kept current by f16_ppo_adam. */
+typedef struct f16_rollout_io {
+    const void *train_blob16; /* weights, 16-byte aligned */
+    const void *logstd;       /* float[1] */
+    const void *obs0;         /* float[n][5]: the observation the first step acts on (of the last reset / step) */
+    void *obs_next;           /* float[K][n][5]: observation returned by step k */
+    void *actions;            /* float[K][n] */
+    void *logprobs;           /* float[K][n] */
+    void *values;             /* float[K][n] */
+    void *rewards;            /* float[K][n] */
+    uint8_t *dones;           /* [K][n] */
+    void *next_value;         /* float[n]: critic value of obs_next[K-1] (GAE bootstrap); may be NULL */
+    void *final_obs;          /* as in f16_step_io; may be NULL */
+    int32_t *final_ep_len;    /* may be NULL */
+    void *final_return;       /* may be NULL */
+    double *stats;            /* double[4] episode statistics accumulators; may be NULL */
+    int32_t sample;           /* 0: eps = 0 (deterministic actions) */
+    int32_t reserved;
+    uint64_t policy_seed;
+} f16_rollout_io;
+int f16_rollout(const f16_config *cfg, const f16_env_buffers *env, const f16_rollout_io *io, int K, void *stream);
+
 /* One clipped-PPO minibatch gradient in ONE kernel (the body of Agent.train's minibatch loop,
  * control/ppo/ppo_model_gsde.py:303-364, without the optimiser step): forward of actor_mean and critic on the rows
  * mb_idx[0..n) of the flattened rollout buffers (obs float[N][5]; actions, logprobs, adv, ret, val float[N]), the loss
