@@ -77,7 +77,7 @@ def test_fused_rollout_equals_two_kernel_path(f16, fast, n, K, logstd):
     for name in ("state", "episode_length", "total_return", "ref_idx", "episode_no", "episode_stats", "_final_obs", "_final_len", "_final_ret"):
         assert torch.equal(getattr(env_f, name), getattr(env_r, name)), name
     assert torch.equal(env_f._obs, env_r._obs)
-    assert int(out["dones"].sum()) > (n if K > 1000 else 8), "the window must contain terminations"
+    assert int(out["dones"].sum()) > (n if K > 1000 else 4), "the window must contain terminations"
     _, v_boot = pol.mean_value(out["obs_next"][K - 1])
     worst_v = max(worst_v, (out["next_value"] - v_boot).abs().max().item())
     print(f"fused vs two-kernel: |d action| {worst_a:.2e}, |d value| {worst_v:.2e}, |d logprob| {worst_lp:.2e}, episodes ended {int(out['dones'].sum())}")
