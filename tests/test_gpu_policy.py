@@ -153,7 +153,7 @@ def test_ppo_updates_run_on_device(f16):
     blob_before = pol._blob.clone()
     hist = trainer.train(num_updates=2)
     assert len(hist) == 2 and all(np.isfinite(h["value_loss"]) and np.isfinite(h["policy_loss"]) for h in hist)
-    assert trainer._graph is not None                       # the rollout was replayed from a CUDA graph
+    assert trainer._fused_rollout and trainer._graph is None   # the rollout is ONE persistent kernel launch (f16_rollout), no graph needed
     assert trainer._update_graph not in (None, False)       # ... and so was the optimiser step
     assert any(not torch.equal(a, b) for a, b in zip(before, pol.parameters()))
     assert not torch.equal(blob_before, pol._blob)
@@ -173,12 +173,13 @@ def test_ppo_updates_run_on_device(f16):
     # eager rollout == graph rollout, bit for bit
     envs2 = f16.F16VecEnv(cfg, 4096, seed=1)
     pol2 = f16.TensorCorePolicy(seed=1, logstd_init=-1.0)
-    t_graph = f16.PPOTrainer(envs2, pol2, f16.PPOConfig(num_steps=16))
+    t_graph = f16.PPOTrainer(envs2, pol2, f16.PPOConfig(num_steps=16, fused_rollout=False))
     envs3 = f16.F16VecEnv(cfg, 4096, seed=1)
     pol3 = f16.TensorCorePolicy(seed=1, logstd_init=-1.0)
-    t_eager = f16.PPOTrainer(envs3, pol3, f16.PPOConfig(num_steps=16, use_cuda_graph=False))
+    t_eager = f16.PPOTrainer(envs3, pol3, f16.PPOConfig(num_steps=16, use_cuda_graph=False, fused_rollout=False))
     ag, rg, _, _ = t_graph.rollout()
     ae, re, _, _ = t_eager.rollout()
+    assert t_graph._graph is not None and t_eager._graph is None   # the two-kernel path: replayed from a CUDA graph vs launched eagerly
     assert torch.equal(t_graph.actions, t_eager.actions) and torch.equal(t_graph.rewards, t_eager.rewards)
     assert torch.equal(ag, ae) and torch.equal(rg, re)
     m, v = pol.mean_value(obs)
