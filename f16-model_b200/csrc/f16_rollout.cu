@@ -11,9 +11,9 @@
 // current observation live in registers -- and row r of the group's tensor-core tiles (TMEM lane r):
 //
 //   per step   X[128 x 16]  (obs, fp16)  --tcgen05.mma-->  D[128 x 128] (TMEM)   layer 1, actor | critic stacked
-//              H1 = tanh(D + b1) -> shared memory (fp16, canonical K-major layout)
+//              H1 = tanh(D) -> shared memory (fp16, canonical K-major layout); the biases ride in the MMAs (see below)
 //              H1[:, net]  --4 x tcgen05.mma per net-->  D[128 x 128]              layer 2 (overwrites layer 1's columns)
-//              mean / value = w3 . tanh(D + b2) + b3                                layer 3 in the epilogue (CUDA cores)
+//              mean / value = w3 . tanh(D) + b3                                     layer 3 in the epilogue (CUDA cores)
 //              action = mean + std * eps (Philox, keyed by the env's own counters), log-probability
 //              F16.step with that action: same arithmetic as env_step_kernel (bit-identical, tested), autoreset included
 //   streams out only the rollout rows: obs[k+1], action, logprob, value, reward, done  (37 B per env-step)
@@ -31,6 +31,18 @@
 #include "f16_umma.cuh"
 
 namespace f16 {
+#ifdef F16_ROLLOUT_TRACE
+// debug build only (make EXTRA=-DF16_ROLLOUT_TRACE=8): clock64 at the phase boundaries of CTA 0's 16 warps, steps 8..15
+__device__ unsigned long long g_rollout_trace[16][8][12];
+__device__ unsigned long long g_rollout_starts[16][128];   // start of every step k < 128
+#define RTRACE(slot)                                                                                  \
+    do {                                                                                              \
+        if (blockIdx.x == 0 && lane == 0 && k >= F16_ROLLOUT_TRACE && k < F16_ROLLOUT_TRACE + 8)              \
+            g_rollout_trace[warp][k - F16_ROLLOUT_TRACE][slot] = clock64();                                   \
+    } while (0)
+#else
+#define RTRACE(slot) do { } while (0)
+#endif
 namespace {
 
 constexpr int kSub = 4;                       // 128-env groups per CTA
@@ -44,10 +56,12 @@ struct alignas(16) RolloutSmem {
     __half w1[2][128][8];
     __half w2[2][8][64][8];
     float b1[128], b2[128], w3[128], b3[4];
-    __half a1[kSub][2][kRowsR][8];            // X : K = 16 (obs[0..4], 1, 0 ...)
+    __half wb2[2][2][64][8];                  // layer-2 bias as one more K = 16 slice of W2: k = 0 fp16(b2), k = 1 the fp16 remainder
+    __half ones[2][kRowsR][8];                // its A operand: k = 0, 1 are 1.0 for every row (shared by the four groups)
+    __half a1[kSub][2][kRowsR][8];            // X : K = 16 (obs[0..4], 1, 1, 0 ...)
     __half a2[kSub][16][kRowsR][8];           // H1: 16 K-chunks (actor 0-7 | critic 8-15) x 128 rows x 8 halfs
     uint64_t bar_tbl, bar_w;
-    uint64_t bar_mma[kSub];
+    uint64_t bar_mma[kSub][3];                // per group: layer 1, layer 2 actor, layer 2 critic (one phase flip per step each)
     uint32_t tmem_base;
     CtaStats stats;
 };
@@ -74,13 +88,15 @@ __global__ void __launch_bounds__(kThreadsR, 1) rollout_kernel(const EnvArgs<flo
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RolloutSmem *sm = reinterpret_cast<RolloutSmem *>(smem_raw);
     const Tables<float> &tbl = sm->tbl;
-    const unsigned t = threadIdx.x, warp = t >> 5, sub = t >> 7, row = t & (kRowsR - 1);
+    const unsigned t = threadIdx.x, row = t & (kRowsR - 1), lane = t & 31u;
+    const unsigned warp = __shfl_sync(0xffffffffu, t >> 5, 0), sub = warp >> 2;   // warp-uniform for the compiler, too
 
     if (t == 0) {
         mbar_init(&sm->bar_tbl, 1);
         mbar_init(&sm->bar_w, 1);
 #pragma unroll
-        for (int s = 0; s < kSub; ++s) mbar_init(&sm->bar_mma[s], 1);
+        for (int s = 0; s < kSub; ++s)
+            for (int j = 0; j < 3; ++j) mbar_init(&sm->bar_mma[s][j], 1);
         sm->stats.count = 0;
         sm->stats.length = 0;
         sm->stats.ret = 0.0;
@@ -113,14 +129,49 @@ __global__ void __launch_bounds__(kThreadsR, 1) rollout_kernel(const EnvArgs<flo
     }
     mbar_wait(&sm->bar_tbl, 0);
     mbar_wait(&sm->bar_w, 0);
+    // The biases ride in the MMAs (no shared-memory loads or adds in the tanh epilogues): b = hi + lo with hi = fp16(b),
+    // lo = fp16(b - hi) (22 significant bits), multiplied by two columns of ones and accumulated in fp32 by the tensor core.
+    // Layer 1: X carries the ones in k = 5, 6 and this CTA's copy of W1 gets (hi, lo) there (zero in the blob);
+    // layer 2: one extra K = 16 MMA per net with A = `ones`, B = `wb2`.
+    if (t < 128) {
+        const float b = sm->b1[t];
+        const __half hi = __float2half_rn(b);
+        sm->w1[0][t][5] = hi;
+        sm->w1[0][t][6] = __float2half_rn(b - __half2float(hi));
+    } else if (t < 256) {
+        const unsigned j = t - 128u;
+        const float b = sm->b2[j];
+        const __half hi = __float2half_rn(b), z = __float2half_rn(0.f);
+        __half *d = sm->wb2[j >> 6][0][j & 63u];
+        d[0] = hi;
+        d[1] = __float2half_rn(b - __half2float(hi));
+#pragma unroll
+        for (int q = 2; q < 8; ++q) d[q] = z;
+        *reinterpret_cast<uint4 *>(sm->wb2[j >> 6][1][j & 63u]) = make_uint4(0u, 0u, 0u, 0u);
+    } else if (t < 384) {
+        const unsigned r = t - 256u;
+        *reinterpret_cast<uint4 *>(sm->ones[0][r]) = make_uint4(0x3C003C00u, 0u, 0u, 0u);   // {1.0h, 1.0h, 0 ...}
+        *reinterpret_cast<uint4 *>(sm->ones[1][r]) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    u::fence_async_smem();
+    __syncthreads();
 
     constexpr uint32_t id_l1 = u::idesc_f16(128, 128), id_l2 = u::idesc_f16(128, 64);
     const uint32_t a1 = smem_u32(sm->a1[sub]), a2 = smem_u32(sm->a2[sub]);
     const uint32_t w1 = smem_u32(sm->w1), w2a = smem_u32(sm->w2[0]), w2c = smem_u32(sm->w2[1]);
+    const uint32_t ones = smem_u32(sm->ones), wb2 = smem_u32(sm->wb2);
     const uint32_t tcol = tmem + sub * 128u;                                  // this group's accumulator columns
     const uint32_t lane_base = tcol + (((warp & 3u) * 32u) << 16);           // this warp's 32 TMEM lanes
-    uint64_t *bar = &sm->bar_mma[sub];
+    uint64_t *bar1 = &sm->bar_mma[sub][0], *bar2a = &sm->bar_mma[sub][1], *bar2c = &sm->bar_mma[sub][2];
     uint32_t phase = 0;
+    // One thread per group issues its MMAs; group g's issuer sits in warp g of the group, i.e. on SM sub-partition g, so
+    // that the four issuers (which block while the tensor-core queue drains the other groups' MMAs) are spread over the
+    // four schedulers instead of all living on sub-partition 0 (r02c trace: that sub-partition's warps ran every phase
+    // 15-40 % longer and the other three waited for them at the group barriers).
+    // The issuing WARP takes the branch as a whole and elects one lane inside it: with warp-uniform descriptors the MMA issue
+    // is a handful of uniform-datapath instructions (a per-thread `if (row == ...)` made ptxas wrap every tcgen05.mma in a
+    // lane-waterfall loop: ~90 clocks per MMA, r02e trace).
+    const bool issuer_warp = (warp & 3u) == sub;
 
     const unsigned n = static_cast<unsigned>(A.n);
     const unsigned n_tiles = (n + kRowsR - 1) / kRowsR;
@@ -160,74 +211,89 @@ __global__ void __launch_bounds__(kThreadsR, 1) rollout_kernel(const EnvArgs<flo
 
         for (int k = 0; k <= K; ++k) {
             // ================= policy forward on the current observation =================
+            // Split-phase schedule: the two nets' layer-2 products are issued as soon as "their" half of H1 is in shared
+            // memory, so the tensor-core round trip of the actor half runs under the critic half's tanh work and the
+            // critic's under the actor head (r02b trace: sync + wait of a single layer-2 commit cost 1.3-1.5 k of the 12 k
+            // clocks of a step).  Accumulator columns [0, 64) are the actor's in both layers, [64, 128) the critic's.
+            RTRACE(0);
+#ifdef F16_ROLLOUT_TRACE
+            if (blockIdx.x == 0 && lane == 0 && k < 128) g_rollout_starts[warp][k] = clock64();
+#endif
             {
-                const float xin[8] = {o[0], o[1], o[2], o[3], o[4], 1.f, 0.f, 0.f};
+                const float xin[8] = {o[0], o[1], o[2], o[3], o[4], 1.f, 1.f, 0.f};
                 *reinterpret_cast<uint4 *>(sm->a1[sub][0][row]) = pack8h(xin);
             }
             u::fence_async_smem();
             u::fence_before_sync();        // this thread's TMEM loads of the previous step are complete (wait_ld) and ordered
             group_sync(sub);
-            if (row == 0) {
+            if (issuer_warp && u::elect_one()) {
                 u::fence_after_sync();
                 u::mma_f16(tcol, u::desc(a1, kLbo, 128), u::desc(w1, 128 * 16, 128), id_l1, 0u);
-                u::commit(bar);
+                u::commit(bar1);
             }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
+            RTRACE(1);
+            mbar_wait(bar1, phase);
             u::fence_after_sync();
-            // ---- H1 = tanh(D + b1) -> a2 (fp16) ----
+            RTRACE(2);
 #pragma unroll
-            for (int pair = 0; pair < 2; ++pair) {
+            for (int net = 0; net < 2; ++net) {
+                // ---- H1[:, net] = tanh(D[:, 64 net .. 64 net + 63]) -> a2 chunks 8 net .. 8 net + 7 (fp16) ----
                 uint32_t ra[32], rb[32];
-                u::tmem_ld32_issue(lane_base + pair * 64, ra);
-                u::tmem_ld32_issue(lane_base + pair * 64 + 32, rb);
+                u::tmem_ld32_issue(lane_base + net * 64, ra);
+                u::tmem_ld32_issue(lane_base + net * 64 + 32, rb);
                 u::wait_ld();
 #pragma unroll
                 for (int blk = 0; blk < 2; ++blk) {
-                    const int col0 = pair * 64 + blk * 32;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const int j = col0 + c * 8;
+                        const int j = net * 64 + blk * 32 + c * 8;
                         float h[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) h[q] = u::tanh_approx(__uint_as_float(blk ? rb[c * 8 + q] : ra[c * 8 + q]) + sm->b1[j + q]);
+                        for (int q = 0; q < 8; ++q) h[q] = u::tanh_approx(__uint_as_float(blk ? rb[c * 8 + q] : ra[c * 8 + q]));
                         *reinterpret_cast<uint4 *>(sm->a2[sub][j >> 3][row]) = pack8h(h);
                     }
                 }
-            }
-            u::fence_async_smem();
-            u::fence_before_sync();
-            group_sync(sub);
-            if (row == 0) {
-                u::fence_after_sync();
+                if (net == 0) RTRACE(3);
+                u::fence_async_smem();
+                u::fence_before_sync();
+                group_sync(sub);
+                if (issuer_warp && u::elect_one()) {   // layer 2 of this net: 4 x (K = 16) over its H1 chunks + the bias slice; overwrites its layer-1 columns
+                    u::fence_after_sync();
+                    const uint32_t w2n = net ? w2c : w2a;
+                    if (net == 0) RTRACE(8);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)   // actor: H1 chunks 0-7, two per MMA (K = 16)
-                    u::mma_f16(tcol, u::desc(a2 + kk * 2 * kLbo, kLbo, 128), u::desc(w2a + kk * 2 * 64 * 16, 64 * 16, 128), id_l2, kk > 0 ? 1u : 0u);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)   // critic: chunks 8-15
-                    u::mma_f16(tcol + 64, u::desc(a2 + (8 + kk * 2) * kLbo, kLbo, 128), u::desc(w2c + kk * 2 * 64 * 16, 64 * 16, 128), id_l2,
-                            kk > 0 ? 1u : 0u);
-                u::commit(bar);
+                    for (int kk = 0; kk < 4; ++kk)
+                        u::mma_f16(tcol + net * 64, u::desc(a2 + (net * 8 + kk * 2) * kLbo, kLbo, 128), u::desc(w2n + kk * 2 * 64 * 16, 64 * 16, 128),
+                                   id_l2, kk > 0 ? 1u : 0u);
+                    if (net == 0) RTRACE(9);
+                    u::mma_f16(tcol + net * 64, u::desc(ones, kLbo, 128), u::desc(wb2 + net * 2 * 64 * 16, 64 * 16, 128), id_l2, 1u);
+                    if (net == 0) RTRACE(10);
+                    u::commit(net ? bar2c : bar2a);
+                    if (net == 0) RTRACE(11);
+                }
             }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            u::fence_after_sync();
-            // ---- heads: mean = w3a . tanh(D[:, :64] + b2a) + b3a, value likewise from the critic columns ----
+            RTRACE(4);
+            // ---- heads: mean = w3a . tanh(D[:, :64]) + b3a, value likewise from the critic columns ----
             float head[2] = {sm->b3[0], sm->b3[1]};
 #pragma unroll
-            for (int pair = 0; pair < 2; ++pair) {
+            for (int net = 0; net < 2; ++net) {
+                mbar_wait(net ? bar2c : bar2a, phase);
+                u::fence_after_sync();
+                if (net == 0) RTRACE(5);
                 uint32_t ra[32], rb[32];
-                u::tmem_ld32_issue(lane_base + pair * 64, ra);
-                u::tmem_ld32_issue(lane_base + pair * 64 + 32, rb);
+                u::tmem_ld32_issue(lane_base + net * 64, ra);
+                u::tmem_ld32_issue(lane_base + net * 64 + 32, rb);
                 u::wait_ld();
                 float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    acc0 = fmaf(u::tanh_approx(__uint_as_float(ra[c]) + sm->b2[pair * 64 + c]), sm->w3[pair * 64 + c], acc0);
-                    acc1 = fmaf(u::tanh_approx(__uint_as_float(rb[c]) + sm->b2[pair * 64 + 32 + c]), sm->w3[pair * 64 + 32 + c], acc1);
+                    acc0 = fmaf(u::tanh_approx(__uint_as_float(ra[c])), sm->w3[net * 64 + c], acc0);
+                    acc1 = fmaf(u::tanh_approx(__uint_as_float(rb[c])), sm->w3[net * 64 + 32 + c], acc1);
                 }
-                head[pair] += acc0 + acc1;
+                head[net] += acc0 + acc1;
             }
+            phase ^= 1u;
+            RTRACE(6);
             const float mean = head[0], value = head[1];
             if (k == K) {   // one forward past the last step: the GAE bootstrap value of the final observation
                 if (live && R.next_value) R.next_value[i] = value;
@@ -286,6 +352,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) rollout_kernel(const EnvArgs<flo
 #pragma unroll
                 for (int j = 0; j < 5; ++j) po[j] = o[j];
             }
+            RTRACE(7);
         }
 
         // ---- write back ----
@@ -351,5 +418,16 @@ cudaError_t launch_rollout(const EnvArgs<float> &A, const RolloutArgs &R, bool f
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
+
+#ifdef F16_ROLLOUT_TRACE
+extern "C" int f16_debug_rollout_trace(unsigned long long *out)
+{
+    return static_cast<int>(cudaMemcpyFromSymbol(out, g_rollout_trace, sizeof(g_rollout_trace)));
+}
+extern "C" int f16_debug_rollout_starts(unsigned long long *out)
+{
+    return static_cast<int>(cudaMemcpyFromSymbol(out, g_rollout_starts, sizeof(g_rollout_starts)));
+}
+#endif
 
 }  // namespace f16
