@@ -707,8 +707,11 @@ static int ppo_grad_impl(bool fp16, void *partials, int64_t n, const void *train
     f16::LaunchGeom g;
     int rc = prep(n, &c, &g);
     if (rc) return rc;
-    if (!train_blob || !obs || !actions || !logprobs || !adv || !ret || !val || !mb_idx || !logstd || !grad)
+    const bool packed = fp16 && !actions;   // rows float[N][8] in `obs`, (ret, val) float[N][2] in `ret` (f16_ppo_pack_rows)
+    if (!train_blob || !obs || !ret || !mb_idx || !logstd || !grad || (!packed && (!actions || !logprobs || !adv || !val)))
         return fail(F16_EINVAL, "NULL pointer");
+    if (packed && (reinterpret_cast<uintptr_t>(obs) % 32 != 0 || reinterpret_cast<uintptr_t>(ret) % 8 != 0))
+        return fail(F16_EINVAL, "packed rows must be 32-byte aligned, (ret, val) pairs 8-byte aligned");
     if (norm_adv && !adv_stats) return fail(F16_EINVAL, "norm_adv needs adv_stats (mean, std of the minibatch advantages)");
     if (reinterpret_cast<uintptr_t>(train_blob) % 16 != 0) return fail(F16_EINVAL, "train_blob must be 16-byte aligned");
     f16::PpoGradArgs P;
@@ -729,6 +732,7 @@ static int ppo_grad_impl(bool fp16, void *partials, int64_t n, const void *train
     P.ent_coef = static_cast<float>(ent_coef);
     P.norm_adv = norm_adv;
     P.clip_vloss = clip_vloss;
+    P.packed = packed ? 1 : 0;
     if (fp16) CUDA_TRY(f16::launch_ppo_grad16(P, static_cast<const f16::TrainBlob16 *>(train_blob), static_cast<float *>(partials), c->n_sm, static_cast<cudaStream_t>(stream)));
     else CUDA_TRY(f16::launch_ppo_grad(P, c->n_sm, static_cast<cudaStream_t>(stream)));
     return F16_OK;
@@ -740,6 +744,22 @@ int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void 
 {
     return ppo_grad_impl(false, nullptr, n, train_blob, obs, actions, logprobs, adv, ret, val, mb_idx, logstd, adv_stats, grad, clip_coef, vf_coef,
                          ent_coef, norm_adv, clip_vloss, stream);
+}
+
+int f16_ppo_pack_rows(int64_t N, const void *obs, const void *actions, const void *logprobs, const void *adv, const void *ret, const void *val,
+                      void *rows, void *rv, void *stream)
+{
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(N, &c, &g);
+    if (rc) return rc;
+    if (!obs || !actions || !logprobs || !adv || !ret || !val || !rows || !rv) return fail(F16_EINVAL, "NULL pointer");
+    if (reinterpret_cast<uintptr_t>(rows) % 32 != 0 || reinterpret_cast<uintptr_t>(rv) % 8 != 0)
+        return fail(F16_EINVAL, "rows must be 32-byte aligned, rv 8-byte aligned");
+    CUDA_TRY(f16::launch_ppo_pack_rows(N, static_cast<const float *>(obs), static_cast<const float *>(actions), static_cast<const float *>(logprobs),
+                                       static_cast<const float *>(adv), static_cast<const float *>(ret), static_cast<const float *>(val),
+                                       static_cast<float *>(rows), static_cast<float *>(rv), c->n_sm, static_cast<cudaStream_t>(stream)));
+    return F16_OK;
 }
 
 int f16_ppo_train_blob16_bytes(void) { return static_cast<int>(sizeof(f16::TrainBlob16)); }

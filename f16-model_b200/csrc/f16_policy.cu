@@ -25,6 +25,7 @@
 #include <cstdint>
 
 #include "f16_policy.h"
+#include "f16_umma.cuh"
 
 namespace f16 {
 namespace {
@@ -699,14 +700,18 @@ constexpr uint32_t kLboH = kRows * 16 + 16;   // bytes between 8-feature chunks 
 
 struct alignas(16) TrainSmem16 {
     TrainBlob16 w;
-    __half a1[2][kRows][8];           // X: chunk 0 = obs[0..4], 1, 0, 0; chunk 1 = 0
-    unsigned char a2[16 * kLboH];     // H1  [chunk j/8][row][8 halfs]
-    unsigned char d2[16 * kLboH];     // dZ2, later dZ1 (a2 | d2 double as the 64 KB scratch of the final dW3 reduction)
+    // two tiles are in flight per CTA (slots 0 / 1, software-pipelined: while one slot's MMAs run, the CTA works on the other's epilogue)
+    __half a1[2][2][kRows][8];        // X: chunk 0 = obs[0..4], 1, 0, 0; chunk 1 = 0
+    unsigned char a2[2][16 * kLboH];  // H1  [chunk j/8][row][8 halfs]  (a2 doubles as the 64 KB scratch of the final dW3 reduction)
+    unsigned char d2[2][16 * kLboH];  // dZ2, later dZ1
+    float stage[2][2][kThreads][8];   // gathered minibatch rows [parity of the tile pair][slot][thread]: x[5], a, b, c
+    int64_t next_idx[2][kThreads];    // minibatch indices of the NEXT pair's rows [slot][thread] (-1: dead row)
     uint64_t bar_w;
-    uint64_t bar_mma;
+    uint64_t bar_mma[2];
     uint32_t tmem_base;
     float red[16];
 };
+static_assert(sizeof(TrainSmem16) <= 227 * 1024, "shared memory per CTA");
 
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool mn_major)
 {
@@ -729,24 +734,40 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8])
     return *reinterpret_cast<const uint4 *>(h);
 }
 
+#ifdef F16_GRAD_TRACE
+// debug build only (make EXTRA=-DF16_GRAD_TRACE): clock64 at the stage boundaries of CTA 0's 8 warps, tile pairs 2..5
+__device__ unsigned long long g_grad_trace[8][4][10];   // [warp][pair 2..5][slot]
+#define GTRACE(slot)                                                                                          \
+    do {                                                                                                      \
+        if (blockIdx.x == 0 && lane == 0 && tile_no >= 2 && tile_no < 6) g_grad_trace[warp][tile_no - 2][slot] = clock64(); \
+    } while (0)
+#else
+#define GTRACE(slot) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradArgs P, const TrainBlob16 *blob16, float *partials)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TrainSmem16 *sm = reinterpret_cast<TrainSmem16 *>(smem_raw);
-    const unsigned t = threadIdx.x, warp = t >> 5, lane = t & 31u;
+    const unsigned t = threadIdx.x, lane = t & 31u;
+    const unsigned warp = __shfl_sync(0xffffffffu, t >> 5, 0);   // warp-uniform for the compiler: the MMA-issuing branch stays on the uniform datapath
 
     if (t == 0) {
         mbar_init(&sm->bar_w, 1);
-        mbar_init(&sm->bar_mma, 1);
+        mbar_init(&sm->bar_mma[0], 1);
+        mbar_init(&sm->bar_mma[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (t < 16) sm->red[t] = 0.f;
-    if (warp == 0) {   // all 512 TMEM columns: D1/D3 [0,128), D2 [128,256), dW2 [256,384), dW1|db1 [384,400), db2 [400,416)
+    if (warp == 0) {   // all 512 TMEM columns: slot s: D1 -> D2 -> D3 in [128 s, 128 s + 128); dW2 [256,384), dW1|db1 [384,400), db2 [400,416)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     const unsigned row = t & (kRows - 1), half = t >> 7;
-    if (half == 1) *reinterpret_cast<uint4 *>(sm->a1[1][row]) = make_uint4(0u, 0u, 0u, 0u);   // K padding 8..15, written once
+    if (half == 1) {   // K padding 8..15 of both slots' X operands, written once
+        *reinterpret_cast<uint4 *>(sm->a1[0][1][row]) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(sm->a1[1][1][row]) = make_uint4(0u, 0u, 0u, 0u);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -762,16 +783,13 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
                      "l"(blob16), "r"(bytes), "r"(smem_u32(&sm->bar_w))
                      : "memory");
     }
-    mbar_wait(&sm->bar_w, 0);
 
     const TrainBlob16 &W = sm->w;
     constexpr uint32_t id_l1 = umma_idesc_f16(128, 128, false), id_l2 = umma_idesc_f16(128, 64, false);
     constexpr uint32_t id_w2 = umma_idesc_f16(128, 128, true), id_w1 = umma_idesc_f16(128, 16, true);
-    const uint32_t a1 = smem_u32(sm->a1), a2 = smem_u32(sm->a2), d2 = smem_u32(sm->d2);
     const uint32_t w1 = smem_u32(W.w1), w2a = smem_u32(W.w2[0]), w2c = smem_u32(W.w2[1]);
     const uint32_t w2ta = smem_u32(W.w2t[0]), w2tc = smem_u32(W.w2t[1]);
     const uint32_t lane_base = tmem + (((warp & 3u) * 32u) << 16);
-    uint32_t phase = 0;
 
     const unsigned n = static_cast<unsigned>(P.n);
     const unsigned n_tiles = (n + kRows - 1) / kRows;
@@ -781,66 +799,89 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
     const float adv_scale = P.norm_adv ? 1.0f / (P.adv_stats[1] + 1e-8f) : 1.f;
     const float eps = P.clip_coef;
 
-    float acc_w3[64];       // this thread's rows only; reduced over the CTA at the end
+    // dW3: per tile the 64 products dy * H2[row][c] of a thread are summed over the warp's 32 rows by a shuffle butterfly that halves
+    // the value count at every step (62 shuffles), leaving lane l with columns 2l, 2l+1 -- two persistent registers instead of 64
+    // (with 64 the two-tile pipeline spilled: 255 registers).
+    float acc_w3a = 0.f, acc_w3b = 0.f;
     float acc_b3 = 0.f, acc_logstd = 0.f;
     float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f, st4 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 64; ++c) acc_w3[c] = 0.f;
-    bool first = true;      // the weight-gradient accumulators in TMEM are initialised by the first tile's MMAs
 
-    // One row of the minibatch = a random 20-byte row of the rollout buffer plus three scalars: two dependent DRAM round trips
-    // (index, then data).  Exposed per tile they were a third of the kernel (long-scoreboard stalls, ncu r01n), so the next
-    // tile's row is requested while the current tile computes and waits in registers.
-    struct RowIn { float x[5]; float a, b, c; bool live; };
-    auto gather = [&](unsigned tile_) {
+    // One row of the minibatch = a random 20-byte row of the rollout buffer plus three scalars behind an index: two dependent DRAM
+    // round trips.  Both are taken off the critical path AND out of the long-lived register set (the kernel sits at 255 registers:
+    // rows held across the loss stage spilled, and a spill store waits for its load): after stage 1 the rows of the next pair are
+    // requested with the indices fetched one round earlier, the indices of the pair after that are requested too, stage 2 runs on
+    // top of those loads, and before stage 3 everything is parked in shared memory.  (`cp.async` straight into shared memory was
+    // tried first: every `fence.proxy.async` of the stages then waits for the outstanding copies.)
+    auto load_index = [&](unsigned tile_) -> int64_t {
+        const unsigned i_ = tile_ * kRows + row;
+        return (tile_ < n_tiles && i_ < n) ? P.mb_idx[i_] : int64_t(-1);
+    };
+    struct RowIn { float v[8]; };   // x[5], a, b, c
+    auto load_row = [&](int64_t src) {
         RowIn g;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) g.x[k] = 0.f;
-        g.a = g.b = g.c = 0.f;
-        const unsigned i_ = tile_ * kRows + row;
-        g.live = tile_ < n_tiles && i_ < n;
-        if (g.live) {
-            const int64_t src = P.mb_idx[i_];
-            if (half == 0) {
+        for (int k = 0; k < 8; ++k) g.v[k] = 0.f;
+        if (src >= 0) {
+            if (P.packed) {            // one aligned 32-byte sector (half 0) / 8 bytes (half 1) per thread
+                if (half == 0) {
+                    const float4 *r = reinterpret_cast<const float4 *>(P.obs + src * 8);
+                    const float4 lo = __ldg(r), hi = __ldg(r + 1);
+                    g.v[0] = lo.x, g.v[1] = lo.y, g.v[2] = lo.z, g.v[3] = lo.w;
+                    g.v[4] = hi.x, g.v[5] = hi.y, g.v[6] = hi.z, g.v[7] = hi.w;
+                } else {
+                    const float2 rv = __ldg(reinterpret_cast<const float2 *>(P.ret + src * 2));
+                    g.v[5] = rv.x, g.v[6] = rv.y;
+                }
+            } else if (half == 0) {
                 const float *o = P.obs + src * 5;
 #pragma unroll
-                for (int k = 0; k < 5; ++k) g.x[k] = o[k];
-                g.a = P.actions[src];
-                g.b = P.logprobs[src];
-                g.c = P.adv[src];
+                for (int k = 0; k < 5; ++k) g.v[k] = o[k];
+                g.v[5] = P.actions[src];
+                g.v[6] = P.logprobs[src];
+                g.v[7] = P.adv[src];
             } else {
-                g.a = P.ret[src];
-                g.b = P.val[src];
+                g.v[5] = P.ret[src];
+                g.v[6] = P.val[src];
             }
         }
         return g;
     };
-    RowIn nxt = gather(blockIdx.x);
-    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const RowIn cur = nxt;
-        const bool live = cur.live;
-        const float s_a = cur.a, s_b = cur.b, s_c = cur.c;
-        if (half == 0) {   // observation row -> X operand, with a 1 in column 5 (bias gradients = that column of dZ^T [X | 1])
-            const float x[8] = {cur.x[0], cur.x[1], cur.x[2], cur.x[3], cur.x[4], 1.f, 0.f, 0.f};
-            *reinterpret_cast<uint4 *>(sm->a1[0][row]) = pack8(x);
+    auto park_row = [&](float *dst, const RowIn &g) {
+        *reinterpret_cast<float4 *>(dst) = make_float4(g.v[0], g.v[1], g.v[2], g.v[3]);
+        *reinterpret_cast<float4 *>(dst + 4) = make_float4(g.v[4], g.v[5], g.v[6], g.v[7]);
+    };
+    auto row_live = [&](unsigned tile_) { return tile_ < n_tiles && tile_ * kRows + row < n; };
+
+    // ---- the four stages of a tile; `s` is the slot (0 / 1): shared-memory buffers, accumulator columns and mbarrier of that slot ----
+    // Every stage ends by handing a batch of MMAs to the tensor core; the wait for them opens the tile's NEXT stage, which runs after a
+    // stage of the other slot: the round trips (r02 trace: 2.5 k of 9.8 k clocks per tile) and the CUDA-core work overlap.
+    // S1: observation row -> X operand (with a 1 in column 5: bias gradients = that column of dZ^T [X | 1]); issue layer 1
+    auto stage1 = [&](const int s, const float *in, const bool live) {
+        if (half == 0) {
+            float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f};
+            if (live) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) x[k] = in[k];
+            }
+            *reinterpret_cast<uint4 *>(sm->a1[s][0][row]) = pack8(x);
         }
-        nxt = gather(tile + gridDim.x);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (t == 0) {
+        if (warp == 0 && umma::elect_one()) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            umma_f16(tmem + 0, umma_desc(a1, kRows * 16, 128), umma_desc(w1, 128 * 16, 128), id_l1, 0u);
-            umma_commit(&sm->bar_mma);
+            umma_f16(tmem + s * 128, umma_desc(smem_u32(sm->a1[s]), kRows * 16, 128), umma_desc(w1, 128 * 16, 128), id_l1, 0u);
+            umma_commit(&sm->bar_mma[s]);
         }
-        mbar_wait(&sm->bar_mma, phase);
-        phase ^= 1u;
+    };
+    // S2: H1 = tanh(D1 + b1) -> a2 (fp16); issue layer 2 (into D1's columns: every thread has read them)
+    auto stage2 = [&](const int s) {
+        mbar_wait(&sm->bar_mma[s], 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-        // ---- H1 = tanh(D1 + b1) -> a2 (fp16); both 32-column TMEM loads are in flight before the one wait ----
+        unsigned char *a2p = sm->a2[s];
         uint32_t ra[32], rb[32];
-        tmem_ld32_issue(lane_base + half * 64, ra);
-        tmem_ld32_issue(lane_base + half * 64 + 32, rb);
+        tmem_ld32_issue(lane_base + s * 128 + half * 64, ra);
+        tmem_ld32_issue(lane_base + s * 128 + half * 64 + 32, rb);
         tmem_wait_ld();
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
@@ -851,33 +892,37 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
                 float h[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) h[q] = fast_tanh(__uint_as_float(blk ? rb[c * 8 + q] : ra[c * 8 + q]) + W.b1[j + q]);
-                *reinterpret_cast<uint4 *>(sm->a2 + (j >> 3) * kLboH + row * 16u) = pack8(h);
+                *reinterpret_cast<uint4 *>(a2p + (j >> 3) * kLboH + row * 16u) = pack8(h);
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (t == 0) {
+        if (warp == 0 && umma::elect_one()) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a2 = smem_u32(a2p);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                umma_f16(tmem + 128, umma_desc(a2 + k * 2 * kLboH, kLboH, 128), umma_desc(w2a + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
+                umma_f16(tmem + s * 128, umma_desc(a2 + k * 2 * kLboH, kLboH, 128), umma_desc(w2a + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
                          k > 0 ? 1u : 0u);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                umma_f16(tmem + 192, umma_desc(a2 + (8 + k * 2) * kLboH, kLboH, 128), umma_desc(w2c + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
+                umma_f16(tmem + s * 128 + 64, umma_desc(a2 + (8 + k * 2) * kLboH, kLboH, 128), umma_desc(w2c + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
                          k > 0 ? 1u : 0u);
-            umma_commit(&sm->bar_mma);
+            umma_commit(&sm->bar_mma[s]);
         }
-        mbar_wait(&sm->bar_mma, phase);
-        phase ^= 1u;
+    };
+    // S3: H2, head, clipped-PPO loss, dZ2 -> d2; issue D3 = dZ2 W2 (into D2's columns) and the weight gradients dW2, db2
+    auto stage3 = [&](const int s, const float *in, const bool live, const bool first) {   // first: this batch initialises the dW2 / db2 accumulators
+        mbar_wait(&sm->bar_mma[s], 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-        // ---- H2 (registers), head ----
+        const float s_a = live ? in[5] : 0.f, s_b = live ? in[6] : 0.f, s_c = live ? in[7] : 0.f;
+        unsigned char *d2p = sm->d2[s];
+        uint32_t ra[32], rb[32];
         float h2[64];
         float head = W.b3[half];
-        tmem_ld32_issue(lane_base + 128 + half * 64, ra);
-        tmem_ld32_issue(lane_base + 128 + half * 64 + 32, rb);
+        tmem_ld32_issue(lane_base + s * 128 + half * 64, ra);
+        tmem_ld32_issue(lane_base + s * 128 + half * 64 + 32, rb);
         tmem_wait_ld();
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
@@ -936,24 +981,37 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float h = h2[c * 8 + q];
-                acc_w3[c * 8 + q] = fmaf(dy, h, acc_w3[c * 8 + q]);
                 g[q] = g_head * W.w3[j + q] * (1.0f - h * h);
+                h2[c * 8 + q] = dy * h;
             }
-            *reinterpret_cast<uint4 *>(sm->d2 + (j >> 3) * kLboH + row * 16u) = pack8(g);
+            *reinterpret_cast<uint4 *>(d2p + (j >> 3) * kLboH + row * 16u) = pack8(g);
         }
+#pragma unroll
+        for (int sz = 32; sz >= 2; sz >>= 1) {   // 64 -> 32 -> 16 -> 8 -> 4 -> 2 values; lanes whose bit sz/2 is set keep the upper half
+            const unsigned o = static_cast<unsigned>(sz) >> 1;
+            const bool upper = (lane & o) != 0u;
+#pragma unroll
+            for (int i = 0; i < sz; ++i) {
+                const float lo = h2[i], hi = h2[i + sz];
+                h2[i] = (upper ? hi : lo) + __shfl_xor_sync(0xffffffffu, upper ? lo : hi, o);
+            }
+        }
+        acc_w3a += h2[0];
+        acc_w3b += h2[1];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // D1 has been read by everyone: D3 may overwrite it
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // D2 has been read by everyone: D3 may overwrite it
         __syncthreads();
-        if (t == 0) {
+        if (warp == 0 && umma::elect_one()) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // D3 = dZ2 * W2 (per net), into D1's columns: dZ2 read K-major (rows x features)
+            const uint32_t a1 = smem_u32(sm->a1[s]), a2 = smem_u32(sm->a2[s]), d2 = smem_u32(d2p);
+            // D3 = dZ2 * W2 (per net): dZ2 read K-major (rows x features)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                umma_f16(tmem + 0, umma_desc(d2 + k * 2 * kLboH, kLboH, 128), umma_desc(w2ta + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
+                umma_f16(tmem + s * 128, umma_desc(d2 + k * 2 * kLboH, kLboH, 128), umma_desc(w2ta + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
                          k > 0 ? 1u : 0u);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                umma_f16(tmem + 64, umma_desc(d2 + (8 + k * 2) * kLboH, kLboH, 128), umma_desc(w2tc + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
+                umma_f16(tmem + s * 128 + 64, umma_desc(d2 + (8 + k * 2) * kLboH, kLboH, 128), umma_desc(w2tc + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
                          k > 0 ? 1u : 0u);
             // dW2 += dZ2^T * H1, db2 += dZ2^T * [X | 1]: the same buffers read MN-major (features x rows), 16 rows per MMA
 #pragma unroll
@@ -963,15 +1021,17 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
             for (int k = 0; k < 8; ++k)
                 umma_f16(tmem + 400, umma_desc(d2 + k * 256, 128, kLboH), umma_desc(a1 + k * 256, 128, kRows * 16), id_w1,
                          (first && k == 0) ? 0u : 1u);
-            umma_commit(&sm->bar_mma);
+            umma_commit(&sm->bar_mma[s]);
         }
-        mbar_wait(&sm->bar_mma, phase);
-        phase ^= 1u;
+    };
+    // S4: n * dZ1 = D3 * (1 - H1^2) -> d2 (every MMA that read dZ2 has completed); issue dW1 | db1 += dZ1^T [X | 1]
+    auto stage4 = [&](const int s, const bool first) {
+        mbar_wait(&sm->bar_mma[s], 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-        // ---- n * dZ1 = D3 * (1 - H1^2) -> d2 (every MMA that read dZ2 has completed) ----
-        tmem_ld32_issue(lane_base + half * 64, ra);
-        tmem_ld32_issue(lane_base + half * 64 + 32, rb);
+        unsigned char *a2p = sm->a2[s], *d2p = sm->d2[s];
+        uint32_t ra[32], rb[32];
+        tmem_ld32_issue(lane_base + s * 128 + half * 64, ra);
+        tmem_ld32_issue(lane_base + s * 128 + half * 64 + 32, rb);
         tmem_wait_ld();
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
@@ -979,7 +1039,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int j = col0 + c * 8;
-                const uint4 raw = *reinterpret_cast<const uint4 *>(sm->a2 + (j >> 3) * kLboH + row * 16u);
+                const uint4 raw = *reinterpret_cast<const uint4 *>(a2p + (j >> 3) * kLboH + row * 16u);
                 const __half2 *hh = reinterpret_cast<const __half2 *>(&raw);
                 float g[8];
 #pragma unroll
@@ -988,25 +1048,71 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
                     g[2 * q] = __uint_as_float(blk ? rb[c * 8 + 2 * q] : ra[c * 8 + 2 * q]) * (1.0f - h.x * h.x);
                     g[2 * q + 1] = __uint_as_float(blk ? rb[c * 8 + 2 * q + 1] : ra[c * 8 + 2 * q + 1]) * (1.0f - h.y * h.y);
                 }
-                *reinterpret_cast<uint4 *>(sm->d2 + (j >> 3) * kLboH + row * 16u) = pack8(g);
+                *reinterpret_cast<uint4 *>(d2p + (j >> 3) * kLboH + row * 16u) = pack8(g);
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (t == 0) {   // dW1 | db1 += dZ1^T * [X | 1]
+        if (warp == 0 && umma::elect_one()) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a1 = smem_u32(sm->a1[s]), d2 = smem_u32(d2p);
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 umma_f16(tmem + 384, umma_desc(d2 + k * 256, 128, kLboH), umma_desc(a1 + k * 256, 128, kRows * 16), id_w1,
                          (first && k == 0) ? 0u : 1u);
-            umma_commit(&sm->bar_mma);
+            umma_commit(&sm->bar_mma[s]);
         }
-        first = false;
-        mbar_wait(&sm->bar_mma, phase);   // the operands are rewritten by the next tile
-        phase ^= 1u;
+    };
+    // the slot's operands are rewritten by its next tile: its last batch (dW1) must have completed
+    auto retire = [&](const int s) {
+        mbar_wait(&sm->bar_mma[s], 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+
+    // a CTA's tiles: blockIdx.x + j gridDim.x, taken two at a time (slot = j & 1); a missing second tile runs as 128 dead rows (zero gradient)
+    const unsigned stride = gridDim.x;
+    park_row(sm->stage[0][0][t], load_row(load_index(blockIdx.x)));
+    park_row(sm->stage[0][1][t], load_row(load_index(blockIdx.x + stride)));
+    sm->next_idx[0][t] = load_index(blockIdx.x + 2 * stride);
+    sm->next_idx[1][t] = load_index(blockIdx.x + 3 * stride);
+    mbar_wait(&sm->bar_w, 0);
+    int tile_no = 0;
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += 2 * stride) {
+        GTRACE(0);
+        const int par = tile_no & 1;
+        const float *in0 = sm->stage[par][0][t], *in1 = sm->stage[par][1][t];
+        const bool live0 = row_live(tile), live1 = row_live(tile + stride);
+        if (tile_no) retire(0);
+        stage1(0, in0, live0);
+        if (tile_no) retire(1);
+        stage1(1, in1, live1);
+        GTRACE(1);
+        stage2(0);
+        GTRACE(2);
+        stage2(1);
+        // Rows of the next pair (indices fetched one round ago) and the indices of the pair after that.  Requested HERE because every
+        // stage ends with fence.proxy.async (= FENCE.VIEW.ASYNC + MEMBAR.ALL.CTA, which waits for the thread's outstanding loads):
+        // the loss stage of slot 0 is the longest stretch without one (~3.5 k clocks), so the DRAM round trip hides under it.
+        const RowIn r0 = load_row(sm->next_idx[0][t]), r1 = load_row(sm->next_idx[1][t]);
+        const int64_t i0 = load_index(tile + 4 * stride), i1 = load_index(tile + 5 * stride);
+        GTRACE(3);
+        stage3(0, in0, live0, tile_no == 0);
+        park_row(sm->stage[par ^ 1][0][t], r0);
+        park_row(sm->stage[par ^ 1][1][t], r1);
+        sm->next_idx[0][t] = i0;
+        sm->next_idx[1][t] = i1;
+        GTRACE(4);
+        stage3(1, in1, live1, false);
+        GTRACE(5);
+        stage4(0, tile_no == 0);
+        GTRACE(6);
+        stage4(1, false);
+        GTRACE(7);
+        ++tile_no;
     }
+    retire(0);
+    retire(1);
 
     // ---- flush ----
     // with `partials` every CTA owns a private copy of the gradient and writes each element exactly once; otherwise atomics
@@ -1035,17 +1141,16 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
         }
     }
     __syncthreads();
-    // dW3: [half][row][64] partials -> scratch (a2 | d2, 64 KB), then 128 threads sum over the 128 rows
+    // dW3: lane l of every warp holds columns 2l, 2l+1 of its net, summed over the warp's rows and the CTA's tiles: the four warps
+    // of a net meet in shared memory and are added in a fixed order (the gradient stays bit-reproducible)
     {
         float *scr = reinterpret_cast<float *>(sm->a2);
-#pragma unroll
-        for (int c = 0; c < 64; ++c) scr[(half * kRows + row) * 64 + c] = acc_w3[c];
+        scr[warp * 64 + 2 * lane] = acc_w3a;
+        scr[warp * 64 + 2 * lane + 1] = acc_w3b;
         __syncthreads();
         if (t < 128) {
             const unsigned net = t >> 6, c = t & 63u;
-            float s = 0.f;
-            for (unsigned r = 0; r < kRows; ++r) s += scr[(net * kRows + r) * 64 + c];
-            put(&G->w3[net][c], s);
+            put(&G->w3[net][c], (scr[(net * 4 + 0) * 64 + c] + scr[(net * 4 + 1) * 64 + c]) + (scr[(net * 4 + 2) * 64 + c] + scr[(net * 4 + 3) * 64 + c]));
         }
     }
     float sc[8] = {st0, st1, st2, st3, st4, acc_logstd, half == 0 ? acc_b3 : 0.f, half == 1 ? acc_b3 : 0.f};
@@ -1065,6 +1170,20 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+// once per update: the six arrays a minibatch row is gathered from -> one 32-byte record + one 8-byte record per rollout row
+__global__ void __launch_bounds__(256) ppo_pack_rows_kernel(int64_t n, const float *__restrict__ obs, const float *__restrict__ actions,
+                                                            const float *__restrict__ logprobs, const float *__restrict__ adv,
+                                                            const float *__restrict__ ret, const float *__restrict__ val,
+                                                            float4 *__restrict__ rows, float2 *__restrict__ rv)
+{
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float *o = obs + i * 5;
+        rows[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
+        rows[2 * i + 1] = make_float4(o[4], actions[i], logprobs[i], adv[i]);
+        rv[i] = make_float2(ret[i], val[i]);
+    }
 }
 
 // sum the CTAs' private gradients: thread (output p, group g of 8) adds every 8th row, the 8 groups meet in shared memory
@@ -1288,6 +1407,14 @@ __global__ void __launch_bounds__(256) gae_kernel(int T, int64_t n, const float 
 
 }  // namespace
 
+#ifdef F16_GRAD_TRACE
+extern "C" int f16_debug_grad_trace(unsigned long long *out)
+{
+    return static_cast<int>(cudaMemcpyFromSymbol(out, g_grad_trace, sizeof(g_grad_trace)));
+}
+#endif
+
+
 cudaError_t launch_gae(int T, int64_t n, const float *rewards, const float *values, const uint8_t *done_after, const float *next_value,
                        float gamma, float lam, float *advantages, float *returns, int n_sm, cudaStream_t st)
 {
@@ -1324,6 +1451,16 @@ cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st)
     lc.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&lc, ppo_adam_kernel, A);
     if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ppo_pack_rows(int64_t n, const float *obs, const float *actions, const float *logprobs, const float *adv, const float *ret,
+                                 const float *val, float *rows, float *rv, int n_sm, cudaStream_t st)
+{
+    const int64_t want = (n + 255) / 256;
+    const int grid = static_cast<int>(want < static_cast<int64_t>(n_sm) * 8 ? want : static_cast<int64_t>(n_sm) * 8);
+    ppo_pack_rows_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(n, obs, actions, logprobs, adv, ret, val, reinterpret_cast<float4 *>(rows),
+                                                             reinterpret_cast<float2 *>(rv));
     return cudaGetLastError();
 }
 

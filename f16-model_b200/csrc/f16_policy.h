@@ -67,6 +67,7 @@ struct PpoGradArgs {
     int64_t n;
     float clip_coef, vf_coef, ent_coef;
     int norm_adv, clip_vloss;
+    int packed;                // ppo_grad16 only: obs = rows float[N][8] (obs[5], action, logprob, adv), ret = float[N][2] (ret, val)
 };
 
 cudaError_t launch_ppo_grad(const PpoGradArgs &P, int n_sm, cudaStream_t st);
@@ -112,6 +113,8 @@ struct PpoAdamArgs {
     int zero_grad;
 };
 cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st);
+cudaError_t launch_ppo_pack_rows(int64_t n, const float *obs, const float *actions, const float *logprobs, const float *adv, const float *ret,
+                                 const float *val, float *rows, float *rv, int n_sm, cudaStream_t st);
 // mean and unbiased std of adv[mb_idx[y*n .. (y+1)*n)] -> out[y][2] for y < n_minibatches; scratch = n_minibatches x 4 doubles,
 // zero before the first call (the kernel re-zeroes it)
 cudaError_t launch_adv_stats(const float *adv, const int64_t *mb_idx, int64_t n, int n_minibatches, float *out, double *scratch, int n_sm,

@@ -306,8 +306,12 @@ class PPOTrainer:
                 if cfg.norm_adv:
                     _capi.check(L.f16_ppo_adv_stats(mb.numel(), 1, b["adv"].data_ptr(), mb.data_ptr(), adv_stats.data_ptr(),
                                                     self._adv_scratch.data_ptr(), st))
-            args = (mb.numel(), self._train_blob.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(),
-                    b["logprobs"].data_ptr(), b["adv"].data_ptr(), b["ret"].data_ptr(), b["val"].data_ptr(),
+            if self._fp16:   # packed rows (f16_ppo_pack_rows, once per update): one DRAM sector per gathered row
+                srcs = (self._rows.data_ptr(), None, None, None, self._rv.data_ptr(), None)
+            else:
+                srcs = (b["obs"].data_ptr(), b["actions"].data_ptr(), b["logprobs"].data_ptr(), b["adv"].data_ptr(), b["ret"].data_ptr(),
+                        b["val"].data_ptr())
+            args = (mb.numel(), self._train_blob.data_ptr(), *srcs,
                     mb.data_ptr(), self.policy.actor_logstd.data_ptr(), adv_stats.data_ptr(),
                     self._g.data_ptr(), float(cfg.clip_coef), float(cfg.vf_coef), float(cfg.ent_coef),
                     int(bool(cfg.norm_adv)), int(bool(cfg.clip_vloss)))
@@ -386,6 +390,15 @@ class PPOTrainer:
         self._adv.copy_(advantages)
         self._ret.copy_(returns)
         self._diag.zero_()
+        if self._fused and self._fp16:
+            b = self._flat
+            if getattr(self, "_rows", None) is None:
+                self._rows = torch.empty((self.batch_size, 8), device=self.device)
+                self._rv = torch.empty((self.batch_size, 2), device=self.device)
+            with torch.cuda.device(self.device):
+                _capi.check(_capi.load_library().f16_ppo_pack_rows(
+                    self.batch_size, b["obs"].data_ptr(), b["actions"].data_ptr(), b["logprobs"].data_ptr(), b["adv"].data_ptr(),
+                    b["ret"].data_ptr(), b["val"].data_ptr(), self._rows.data_ptr(), self._rv.data_ptr(), _capi.stream_ptr(self.device)))
 
     def _capture_update(self):
         """Capture one optimiser step (forward, backward, clip, Adam) in a CUDA graph: ~150 small launches

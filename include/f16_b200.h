@@ -261,6 +261,12 @@ int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void 
  * tensor cores as well; train_blob16 (f16_ppo_train_blob16_bytes) = W1, W2, W2^T in fp16, then the fp32 biases / heads.
  * scratch: optional f16_ppo_grad16_scratch_floats(device) floats.  With it every CTA stores a private gradient and a second
  * small kernel sums them into grad, which is then OVERWRITTEN (no zeroing needed); without it grad is accumulated with atomics. */
+/* Packed minibatch rows (f16_ppo_pack_rows): a minibatch row is gathered through mb_idx from six arrays, i.e. from 4-5 different
+ * 32-byte DRAM sectors; packed once per update into rows float[N][8] = (obs[5], action, logprob, adv) -- one aligned sector -- and
+ * rv float[N][2] = (ret, val), the gather of f16_ppo_grad16 is one sector per thread.  f16_ppo_grad16 reads the packed form when
+ * `actions` is NULL: `obs` then points to rows, `ret` to rv, and logprobs / adv / val are ignored. */
+int f16_ppo_pack_rows(int64_t N, const void *obs, const void *actions, const void *logprobs, const void *adv, const void *ret,
+                      const void *val, void *rows, void *rv, void *stream);
 int f16_ppo_grad16_scratch_floats(int device);
 int f16_ppo_grad16(int64_t n, const void *train_blob16, const void *obs, const void *actions, const void *logprobs,
                    const void *adv, const void *ret, const void *val, const int64_t *mb_idx, const void *logstd,

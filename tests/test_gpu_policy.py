@@ -252,6 +252,18 @@ def test_fused_ppo_gradient_matches_autograd(f16, n, clip, norm_adv, clip_vloss,
         g.fill_(123.0)
         _capi.check(L.f16_ppo_grad16(*args, scratch.data_ptr(), _capi.stream_ptr(obs.device)))
         assert torch.allclose(g, g_atomic, rtol=1e-4, atol=1e-7)
+        # packed rows (f16_ppo_pack_rows: one 32-byte record + one (ret, val) pair per rollout row): the same gradient
+        rows, rv = torch.empty((N, 8), device="cuda"), torch.empty((N, 2), device="cuda")
+        _capi.check(L.f16_ppo_pack_rows(N, obs.data_ptr(), actions.data_ptr(), logprobs.data_ptr(), adv.data_ptr(), ret.data_ptr(), val.data_ptr(),
+                                        rows.data_ptr(), rv.data_ptr(), _capi.stream_ptr(obs.device)))
+        assert torch.equal(rows[:, :5], obs) and torch.equal(rows[:, 7], adv) and torch.equal(rv[:, 0], ret) and torch.equal(rv[:, 1], val)
+        g_packed = torch.empty_like(g)
+        _capi.check(L.f16_ppo_grad16(n, blob.data_ptr(), rows.data_ptr(), None, None, None, rv.data_ptr(), None, *args[8:11], g_packed.data_ptr(),
+                                     *args[12:], scratch.data_ptr(), _capi.stream_ptr(obs.device)))
+        Gp, Gu = grad_views(g_packed), grad_views(g)
+        for k in ("w1", "b1", "w2", "b2", "w3"):          # tensor-core / fixed-order sums: bit for bit
+            assert torch.equal(Gp[k], Gu[k]), k
+        assert torch.allclose(g_packed, g, rtol=1e-5, atol=1e-8)   # b3, logstd and the statistics meet in shared-memory atomics
     else:
         _capi.check(L.f16_ppo_grad(*args, _capi.stream_ptr(obs.device)))
     G = grad_views(g)
