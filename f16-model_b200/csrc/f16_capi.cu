@@ -746,6 +746,17 @@ int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void 
                          ent_coef, norm_adv, clip_vloss, stream);
 }
 
+int f16_ppo_randperm(int64_t n, uint64_t seed, int64_t *out, void *stream)
+{
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(n, &c, &g);
+    if (rc) return rc;
+    if (!out) return fail(F16_EINVAL, "NULL pointer");
+    CUDA_TRY(f16::launch_ppo_randperm(n, seed, out, c->n_sm, static_cast<cudaStream_t>(stream)));
+    return F16_OK;
+}
+
 int f16_ppo_pack_rows(int64_t N, const void *obs, const void *actions, const void *logprobs, const void *adv, const void *ret, const void *val,
                       void *rows, void *rv, void *stream)
 {

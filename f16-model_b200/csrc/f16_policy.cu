@@ -1172,6 +1172,26 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
+// keyed bijection of [0, n): see f16_ppo_randperm in the header.  Every round is invertible on `bits` bits (odd multiplier, right
+// xor-shift, addition), so the composition is a permutation of [0, 2^bits); values >= n walk the cycle until they fall below n.
+struct PermKey { uint64_t mul[4], add[4]; int shift[4]; int bits; };
+__global__ void __launch_bounds__(256) ppo_randperm_kernel(int64_t n, PermKey K, int64_t *__restrict__ out)
+{
+    const uint64_t mask = (K.bits >= 64) ? ~0ull : ((1ull << K.bits) - 1ull);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        uint64_t x = static_cast<uint64_t>(i);
+        do {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                x = (x * K.mul[r]) & mask;
+                x ^= x >> K.shift[r];
+                x = (x + K.add[r]) & mask;
+            }
+        } while (x >= static_cast<uint64_t>(n));
+        out[i] = static_cast<int64_t>(x);
+    }
+}
+
 // once per update: the six arrays a minibatch row is gathered from -> one 32-byte record + one 8-byte record per rollout row
 __global__ void __launch_bounds__(256) ppo_pack_rows_kernel(int64_t n, const float *__restrict__ obs, const float *__restrict__ actions,
                                                             const float *__restrict__ logprobs, const float *__restrict__ adv,
@@ -1451,6 +1471,32 @@ cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st)
     lc.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&lc, ppo_adam_kernel, A);
     if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ppo_randperm(int64_t n, uint64_t seed, int64_t *out, int n_sm, cudaStream_t st)
+{
+    PermKey K;
+    K.bits = 1;
+    while (K.bits < 63 && (1ll << K.bits) < n) ++K.bits;
+    uint64_t z = seed;
+    auto next = [&z]() {   // splitmix64
+        z += 0x9E3779B97F4A7C15ull;
+        uint64_t x = z;
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        return x ^ (x >> 31);
+    };
+    for (int r = 0; r < 4; ++r) {
+        K.mul[r] = next() | 1ull;
+        K.add[r] = next();
+        const int half = K.bits / 2 > 0 ? K.bits / 2 : 1;
+        K.shift[r] = half + static_cast<int>(next() % 3) - (half > 1 ? 1 : 0);   // around half the width
+        if (K.shift[r] < 1) K.shift[r] = 1;
+    }
+    const int64_t want = (n + 255) / 256;
+    const int grid = static_cast<int>(want < static_cast<int64_t>(n_sm) * 8 ? want : static_cast<int64_t>(n_sm) * 8);
+    ppo_randperm_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(n, K, out);
     return cudaGetLastError();
 }
 

@@ -113,6 +113,7 @@ struct PpoAdamArgs {
     int zero_grad;
 };
 cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st);
+cudaError_t launch_ppo_randperm(int64_t n, uint64_t seed, int64_t *out, int n_sm, cudaStream_t st);
 cudaError_t launch_ppo_pack_rows(int64_t n, const float *obs, const float *actions, const float *logprobs, const float *adv, const float *ret,
                                  const float *val, float *rows, float *rv, int n_sm, cudaStream_t st);
 // mean and unbiased std of adv[mb_idx[y*n .. (y+1)*n)] -> out[y][2] for y < n_minibatches; scratch = n_minibatches x 4 doubles,

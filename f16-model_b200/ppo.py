@@ -141,6 +141,7 @@ class PPOTrainer:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size()
         self._gen = torch.Generator(device=dev).manual_seed(self.cfg.seed)
+        self._perm_calls = 0
         self._graph = None
         self._update_graph = None
         self._flat = None
@@ -471,14 +472,23 @@ class PPOTrainer:
         n_steps = 0
         per_epoch = len(range(0, self.batch_size - self.minibatch_size + 1, self.minibatch_size))
         for epoch in range(cfg.update_epochs):
-            if use_graph and self._update_graph and self._fused:
-                torch.randperm(self.batch_size, device=self.device, generator=self._gen, out=self._perm_buf)
-                self._update_graph.replay()
-                n_steps += per_epoch
-                if kl_early_stop(self._diag[1], cfg.target_kl, self.world):
-                    break
-                continue
-            perm = torch.randperm(self.batch_size, device=self.device, generator=self._gen)
+            if self._fused:
+                # the epoch's permutation from the keyed-bijection kernel (no sort: torch.randperm was a fifth of the fused update);
+                # the same on every rank, as the reference's single process would draw it
+                self._perm_calls += 1
+                with torch.cuda.device(self.device):
+                    _capi.check(_capi.load_library().f16_ppo_randperm(
+                        self.batch_size, (int(cfg.seed) * 0x9E3779B97F4A7C15 + self._perm_calls) & 0xFFFFFFFFFFFFFFFF,
+                        self._perm_buf.data_ptr(), _capi.stream_ptr(self.device)))
+                perm = self._perm_buf
+                if use_graph and self._update_graph:
+                    self._update_graph.replay()
+                    n_steps += per_epoch
+                    if kl_early_stop(self._diag[1], cfg.target_kl, self.world):
+                        break
+                    continue
+            else:
+                perm = torch.randperm(self.batch_size, device=self.device, generator=self._gen)
             for start in range(0, self.batch_size - self.minibatch_size + 1, self.minibatch_size):
                 mb = perm[start:start + self.minibatch_size]
                 if use_graph and self._update_graph:

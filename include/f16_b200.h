@@ -261,6 +261,12 @@ int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void 
  * tensor cores as well; train_blob16 (f16_ppo_train_blob16_bytes) = W1, W2, W2^T in fp16, then the fp32 biases / heads.
  * scratch: optional f16_ppo_grad16_scratch_floats(device) floats.  With it every CTA stores a private gradient and a second
  * small kernel sums them into grad, which is then OVERWRITTEN (no zeroing needed); without it grad is accumulated with atomics. */
+/* The minibatch permutation of an epoch (np.random.permutation(batch) in Agent.train, control/ppo/ppo_model_gsde.py:296-300) without
+ * a sort: out[i] = pi(i), pi a keyed bijection of [0, n) -- four rounds of (odd multiply, xor-shift, add) on ceil(log2 n) bits,
+ * cycle-walked into range.  One pass over 8 bytes per element (torch.randperm's radix sort costs 0.9 ms for 2^23 elements, a
+ * fifth of the fused update); every (n, seed) gives the same permutation on every device. */
+int f16_ppo_randperm(int64_t n, uint64_t seed, int64_t *out, void *stream);
+
 /* Packed minibatch rows (f16_ppo_pack_rows): a minibatch row is gathered through mb_idx from six arrays, i.e. from 4-5 different
  * 32-byte DRAM sectors; packed once per update into rows float[N][8] = (obs[5], action, logprob, adv) -- one aligned sector -- and
  * rv float[N][2] = (ret, val), the gather of f16_ppo_grad16 is one sector per thread.  f16_ppo_grad16 reads the packed form when

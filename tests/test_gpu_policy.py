@@ -336,3 +336,26 @@ def test_adv_stats_kernel_matches_torch(f16):
     _capi.check(L.f16_ppo_adv_stats(5000, 7, adv.data_ptr(), perm.data_ptr(), out7.data_ptr(), scratch7.data_ptr(), _capi.stream_ptr(adv.device)))
     a7 = adv[perm].view(7, 5000)
     assert torch.allclose(out7, torch.stack([a7.mean(1), a7.std(1)], 1), rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("n", [1, 2, 1000, 65536, (1 << 20) + 17])
+def test_randperm_kernel_is_a_permutation(f16, n):
+    """f16_ppo_randperm: the epoch's minibatch order (np.random.permutation in ppo_model_gsde.py:296-300) as a keyed bijection of
+    [0, n) -- every index exactly once, reproducible per (n, seed), different per seed, and mixed: every slice of the output
+    (a minibatch) spreads over the whole range."""
+    from f16_model_b200 import _capi
+    L = _capi.load_library()
+    outs = []
+    for seed in (1, 1, 2):
+        out = torch.full((n,), -1, dtype=torch.long, device="cuda")
+        _capi.check(L.f16_ppo_randperm(n, seed, out.data_ptr(), _capi.stream_ptr(out.device)))
+        assert torch.equal(torch.sort(out).values, torch.arange(n, device="cuda"))
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    if n >= 1000:
+        assert not torch.equal(outs[0], outs[2])
+        assert (outs[0] == torch.arange(n, device="cuda")).float().mean().item() < 0.01      # few fixed points
+        for part in outs[0].float().chunk(8):                                                # each eighth looks uniform on [0, n)
+            assert abs(part.mean().item() / n - 0.5) < 0.05 and abs(part.std().item() / n - 0.2887) < 0.03
+        # neighbours in the output are not neighbours in the input
+        assert (outs[0][1:] - outs[0][:-1]).abs().float().median().item() > n / 20

@@ -43,12 +43,38 @@ def main():
     cfg = f16.PPOConfig(num_steps=args.num_steps, num_minibatches=32, update_epochs=4, tf32_update=bool(args.tf32_update))
     tr = f16.PPOTrainer(envs, pol, cfg)
     hist = tr.train(num_updates=args.updates)
+    # the gradient all-reduce on its own: 128 eager NCCL calls on the 37 KB flat gradient, as the update issues them
+    allreduce_us = None
+    if world > 1 and getattr(tr, "_g", None) is not None:
+        g = tr._g.clone()
+        for _ in range(10):
+            torch.distributed.all_reduce(g)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(128):
+            torch.distributed.all_reduce(g)
+        e1.record()
+        torch.cuda.synchronize()
+        allreduce_us = e0.elapsed_time(e1) * 1e3 / 128
+    # parameters must be identical on every rank after the updates (same gradients, same optimiser state)
+    flat = torch.cat([p.detach().reshape(-1) for p in pol.parameters()])
+    same = True
+    if world > 1:
+        ref = flat.clone()
+        torch.distributed.broadcast(ref, 0)
+        ok = torch.tensor([1 if torch.equal(ref, flat) else 0], device=dev)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        same = bool(ok.item())
     if rank == 0:
         h = hist[-1]
         print(json.dumps({"config": "4: PPO rollout+update, %d envs/GPU x %d steps, %d GPU(s)" % (args.envs, args.num_steps, world),
                           "rollout_env_steps_per_s": h["rollout_sps"] * world, "rollout_s": h["rollout_s"], "update_s": h["update_s"],
                           "minibatches_per_update": cfg.num_minibatches * cfg.update_epochs, "value_loss": h["value_loss"],
-                          "approx_kl": h["approx_kl"]}), flush=True)
+                          "approx_kl": h["approx_kl"], "grad_allreduce": getattr(tr, "_allreduce_kind", "nccl (eager)") if world > 1 else None,
+                          "nccl_allreduce_us_per_call_37KB": allreduce_us,
+                          "allreduce_share_of_update": (allreduce_us * cfg.num_minibatches * cfg.update_epochs * 1e-6 / h["update_s"]) if allreduce_us else None,
+                          "parameters_identical_on_all_ranks": same}), flush=True)
 
     # policy forward alone (tensor-core kernel): CUDA events around replays of a graph of 20 launches (an eager Python
     # loop is bound by the interpreter + ctypes call, ~20 us per launch, not by the kernel)
