@@ -38,6 +38,7 @@ class PPOConfig:
     tf32_update: bool = False            # run the update's matmuls on the TF32 tensor cores (default: torch's fp32)
     fused_update: bool = True            # minibatch forward + loss + backward in ONE tcgen05 kernel (f16_ppo_grad16); False: torch autograd
     fused_precision: str = "fp16"        # tensor-core operands of the fused kernel: "fp16" (weight gradients on the tensor cores too) or "tf32"
+    graph_allreduce: bool = True         # world > 1: capture the NCCL gradient all-reduce inside the update's CUDA graph (call close() before destroy_process_group)
     fused_rollout: bool = True           # the whole closed-loop rollout in ONE persistent kernel (f16_rollout): policy -> head -> env step, K times
 
 
@@ -321,8 +322,8 @@ class PPOTrainer:
             else:
                 _capi.check(L.f16_ppo_grad(*args, st))
             if self.world > 1:
-                torch.distributed.all_reduce(self._g)              # one NCCL call on the flat buffer (gradients and statistics)
-                self._g /= self.world
+                torch.distributed.all_reduce(self._g)              # one NCCL call on the flat buffer (gradients and statistics), captured
+                self._g /= self.world                              # in the update graph like the kernels around it
             _capi.check(L.f16_ppo_adam(self._n_params, self._pflat.data_ptr(), self._g.data_ptr(), m.data_ptr(), v.data_ptr(),
                                        vmax.data_ptr(), step.data_ptr(), self._lr.data_ptr(), 0.9, 0.999, 1e-8,
                                        float(cfg.max_grad_norm), self._fwd_perm.data_ptr(), self.policy._blob.data_ptr(),
@@ -462,7 +463,7 @@ class PPOTrainer:
             self._g.zero_()
             from .policy import pack_train_blob, pack_train_blob16
             self._train_blob.copy_((pack_train_blob16 if self._fp16 else pack_train_blob)(self.policy.actor_mean, self.policy.critic))
-        use_graph = cfg.use_cuda_graph and self.world == 1
+        use_graph = cfg.use_cuda_graph and (self.world == 1 or cfg.graph_allreduce)
         if use_graph and self._update_graph is None:
             try:
                 self._update_graph = self._capture_update()
@@ -503,6 +504,13 @@ class PPOTrainer:
         d = self._diag.tolist()
         return dict(old_approx_kl=d[0], approx_kl=d[1], clipfrac=d[2] / max(n_steps, 1), value_loss=d[3], policy_loss=d[4],
                     entropy=d[5])
+
+    def close(self):
+        """Release the captured CUDA graphs.  With more than one rank the update graph holds NCCL work: drop it (and drain the
+        device) BEFORE torch.distributed.destroy_process_group(), which otherwise waits forever for the communicator."""
+        self._graph = None
+        self._update_graph = None
+        self._torch.cuda.synchronize(self.device)
 
     def train(self, num_updates=None, log=None):
         """The reference's outer loop: lr annealing, rollout, GAE, update; returns per-update stats."""

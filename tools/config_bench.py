@@ -71,11 +71,13 @@ def main():
         print(json.dumps({"config": "4: PPO rollout+update, %d envs/GPU x %d steps, %d GPU(s)" % (args.envs, args.num_steps, world),
                           "rollout_env_steps_per_s": h["rollout_sps"] * world, "rollout_s": h["rollout_s"], "update_s": h["update_s"],
                           "minibatches_per_update": cfg.num_minibatches * cfg.update_epochs, "value_loss": h["value_loss"],
-                          "approx_kl": h["approx_kl"], "grad_allreduce": getattr(tr, "_allreduce_kind", "nccl (eager)") if world > 1 else None,
+                          "approx_kl": h["approx_kl"],
+                          "grad_allreduce": ("nccl, captured in the update graph" if tr._update_graph else "nccl, eager") if world > 1 else None,
                           "nccl_allreduce_us_per_call_37KB": allreduce_us,
                           "allreduce_share_of_update": (allreduce_us * cfg.num_minibatches * cfg.update_epochs * 1e-6 / h["update_s"]) if allreduce_us else None,
                           "parameters_identical_on_all_ranks": same}), flush=True)
 
+    tr.close()                                  # the update graph holds NCCL work: release it before the process group goes away
     # policy forward alone (tensor-core kernel): CUDA events around replays of a graph of 20 launches (an eager Python
     # loop is bound by the interpreter + ctypes call, ~20 us per launch, not by the kernel)
     obs = torch.rand((args.envs, 5), device=dev) * 2 - 1
