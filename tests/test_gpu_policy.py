@@ -355,7 +355,8 @@ def test_randperm_kernel_is_a_permutation(f16, n):
     if n >= 1000:
         assert not torch.equal(outs[0], outs[2])
         assert (outs[0] == torch.arange(n, device="cuda")).float().mean().item() < 0.01      # few fixed points
-        for part in outs[0].float().chunk(8):                                                # each eighth looks uniform on [0, n)
-            assert abs(part.mean().item() / n - 0.5) < 0.05 and abs(part.std().item() / n - 0.2887) < 0.03
+        if n >= 65536:
+            for part in outs[0].float().chunk(8):                                            # each eighth looks uniform on [0, n)
+                assert abs(part.mean().item() / n - 0.5) < 0.02 and abs(part.std().item() / n - 0.2887) < 0.01
         # neighbours in the output are not neighbours in the input
         assert (outs[0][1:] - outs[0][:-1]).abs().float().median().item() > n / 20

@@ -55,3 +55,29 @@ under both floor sets."""
 def rel_err(a, ref, scale):
     a, ref = np.asarray(a, dtype=np.float64), np.asarray(ref, dtype=np.float64)
     return np.abs(a - ref) / np.maximum(np.abs(ref), scale)
+
+
+def fp32_storage_sensitivity(orc, x0, acts, bank, ref_idx, ref, T=1000):
+    """How far does the fp64 MODEL move when nothing but its state is kept in fp32?  The oracle is stepped one step at a time in its
+    exact fp64 arithmetic; between steps the nine state values are rounded to fp32 (run 0), and additionally jittered by a uniform
+    +-2^-24 relative error (runs 1, 2: the half-ulp a rounded fp32 right-hand side would add).  Returns [3, n]: per run and env the
+    deviation of the final state from the pure-fp64 trajectory in the units of the fp32 bound (FP32_FIELD_SCALE floors); NaN for
+    envs that do not fly the whole episode in every run.  (tests/studies/fp32_error_study.py
+    has the per-field breakdown; this is the assertion-grade version.)"""
+    f32 = lambda a: np.asarray(a, dtype=np.float64).astype(np.float32).astype(np.float64)
+    a32 = f32(acts)
+    out = np.zeros((3, x0.shape[0]))
+    ok = ref["ep_len"] == T
+    for run in range(3):
+        rng = np.random.default_rng(run) if run else None
+        x = f32(x0)
+        alive = np.ones(x0.shape[0], dtype=bool)
+        for k in range(T):
+            r = orc.rollout(x, a32[k:k + 1], bank, ref_idx, want_states=False, want_obs=False)   # the state does not depend on the reference row
+            alive &= r["ep_len"] == 1
+            x = f32(r["final_state"])
+            if rng is not None:
+                x = x * (1.0 + rng.uniform(-1.0, 1.0, x.shape) * 2.0 ** -24)
+        ok &= alive
+        out[run] = rel_err(x, ref["final_state"], FP32_FIELD_SCALE).max(axis=1)
+    return np.where(ok[None], out, np.nan)
