@@ -794,19 +794,31 @@ def kernel_rooflines(torch, f16, _capi, L, device, rank, world, peaks, peak_kind
         entry("gae_kernel (reverse scan, one thread per env)", "hbm", 17 * n4 * T4 / (us * 1e-6) / 1e9, hbm, "GB/s", us, n4 * T4,
               peak_kind=f"of {peak_kind}", algorithmic_per_unit="17 B per (step, env): reward, value, done read; advantage, return written",
               l2="151 MB per launch, larger than L2")
-        args16 = (mb.numel(), tr._train_blob.data_ptr(), b["obs"].data_ptr(), b["actions"].data_ptr(), b["logprobs"].data_ptr(),
-                  b["adv"].data_ptr(), b["ret"].data_ptr(), b["val"].data_ptr(), mb.data_ptr(), pol4.actor_logstd.data_ptr(),
-                  tr._adv_stats.data_ptr(), tr._g.data_ptr(), 0.5, 0.5, 0.0, 1, 1)
+        # packed minibatch rows (f16_ppo_pack_rows, once per update) and the keyed-bijection permutation (once per epoch)
+        us = graph_us(lambda: _capi.check(L.f16_ppo_pack_rows(tr.batch_size, b["obs"].data_ptr(), b["actions"].data_ptr(), b["logprobs"].data_ptr(),
+                                                               b["adv"].data_ptr(), b["ret"].data_ptr(), b["val"].data_ptr(), tr._rows.data_ptr(),
+                                                               tr._rv.data_ptr(), st())), reps=5)
+        entry("ppo_pack_rows_kernel (six rollout arrays -> one 32-byte + one 8-byte record per row, once per update)", "hbm",
+              80 * tr.batch_size / (us * 1e-6) / 1e9, hbm, "GB/s", us, tr.batch_size, peak_kind=f"of {peak_kind}",
+              algorithmic_per_unit="80 B per rollout row: 40 read (obs[5], action, logprob, adv, ret, val), 40 written", l2="671 MB per launch, larger than L2")
+        us = graph_us(lambda: _capi.check(L.f16_ppo_randperm(tr.batch_size, 12345, tr._perm_buf.data_ptr(), st())), reps=5)
+        entry("ppo_randperm_kernel (minibatch order of an epoch as a keyed bijection of [0, n): no sort)", "hbm",
+              8 * tr.batch_size / (us * 1e-6) / 1e9, hbm, "GB/s", us, tr.batch_size, peak_kind=f"of {peak_kind}",
+              algorithmic_per_unit="8 B written per element (int64 index); torch.randperm: 0.9 ms for the same 2^23 elements",
+              l2="67 MB per launch: fits L2, the write-back overlaps the next launch")
+        args16 = (mb.numel(), tr._train_blob.data_ptr(), tr._rows.data_ptr(), None, None, None, tr._rv.data_ptr(), None, mb.data_ptr(),
+                  pol4.actor_logstd.data_ptr(), tr._adv_stats.data_ptr(), tr._g.data_ptr(), 0.5, 0.5, 0.0, 1, 1)
         rows = mb.numel()
         us = graph_us(lambda: _capi.check(L.f16_ppo_grad16(*args16, tr._grad_scratch.data_ptr(), st())), reps=10)
         flops = 2.0 * rows * (16 * 128 + 2 * 64 * 64 + 2 * 64 * 64 + 128 * 128 + 16 * 128 + 16 * 128)   # MACs issued per row: fwd L1, L2; dZ2 W2; dW2 (both nets in one M=N=128 product); db2|dW1
-        entry("ppo_grad16_kernel + ppo_grad_reduce (forward + clipped-PPO loss + backward of both MLPs, tcgen05 kind::f16)", "mufu",
+        entry("ppo_grad16_kernel + ppo_grad_reduce (forward + clipped-PPO loss + backward of both MLPs, tcgen05 kind::f16; two tiles in flight per CTA, packed rows)", "mufu",
               256 * rows / (us * 1e-6) / 1e9, pipe["mufu_tanh"] / 1e9, "G tanh/s", us, rows,
               peak_kind="MUFU.TANH results/s of f16_peak_probe in this run",
               algorithmic_per_unit="256 tanh per minibatch row (the forward); the backward reuses H1, H2",
               tensor_tflops=flops / (us * 1e-6) / 1e12, tensor_frac=flops / (us * 1e-6) / 1e12 / peaks["bf16_tflops"],
               tensor_note="fp16 MACs issued against the measured bf16 burst rate: the tensor cores are not the bound of a 64-wide MLP",
-              gather_gbs=rows * (20 + 5 * 4 + 8) / (us * 1e-6) / 1e9)
+              gather_gbs=rows * (32 + 8 + 8) / (us * 1e-6) / 1e9,
+              gather_note="per row: one 32-byte record, one 8-byte (ret, val) pair, one 8-byte index")
         m, v, vmax, step = tr._adam
         us = graph_us(lambda: _capi.check(L.f16_ppo_adam(
             tr._n_params, tr._pflat.data_ptr(), tr._g.data_ptr(), m.data_ptr(), v.data_ptr(), vmax.data_ptr(), step.data_ptr(), tr._lr.data_ptr(),
