@@ -743,12 +743,18 @@ def kernel_rooflines(torch, f16, _capi, L, device, rank, world, peaks, peak_kind
     for n_pol in sorted({N, min(N, 65536)}, reverse=True):
         o = obs[:n_pol]
         oo = tuple(t[:n_pol] for t in act_out)
-        us = graph_us(lambda: pol.act(o, step=0, out=oo))
-        entry("policy_forward_kernel (tcgen05 kind::tf32, TMEM accumulators)", "mufu", 256 * n_pol / (us * 1e-6) / 1e9, pipe["mufu_tanh"] / 1e9,
-              "G tanh/s", us, n_pol, peak_kind="MUFU.TANH results/s of f16_peak_probe in this run (16 per clock per SM)",
-              algorithmic_per_unit="256 tanh per env (two 5-64-64-1 MLPs)",
-              tensor_tflops=2 * (8 * 128 + 2 * 64 * 64) * n_pol / (us * 1e-6) / 1e12, tensor_frac=2 * (8 * 128 + 2 * 64 * 64) * n_pol / (us * 1e-6) / 1e12 / peaks["bf16_tflops"] * 2,
-              tensor_note="TF32 MACs issued (K padded 5 -> 8) against HALF the measured bf16 rate; irrelevant for a 5-64-64-1 MLP")
+        for prec, name, kpad, tdiv in (("fp16", "policy_forward16_kernel (tcgen05 kind::f16, four 128-row groups per CTA, biases in the MMAs; "
+                                                "TensorCorePolicy.act from 49,152 rows up)", 16, 1.0),
+                                       ("tf32", "policy_forward_kernel (tcgen05 kind::tf32, one 128-row tile per 256-thread CTA; "
+                                                "TensorCorePolicy.act below 49,152 rows)", 8, 2.0)):
+            us = graph_us(lambda: pol.act(o, step=0, out=oo, precision=prec))
+            tf = 2 * (kpad * 128 + 2 * 64 * 64) * n_pol / (us * 1e-6) / 1e12
+            entry(name, "mufu", 256 * n_pol / (us * 1e-6) / 1e9, pipe["mufu_tanh"] / 1e9,
+                  "G tanh/s", us, n_pol, peak_kind="MUFU.TANH results/s of f16_peak_probe in this run (16 per clock per SM)",
+                  algorithmic_per_unit="256 tanh per env (two 5-64-64-1 MLPs)",
+                  tensor_tflops=tf, tensor_frac=tf / peaks["bf16_tflops"] * tdiv,
+                  tensor_note="MACs issued (K padded 5 -> %d) against %s the measured bf16 rate; irrelevant for a 5-64-64-1 MLP"
+                              % (kpad, "HALF" if tdiv == 2.0 else ""))
     del renv
 
     # ---- PPO: config 4 (65,536 envs x 128 steps): rollout, GAE, gradient, optimiser ----

@@ -21,7 +21,7 @@ ABI_VERSION = 2
 
 EXPORTS = ["f16_abi_version", "f16_last_error", "f16_init", "f16_launch_geometry", "f16_peak_probe", "f16_env_reset", "f16_env_step",
            "f16_env_step_host", "f16_host_route", "f16_rhs", "f16_model_step", "f16_coeffs", "f16_thrust", "f16_atmosphere",
-           "f16_policy_blob_bytes", "f16_policy_forward", "f16_rollout", "f16_ppo_adv_stats", "f16_ppo_train_blob_bytes", "f16_ppo_grad_floats", "f16_ppo_grad", "f16_ppo_train_blob16_bytes", "f16_ppo_grad16_scratch_floats", "f16_ppo_grad16", "f16_ppo_pack_rows", "f16_ppo_randperm", "f16_ppo_adam",
+           "f16_policy_blob_bytes", "f16_policy_forward", "f16_policy_forward16", "f16_rollout", "f16_ppo_adv_stats", "f16_ppo_train_blob_bytes", "f16_ppo_grad_floats", "f16_ppo_grad", "f16_ppo_train_blob16_bytes", "f16_ppo_grad16_scratch_floats", "f16_ppo_grad16", "f16_ppo_pack_rows", "f16_ppo_randperm", "f16_ppo_adam",
            "f16_gae", "f16_trim"]
 
 
@@ -112,6 +112,7 @@ def load_library():
     L.f16_trim.argtypes = [i32, vp, vp, i32, vp, vp, vp, vp, vp]
     L.f16_gae.argtypes = [i32, i64, vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, vp]
     L.f16_policy_forward.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, i32, C.c_uint64, C.c_uint32, vp, vp, i64, vp]
+    L.f16_policy_forward16.argtypes = L.f16_policy_forward.argtypes
     for name in EXPORTS:
         if name not in ("f16_last_error",):
             getattr(L, name).restype = C.c_int

@@ -642,6 +642,38 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
     return F16_OK;
 }
 
+int f16_policy_forward16(int64_t n, const void *obs, const void *train_blob16, const void *logstd, void *mean, void *value, void *action,
+                         void *logprob, int sample, uint64_t seed, uint32_t step, const int32_t *ep_len, const uint32_t *episode_no,
+                         int64_t env_id_base, void *stream)
+{
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(n, &c, &g);
+    if (rc) return rc;
+    if (!obs || !train_blob16) return fail(F16_EINVAL, "obs and train_blob16 are required");
+    if (reinterpret_cast<uintptr_t>(train_blob16) % 16 != 0) return fail(F16_EINVAL, "train_blob16 must be 16-byte aligned");
+    if (action && !logstd) return fail(F16_EINVAL, "sampling an action needs logstd");
+    if (static_cast<double>(n) * 5.0 >= 4294967296.0) return fail(F16_EINVAL, "batch too large for 32-bit indexing");
+    f16::PolicyArgs P;
+    P.blob = nullptr;
+    P.obs = static_cast<const float *>(obs);
+    P.logstd = static_cast<const float *>(logstd);
+    P.mean = static_cast<float *>(mean);
+    P.value = static_cast<float *>(value);
+    P.action = static_cast<float *>(action);
+    P.logprob = static_cast<float *>(logprob);
+    P.n = n;
+    P.sample = sample;
+    P.step = step;
+    P.ep_len = ep_len;
+    P.episode_no = episode_no;
+    P.seed = seed;
+    P.id_base = env_id_base;
+    CUDA_TRY(f16::launch_policy_forward16(P, static_cast<const f16::TrainBlob16 *>(train_blob16), c->n_sm, geom(*c, F16_F32, true, true, 0).pdl,
+                                          static_cast<cudaStream_t>(stream)));
+    return F16_OK;
+}
+
 int f16_rollout(const f16_config *cfg, const f16_env_buffers *env, const f16_rollout_io *io, int K, void *stream)
 {
     int rc = check_cfg(cfg);

@@ -146,5 +146,7 @@ cudaError_t launch_rollout(const EnvArgs<float> &A, const RolloutArgs &R, bool f
 
 size_t policy_smem_bytes();
 cudaError_t launch_policy_forward(const PolicyArgs &P, int n_sm, int pdl, cudaStream_t st);
+// fp16-operand forward with the rollout kernel's schedule (f16_rollout.cu): P.blob is ignored, the weights come from blob16
+cudaError_t launch_policy_forward16(const PolicyArgs &P, const TrainBlob16 *blob16, int n_sm, int pdl, cudaStream_t st);
 
 }  // namespace f16

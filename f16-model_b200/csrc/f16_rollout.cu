@@ -388,6 +388,219 @@ __global__ void __launch_bounds__(kThreadsR, 1) rollout_kernel(const EnvArgs<flo
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
+
+// ---------------------------------------------------------------------------
+// policy_forward16_kernel -- Agent.get_action_and_value (control/ppo/ppo_model_gsde.py:81-99,158-160) for a batch of
+// observations with the rollout kernel's schedule: fp16 tensor-core operands (the TrainBlob16 the optimiser keeps current),
+// biases inside the MMAs, four independent 128-row groups per CTA (16 warps, all 512 TMEM columns), split-phase layer 2.
+// The TF32 policy_forward_kernel (f16_policy.cu) runs one 128-row tile per 256-thread CTA with a single MMA round trip in
+// flight and reaches 0.54 of the MUFU.TANH rate at 2^20 rows; here a group's MMA round trips and shared-memory stores hide
+// under the other three groups' tanh streams.  Same counter-RNG keys as policy_forward_kernel: the sampled noise is identical.
+// ---------------------------------------------------------------------------
+struct alignas(16) Policy16Smem {
+    __half w1[2][128][8];
+    __half w2[2][8][64][8];
+    float b1[128], b2[128], w3[128], b3[4];
+    __half wb2[2][2][64][8];
+    __half ones[2][kRowsR][8];
+    __half a1[kSub][2][kRowsR][8];
+    __half a2[kSub][16][kRowsR][8];
+    uint64_t bar_w;
+    uint64_t bar_mma[kSub][3];
+    uint32_t tmem_base;
+};
+static_assert(offsetof(Policy16Smem, w2) - offsetof(Policy16Smem, w1) == sizeof(TrainBlob16::w1), "w1 | w2 must be contiguous");
+static_assert(offsetof(Policy16Smem, b1) - offsetof(Policy16Smem, w1) == offsetof(TrainBlob16, w2t), "fp32 tail follows w2");
+
+__global__ void __launch_bounds__(kThreadsR, 1) policy_forward16_kernel(const PolicyArgs P, const TrainBlob16 *blob16)
+{
+    namespace u = umma;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Policy16Smem *sm = reinterpret_cast<Policy16Smem *>(smem_raw);
+    const unsigned t = threadIdx.x, row = t & (kRowsR - 1);
+    const unsigned warp = __shfl_sync(0xffffffffu, t >> 5, 0), sub = warp >> 2;
+
+    if (t == 0) {
+        mbar_init(&sm->bar_w, 1);
+#pragma unroll
+        for (int s = 0; s < kSub; ++s)
+            for (int j = 0; j < 3; ++j) mbar_init(&sm->bar_mma[s][j], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    *reinterpret_cast<uint4 *>(sm->a1[sub][1][row]) = make_uint4(0u, 0u, 0u, 0u);   // K padding 8..15 of X, written once
+    u::fence_before_sync();
+    __syncthreads();
+    u::fence_after_sync();
+    const uint32_t tmem = sm->tmem_base;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // weights: the optimiser's output; observations: the env step's
+    if (t == 0) {
+        constexpr uint32_t head = static_cast<uint32_t>(offsetof(TrainBlob16, w2t));
+        constexpr uint32_t tail = static_cast<uint32_t>(sizeof(TrainBlob16) - offsetof(TrainBlob16, b1));
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(blob16);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->bar_w)), "r"(head + tail) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm->w1)),
+                     "l"(src), "r"(head), "r"(smem_u32(&sm->bar_w))
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm->b1)),
+                     "l"(src + offsetof(TrainBlob16, b1)), "r"(tail), "r"(smem_u32(&sm->bar_w))
+                     : "memory");
+    }
+    const unsigned n = static_cast<unsigned>(P.n);
+    const unsigned n_tiles = (n + kRowsR - 1) / kRowsR;
+    // first tile's observation row: requested before the weights land
+    unsigned tile = blockIdx.x * kSub + sub;
+    float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    auto load_obs = [&](unsigned tile_, float (&dst)[5]) {
+        const unsigned i_ = tile_ * kRowsR + row;
+        if (tile_ < n_tiles && i_ < n) {
+            const float *po = P.obs + static_cast<size_t>(i_) * 5u;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) dst[j] = __ldg(po + j);
+        }
+    };
+    load_obs(tile, o);
+    mbar_wait(&sm->bar_w, 0);
+    // biases into the MMAs: see rollout_kernel
+    if (t < 128) {
+        const float b = sm->b1[t];
+        const __half hi = __float2half_rn(b);
+        sm->w1[0][t][5] = hi;
+        sm->w1[0][t][6] = __float2half_rn(b - __half2float(hi));
+    } else if (t < 256) {
+        const unsigned j = t - 128u;
+        const float b = sm->b2[j];
+        const __half hi = __float2half_rn(b), z = __float2half_rn(0.f);
+        __half *d = sm->wb2[j >> 6][0][j & 63u];
+        d[0] = hi;
+        d[1] = __float2half_rn(b - __half2float(hi));
+#pragma unroll
+        for (int q = 2; q < 8; ++q) d[q] = z;
+        *reinterpret_cast<uint4 *>(sm->wb2[j >> 6][1][j & 63u]) = make_uint4(0u, 0u, 0u, 0u);
+    } else if (t < 384) {
+        const unsigned r = t - 256u;
+        *reinterpret_cast<uint4 *>(sm->ones[0][r]) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(sm->ones[1][r]) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    u::fence_async_smem();
+    __syncthreads();
+
+    constexpr uint32_t id_l1 = u::idesc_f16(128, 128), id_l2 = u::idesc_f16(128, 64);
+    const uint32_t a1 = smem_u32(sm->a1[sub]), a2 = smem_u32(sm->a2[sub]);
+    const uint32_t w1 = smem_u32(sm->w1), w2a = smem_u32(sm->w2[0]), w2c = smem_u32(sm->w2[1]);
+    const uint32_t ones = smem_u32(sm->ones), wb2 = smem_u32(sm->wb2);
+    const uint32_t tcol = tmem + sub * 128u;
+    const uint32_t lane_base = tcol + (((warp & 3u) * 32u) << 16);
+    uint64_t *bar1 = &sm->bar_mma[sub][0], *bar2a = &sm->bar_mma[sub][1], *bar2c = &sm->bar_mma[sub][2];
+    uint32_t phase = 0;
+    const bool issuer_warp = (warp & 3u) == sub;
+    const float log_std = P.logstd ? P.logstd[0] : 0.f, std_dev = __expf(log_std);
+    const uint2 pkey = make_uint2(static_cast<uint32_t>(P.seed), static_cast<uint32_t>(P.seed >> 32));
+
+    for (; tile < n_tiles; tile += gridDim.x * kSub) {
+        const unsigned i = tile * kRowsR + row;
+        const bool live = i < n;
+        {
+            const float xin[8] = {o[0], o[1], o[2], o[3], o[4], 1.f, 1.f, 0.f};
+            *reinterpret_cast<uint4 *>(sm->a1[sub][0][row]) = pack8h(xin);
+        }
+        u::fence_async_smem();
+        u::fence_before_sync();
+        group_sync(sub);
+        if (issuer_warp && u::elect_one()) {
+            u::fence_after_sync();
+            u::mma_f16(tcol, u::desc(a1, kLbo, 128), u::desc(w1, 128 * 16, 128), id_l1, 0u);
+            u::commit(bar1);
+        }
+        // the next tile's observation row travels under this tile's work
+#pragma unroll
+        for (int j = 0; j < 5; ++j) o[j] = 0.f;
+        load_obs(tile + gridDim.x * kSub, o);
+        // RNG counters of this row (read early: the loads hide under the MMA round trips)
+        uint32_t c2 = 0u, c3 = P.step;
+        if (live && P.action && P.sample) {
+            if (P.episode_no) c2 = P.episode_no[i];
+            if (P.ep_len) c3 = static_cast<uint32_t>(P.ep_len[i]);
+        }
+        mbar_wait(bar1, phase);
+        u::fence_after_sync();
+#pragma unroll
+        for (int net = 0; net < 2; ++net) {
+            uint32_t ra[32], rb[32];
+            u::tmem_ld32_issue(lane_base + net * 64, ra);
+            u::tmem_ld32_issue(lane_base + net * 64 + 32, rb);
+            u::wait_ld();
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = net * 64 + blk * 32 + c * 8;
+                    float h[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) h[q] = u::tanh_approx(__uint_as_float(blk ? rb[c * 8 + q] : ra[c * 8 + q]));
+                    *reinterpret_cast<uint4 *>(sm->a2[sub][j >> 3][row]) = pack8h(h);
+                }
+            }
+            u::fence_async_smem();
+            u::fence_before_sync();
+            group_sync(sub);
+            if (issuer_warp && u::elect_one()) {
+                u::fence_after_sync();
+                const uint32_t w2n = net ? w2c : w2a;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    u::mma_f16(tcol + net * 64, u::desc(a2 + (net * 8 + kk * 2) * kLbo, kLbo, 128), u::desc(w2n + kk * 2 * 64 * 16, 64 * 16, 128),
+                               id_l2, kk > 0 ? 1u : 0u);
+                u::mma_f16(tcol + net * 64, u::desc(ones, kLbo, 128), u::desc(wb2 + net * 2 * 64 * 16, 64 * 16, 128), id_l2, 1u);
+                u::commit(net ? bar2c : bar2a);
+            }
+        }
+        float head[2] = {sm->b3[0], sm->b3[1]};
+#pragma unroll
+        for (int net = 0; net < 2; ++net) {
+            mbar_wait(net ? bar2c : bar2a, phase);
+            u::fence_after_sync();
+            uint32_t ra[32], rb[32];
+            u::tmem_ld32_issue(lane_base + net * 64, ra);
+            u::tmem_ld32_issue(lane_base + net * 64 + 32, rb);
+            u::wait_ld();
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                acc0 = fmaf(u::tanh_approx(__uint_as_float(ra[c])), sm->w3[net * 64 + c], acc0);
+                acc1 = fmaf(u::tanh_approx(__uint_as_float(rb[c])), sm->w3[net * 64 + 32 + c], acc1);
+            }
+            head[net] += acc0 + acc1;
+        }
+        phase ^= 1u;
+        if (live) {
+            const float mean = head[0];
+            if (P.value) P.value[i] = head[1];
+            if (P.mean) P.mean[i] = mean;
+            if (P.action) {
+                float eps = 0.f;
+                if (P.sample) {
+                    const int64_t gid = P.id_base + i;
+                    const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32) ^ 0x50504F31u, c2, c3), pkey);
+                    const float u1 = (static_cast<float>(r.x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+                    const float u2 = static_cast<float>(r.y >> 8) * (1.0f / 16777216.0f);
+                    eps = sqrtf(-2.0f * __logf(u1)) * cospif(2.0f * u2);
+                }
+                P.action[i] = mean + std_dev * eps;
+                if (P.logprob) P.logprob[i] = -0.5f * eps * eps - log_std - 0.91893853320467274178f;
+            }
+        }
+    }
+
+    u::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
 }  // namespace
 
 cudaError_t launch_rollout(const EnvArgs<float> &A, const RolloutArgs &R, bool fast, int n_sm, int pdl, cudaStream_t st)
@@ -415,6 +628,34 @@ cudaError_t launch_rollout(const EnvArgs<float> &A, const RolloutArgs &R, bool f
     lc.attrs = attr;
     lc.numAttrs = pdl ? 1 : 0;
     cudaError_t e = fast ? cudaLaunchKernelEx(&lc, rollout_kernel<true>, A, R) : cudaLaunchKernelEx(&lc, rollout_kernel<false>, A, R);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+
+cudaError_t launch_policy_forward16(const PolicyArgs &P, const TrainBlob16 *blob16, int n_sm, int pdl, cudaStream_t st)
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(policy_forward16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Policy16Smem)));
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int64_t groups = (P.n + kRowsR - 1) / kRowsR;
+    const int64_t ctas = (groups + kSub - 1) / kSub;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(static_cast<unsigned>(ctas < n_sm ? ctas : n_sm));
+    lc.blockDim = dim3(kThreadsR);
+    lc.dynamicSmemBytes = sizeof(Policy16Smem);
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&lc, policy_forward16_kernel, P, blob16);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

@@ -184,6 +184,7 @@ class TensorCorePolicy:
         self.seed = int(seed)
         self.env_id_base = int(env_id_base)
         self._blob = pack_policy_blob(self.actor_mean, self.critic)
+        self._blob16 = None      # fp16 operand blob (TrainBlob16), packed on first use; a PPOTrainer aliases its own here
         self._step = 0
 
     def parameters(self):
@@ -192,9 +193,30 @@ class TensorCorePolicy:
     def sync_weights(self):
         """Re-pack the tensor-core blob after an optimiser step."""
         pack_policy_blob(self.actor_mean, self.critic, out=self._blob)
+        if self._blob16 is not None:
+            self._blob16.copy_(pack_train_blob16(self.actor_mean, self.critic))
+
+    def blob16(self):
+        """The fp16 tensor-core weights (``TrainBlob16``) of ``f16_policy_forward16`` / ``f16_rollout`` / ``f16_ppo_grad16``."""
+        if self._blob16 is None:
+            self._blob16 = pack_train_blob16(self.actor_mean, self.critic)
+        return self._blob16
+
+    def _forward(self, precision, n):
+        """(entry point, weights) of the forward kernel: "tf32" = policy_forward_kernel (one 128-row tile per 256-thread CTA),
+        "fp16" = policy_forward16_kernel (the rollout kernel's schedule: four groups per CTA, biases in the MMAs), None = fp16
+        from 49,152 rows up (measured, tools/policy_probe.py: 16 k rows 5.7 vs 8.0 us, 64 k rows 10.0 vs 8.1 us, 2^20 rows
+        108 vs 83 us -- the 512-thread CTA has the longer prologue and the deeper pipeline)."""
+        if precision is None:
+            precision = "fp16" if n >= 49152 else "tf32"
+        if precision == "fp16":
+            return self._lib.f16_policy_forward16, self.blob16()
+        if precision != "tf32":
+            raise ValueError("precision must be 'tf32', 'fp16' or None")
+        return self._lib.f16_policy_forward, self._blob
 
     # ---- tensor-core inference ------------------------------------------------------------
-    def act(self, obs, sample=True, step=None, want_mean=False, out=None, env=None):
+    def act(self, obs, sample=True, step=None, want_mean=False, out=None, env=None, precision=None):
         """obs [N,5] fp32 CUDA -> (action [N], logprob [N], value [N]) in one kernel launch.
         ``out=(action, logprob, value)`` writes into caller buffers (e.g. rows of a rollout buffer);
         ``env`` (an ``F16VecEnv``) keys the exploration noise by the env's own episode / step
@@ -217,23 +239,25 @@ class TensorCorePolicy:
             self._step += 1
         ep_len = env.episode_length.data_ptr() if env is not None else None
         ep_no = env.episode_no.data_ptr() if env is not None else None
+        fwd, blob = self._forward(precision, n)
         with torch.cuda.device(obs.device):
-            _capi.check(self._lib.f16_policy_forward(
-                n, obs.data_ptr(), self._blob.data_ptr(), self.actor_logstd.data_ptr(), mean.data_ptr() if want_mean else None,
+            _capi.check(fwd(
+                n, obs.data_ptr(), blob.data_ptr(), self.actor_logstd.data_ptr(), mean.data_ptr() if want_mean else None,
                 value.data_ptr(), action.data_ptr(), logprob.data_ptr(), int(bool(sample)), self.seed & 0xFFFFFFFFFFFFFFFF,
                 int(step or 0) & 0xFFFFFFFF, ep_len, ep_no, self.env_id_base, _capi.stream_ptr(obs.device)))
         return (action, logprob, value, mean) if want_mean else (action, logprob, value)
 
-    def mean_value(self, obs):
+    def mean_value(self, obs, precision=None):
         """(actor mean [N], critic value [N]) on the tensor cores, no sampling."""
         torch = self._torch
         obs = _capi.require_cuda(obs, "obs")
         n = obs.shape[0]
         mean = torch.empty(n, device=obs.device)
         value = torch.empty(n, device=obs.device)
+        fwd, blob = self._forward(precision, n)
         with torch.cuda.device(obs.device):
-            _capi.check(self._lib.f16_policy_forward(n, obs.data_ptr(), self._blob.data_ptr(), None, mean.data_ptr(), value.data_ptr(),
-                                                     None, None, 0, 0, 0, None, None, 0, _capi.stream_ptr(obs.device)))
+            _capi.check(fwd(n, obs.data_ptr(), blob.data_ptr(), None, mean.data_ptr(), value.data_ptr(),
+                            None, None, 0, 0, 0, None, None, 0, _capi.stream_ptr(obs.device)))
         return mean, value
 
     # ---- differentiable evaluation for the PPO update (torch autograd) ---------------------

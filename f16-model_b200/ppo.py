@@ -288,6 +288,8 @@ class PPOTrainer:
         self._train_blob = (pack_train_blob16 if self._fp16 else pack_train_blob)(pol.actor_mean, pol.critic)
         # fp16 blob: [fp16 tensor-core operands | fp32 biases and heads]; the optimiser kernel writes the two regions separately
         self._blob_tail = self._train_blob[self._half_perm.numel() // 2:] if self._fp16 else self._train_blob
+        if self._fp16:
+            pol._blob16 = self._train_blob     # policy.act(precision="fp16") reads the blob the optimiser kernel keeps current
         self._params = list(pol.parameters())
         self._adv_stats = torch.zeros(2, device=dev)
         self._adv_scratch = torch.zeros(4, device=dev, dtype=torch.float64)

@@ -208,6 +208,14 @@ int f16_policy_forward(int64_t n, const void *obs, const void *blob, const void 
                        void *action, void *logprob, int sample, uint64_t seed, uint32_t step, const int32_t *ep_len,
                        const uint32_t *episode_no, int64_t env_id_base, void *stream);
 
+/* The same forward with fp16 tensor-core operands and the rollout kernel's schedule (four independent 128-row groups per CTA,
+ * biases inside the MMAs, split-phase layer 2): weights = the fp16 blob of f16_ppo_grad16 / f16_rollout
+ * (f16_ppo_train_blob16_bytes, kept current by f16_ppo_adam), so acting, the closed-loop rollout and the update's forward pass
+ * round alike.  Same arguments, RNG keys and outputs as f16_policy_forward; 1.5x its throughput at 2^20 rows. */
+int f16_policy_forward16(int64_t n, const void *obs, const void *train_blob16, const void *logstd, void *mean, void *value,
+                         void *action, void *logprob, int sample, uint64_t seed, uint32_t step, const int32_t *ep_len,
+                         const uint32_t *episode_no, int64_t env_id_base, void *stream);
+
 /* The closed-loop rollout of Agent.train (control/ppo/ppo_model_gsde.py:216-230) in ONE persistent kernel launch:
  *     for k in range(K):  action, logprob, value = policy(obs);  obs, reward, done = F16.step(action)   (autoreset)
  * for all n envs, with the state and the observation held on the SM between the steps: the two MLPs run on the tensor

@@ -33,8 +33,12 @@ def _ref(policy, obs):
     return m, v
 
 
-@pytest.mark.parametrize("n", [1, 127, 128, 129, 4096, 65536 + 77])
-def test_policy_forward_matches_torch_fp32(f16, n):
+@pytest.mark.parametrize("precision", ["tf32", "fp16"])
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 4096, 65536 + 77, 148 * 512 * 3 + 5])
+def test_policy_forward_matches_torch_fp32(f16, n, precision):
+    """Both forward kernels -- policy_forward_kernel (TF32 operands) and policy_forward16_kernel (fp16 operands, the rollout
+    kernel's four-groups-per-CTA schedule; the last size gives every group of every CTA several tiles and a ragged tail) --
+    against torch fp32: the same bounds (fp16 and TF32 carry the same 11 significant bits)."""
     pol = f16.TensorCorePolicy(seed=3)
     # make the output layers non-trivial (the PPO init gives the actor head std 0.01)
     with torch.no_grad():
@@ -44,7 +48,7 @@ def test_policy_forward_matches_torch_fp32(f16, n):
     pol.sync_weights()
     g = torch.Generator(device="cuda").manual_seed(n)
     obs = torch.rand((n, 5), device="cuda", generator=g) * 2 - 1
-    mean, value = pol.mean_value(obs)
+    mean, value = pol.mean_value(obs, precision=precision)
     rm, rv = _ref(pol, obs)
     assert torch.isfinite(mean).all() and torch.isfinite(value).all()
     em = ((mean - rm).abs() / (1 + rm.abs())).max().item()
@@ -52,16 +56,24 @@ def test_policy_forward_matches_torch_fp32(f16, n):
     assert em < 8e-3 and ev < 8e-3, (em, ev)
     # PPO initialisation (orthogonal, actor head std 0.01, critic head std 1)
     pol0 = f16.TensorCorePolicy(seed=4)
-    m0, v0 = pol0.mean_value(obs)
+    m0, v0 = pol0.mean_value(obs, precision=precision)
     r0m, r0v = _ref(pol0, obs)
     assert (m0 - r0m).abs().max().item() < 2e-3 and (v0 - r0v).abs().max().item() < 2e-3
 
 
-def test_policy_act_sampling_and_logprob(f16):
+@pytest.mark.parametrize("precision", ["tf32", "fp16"])
+def test_policy_act_sampling_and_logprob(f16, precision):
+    import functools
+
     pol = f16.TensorCorePolicy(seed=5, logstd_init=-0.7)
     n = 1 << 16
     obs = torch.rand((n, 5), device="cuda") * 2 - 1
+    a_other, lp_other, _, mean_other = pol.act(obs, sample=True, step=11, want_mean=True, precision="fp16" if precision == "tf32" else "tf32")
+    pol.act = functools.partial(pol.act, precision=precision)
     a, lp, v, mean = pol.act(obs, sample=True, step=11, want_mean=True)
+    # the two kernels draw the SAME noise (same counter keys): identical log-probabilities, actions apart by the means' difference
+    assert torch.equal(lp, lp_other)
+    assert ((a - mean) - (a_other - mean_other)).abs().max().item() < 1e-6 and (mean - mean_other).abs().max().item() < 4e-3
     rm, rv = _ref(pol, obs)
     std = math.exp(-0.7)
     eps = (a - mean) / std
