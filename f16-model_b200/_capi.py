@@ -21,7 +21,7 @@ ABI_VERSION = 2
 
 EXPORTS = ["f16_abi_version", "f16_last_error", "f16_init", "f16_launch_geometry", "f16_peak_probe", "f16_env_reset", "f16_env_step",
            "f16_env_step_host", "f16_host_route", "f16_rhs", "f16_model_step", "f16_coeffs", "f16_thrust", "f16_atmosphere",
-           "f16_policy_blob_bytes", "f16_policy_forward", "f16_policy_forward16", "f16_rollout", "f16_ppo_adv_stats", "f16_ppo_train_blob_bytes", "f16_ppo_grad_floats", "f16_ppo_grad", "f16_ppo_train_blob16_bytes", "f16_ppo_grad16_scratch_floats", "f16_ppo_grad16", "f16_ppo_pack_rows", "f16_ppo_randperm", "f16_ppo_adam",
+           "f16_policy_blob_bytes", "f16_policy_forward", "f16_policy_forward16", "f16_rollout", "f16_ppo_adv_stats", "f16_ppo_train_blob_bytes", "f16_ppo_grad_floats", "f16_ppo_grad", "f16_ppo_train_blob16_bytes", "f16_ppo_grad16_scratch_floats", "f16_ppo_grad16", "f16_ppo_grad16_peer", "f16_peer_buffer_bytes", "f16_peer_seq_words", "f16_peer_alloc", "f16_peer_open", "f16_peer_close", "f16_peer_free", "f16_ppo_pack_rows", "f16_ppo_randperm", "f16_ppo_adam",
            "f16_gae", "f16_trim"]
 
 
@@ -47,6 +47,10 @@ class StepIO(C.Structure):
     _fields_ = [("actions", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
                 ("final_obs", C.c_void_p), ("final_ep_len", C.c_void_p), ("final_return", C.c_void_p),
                 ("obs_every_step", C.c_int32), ("reserved", C.c_int32), ("stats", C.c_void_p)]
+
+
+class PeerGroup(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("bufs", C.c_void_p), ("seq", C.c_void_p)]
 
 
 class RolloutIO(C.Structure):
@@ -107,6 +111,13 @@ def load_library():
     L.f16_ppo_grad.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, i32, i32, vp]
     L.f16_ppo_grad16.argtypes = L.f16_ppo_grad.argtypes[:-1] + [vp, vp]
     L.f16_ppo_grad16_scratch_floats.argtypes = [i32]
+    L.f16_ppo_grad16_peer.argtypes = L.f16_ppo_grad.argtypes[:-1] + [vp, C.POINTER(PeerGroup), vp]
+    L.f16_peer_buffer_bytes.argtypes = [i32]
+    L.f16_peer_seq_words.argtypes = []
+    L.f16_peer_alloc.argtypes = [i64, C.POINTER(C.c_void_p), vp]
+    L.f16_peer_open.argtypes = [vp, C.POINTER(C.c_void_p)]
+    L.f16_peer_close.argtypes = [vp]
+    L.f16_peer_free.argtypes = [vp]
     L.f16_ppo_randperm.argtypes = [i64, C.c_uint64, vp, vp]
     L.f16_ppo_pack_rows.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.f16_trim.argtypes = [i32, vp, vp, i32, vp, vp, vp, vp, vp]
@@ -116,6 +127,7 @@ def load_library():
     for name in EXPORTS:
         if name not in ("f16_last_error",):
             getattr(L, name).restype = C.c_int
+    L.f16_peer_buffer_bytes.restype = C.c_int64
     _lib = L
     return L
 

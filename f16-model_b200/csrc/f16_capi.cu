@@ -731,7 +731,7 @@ int f16_ppo_adv_stats(int64_t n, int n_minibatches, const void *adv, const int64
 int f16_ppo_train_blob_bytes(void) { return static_cast<int>(sizeof(f16::TrainBlob)); }
 int f16_ppo_grad_floats(void) { return static_cast<int>(sizeof(f16::PolicyGrad) / sizeof(float)); }
 
-static int ppo_grad_impl(bool fp16, void *partials, int64_t n, const void *train_blob, const void *obs, const void *actions, const void *logprobs, const void *adv,
+static int ppo_grad_impl(bool fp16, void *partials, const f16_peer_group *peer, int64_t n, const void *train_blob, const void *obs, const void *actions, const void *logprobs, const void *adv,
                  const void *ret, const void *val, const int64_t *mb_idx, const void *logstd, const void *adv_stats, void *grad,
                  double clip_coef, double vf_coef, double ent_coef, int norm_adv, int clip_vloss, void *stream)
 {
@@ -765,7 +765,17 @@ static int ppo_grad_impl(bool fp16, void *partials, int64_t n, const void *train
     P.norm_adv = norm_adv;
     P.clip_vloss = clip_vloss;
     P.packed = packed ? 1 : 0;
-    if (fp16) CUDA_TRY(f16::launch_ppo_grad16(P, static_cast<const f16::TrainBlob16 *>(train_blob), static_cast<float *>(partials), c->n_sm, static_cast<cudaStream_t>(stream)));
+    f16::PeerArgs pa;
+    if (peer) {
+        if (!fp16 || !partials) return fail(F16_EINVAL, "the peer all-reduce rides in the reduction kernel of f16_ppo_grad16: scratch is required");
+        if (peer->world < 1 || peer->world > 32 || peer->rank < 0 || peer->rank >= peer->world || !peer->bufs || !peer->seq)
+            return fail(F16_EINVAL, "bad f16_peer_group (1 <= world <= 32, 0 <= rank < world, bufs and seq set)");
+        pa.bufs = reinterpret_cast<uint2 *const *>(peer->bufs);
+        pa.seq = peer->seq;
+        pa.rank = peer->rank;
+        pa.world = peer->world;
+    }
+    if (fp16) CUDA_TRY(f16::launch_ppo_grad16(P, static_cast<const f16::TrainBlob16 *>(train_blob), static_cast<float *>(partials), c->n_sm, static_cast<cudaStream_t>(stream), peer ? &pa : nullptr));
     else CUDA_TRY(f16::launch_ppo_grad(P, c->n_sm, static_cast<cudaStream_t>(stream)));
     return F16_OK;
 }
@@ -774,7 +784,7 @@ int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void 
                  const void *ret, const void *val, const int64_t *mb_idx, const void *logstd, const void *adv_stats, void *grad,
                  double clip_coef, double vf_coef, double ent_coef, int norm_adv, int clip_vloss, void *stream)
 {
-    return ppo_grad_impl(false, nullptr, n, train_blob, obs, actions, logprobs, adv, ret, val, mb_idx, logstd, adv_stats, grad, clip_coef, vf_coef,
+    return ppo_grad_impl(false, nullptr, nullptr, n, train_blob, obs, actions, logprobs, adv, ret, val, mb_idx, logstd, adv_stats, grad, clip_coef, vf_coef,
                          ent_coef, norm_adv, clip_vloss, stream);
 }
 
@@ -818,8 +828,66 @@ int f16_ppo_grad16(int64_t n, const void *train_blob16, const void *obs, const v
                    const void *ret, const void *val, const int64_t *mb_idx, const void *logstd, const void *adv_stats, void *grad,
                    double clip_coef, double vf_coef, double ent_coef, int norm_adv, int clip_vloss, void *scratch, void *stream)
 {
-    return ppo_grad_impl(true, scratch, n, train_blob16, obs, actions, logprobs, adv, ret, val, mb_idx, logstd, adv_stats, grad, clip_coef, vf_coef,
+    return ppo_grad_impl(true, scratch, nullptr, n, train_blob16, obs, actions, logprobs, adv, ret, val, mb_idx, logstd, adv_stats, grad, clip_coef, vf_coef,
                          ent_coef, norm_adv, clip_vloss, stream);
+}
+
+int f16_ppo_grad16_peer(int64_t n, const void *train_blob16, const void *obs, const void *actions, const void *logprobs, const void *adv,
+                        const void *ret, const void *val, const int64_t *mb_idx, const void *logstd, const void *adv_stats, void *grad,
+                        double clip_coef, double vf_coef, double ent_coef, int norm_adv, int clip_vloss, void *scratch,
+                        const f16_peer_group *peer, void *stream)
+{
+    if (!peer) return fail(F16_EINVAL, "peer is NULL");
+    return ppo_grad_impl(true, scratch, peer, n, train_blob16, obs, actions, logprobs, adv, ret, val, mb_idx, logstd, adv_stats, grad, clip_coef, vf_coef,
+                         ent_coef, norm_adv, clip_vloss, stream);
+}
+
+// ---- exchange buffers in peer memory (CUDA IPC; the ranks of one node) ----
+int64_t f16_peer_buffer_bytes(int world)
+{
+    if (world < 1 || world > 32) return -1;
+    return static_cast<int64_t>(2) * world * f16::ppo_grad_floats_padded() * 8;   // (value, call) words [2 slots][world][padded gradient]
+}
+int f16_peer_seq_words(void) { return f16::ppo_grad_reduce_ctas(); }
+
+int f16_peer_alloc(int64_t bytes, void **ptr, void *ipc_handle)
+{
+    if (bytes <= 0 || !ptr || !ipc_handle) return fail(F16_EINVAL, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the handle crosses the ABI as 64 opaque bytes");
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, static_cast<size_t>(bytes)));
+    cudaError_t e = cudaMemset(p, 0, static_cast<size_t>(bytes));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(F16_ECUDA, cudaGetErrorString(e));
+    }
+    std::memcpy(ipc_handle, &h, sizeof(h));
+    *ptr = p;
+    return F16_OK;
+}
+
+int f16_peer_open(const void *ipc_handle, void **ptr)
+{
+    if (!ipc_handle || !ptr) return fail(F16_EINVAL, "bad argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handle, sizeof(h));
+    CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return F16_OK;
+}
+
+int f16_peer_close(void *ptr)
+{
+    if (ptr) CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+    return F16_OK;
+}
+
+int f16_peer_free(void *ptr)
+{
+    if (ptr) CUDA_TRY(cudaFree(ptr));
+    return F16_OK;
 }
 
 int f16_ppo_adam(int n_params, void *param, const void *grad, void *exp_avg, void *exp_avg_sq, void *max_exp_avg_sq, void *step,

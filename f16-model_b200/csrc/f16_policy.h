@@ -84,7 +84,16 @@ struct alignas(16) TrainBlob16 {
 };
 // partials: optional [n_sm][sizeof(PolicyGrad)/4] floats.  With it every CTA stores its own gradient (no atomics: 148 CTAs adding
 // into the same 9 k addresses cost a fifth of the kernel) and a second small kernel sums the CTAs' rows into P.grad (overwritten).
-cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials, int n_sm, cudaStream_t st);
+// peer: optional cross-rank exchange (see ppo_grad_reduce_peer_kernel): the reduction kernel then also all-reduces (means) the gradient
+// over the ranks of the node through peer memory; needs `partials`.
+struct PeerArgs {
+    uint2 *const *bufs;   // DEVICE array of `world` pointers: every rank's exchange buffer as mapped into this process (own one at [rank])
+    uint32_t *seq;        // DEVICE call counters of this rank, one per reduction CTA, zeroed once
+    int rank, world;
+};
+int ppo_grad_floats_padded();
+int ppo_grad_reduce_ctas();
+cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials, int n_sm, cudaStream_t st, const PeerArgs *peer = nullptr);
 
 // clip_grad_norm_ + Adam(amsgrad) + re-packing of the two weight blobs, one CTA (the whole model is 9.3 k parameters)
 struct PpoAdamArgs {

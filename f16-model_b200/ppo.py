@@ -8,6 +8,7 @@ Flags keep the reference's names and defaults (control/ppo/utils.py:11-142).  De
 deviations: the reference's gSDE noise path is broken as committed
 (``theta_gsde`` is never created in ``train``); here exploration is the standard Gaussian policy
 ``a = mean + exp(logstd) * eps`` with eps drawn by the counter RNG inside the policy kernel."""
+import ctypes as C
 import dataclasses
 import time
 
@@ -38,6 +39,8 @@ class PPOConfig:
     tf32_update: bool = False            # run the update's matmuls on the TF32 tensor cores (default: torch's fp32)
     fused_update: bool = True            # minibatch forward + loss + backward in ONE tcgen05 kernel (f16_ppo_grad16); False: torch autograd
     fused_precision: str = "fp16"        # tensor-core operands of the fused kernel: "fp16" (weight gradients on the tensor cores too) or "tf32"
+    peer_allreduce: bool = True          # world > 1, fused fp16 update: the gradient all-reduce rides in the gradient-reduction kernel over NVLink peer
+                                         # memory (f16_ppo_grad16_peer) instead of an NCCL call per minibatch; falls back to NCCL when the ranks cannot map each other
     graph_allreduce: bool = True         # world > 1: capture the NCCL gradient all-reduce inside the update's CUDA graph (call close() before destroy_process_group)
     fused_rollout: bool = True           # the whole closed-loop rollout in ONE persistent kernel (f16_rollout): policy -> head -> env step, K times
 
@@ -147,8 +150,13 @@ class PPOTrainer:
         self._update_graph = None
         self._flat = None
         self._fused = bool(self.cfg.fused_update) and envs.obs_layout == "aos"
+        self._peer = None
         if self._fused:
             self._setup_fused()
+            if self.world > 1 and self._fp16 and self.cfg.peer_allreduce:
+                from .sharding import PeerExchange
+
+                self._peer = PeerExchange.create(torch.distributed.get_rank(), self.world, dev)   # None: the ranks cannot map each other -> NCCL
         self._next_value = torch.zeros(N, device=dev)
         c = envs._cfg
         self._fused_rollout = (bool(self.cfg.fused_rollout) and aos and envs.dtype == torch.float32 and envs.autoreset
@@ -319,11 +327,14 @@ class PPOTrainer:
                     mb.data_ptr(), self.policy.actor_logstd.data_ptr(), adv_stats.data_ptr(),
                     self._g.data_ptr(), float(cfg.clip_coef), float(cfg.vf_coef), float(cfg.ent_coef),
                     int(bool(cfg.norm_adv)), int(bool(cfg.clip_vloss)))
-            if self._fp16:   # per-CTA partial gradients + a reduction kernel instead of 1.4 M atomics
+            peer = self._peer if self._fp16 else None
+            if peer is not None:   # ... and the cross-rank mean in the same reduction kernel (peer memory, no NCCL call)
+                _capi.check(L.f16_ppo_grad16_peer(*args, self._grad_scratch.data_ptr(), C.byref(peer.group), st))
+            elif self._fp16:   # per-CTA partial gradients + a reduction kernel instead of 1.4 M atomics
                 _capi.check(L.f16_ppo_grad16(*args, self._grad_scratch.data_ptr(), st))
             else:
                 _capi.check(L.f16_ppo_grad(*args, st))
-            if self.world > 1:
+            if self.world > 1 and peer is None:
                 torch.distributed.all_reduce(self._g)              # one NCCL call on the flat buffer (gradients and statistics), captured
                 self._g /= self.world                              # in the update graph like the kernels around it
             _capi.check(L.f16_ppo_adam(self._n_params, self._pflat.data_ptr(), self._g.data_ptr(), m.data_ptr(), v.data_ptr(),
@@ -513,6 +524,9 @@ class PPOTrainer:
         self._graph = None
         self._update_graph = None
         self._torch.cuda.synchronize(self.device)
+        if self._peer is not None:
+            self._peer.close()
+            self._peer = None
 
     def train(self, num_updates=None, log=None):
         """The reference's outer loop: lr annealing, rollout, GAE, update; returns per-update stats."""

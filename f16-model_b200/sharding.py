@@ -84,3 +84,92 @@ def trim_grid_sharded(V, H, rank, world_size, device="cuda", group=None, trim_fn
            "iterations": full[:, 4].astype(np.int32), "n_starts": n_starts}
     out["accepted"] = out["cost"] <= 10e-6
     return out
+
+
+class PeerExchange:
+    """The exchange buffers of ``f16_ppo_grad16_peer`` (the gradient all-reduce fused into the gradient-reduction kernel over
+    NVLink / NVSwitch peer memory): every rank of the node allocates one buffer, the CUDA-IPC handles travel through ONE
+    ``all_gather`` of 64 bytes per rank, every rank maps the others' buffers and keeps the pointer table on its device.
+    ``group`` = the C struct to pass to the kernel launch.  Ranks must live on one node with peer access between their
+    devices; ``PeerExchange.create`` returns None (and the trainer keeps the NCCL all-reduce) when the mapping fails on
+    any rank.  Call ``close()`` before the process group is destroyed."""
+
+    def __init__(self, rank, world, device, own, handles):
+        import ctypes as C
+
+        import torch
+
+        from . import _capi
+
+        L = _capi.load_library()
+        self.rank, self.world, self.device = rank, world, device
+        self._own, self._opened = own, []
+        ptrs = []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(own)
+                continue
+            p = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(bytes(handles[r]))
+            _capi.check(L.f16_peer_open(buf, C.byref(p)))
+            self._opened.append(p.value)
+            ptrs.append(p.value)
+        self.bufs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.seq = torch.zeros(L.f16_peer_seq_words(), dtype=torch.int32, device=device)
+        self.group = _capi.PeerGroup(rank, world, self.bufs.data_ptr(), self.seq.data_ptr())
+
+    @classmethod
+    def create(cls, rank, world, device, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _capi
+
+        L = _capi.load_library()
+        ok, own, handle = 1, None, (C.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            try:
+                p = C.c_void_p()
+                _capi.check(L.f16_peer_alloc(L.f16_peer_buffer_bytes(world), C.byref(p), handle))
+                own = p.value
+            except Exception:
+                ok = 0
+            on_gpu = dist.get_backend(group) == "nccl"
+            dev = device if on_gpu else "cpu"
+            mine = torch.tensor(list(bytes(handle)) + [ok], dtype=torch.uint8, device=dev)
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine, group=group)
+            rows = [x.cpu().numpy() for x in parts]
+            self = None
+            if all(int(r[64]) == 1 for r in rows):
+                try:
+                    self = cls(rank, world, device, own, [r[:64].tobytes() for r in rows])
+                except Exception:
+                    self = None
+            # every rank must agree: one failed mapping sends everybody back to NCCL
+            flag = torch.tensor([1 if self is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                if self is not None:
+                    self.close()
+                elif own is not None:
+                    L.f16_peer_free(own)
+                return None
+            return self
+
+    def close(self):
+        from . import _capi
+
+        L = _capi.load_library()
+        import torch
+
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for p in self._opened:
+                L.f16_peer_close(p)
+            self._opened = []
+            if self._own is not None:
+                L.f16_peer_free(self._own)
+                self._own = None

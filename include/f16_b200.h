@@ -287,6 +287,34 @@ int f16_ppo_grad16(int64_t n, const void *train_blob16, const void *obs, const v
                    const void *adv_stats, void *grad, double clip_coef, double vf_coef, double ent_coef, int norm_adv,
                    int clip_vloss, void *scratch, void *stream);
 
+/* f16_ppo_grad16 fused with the trainer's only collective, the gradient all-reduce over the ranks of one node
+ * (torch DistributedDataParallel's role around ppo_model_gsde.py:360-364; NCCL needs 20-29 us per call for this 37 KB message):
+ * the reduction kernel that sums the CTAs' private gradients also exchanges them through NVLink / NVSwitch PEER MEMORY -- every
+ * rank pushes its 32-element slices as (value, call number) 8-byte words into all ranks' exchange buffers (the payload carries its
+ * own flag: no fence, no round trip), polls its own buffer until every rank's words show the current call and adds the rows in
+ * rank order (bit-identical results on every rank) -- and leaves the MEAN over the ranks in grad.  No NCCL call, no extra launch;
+ * replayable from a CUDA graph (the call counters live in peer->seq).
+ * Setup, once: every rank f16_peer_alloc()s an exchange buffer of f16_peer_buffer_bytes(world) bytes (zeroed), the 64-byte IPC
+ * handles are exchanged by any means (torch.distributed.all_gather), every rank f16_peer_open()s the others' handles, uploads the
+ * `world` pointers (own buffer at [rank]) as a device array, zeroes f16_peer_seq_words() uint32 counters, and all ranks meet at a
+ * barrier before the first call.  Every rank must make the same sequence of calls.  A rank that never arrives traps the waiting
+ * kernel after ~10 s instead of hanging the device. */
+typedef struct f16_peer_group {
+    int32_t rank, world;   /* 1 <= world <= 32, ranks of ONE node (peer access between their devices) */
+    void *const *bufs;     /* DEVICE array void*[world]: rank r's exchange buffer as mapped into this process */
+    uint32_t *seq;         /* DEVICE uint32[f16_peer_seq_words()], zeroed once */
+} f16_peer_group;
+int64_t f16_peer_buffer_bytes(int world);
+int f16_peer_seq_words(void);
+int f16_peer_alloc(int64_t bytes, void **ptr, void *ipc_handle /* 64 bytes out */);
+int f16_peer_open(const void *ipc_handle /* 64 bytes */, void **ptr);
+int f16_peer_close(void *ptr);
+int f16_peer_free(void *ptr);
+int f16_ppo_grad16_peer(int64_t n, const void *train_blob16, const void *obs, const void *actions, const void *logprobs,
+                        const void *adv, const void *ret, const void *val, const int64_t *mb_idx, const void *logstd,
+                        const void *adv_stats, void *grad, double clip_coef, double vf_coef, double ent_coef, int norm_adv,
+                        int clip_vloss, void *scratch, const f16_peer_group *peer, void *stream);
+
 /* The optimiser half of the minibatch step (ppo_model_gsde.py:360-364: clip_grad_norm_(max_grad_norm) then
  * Adam(amsgrad=True).step()) on the flat parameter vector (same field order as the gradient of f16_ppo_grad), followed
  * by re-packing the rollout blob and the training blob from the updated parameters: blob word k = param[perm[k] - 1],

@@ -70,12 +70,57 @@ def _worker(rank, world, port, out):
         res["grad_rel_err"] = rel
         res["stats_rel_err"] = ((mine[n_par:] - whole[n_par:]).abs() / (whole[n_par:].abs() + 1.0)).max().item()   # the five sums add up
 
+        # (1b) the same all-reduce fused into the gradient-reduction kernel over peer memory (f16_ppo_grad16_peer): the MEAN over the
+        # ranks, bit-identical on both ranks and equal to the NCCL result; eager calls and CUDA-graph replays (slot reuse, counters)
+        import ctypes as C
+
+        from f16_model_b200.sharding import PeerExchange
+
+        px = PeerExchange.create(rank, world, dev)
+        res["peer_mapped"] = px is not None
+        if px is not None:
+            idx = mb[rank * half:(rank + 1) * half].contiguous()
+            gp = torch.empty(L.f16_ppo_grad_floats(), device=dev)
+
+            def grad_peer():
+                _capi.check(L.f16_ppo_grad16_peer(idx.numel(), blob.data_ptr(), obs.data_ptr(), actions.data_ptr(), logprobs.data_ptr(),
+                                                  adv.data_ptr(), ret.data_ptr(), val.data_ptr(), idx.data_ptr(), pol.actor_logstd.data_ptr(),
+                                                  stats.data_ptr(), gp.data_ptr(), 0.2, 0.5, 0.01, 1, 1, scratch.data_ptr(), C.byref(px.group),
+                                                  _capi.stream_ptr(dev)))
+
+            errs = []
+            for _ in range(5):
+                gp.fill_(7.0)
+                grad_peer()
+                errs.append(((gp - mine / world).abs() / (mine.abs() / world + 1e-6)).max().item())
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                grad_peer()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for _ in range(3):
+                    grad_peer()
+            for _ in range(4):
+                gp.fill_(7.0)
+                gr.replay()
+                errs.append(((gp - mine / world).abs() / (mine.abs() / world + 1e-6)).max().item())
+            res["peer_rel_err"] = max(errs)
+            other = gp.clone()
+            dist.broadcast(other, 0)
+            res["peer_ranks_equal"] = bool(torch.equal(other, gp))
+            res["peer_calls"] = int(px.seq.min().item())
+            torch.cuda.synchronize(dev)
+            px.close()
+
         # (2) the trainer: two updates with the all-reduce inside the update graph and a KL early stop; parameters stay identical
         envs = make_sharded_env(CFG, 8192 * world, rank, world, dev, seed=1, fast_math=True)
         pol2 = f16.TensorCorePolicy(device=dev, seed=1, logstd_init=-1.0, env_id_base=shard_range(8192 * world, rank, world)[0])
         tr = f16.PPOTrainer(envs, pol2, f16.PPOConfig(num_steps=32, num_minibatches=8, update_epochs=4, learning_rate=1e-3, target_kl=0.02))
         hist = tr.train(num_updates=3)
         res["graph"] = bool(tr._update_graph)
+        res["trainer_peer"] = tr._peer is not None
         flat = torch.cat([p.detach().reshape(-1) for p in pol2.parameters()])
         ref = flat.clone()
         dist.broadcast(ref, 0)
@@ -87,6 +132,16 @@ def _worker(rank, world, port, out):
         dist.all_gather(both, r0)
         res["different_shards"] = bool(both[0].item() != both[1].item())
         tr.close()
+        # the same training with the NCCL all-reduce: same parameters up to the order of the fp32 atomics inside each rank's kernel
+        envs_n = make_sharded_env(CFG, 8192 * world, rank, world, dev, seed=1, fast_math=True)
+        pol_n = f16.TensorCorePolicy(device=dev, seed=1, logstd_init=-1.0, env_id_base=shard_range(8192 * world, rank, world)[0])
+        tr_n = f16.PPOTrainer(envs_n, pol_n, f16.PPOConfig(num_steps=32, num_minibatches=8, update_epochs=4, learning_rate=1e-3, target_kl=0.02,
+                                                           peer_allreduce=False))
+        tr_n.train(num_updates=3)
+        flat_n = torch.cat([p.detach().reshape(-1) for p in pol_n.parameters()])
+        res["nccl_trainer_peer"] = tr_n._peer is not None
+        res["peer_vs_nccl_params"] = ((flat_n - flat).norm() / flat.norm()).item()
+        tr_n.close()
         dist.destroy_process_group()
         out.put((rank, res))
     except Exception as exc:   # surface the failure instead of a silent timeout
@@ -105,7 +160,7 @@ def test_two_rank_ppo_gradient_allreduce():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
-    results = dict(out.get(timeout=240) for _ in procs)
+    results = dict(out.get(timeout=300) for _ in procs)
     for p in procs:
         p.join(timeout=60)
     for r in (0, 1):
@@ -114,3 +169,6 @@ def test_two_rank_ppo_gradient_allreduce():
         assert res["grad_rel_err"] < 1e-4, res           # fp32 sums in a different order
         assert res["stats_rel_err"] < 1e-4, res
         assert res["graph"] and res["params_equal"] and res["finite"] and res["different_shards"], res
+        assert res["peer_mapped"] and res["trainer_peer"] and not res["nccl_trainer_peer"], res    # NVLink peer mapping works on a B200 box
+        assert res["peer_rel_err"] < 1e-6 and res["peer_ranks_equal"] and res["peer_calls"] == 5 + 1 + 4 * 3, res
+        assert res["peer_vs_nccl_params"] < 1e-3, res

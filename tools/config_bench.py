@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--envs", type=int, default=65536)
     ap.add_argument("--num-steps", type=int, default=128)
     ap.add_argument("--tf32-update", type=int, default=0)
+    ap.add_argument("--peer", type=int, default=1, help="0: NCCL gradient all-reduce instead of the peer-memory one fused into the reduction kernel")
+    ap.add_argument("--only-ppo", action="store_true")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -40,7 +42,7 @@ def main():
     # ---- config 4 -------------------------------------------------------------------------
     envs = make_sharded_env(CFG, args.envs * world, rank, world, dev, seed=1, fast_math=True)
     pol = f16.TensorCorePolicy(device=dev, seed=1, logstd_init=-1.0, env_id_base=shard_range(args.envs * world, rank, world)[0])
-    cfg = f16.PPOConfig(num_steps=args.num_steps, num_minibatches=32, update_epochs=4, tf32_update=bool(args.tf32_update))
+    cfg = f16.PPOConfig(num_steps=args.num_steps, num_minibatches=32, update_epochs=4, tf32_update=bool(args.tf32_update), peer_allreduce=bool(args.peer))
     tr = f16.PPOTrainer(envs, pol, cfg)
     hist = tr.train(num_updates=args.updates)
     # the gradient all-reduce on its own: 128 eager NCCL calls on the 37 KB flat gradient, as the update issues them
@@ -72,12 +74,18 @@ def main():
                           "rollout_env_steps_per_s": h["rollout_sps"] * world, "rollout_s": h["rollout_s"], "update_s": h["update_s"],
                           "minibatches_per_update": cfg.num_minibatches * cfg.update_epochs, "value_loss": h["value_loss"],
                           "approx_kl": h["approx_kl"],
-                          "grad_allreduce": ("nccl, captured in the update graph" if tr._update_graph else "nccl, eager") if world > 1 else None,
+                          "grad_allreduce": (("peer memory (NVLink), fused into ppo_grad_reduce_peer_kernel" if tr._peer is not None else "nccl")
+                                             + (", captured in the update graph" if tr._update_graph else ", eager")) if world > 1 else None,
+                          "update_s_all": [round(x["update_s"], 6) for x in hist],
                           "nccl_allreduce_us_per_call_37KB": allreduce_us,
                           "allreduce_share_of_update": (allreduce_us * cfg.num_minibatches * cfg.update_epochs * 1e-6 / h["update_s"]) if allreduce_us else None,
                           "parameters_identical_on_all_ranks": same}), flush=True)
 
     tr.close()                                  # the update graph holds NCCL work: release it before the process group goes away
+    if args.only_ppo:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
     # policy forward alone (tensor-core kernel): CUDA events around replays of a graph of 20 launches (an eager Python
     # loop is bound by the interpreter + ctypes call, ~20 us per launch, not by the kernel)
     obs = torch.rand((args.envs, 5), device=dev) * 2 - 1
