@@ -1476,7 +1476,32 @@ __global__ void __launch_bounds__(256) gae_kernel(int T, int64_t n, const float 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float nextvalues = next_value[i];
         float lastgaelam = 0.f;
-        for (int t = T - 1; t >= 0; --t) {
+        // the scan is serial in t but its loads are not: eight steps' rows are requested together (24 independent loads in flight per
+        // thread: with one thread per env -- 65,536 in config 4 -- the kernel is bound by memory latency, not by the dependent FMAs)
+        constexpr int U = 8;
+        int t = T - 1;
+        for (; t >= U - 1; t -= U) {
+            float r[U], v[U];
+            uint8_t d[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t k = (int64_t)(t - u) * n + i;
+                r[u] = __ldg(rewards + k);
+                v[u] = __ldg(values + k);
+                d[u] = __ldg(done_after + k);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t k = (int64_t)(t - u) * n + i;
+                const float nextnonterminal = d[u] ? 0.f : 1.f;
+                const float delta = r[u] + gamma * nextvalues * nextnonterminal - v[u];
+                lastgaelam = delta + gamma * lam * nextnonterminal * lastgaelam;
+                advantages[k] = lastgaelam;
+                returns[k] = lastgaelam + v[u];
+                nextvalues = v[u];
+            }
+        }
+        for (; t >= 0; --t) {
             const int64_t k = (int64_t)t * n + i;
             const float nextnonterminal = done_after[k] ? 0.f : 1.f;
             const float v = values[k];
