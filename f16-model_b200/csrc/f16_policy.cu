@@ -775,14 +775,6 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
     // programmatic dependent launch: everything above overlapped the previous kernel's tail; the weights, log-std and
     // statistics read below are that kernel's (the optimiser's) output
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (t == 0) {
-        constexpr uint32_t bytes = static_cast<uint32_t>(sizeof(TrainBlob16));
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->bar_w)), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&sm->w)),
-                     "l"(blob16), "r"(bytes), "r"(smem_u32(&sm->bar_w))
-                     : "memory");
-    }
 
     const TrainBlob16 &W = sm->w;
     constexpr uint32_t id_l1 = umma_idesc_f16(128, 128, false), id_l2 = umma_idesc_f16(128, 64, false);
@@ -794,9 +786,6 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
     const unsigned n = static_cast<unsigned>(P.n);
     const unsigned n_tiles = (n + kRows - 1) / kRows;
     const float n_f = static_cast<float>(n), inv_n = 1.0f / n_f;
-    const float log_std = P.logstd[0], inv_std = __expf(-log_std);
-    const float adv_mean = P.norm_adv ? P.adv_stats[0] : 0.f;
-    const float adv_scale = P.norm_adv ? 1.0f / (P.adv_stats[1] + 1e-8f) : 1.f;
     const float eps = P.clip_coef;
 
     // dW3: per tile the 64 products dy * H2[row][c] of a thread are summed over the warp's 32 rows by a shuffle butterfly that halves
@@ -851,6 +840,26 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
         *reinterpret_cast<float4 *>(dst + 4) = make_float4(g.v[4], g.v[5], g.v[6], g.v[7]);
     };
     auto row_live = [&](unsigned tile_) { return tile_ < n_tiles && tile_ * kRows + row < n; };
+
+    // The first two pairs' gathers (index, then row: two dependent DRAM round trips) are requested BEFORE the grid dependency resolves:
+    // the minibatch indices and the packed rows are written once per epoch / update by plain (fully ordered) launches, never by the
+    // optimiser kernel this launch is chained to with PDL, whose single CTA leaves the other SMs idle for its ~14 us anyway.
+    park_row(sm->stage[0][0][t], load_row(load_index(blockIdx.x)));
+    park_row(sm->stage[0][1][t], load_row(load_index(blockIdx.x + gridDim.x)));
+    sm->next_idx[0][t] = load_index(blockIdx.x + 2 * gridDim.x);
+    sm->next_idx[1][t] = load_index(blockIdx.x + 3 * gridDim.x);
+    // the weights, log-std and advantage statistics are the previous kernels' (optimiser / adv_stats) output
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (t == 0) {
+        constexpr uint32_t bytes = static_cast<uint32_t>(sizeof(TrainBlob16));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->bar_w)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&sm->w)),
+                     "l"(blob16), "r"(bytes), "r"(smem_u32(&sm->bar_w))
+                     : "memory");
+    }
+    const float log_std = P.logstd[0], inv_std = __expf(-log_std);
+    const float adv_mean = P.norm_adv ? P.adv_stats[0] : 0.f;
+    const float adv_scale = P.norm_adv ? 1.0f / (P.adv_stats[1] + 1e-8f) : 1.f;
 
     // ---- the four stages of a tile; `s` is the slot (0 / 1): shared-memory buffers, accumulator columns and mbarrier of that slot ----
     // Every stage ends by handing a batch of MMAs to the tensor core; the wait for them opens the tile's NEXT stage, which runs after a
@@ -1072,10 +1081,6 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
 
     // a CTA's tiles: blockIdx.x + j gridDim.x, taken two at a time (slot = j & 1); a missing second tile runs as 128 dead rows (zero gradient)
     const unsigned stride = gridDim.x;
-    park_row(sm->stage[0][0][t], load_row(load_index(blockIdx.x)));
-    park_row(sm->stage[0][1][t], load_row(load_index(blockIdx.x + stride)));
-    sm->next_idx[0][t] = load_index(blockIdx.x + 2 * stride);
-    sm->next_idx[1][t] = load_index(blockIdx.x + 3 * stride);
     mbar_wait(&sm->bar_w, 0);
     int tile_no = 0;
     for (unsigned tile = blockIdx.x; tile < n_tiles; tile += 2 * stride) {
@@ -1301,13 +1306,23 @@ __global__ void __launch_bounds__(256) ppo_grad_reduce_peer_kernel(const float *
 // then both weight blobs are re-packed from the updated parameters: what torch runs as ~60 launches per minibatch.
 constexpr int kAdamMaxParams = 10240;   // updated parameters are staged in shared memory for the blob gathers (40 KB)
 
-__global__ void __launch_bounds__(1024) ppo_adam_kernel(const PpoAdamArgs A)
+// The gather permutations are constants of the training run: with cache_perms they are staged in shared memory as 16-bit indices BEFORE
+// the grid dependency resolves (i.e. under the tail of the gradient reduction this launch is chained to), so that the re-packing after the
+// optimiser step is a shared-memory gather instead of ~45 k dependent 8-byte loads from L2 by one SM (it was half of the kernel's 14 us).
+__global__ void __launch_bounds__(1024) ppo_adam_kernel(const PpoAdamArgs A, const int cache_perms)
 {
     __shared__ float warp_sum[32];
     __shared__ float s_coef;
-    __shared__ float s_param[kAdamMaxParams];
+    extern __shared__ __align__(16) unsigned char adam_smem[];
+    float *s_param = reinterpret_cast<float *>(adam_smem);                                  // [kAdamMaxParams]
+    uint16_t *s_perm = reinterpret_cast<uint16_t *>(adam_smem + kAdamMaxParams * sizeof(float));   // fwd | train | half, when cache_perms
     const unsigned t = threadIdx.x;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (cache_perms) {
+        for (int k = t; k < A.n_fwd; k += 1024) s_perm[k] = static_cast<uint16_t>(A.fwd_perm[k]);
+        for (int k = t; k < A.n_train; k += 1024) s_perm[A.n_fwd + k] = static_cast<uint16_t>(A.train_perm[k]);
+        for (int k = t; k < A.n_half; k += 1024) s_perm[A.n_fwd + A.n_train + k] = static_cast<uint16_t>(A.half_perm[k]);
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     float ss = 0.f;
     for (int i = t; i < A.n; i += 1024) {
@@ -1370,13 +1385,13 @@ __global__ void __launch_bounds__(1024) ppo_adam_kernel(const PpoAdamArgs A)
     __syncthreads();   // the CTA's own writes (shared and global) are visible to it after the barrier
     if (t == 0) A.step[0] = step;
     const float *src = staged ? s_param : A.param;
-    auto repack = [&](const int64_t *perm, float *blob, int count) {
+    auto repack = [&](const int64_t *perm, const uint16_t *cached, float *blob, int count) {
         for (int k0 = t; k0 < count; k0 += 8 * 1024) {
             int q[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int k = k0 + u * 1024;
-                q[u] = k < count ? static_cast<int>(perm[k]) : -1;
+                q[u] = k < count ? (cache_perms ? static_cast<int>(cached[k]) : static_cast<int>(perm[k])) : -1;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -1385,19 +1400,31 @@ __global__ void __launch_bounds__(1024) ppo_adam_kernel(const PpoAdamArgs A)
             }
         }
     };
-    repack(A.fwd_perm, A.fwd_blob, A.n_fwd);
-    repack(A.train_perm, A.train_blob, A.n_train);
-    for (int k0 = t; k0 < A.n_half; k0 += 8 * 1024) {
-        int q[8];
+    repack(A.fwd_perm, s_perm, A.fwd_blob, A.n_fwd);
+    repack(A.train_perm, s_perm + A.n_fwd, A.train_blob, A.n_train);
+    {
+        const uint16_t *cached = s_perm + A.n_fwd + A.n_train;
+        __half2 *dst2 = reinterpret_cast<__half2 *>(A.half_blob);
+        if (cache_perms && (A.n_half & 1) == 0 && (reinterpret_cast<uintptr_t>(A.half_blob) & 3u) == 0) {
+            // two fp16 words per store
+            for (int k = t; k < A.n_half / 2; k += 1024) {
+                const int q0 = cached[2 * k], q1 = cached[2 * k + 1];
+                dst2[k] = __floats2half2_rn(q0 ? src[q0 - 1] : 0.f, q1 ? src[q1 - 1] : 0.f);
+            }
+        } else {
+            for (int k0 = t; k0 < A.n_half; k0 += 8 * 1024) {
+                int q[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int k = k0 + u * 1024;
-            q[u] = k < A.n_half ? static_cast<int>(A.half_perm[k]) : -1;
-        }
+                for (int u = 0; u < 8; ++u) {
+                    const int k = k0 + u * 1024;
+                    q[u] = k < A.n_half ? (cache_perms ? static_cast<int>(cached[k]) : static_cast<int>(A.half_perm[k])) : -1;
+                }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int k = k0 + u * 1024;
-            if (q[u] >= 0) A.half_blob[k] = __float2half_rn(q[u] ? src[q[u] - 1] : 0.f);
+                for (int u = 0; u < 8; ++u) {
+                    const int k = k0 + u * 1024;
+                    if (q[u] >= 0) A.half_blob[k] = __float2half_rn(q[u] ? src[q[u] - 1] : 0.f);
+                }
+            }
         }
     }
     if (A.diag && t == 0) {
@@ -1564,7 +1591,20 @@ cudaError_t launch_ppo_adam(const PpoAdamArgs &A, cudaStream_t st)
     lc.stream = st;
     lc.attrs = attr;
     lc.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&lc, ppo_adam_kernel, A);
+    // shared memory: the updated parameters (40 KB) + the three gather permutations as 16-bit indices, when they fit
+    const size_t n_perm = static_cast<size_t>(A.n_fwd) + static_cast<size_t>(A.n_train) + static_cast<size_t>(A.n_half);
+    const size_t base = kAdamMaxParams * sizeof(float);
+    const int cache = (A.n < 65535 && base + n_perm * 2 <= 200 * 1024) ? 1 : 0;
+    lc.dynamicSmemBytes = base + (cache ? (n_perm * 2 + 15) / 16 * 16 : 0);
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e0 = cudaFuncSetAttribute(ppo_adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16);
+        if (e0 != cudaSuccess) return e0;
+        configured[dev] = true;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&lc, ppo_adam_kernel, A, cache);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

@@ -267,6 +267,9 @@ int f16_ppo_grad(int64_t n, const void *train_blob, const void *obs, const void 
                  int clip_vloss, void *stream);
 /* Same computation with fp16 tensor-core operands (the 11 significant bits of TF32) and the weight gradients on the
  * tensor cores as well; train_blob16 (f16_ppo_train_blob16_bytes) = W1, W2, W2^T in fp16, then the fp32 biases / heads.
+ * mb_idx and the gathered row arrays are requested BEFORE the launch's grid dependency resolves (the launch is chained to the
+ * optimiser kernel with programmatic dependent launch): they must come from plain, fully ordered launches (any torch kernel,
+ * f16_ppo_randperm, f16_ppo_pack_rows), not from a kernel that releases its programmatic dependents early.
  * scratch: optional f16_ppo_grad16_scratch_floats(device) floats.  With it every CTA stores a private gradient and a second
  * small kernel sums them into grad, which is then OVERWRITTEN (no zeroing needed); without it grad is accumulated with atomics. */
 /* The minibatch permutation of an epoch (np.random.permutation(batch) in Agent.train, control/ppo/ppo_model_gsde.py:296-300) without
