@@ -21,7 +21,7 @@ ABI_VERSION = 2
 
 EXPORTS = ["f16_abi_version", "f16_last_error", "f16_init", "f16_launch_geometry", "f16_peak_probe", "f16_env_reset", "f16_env_step",
            "f16_env_step_host", "f16_host_route", "f16_rhs", "f16_model_step", "f16_coeffs", "f16_thrust", "f16_atmosphere",
-           "f16_policy_blob_bytes", "f16_policy_forward", "f16_policy_forward16", "f16_rollout", "f16_ppo_adv_stats", "f16_ppo_train_blob_bytes", "f16_ppo_grad_floats", "f16_ppo_grad", "f16_ppo_train_blob16_bytes", "f16_ppo_grad16_scratch_floats", "f16_ppo_grad16", "f16_ppo_grad16_peer", "f16_peer_buffer_bytes", "f16_peer_seq_words", "f16_peer_alloc", "f16_peer_open", "f16_peer_close", "f16_peer_free", "f16_ppo_pack_rows", "f16_ppo_randperm", "f16_ppo_adam",
+           "f16_policy_blob_bytes", "f16_policy_forward", "f16_policy_forward16", "f16_rollout", "f16_ppo_adv_stats", "f16_ppo_train_blob_bytes", "f16_ppo_grad_floats", "f16_ppo_grad", "f16_ppo_train_blob16_bytes", "f16_ppo_grad16_scratch_floats", "f16_ppo_grad16", "f16_ppo_grad16_peer", "f16_ppo_step16", "f16_ppo_step16_sync_bytes", "f16_peer_buffer_bytes", "f16_peer_seq_words", "f16_peer_alloc", "f16_peer_open", "f16_peer_close", "f16_peer_free", "f16_ppo_pack_rows", "f16_ppo_randperm", "f16_ppo_adam",
            "f16_gae", "f16_trim"]
 
 
@@ -51,6 +51,18 @@ class StepIO(C.Structure):
 
 class PeerGroup(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("bufs", C.c_void_p), ("seq", C.c_void_p)]
+
+
+class PpoStep16(C.Structure):
+    """f16_ppo_step16_args (include/f16_b200.h): gradient kernel + fused reduction / all-reduce / clip / Adam / blob scatter."""
+    _fields_ = [("n", C.c_int64), ("train_blob16", C.c_void_p), ("obs", C.c_void_p), ("actions", C.c_void_p), ("logprobs", C.c_void_p),
+                ("adv", C.c_void_p), ("ret", C.c_void_p), ("val", C.c_void_p), ("mb_idx", C.c_void_p), ("logstd", C.c_void_p),
+                ("adv_stats", C.c_void_p), ("grad", C.c_void_p), ("clip_coef", C.c_double), ("vf_coef", C.c_double), ("ent_coef", C.c_double),
+                ("norm_adv", C.c_int32), ("clip_vloss", C.c_int32), ("scratch", C.c_void_p), ("peer", C.POINTER(PeerGroup)),
+                ("n_params", C.c_int32), ("reserved", C.c_int32), ("param", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("max_exp_avg_sq", C.c_void_p), ("step", C.c_void_p), ("lr", C.c_void_p), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("max_grad_norm", C.c_double), ("scatter", C.c_void_p), ("fwd_blob", C.c_void_p), ("tail_blob", C.c_void_p),
+                ("half_blob", C.c_void_p), ("diag", C.c_void_p), ("inv_rows", C.c_double), ("sync", C.c_void_p)]
 
 
 class RolloutIO(C.Structure):
@@ -112,6 +124,8 @@ def load_library():
     L.f16_ppo_grad16.argtypes = L.f16_ppo_grad.argtypes[:-1] + [vp, vp]
     L.f16_ppo_grad16_scratch_floats.argtypes = [i32]
     L.f16_ppo_grad16_peer.argtypes = L.f16_ppo_grad.argtypes[:-1] + [vp, C.POINTER(PeerGroup), vp]
+    L.f16_ppo_step16.argtypes = [C.POINTER(PpoStep16), vp]
+    L.f16_ppo_step16_sync_bytes.argtypes = []
     L.f16_peer_buffer_bytes.argtypes = [i32]
     L.f16_peer_seq_words.argtypes = []
     L.f16_peer_alloc.argtypes = [i64, C.POINTER(C.c_void_p), vp]

@@ -842,6 +842,82 @@ int f16_ppo_grad16_peer(int64_t n, const void *train_blob16, const void *obs, co
                          ent_coef, norm_adv, clip_vloss, stream);
 }
 
+int f16_ppo_step16_sync_bytes(void) { return static_cast<int>((f16::ppo_step16_sync_bytes() + 15) / 16 * 16); }
+
+int f16_ppo_step16(const f16_ppo_step16_args *a, void *stream)
+{
+    if (!a) return fail(F16_EINVAL, "args is NULL");
+    DeviceCtx *c;
+    f16::LaunchGeom g;
+    int rc = prep(a->n, &c, &g);
+    if (rc) return rc;
+    const bool packed = !a->actions;
+    if (!a->train_blob16 || !a->obs || !a->ret || !a->mb_idx || !a->logstd || !a->grad || !a->scratch ||
+        (!packed && (!a->actions || !a->logprobs || !a->adv || !a->val)))
+        return fail(F16_EINVAL, "NULL pointer");
+    if (packed && (reinterpret_cast<uintptr_t>(a->obs) % 32 != 0 || reinterpret_cast<uintptr_t>(a->ret) % 8 != 0))
+        return fail(F16_EINVAL, "packed rows must be 32-byte aligned, (ret, val) pairs 8-byte aligned");
+    if (a->norm_adv && !a->adv_stats) return fail(F16_EINVAL, "norm_adv needs adv_stats");
+    if (reinterpret_cast<uintptr_t>(a->train_blob16) % 16 != 0) return fail(F16_EINVAL, "train_blob16 must be 16-byte aligned");
+    if (a->n_params != f16_ppo_grad_floats() - 5) return fail(F16_EINVAL, "n_params must be f16_ppo_grad_floats() - 5");
+    if (!a->param || !a->exp_avg || !a->exp_avg_sq || !a->max_exp_avg_sq || !a->step || !a->lr || !a->scatter || !a->fwd_blob || !a->tail_blob ||
+        !a->half_blob || !a->sync)
+        return fail(F16_EINVAL, "NULL pointer (optimiser state, scatter table, blobs or sync)");
+    if (reinterpret_cast<uintptr_t>(a->scatter) % 16 != 0 || reinterpret_cast<uintptr_t>(a->sync) % 8 != 0)
+        return fail(F16_EINVAL, "scatter must be 16-byte aligned, sync 8-byte aligned");
+    f16::PpoGradArgs P;
+    P.blob = nullptr;
+    P.obs = static_cast<const float *>(a->obs);
+    P.actions = static_cast<const float *>(a->actions);
+    P.logprobs = static_cast<const float *>(a->logprobs);
+    P.adv = static_cast<const float *>(a->adv);
+    P.ret = static_cast<const float *>(a->ret);
+    P.val = static_cast<const float *>(a->val);
+    P.mb_idx = a->mb_idx;
+    P.logstd = static_cast<const float *>(a->logstd);
+    P.adv_stats = static_cast<const float *>(a->adv_stats);
+    P.grad = static_cast<f16::PolicyGrad *>(a->grad);
+    P.n = a->n;
+    P.clip_coef = static_cast<float>(a->clip_coef);
+    P.vf_coef = static_cast<float>(a->vf_coef);
+    P.ent_coef = static_cast<float>(a->ent_coef);
+    P.norm_adv = a->norm_adv;
+    P.clip_vloss = a->clip_vloss;
+    P.packed = packed ? 1 : 0;
+    f16::ReduceAdamArgs R;
+    std::memset(&R, 0, sizeof R);
+    if (a->peer) {
+        const f16_peer_group *peer = a->peer;
+        if (peer->world < 1 || peer->world > 32 || peer->rank < 0 || peer->rank >= peer->world || !peer->bufs || !peer->seq)
+            return fail(F16_EINVAL, "bad f16_peer_group (1 <= world <= 32, 0 <= rank < world, bufs and seq set)");
+        R.bufs = reinterpret_cast<uint2 *const *>(peer->bufs);
+        R.seq = peer->seq;
+        R.rank = peer->rank;
+        R.world = peer->world;
+    }
+    R.n = a->n_params;
+    R.param = static_cast<float *>(a->param);
+    R.exp_avg = static_cast<float *>(a->exp_avg);
+    R.exp_avg_sq = static_cast<float *>(a->exp_avg_sq);
+    R.max_exp_avg_sq = static_cast<float *>(a->max_exp_avg_sq);
+    R.step = static_cast<float *>(a->step);
+    R.lr = static_cast<const float *>(a->lr);
+    R.beta1 = static_cast<float>(a->beta1);
+    R.beta2 = static_cast<float>(a->beta2);
+    R.eps = static_cast<float>(a->eps);
+    R.max_grad_norm = static_cast<float>(a->max_grad_norm);
+    R.scatter = a->scatter;
+    R.fwd_blob = static_cast<float *>(a->fwd_blob);
+    R.tail_blob = static_cast<float *>(a->tail_blob);
+    R.half_blob = static_cast<__half *>(a->half_blob);
+    R.diag = static_cast<float *>(a->diag);
+    R.inv_rows = static_cast<float>(a->inv_rows);
+    R.sync = static_cast<unsigned char *>(a->sync);
+    CUDA_TRY(f16::launch_ppo_step16(P, static_cast<const f16::TrainBlob16 *>(a->train_blob16), static_cast<float *>(a->scratch), R, c->n_sm,
+                                    static_cast<cudaStream_t>(stream)));
+    return F16_OK;
+}
+
 // ---- exchange buffers in peer memory (CUDA IPC; the ranks of one node) ----
 int64_t f16_peer_buffer_bytes(int world)
 {

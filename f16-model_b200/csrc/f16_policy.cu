@@ -774,8 +774,6 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
     const uint32_t tmem = sm->tmem_base;
     // programmatic dependent launch: everything above overlapped the previous kernel's tail; the weights, log-std and
     // statistics read below are that kernel's (the optimiser's) output
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
     const TrainBlob16 &W = sm->w;
     constexpr uint32_t id_l1 = umma_idesc_f16(128, 128, false), id_l2 = umma_idesc_f16(128, 64, false);
     constexpr uint32_t id_w2 = umma_idesc_f16(128, 128, true), id_w1 = umma_idesc_f16(128, 16, true);
@@ -850,6 +848,9 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
     sm->next_idx[1][t] = load_index(blockIdx.x + 3 * gridDim.x);
     // the weights, log-std and advantage statistics are the previous kernels' (optimiser / adv_stats) output
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // dependents are released only now: whatever the next kernel does ahead of ITS wait then runs after everything older than this
+    // kernel has completed (ppo_reduce_adam_kernel pre-loads the optimiser state its previous call wrote)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (t == 0) {
         constexpr uint32_t bytes = static_cast<uint32_t>(sizeof(TrainBlob16));
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->bar_w)), "r"(bytes) : "memory");
@@ -1302,6 +1303,146 @@ __global__ void __launch_bounds__(256) ppo_grad_reduce_peer_kernel(const float *
     if (lane == 0) seq[blockIdx.x] = call;
 }
 
+// ---------------------------------------------------------------------------
+// ppo_reduce_adam_kernel: the gradient reduction (and, with PEER, the cross-rank exchange above) FUSED with the optimiser step --
+// clip_grad_norm_ + Adam(amsgrad) + re-packing of the weight blobs -- in one multi-CTA launch.  The single-CTA ppo_adam_kernel is a chain
+// of dependent latencies (gradient loads, CTA-wide norm, state loads, ~45 k gathered blob words: 13 us) behind a launch of its own; here
+// every CTA owns 32 parameters end to end: it reduces their gradients, contributes its partial sum of squares, meets the other CTAs at ONE
+// grid-wide arrival counter (the grid is 289 small CTAs, all resident once the gradient kernel has left), adds the partials in a fixed
+// order (the norm is bit-identical in every CTA and on every rank), updates its parameters and Adam state (loaded BEFORE the grid
+// dependency resolved), and SCATTERS each new parameter to its <= 4 places in the blobs through an inverse table instead of gathering.
+// ---------------------------------------------------------------------------
+template <bool PEER>
+__global__ void __launch_bounds__(256) ppo_reduce_adam_kernel(const ReduceAdamArgs A)
+{
+    __shared__ float part[8][32];
+    const unsigned lane = threadIdx.x & 31u, g = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + lane;
+    const bool is_param = p < A.n;
+    // ---- before the grid dependency resolves: this slice's optimiser state and scatter table (written by the PREVIOUS call of this kernel,
+    // which had completed before the gradient kernel in between released this launch: that kernel triggers its dependents after its own wait)
+    float m = 0.f, v = 0.f, vm = 0.f, prm = 0.f;
+    int4 dst = make_int4(-1, -1, -1, -1);
+    if (g == 0 && is_param) {
+        m = A.exp_avg[p];
+        v = A.exp_avg_sq[p];
+        vm = A.max_exp_avg_sq[p];
+        prm = A.param[p];
+        dst = reinterpret_cast<const int4 *>(A.scatter)[p];
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    float s = 0.f;
+    if (p < A.n_out)
+        for (int b = g; b < A.n_rows; b += 8) s += A.partials[static_cast<size_t>(b) * A.n_out + p];
+    part[g][lane] = s;
+    __syncthreads();
+    if (g != 0) return;
+    float grad = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) grad += part[k][lane];
+    uint32_t *calls = reinterpret_cast<uint32_t *>(A.sync + 8 + sizeof(float) * gridDim.x);
+    const uint32_t call = calls[blockIdx.x] + 1u;
+    unsigned long long t0 = 0ull;
+    auto impatient = [&](unsigned spin) {   // a CTA / rank that never arrives must not hang the GPU: fail loudly after ~10 s
+        if ((spin & 1023u) == 1023u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0ull) t0 = now;
+            else if (now - t0 > 10000000000ull) __trap();
+        }
+    };
+    if constexpr (PEER) {   // see ppo_grad_reduce_peer_kernel; the exchange numbers its calls in peer->seq, shared with that kernel
+        const uint32_t call = A.seq[blockIdx.x] + 1u;
+        const size_t slot_at = static_cast<size_t>(call & 1u) * A.world * A.n_pad;
+        const size_t mine = slot_at + static_cast<size_t>(A.rank) * A.n_pad + p;
+        for (int r = 1; r < A.world; ++r) {
+            uint2 *to = A.bufs[(A.rank + r) % A.world] + mine;
+            asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(to), "r"(__float_as_uint(grad)), "r"(call) : "memory");
+        }
+        const uint2 *own = A.bufs[A.rank] + slot_at + p;
+        float sum = 0.f;
+        for (int r = 0; r < A.world; ++r) {
+            float val = grad;
+            if (r != A.rank) {
+                const uint2 *src = own + static_cast<size_t>(r) * A.n_pad;
+                uint32_t bits, flag;
+                for (unsigned spin = 0;; ++spin) {
+                    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(bits), "=r"(flag) : "l"(src) : "memory");
+                    if (flag == call) break;
+                    impatient(spin);
+                }
+                val = __uint_as_float(bits);
+            }
+            sum += val;
+        }
+        grad = sum * (1.0f / static_cast<float>(A.world));
+        __syncwarp();
+        if (lane == 0) A.seq[blockIdx.x] = call;
+    }
+    if (p < A.n_out) A.grad[p] = grad;
+    // ---- clip_grad_norm_: this CTA's share of the squared norm, then the grid-wide meeting ----
+    float sq = is_param ? grad * grad : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    float *sq_all = reinterpret_cast<float *>(A.sync + 8);
+    unsigned long long *arrive = reinterpret_cast<unsigned long long *>(A.sync);
+    const float step = A.step[0] + 1.0f;           // read before arriving: CTA 0 writes the new value after the meeting
+    const float lr = A.lr[0];
+    if (lane == 0) {
+        sq_all[blockIdx.x] = sq;
+        __threadfence();
+        atomicAdd(arrive, 1ull);
+        const unsigned long long want = static_cast<unsigned long long>(call) * gridDim.x;
+        for (unsigned spin = 0;; ++spin) {
+            unsigned long long seen;
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(arrive) : "memory");
+            if (seen >= want) break;
+            impatient(spin);
+        }
+    }
+    __syncwarp();
+    float tot = 0.f;
+    for (unsigned c = lane; c < gridDim.x; c += 32) tot += __ldcg(sq_all + c);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    float coef = A.max_grad_norm / (sqrtf(tot) + 1e-6f);
+    coef = coef < 1.0f ? coef : 1.0f;
+    // ---- Adam(amsgrad), as torch.optim.Adam computes it ----
+    const float bc1 = 1.0f - powf(A.beta1, step), bc2 = 1.0f - powf(A.beta2, step);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    float pn = prm;
+    if (is_param) {
+        const float gc = grad * coef;
+        const float mn = m + (gc - m) * (1.0f - A.beta1);
+        const float vn = v * A.beta2 + (1.0f - A.beta2) * gc * gc;
+        const float vmax = fmaxf(vm, vn);
+        const float denom = sqrtf(vmax) * inv_sqrt_bc2 + A.eps;
+        pn = prm - step_size * (mn / denom);
+        A.exp_avg[p] = mn;
+        A.exp_avg_sq[p] = vn;
+        A.max_exp_avg_sq[p] = vmax;
+        A.param[p] = pn;
+        if (dst.x >= 0) A.fwd_blob[dst.x] = pn;
+        if (dst.y >= 0) A.tail_blob[dst.y] = pn;
+        if (dst.z >= 0) A.half_blob[dst.z] = __float2half_rn(pn);
+        if (dst.w >= 0) A.half_blob[dst.w] = __float2half_rn(pn);
+    }
+    if (A.diag) {   // the five loss statistics sit right behind the parameters, log-std is the last parameter
+        const int k = p - A.n;
+        if (k >= 0 && k < 5) {
+            if (k == 2) A.diag[2] += grad * A.inv_rows;
+            else A.diag[k] = grad * A.inv_rows;
+        }
+        if (p == A.n - 1) A.diag[5] = pn + 1.4189385332046727f;   // Gaussian entropy 0.5 + 0.5 log(2 pi) + log std (after the step)
+    }
+    __syncwarp();
+    if (lane == 0) {
+        calls[blockIdx.x] = call;
+        if (blockIdx.x == 0) A.step[0] = step;
+    }
+}
+
 // torch.nn.utils.clip_grad_norm_ (L2, max_norm) followed by torch.optim.Adam(amsgrad=True) on the flat parameter vector,
 // then both weight blobs are re-packed from the updated parameters: what torch runs as ~60 launches per minibatch.
 constexpr int kAdamMaxParams = 10240;   // updated parameters are staged in shared memory for the blob gathers (40 KB)
@@ -1684,6 +1825,45 @@ cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, f
             e = cudaLaunchKernelEx(&lc, ppo_grad_reduce_kernel, static_cast<const float *>(partials), grid, n_out, reinterpret_cast<float *>(P.grad));
         if (e != cudaSuccess) return e;
     }
+    return cudaGetLastError();
+}
+
+size_t ppo_step16_sync_bytes() { return 8 + static_cast<size_t>(ppo_grad_reduce_ctas()) * (sizeof(float) + sizeof(uint32_t)); }
+
+cudaError_t launch_ppo_step16(const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials, ReduceAdamArgs RA, int n_sm, cudaStream_t st)
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(ppo_grad16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TrainSmem16)));
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int64_t tiles = (P.n + kRows - 1) / kRows;
+    const int grid = static_cast<int>(tiles < n_sm ? tiles : n_sm);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kThreads);
+    lc.dynamicSmemBytes = sizeof(TrainSmem16);
+    lc.stream = st;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&lc, ppo_grad16_kernel, P, blob16, partials);
+    if (e != cudaSuccess) return e;
+    RA.partials = partials;
+    RA.n_rows = grid;
+    RA.n_out = static_cast<int>(sizeof(PolicyGrad) / sizeof(float));
+    RA.grad = reinterpret_cast<float *>(P.grad);
+    RA.n_pad = ppo_grad_floats_padded();
+    lc.gridDim = dim3(ppo_grad_reduce_ctas());
+    lc.blockDim = dim3(256);
+    lc.dynamicSmemBytes = 0;
+    e = RA.bufs ? cudaLaunchKernelEx(&lc, ppo_reduce_adam_kernel<true>, RA) : cudaLaunchKernelEx(&lc, ppo_reduce_adam_kernel<false>, RA);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

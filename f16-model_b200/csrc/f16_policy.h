@@ -91,6 +91,27 @@ struct PeerArgs {
     uint32_t *seq;        // DEVICE call counters of this rank, one per reduction CTA, zeroed once
     int rank, world;
 };
+// gradient reduction (+ optional peer exchange) fused with clip_grad_norm_ + Adam(amsgrad) + blob re-packing: ppo_reduce_adam_kernel
+struct ReduceAdamArgs {
+    const float *partials;   // filled in by the launcher
+    int n_rows, n_out;
+    float *grad;
+    uint2 *const *bufs;      // peer exchange (nullptr: single rank), see PeerArgs
+    uint32_t *seq;           // peer exchange: its call counters (PeerArgs::seq)
+    int rank, world, n_pad;
+    int n;                   // parameters (n_out - 5)
+    float *param, *exp_avg, *exp_avg_sq, *max_exp_avg_sq, *step;
+    const float *lr;
+    float beta1, beta2, eps, max_grad_norm;
+    const int32_t *scatter;  // [n][4]: destination word of parameter j in fwd_blob, tail_blob, half_blob (twice), -1 = none; 16-byte aligned
+    float *fwd_blob, *tail_blob;
+    __half *half_blob;
+    float *diag;             // [6] or nullptr
+    float inv_rows;
+    unsigned char *sync;     // ppo_step16_sync_bytes() bytes, zeroed once: arrival counter, per-CTA squared-norm shares, per-CTA call counters
+};
+size_t ppo_step16_sync_bytes();
+cudaError_t launch_ppo_step16(const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials, ReduceAdamArgs RA, int n_sm, cudaStream_t st);
 int ppo_grad_floats_padded();
 int ppo_grad_reduce_ctas();
 cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials, int n_sm, cudaStream_t st, const PeerArgs *peer = nullptr);

@@ -146,6 +146,28 @@ def pack_train_blob16(actor, critic, logical=False):
     return flat.contiguous()
 
 
+def scatter_table(n_params, fwd_perm, tail_perm, half_perm):
+    """The inverse of the optimiser kernel's gather permutations (blob word k <- parameter perm[k] - 1, 0 = padding): for every
+    parameter the word it occupies in the forward blob, in the fp32 tail of the training blob, and its (up to two: W2 and W2^T)
+    fp16 words -- int32 [n_params, 4], -1 = none.  ``f16_ppo_step16`` scatters each updated parameter through it."""
+    import torch
+
+    out = torch.full((n_params, 4), -1, dtype=torch.int32, device=fwd_perm.device)
+    for col, perm, mult in ((0, fwd_perm, 1), (1, tail_perm, 1), (2, half_perm, 2)):
+        k = torch.nonzero(perm > 0).reshape(-1)
+        j = perm[k] - 1
+        order = torch.argsort(j, stable=True)
+        j, k = j[order], k[order]
+        first = torch.ones_like(j, dtype=torch.bool)
+        first[1:] = j[1:] != j[:-1]
+        start = torch.cummax(torch.where(first, torch.arange(j.numel(), device=j.device), torch.zeros_like(j)), 0).values
+        rank = torch.arange(j.numel(), device=j.device) - start
+        if j.numel() and int(rank.max()) >= mult:
+            raise ValueError("a parameter occupies more blob words than the scatter table holds")
+        out[j, col + rank] = k.to(torch.int32)
+    return out.contiguous()
+
+
 GRAD_FIELDS = (("w1", (2, 64, 5)), ("b1", (2, 64)), ("w2", (2, 64, 64)), ("b2", (2, 64)), ("w3", (2, 64)), ("b3", (2,)),
                ("logstd", (1,)), ("stats", (5,)))
 

@@ -39,6 +39,8 @@ class PPOConfig:
     tf32_update: bool = False            # run the update's matmuls on the TF32 tensor cores (default: torch's fp32)
     fused_update: bool = True            # minibatch forward + loss + backward in ONE tcgen05 kernel (f16_ppo_grad16); False: torch autograd
     fused_precision: str = "fp16"        # tensor-core operands of the fused kernel: "fp16" (weight gradients on the tensor cores too) or "tf32"
+    fused_optimizer: bool = True         # fused fp16 update: reduction (+ all-reduce) + clip + Adam + blob re-packing in ONE multi-CTA kernel (f16_ppo_step16)
+                                         # instead of the reduction kernel followed by the single-CTA optimiser kernel
     peer_allreduce: bool = True          # world > 1, fused fp16 update: the gradient all-reduce rides in the gradient-reduction kernel over NVLink peer
                                          # memory (f16_ppo_grad16_peer) instead of an NCCL call per minibatch; falls back to NCCL when the ranks cannot map each other
     graph_allreduce: bool = True         # world > 1: capture the NCCL gradient all-reduce inside the update's CUDA graph (call close() before destroy_process_group)
@@ -298,6 +300,13 @@ class PPOTrainer:
         self._blob_tail = self._train_blob[self._half_perm.numel() // 2:] if self._fp16 else self._train_blob
         if self._fp16:
             pol._blob16 = self._train_blob     # policy.act(precision="fp16") reads the blob the optimiser kernel keeps current
+        self._step16 = None
+        if self._fp16 and self.cfg.fused_optimizer:
+            from .policy import scatter_table
+
+            self._scatter = scatter_table(self._n_params, self._fwd_perm, self._train_perm, self._half_perm)
+            self._sync16 = torch.zeros(L.f16_ppo_step16_sync_bytes(), dtype=torch.uint8, device=dev)
+            self._step16 = _capi.PpoStep16()
         self._params = list(pol.parameters())
         self._adv_stats = torch.zeros(2, device=dev)
         self._adv_scratch = torch.zeros(4, device=dev, dtype=torch.float64)
@@ -328,6 +337,21 @@ class PPOTrainer:
                     self._g.data_ptr(), float(cfg.clip_coef), float(cfg.vf_coef), float(cfg.ent_coef),
                     int(bool(cfg.norm_adv)), int(bool(cfg.clip_vloss)))
             peer = self._peer if self._fp16 else None
+            if self._step16 is not None and (self.world == 1 or peer is not None):   # gradient kernel + ONE kernel for reduction / all-reduce / clip / Adam / blob scatter
+                a = self._step16
+                (a.n, a.train_blob16, a.obs, a.actions, a.logprobs, a.adv, a.ret, a.val, a.mb_idx, a.logstd, a.adv_stats, a.grad, a.clip_coef,
+                 a.vf_coef, a.ent_coef, a.norm_adv, a.clip_vloss) = args
+                a.scratch = self._grad_scratch.data_ptr()
+                a.peer = C.pointer(peer.group) if peer is not None else None
+                a.n_params = self._n_params
+                a.param, a.exp_avg, a.exp_avg_sq, a.max_exp_avg_sq, a.step = (self._pflat.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                                                                vmax.data_ptr(), step.data_ptr())
+                a.lr, a.beta1, a.beta2, a.eps, a.max_grad_norm = self._lr.data_ptr(), 0.9, 0.999, 1e-8, float(cfg.max_grad_norm)
+                a.scatter, a.fwd_blob, a.tail_blob, a.half_blob = (self._scatter.data_ptr(), self.policy._blob.data_ptr(),
+                                                                    self._blob_tail.data_ptr(), self._train_blob.data_ptr())
+                a.diag, a.inv_rows, a.sync = self._diag.data_ptr(), 1.0 / mb.numel(), self._sync16.data_ptr()
+                _capi.check(L.f16_ppo_step16(C.byref(a), st))
+                return
             if peer is not None:   # ... and the cross-rank mean in the same reduction kernel (peer memory, no NCCL call)
                 _capi.check(L.f16_ppo_grad16_peer(*args, self._grad_scratch.data_ptr(), C.byref(peer.group), st))
             elif self._fp16:   # per-CTA partial gradients + a reduction kernel instead of 1.4 M atomics

@@ -318,6 +318,40 @@ int f16_ppo_grad16_peer(int64_t n, const void *train_blob16, const void *obs, co
                         const void *adv_stats, void *grad, double clip_coef, double vf_coef, double ent_coef, int norm_adv,
                         int clip_vloss, void *scratch, const f16_peer_group *peer, void *stream);
 
+/* One whole minibatch step of Agent.train's update loop (control/ppo/ppo_model_gsde.py:303-364) in TWO launches: the gradient
+ * kernel of f16_ppo_grad16, then ONE multi-CTA kernel that sums the CTAs' private gradients (with `peer`: also all-reduces them over
+ * NVLink peer memory, as f16_ppo_grad16_peer does), takes the global gradient norm at a grid-wide arrival counter, applies
+ * clip_grad_norm_ + Adam(amsgrad) to its 32 parameters and scatters each new parameter to its places in the three weight blobs --
+ * f16_ppo_grad16 + f16_ppo_adam without the single-CTA optimiser launch (13 us of dependent latency per minibatch).
+ * scatter: int32[n_params][4], 16-byte aligned = the inverse of f16_ppo_adam's gather permutations: for parameter j the word
+ * index it occupies in fwd_blob, in tail_blob (the fp32 tail of the fp16 training blob) and up to two fp16 words of half_blob
+ * (W2 and W2^T), -1 = none.  sync: f16_ppo_step16_sync_bytes() bytes of device memory, zeroed once (arrival counter, per-CTA norm
+ * shares and call counters).  grad receives the (mean) gradient and the five statistics as f16_ppo_grad16 leaves them; diag as in
+ * f16_ppo_adam (diag[2] is ADDED to).  step and lr are device scalars: the call replays from a CUDA graph. */
+typedef struct f16_ppo_step16_args {
+    int64_t n;                 /* minibatch rows */
+    const void *train_blob16;
+    const void *obs, *actions, *logprobs, *adv, *ret, *val;   /* packed rows when actions == NULL, as in f16_ppo_grad16 */
+    const int64_t *mb_idx;
+    const void *logstd, *adv_stats;
+    void *grad;
+    double clip_coef, vf_coef, ent_coef;
+    int32_t norm_adv, clip_vloss;
+    void *scratch;             /* f16_ppo_grad16_scratch_floats(device) floats, required */
+    const f16_peer_group *peer; /* or NULL */
+    int32_t n_params, reserved;
+    void *param, *exp_avg, *exp_avg_sq, *max_exp_avg_sq, *step;
+    const void *lr;
+    double beta1, beta2, eps, max_grad_norm;
+    const int32_t *scatter;
+    void *fwd_blob, *tail_blob, *half_blob;
+    void *diag;                /* float[6] or NULL */
+    double inv_rows;
+    void *sync;
+} f16_ppo_step16_args;
+int f16_ppo_step16_sync_bytes(void);
+int f16_ppo_step16(const f16_ppo_step16_args *a, void *stream);
+
 /* The optimiser half of the minibatch step (ppo_model_gsde.py:360-364: clip_grad_norm_(max_grad_norm) then
  * Adam(amsgrad=True).step()) on the flat parameter vector (same field order as the gradient of f16_ppo_grad), followed
  * by re-packing the rollout blob and the training blob from the updated parameters: blob word k = param[perm[k] - 1],

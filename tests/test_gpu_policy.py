@@ -372,3 +372,37 @@ def test_randperm_kernel_is_a_permutation(f16, n):
                 assert abs(part.mean().item() / n - 0.5) < 0.02 and abs(part.std().item() / n - 0.2887) < 0.01
         # neighbours in the output are not neighbours in the input
         assert (outs[0][1:] - outs[0][:-1]).abs().float().median().item() > n / 20
+
+
+def test_fused_step16_equals_gradient_then_adam(f16):
+    """f16_ppo_step16 (gradient kernel + ONE multi-CTA kernel: reduction, global-norm meeting, clip + Adam(amsgrad), blob scatter)
+    against the two-call path f16_ppo_grad16 -> f16_ppo_adam on the same minibatches: identical gradients, parameters / Adam state equal
+    up to the summation order of the gradient norm, and every blob word equal to a fresh packing of the parameters it ends with."""
+    import ctypes as C
+
+    from f16_model_b200 import _capi
+    from f16_model_b200.policy import pack_policy_blob, pack_train_blob16
+
+    cfg = {"dt": 0.01, "tn": 10, "debug_state": False, "determenistic_ref": False, "scenario": "combo"}
+    trainers = []
+    for fused in (True, False):
+        envs = f16.F16VecEnv(cfg, 4096, seed=2, fast_math=True)
+        pol = f16.TensorCorePolicy(seed=2, logstd_init=-0.5)
+        tr = f16.PPOTrainer(envs, pol, f16.PPOConfig(num_steps=16, num_minibatches=4, update_epochs=3, learning_rate=3e-3, max_grad_norm=0.05,
+                                                     fused_optimizer=fused, use_cuda_graph=fused))
+        assert (tr._step16 is not None) == fused
+        tr.train(num_updates=2)
+        trainers.append(tr)
+    a, b = trainers
+    n = a._n_params
+    assert float(a._adam[3].item()) == float(b._adam[3].item()) == 2 * 3 * 4            # optimiser steps taken
+    # max_grad_norm = 0.05 clips every step: the global norm (a grid-wide sum in the fused kernel) really enters the update
+    rel = lambda x, y: ((x - y).norm() / (y.norm() + 1e-12)).item()   # noqa: E731
+    assert rel(a._pflat[:n], b._pflat[:n]) < 2e-5, rel(a._pflat[:n], b._pflat[:n])
+    for k in range(3):
+        assert rel(a._adam[k], b._adam[k]) < 1e-3
+    # the scattered blobs ARE the packing of the fused trainer's own parameters
+    pol = a.policy
+    assert torch.equal(pol._blob, pack_policy_blob(pol.actor_mean, pol.critic))
+    assert torch.equal(a._train_blob, pack_train_blob16(pol.actor_mean, pol.critic))
+    assert torch.isfinite(a._diag).all() and abs(a._diag[5].item() - (pol.actor_logstd.item() + 1.4189385332046727)) < 1e-6
