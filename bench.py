@@ -837,6 +837,18 @@ def kernel_rooflines(torch, f16, _capi, L, device, rank, world, peaks, peak_kind
               algorithmic_per_unit="9.3 k parameters: ~0.9 MB touched per launch, all L2-resident",
               note="a 9.3 k-parameter model has no throughput roofline: the launch is a chain of three CTA-wide reductions / barriers; "
                    "its cost is latency (us), which the PDL chain of the update graph overlaps with the next gradient kernel's prologue")
+        # the trainer's default minibatch step: gradient kernel + ONE multi-CTA kernel (reduction, clip, Adam, blob scatter)
+        if getattr(tr, "_step16", None) is not None:
+            us_step = graph_us(lambda: tr._fused_minibatch_step(mb, adv_stats=tr._adv_stats), reps=10)
+            us_grad = [e for e in out if e.get("kernel", "").startswith("ppo_grad16_kernel")][-1]["avg_launch_us"]
+            entry("f16_ppo_step16 = ppo_grad16_kernel + ppo_reduce_adam_kernel (gradient reduction + clip_grad_norm + Adam(amsgrad) + blob scatter in one "
+                  "289-CTA launch with a grid-wide arrival counter): one whole minibatch step, two launches", "mufu",
+                  256 * rows / (us_step * 1e-6) / 1e9, pipe["mufu_tanh"] / 1e9, "G tanh/s", us_step, rows,
+                  peak_kind="MUFU.TANH results/s of f16_peak_probe in this run",
+                  algorithmic_per_unit="256 tanh per minibatch row; the optimiser half has no throughput roofline (9.3 k parameters)",
+                  optimizer_half_us=us_step - us_grad,
+                  note="optimizer_half_us = this entry minus the gradient + plain-reduction entry above: what reduction + clip + Adam + re-packing cost "
+                       "inside the chain (the separate single-CTA ppo_adam_kernel below costs its whole launch)")
         del tr, envs4, pol4
 
     # ---- trim search (FP64 pipe) ----
@@ -852,7 +864,7 @@ def kernel_rooflines(torch, f16, _capi, L, device, rank, world, peaks, peak_kind
     iters = float(np.sum(r["all_iterations"]))
     per_iter = consts.get("trim_fp64_thread_instr_per_iteration")
     ach = iters * per_iter / dt if per_iter else None
-    e = {"kernel": "trim_kernel<double> (one Nelder-Mead search per thread, scipy.optimize.fmin rules)", "bound": "fp64",
+    e = {"kernel": "trim_kernel<double> (Nelder-Mead searches, scipy.optimize.fmin rules, as a warp-synchronous state machine: one cost evaluation per loop trip)", "bound": "fp64",
          "achieved": ach / 1e9 if ach else None, "peak": pipe["fp64_fma"] / 1e9, "unit": "G fp64-instr/s",
          "frac": ach / pipe["fp64_fma"] if ach else None, "avg_launch_us": dt * 1e6, "units_per_launch": searches,
          "timing": "wall clock around one trim_grid call (upload, kernel, arg-min, download)",

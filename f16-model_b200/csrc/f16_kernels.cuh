@@ -1066,6 +1066,13 @@ __device__ __forceinline__ R trim_cost(const Tables<R> &T, R V, R H, const R (&u
     return c;
 }
 
+// One thread = one Nelder-Mead search at a time, written as a STATE MACHINE around a single cost evaluation: every trip of the loop
+// evaluates the cost at one query point, and the bookkeeping between two evaluations (accept / expand / contract / shrink, the stable sort,
+// the convergence test, writing a finished search out and loading the thread's next one) is a handful of cheap divergent branches.  The
+// expensive part -- the right-hand side with its table lookups, ~300 FP64 instructions -- is therefore executed by ALL lanes of a warp on
+// every trip, whatever iteration, branch or search each lane is in.  (The first version ran one search per thread as straight-line code with
+// seven inlined cost evaluations: a warp stayed until its slowest search converged and lanes in different branches took turns -- ncu: 30 % of
+// the FP64 lanes active.)  The arithmetic of a search is unchanged, so results are bit-identical.
 template <typename R>
 __global__ void __launch_bounds__(128) trim_kernel(const Tables<R> *tables, int n_cells, int n_starts, const R *Vc, const R *Hc,
                                                     const R *starts /*[S][3]*/, R *out_x /*[cells][S][3]*/, R *out_cost /*[cells][S]*/,
@@ -1076,70 +1083,168 @@ __global__ void __launch_bounds__(128) trim_kernel(const Tables<R> *tables, int 
     tables_issue(&tbl, tables, &bar);
     tables_wait(&bar);
     const int64_t total = (int64_t)n_cells * n_starts;
-    for (int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = id < total;
+
+    enum { PH_INIT, PH_REFLECT, PH_EXPAND, PH_CONTRACT_OUT, PH_CONTRACT_IN, PH_SHRINK };
+    R V = R(200), H = R(3000), sim[4][3], fs[4] = {R(0), R(0), R(0), R(0)}, xr[3] = {R(0), R(0), R(0)}, fxr = R(0);
+    R xq[3] = {R(-0.05), R(0.3), R(0.05)};                   // a harmless query for lanes without work
+    int phase = PH_INIT, k = 0, fcalls = 0, iters = 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sim[q][j] = xq[j];
+
+    auto start_search = [&]() {
         const int cell = (int)(id / n_starts), st = (int)(id % n_starts);
-        const R V = Vc[cell], H = Hc[cell];
-        R sim[4][3], fs[4];
+        V = Vc[cell];
+        H = Hc[cell];
 #pragma unroll
         for (int j = 0; j < 3; ++j) sim[0][j] = starts[st * 3 + j];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int kk = 0; kk < 3; ++kk) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) sim[k + 1][j] = sim[0][j];
-            sim[k + 1][k] = sim[0][k] != R(0) ? (R(1) + R(0.05)) * sim[0][k] : R(0.00025);
+            for (int j = 0; j < 3; ++j) sim[kk + 1][j] = sim[0][j];
+            sim[kk + 1][kk] = sim[0][kk] != R(0) ? (R(1) + R(0.05)) * sim[0][kk] : R(0.00025);
         }
-        int fcalls = 0, iters = 1;
-        for (int k = 0; k < 4; ++k) { fs[k] = trim_cost<R>(tbl, V, H, sim[k]); ++fcalls; }
-        auto sort4 = [&]() {   // stable insertion sort == np.argsort(kind='stable') on 4 keys
-            for (int a = 1; a < 4; ++a)
-                for (int b = a; b > 0 && fs[b] < fs[b - 1]; --b) {
+        fcalls = 0;
+        iters = 1;
+        phase = PH_INIT;
+        k = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) xq[j] = sim[0][j];
+    };
+    auto sort4 = [&]() {   // stable insertion sort == np.argsort(kind='stable') on 4 keys
+#pragma unroll
+        for (int a = 1; a < 4; ++a)
+#pragma unroll
+            for (int b = a; b > 0; --b) {
+                if (fs[b] < fs[b - 1]) {
                     const R tf = fs[b]; fs[b] = fs[b - 1]; fs[b - 1] = tf;
+#pragma unroll
                     for (int j = 0; j < 3; ++j) { const R tx = sim[b][j]; sim[b][j] = sim[b - 1][j]; sim[b - 1][j] = tx; }
+                } else {
+                    break;
                 }
-        };
-        sort4();
-        while (fcalls < 5000 && iters < 1000) {
-            R dx = R(0), df = R(0);
-            for (int k = 1; k < 4; ++k) {
-                for (int j = 0; j < 3; ++j) dx = fmax(dx, fabs(sim[k][j] - sim[0][j]));
-                df = fmax(df, fabs(fs[0] - fs[k]));
             }
-            if (dx <= R(1e-10) && df <= R(1e-10)) break;
-            R xbar[3], xr[3], xt[3];
-            for (int j = 0; j < 3; ++j) xbar[j] = ((sim[0][j] + sim[1][j]) + sim[2][j]) / R(3);
-            for (int j = 0; j < 3; ++j) xr[j] = (R(1) + R(1)) * xbar[j] - R(1) * sim[3][j];
-            const R fxr = trim_cost<R>(tbl, V, H, xr); ++fcalls;
-            bool shrink = false;
-            if (fxr < fs[0]) {
-                for (int j = 0; j < 3; ++j) xt[j] = (R(1) + R(2)) * xbar[j] - R(2) * sim[3][j];
-                const R fxe = trim_cost<R>(tbl, V, H, xt); ++fcalls;
-                if (fxe < fxr) { for (int j = 0; j < 3; ++j) sim[3][j] = xt[j]; fs[3] = fxe; }
-                else { for (int j = 0; j < 3; ++j) sim[3][j] = xr[j]; fs[3] = fxr; }
-            } else if (fxr < fs[2]) {
-                for (int j = 0; j < 3; ++j) sim[3][j] = xr[j];
-                fs[3] = fxr;
-            } else if (fxr < fs[3]) {
-                for (int j = 0; j < 3; ++j) xt[j] = (R(1) + R(0.5)) * xbar[j] - R(0.5) * sim[3][j];
-                const R fxc = trim_cost<R>(tbl, V, H, xt); ++fcalls;
-                if (fxc <= fxr) { for (int j = 0; j < 3; ++j) sim[3][j] = xt[j]; fs[3] = fxc; }
-                else shrink = true;
-            } else {
-                for (int j = 0; j < 3; ++j) xt[j] = (R(1) - R(0.5)) * xbar[j] + R(0.5) * sim[3][j];
-                const R fxcc = trim_cost<R>(tbl, V, H, xt); ++fcalls;
-                if (fxcc < fs[3]) { for (int j = 0; j < 3; ++j) sim[3][j] = xt[j]; fs[3] = fxcc; }
-                else shrink = true;
+    };
+    auto vertex_to_query = [&](int kk) {   // xq = sim[kk] without a dynamically indexed register array
+#pragma unroll
+        for (int q = 1; q < 4; ++q)
+            if (kk == q) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) xq[j] = sim[q][j];
             }
-            if (shrink)
-                for (int k = 1; k < 4; ++k) {
-                    for (int j = 0; j < 3; ++j) sim[k][j] = sim[0][j] + R(0.5) * (sim[k][j] - sim[0][j]);
-                    fs[k] = trim_cost<R>(tbl, V, H, sim[k]); ++fcalls;
-                }
-            ++iters;
-            sort4();
+    };
+    auto store_f = [&](int kk, R f) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (kk == q) fs[q] = f;
+    };
+    auto centroid_query = [&](R a, R b) {   // xq = a * xbar + b * worst, xbar = centroid of the three best (scipy's expression order)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const R xbar = ((sim[0][j] + sim[1][j]) + sim[2][j]) / R(3);
+            xq[j] = a * xbar + b * sim[3][j];
         }
-        for (int j = 0; j < 3; ++j) out_x[id * 3 + j] = sim[0][j];
-        out_cost[id] = fs[0];
-        if (out_iters) out_iters[id] = iters;
+    };
+    auto accept = [&](const R (&x)[3], R f) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sim[3][j] = x[j];
+        fs[3] = f;
+    };
+
+    if (active) start_search();
+    // The loop is warp-synchronous on purpose: __any_sync at its head re-converges the warp before EVERY cost evaluation (with `continue`s
+    // out of the divergent bookkeeping the lanes drifted apart again: 13 of 32 lanes active per instruction, measured), and lanes that have
+    // run out of searches keep evaluating a dummy point until the whole warp is done.
+    while (__any_sync(0xffffffffu, active)) {
+        const R f = trim_cost<R>(tbl, V, H, xq);
+        if (!active) continue;
+        ++fcalls;
+        // ---- what the value means; `next`: 0 = the query for the next evaluation is set, 1 = iteration finished, 2 = shrink, 3 = simplex ready (after INIT)
+        int next = 0;
+        if (phase == PH_INIT || phase == PH_SHRINK) {
+            store_f(k, f);
+            ++k;
+            if (k < 4) vertex_to_query(k);
+            else next = phase == PH_INIT ? 3 : 1;
+        } else if (phase == PH_REFLECT) {
+            fxr = f;
+            if (fxr < fs[0]) {
+                centroid_query(R(1) + R(2), -R(2));
+                phase = PH_EXPAND;
+            } else if (fxr < fs[2]) {
+                accept(xr, fxr);
+                next = 1;
+            } else if (fxr < fs[3]) {
+                centroid_query(R(1) + R(0.5), -R(0.5));
+                phase = PH_CONTRACT_OUT;
+            } else {
+                centroid_query(R(1) - R(0.5), R(0.5));
+                phase = PH_CONTRACT_IN;
+            }
+        } else if (phase == PH_EXPAND) {
+            if (f < fxr) accept(xq, f);
+            else accept(xr, fxr);
+            next = 1;
+        } else if (phase == PH_CONTRACT_OUT) {
+            if (f <= fxr) {
+                accept(xq, f);
+                next = 1;
+            } else {
+                next = 2;
+            }
+        } else {   // PH_CONTRACT_IN
+            if (f < fs[3]) {
+                accept(xq, f);
+                next = 1;
+            } else {
+                next = 2;
+            }
+        }
+        if (next == 2) {
+#pragma unroll
+            for (int q = 1; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) sim[q][j] = sim[0][j] + R(0.5) * (sim[q][j] - sim[0][j]);
+            phase = PH_SHRINK;
+            k = 1;
+            vertex_to_query(1);
+        } else if (next != 0) {
+            if (next == 1) ++iters;
+            sort4();
+            // ---- top of scipy's loop: limits, convergence test, or the next reflection ----
+            bool done = !(fcalls < 5000 && iters < 1000);
+            if (!done) {
+                R dx = R(0), df = R(0);
+#pragma unroll
+                for (int q = 1; q < 4; ++q) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) dx = fmax(dx, fabs(sim[q][j] - sim[0][j]));
+                    df = fmax(df, fabs(fs[0] - fs[q]));
+                }
+                done = dx <= R(1e-10) && df <= R(1e-10);
+            }
+            if (done) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) out_x[id * 3 + j] = sim[0][j];
+                out_cost[id] = fs[0];
+                if (out_iters) out_iters[id] = iters;
+                id += stride;
+                active = id < total;
+                if (active) start_search();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const R xbar = ((sim[0][j] + sim[1][j]) + sim[2][j]) / R(3);
+                    xr[j] = (R(1) + R(1)) * xbar - R(1) * sim[3][j];
+                    xq[j] = xr[j];
+                }
+                phase = PH_REFLECT;
+            }
+        }
     }
 }
 
