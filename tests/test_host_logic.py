@@ -310,3 +310,60 @@ def test_split_k_linear_gradients_match_plain_linear():
         assert torch.allclose(a, b, rtol=2e-4, atol=1e-7), (a - b).abs().max().item()
     # small or ragged batches fall back to F.linear
     assert pol.split_k_linear(x[:100], net[0].weight, net[0].bias).shape == (100, 64)
+
+
+def test_every_abi_struct_is_laid_out_like_the_c_compiler_does(tmp_path):
+    """sizeof and every field offset of the ctypes mirrors against a C program compiled from the header itself (gcc): covers the
+    structs the size test above does not spell out (f16_rollout_io, f16_peer_group, f16_ppo_step16_args)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = [("f16_config", _capi.Config), ("f16_env_buffers", _capi.EnvBuffers), ("f16_step_io", _capi.StepIO), ("f16_rollout_io", _capi.RolloutIO),
+             ("f16_peer_group", _capi.PeerGroup), ("f16_ppo_step16_args", _capi.PpoStep16)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "f16_b200.h"', 'int main(void) {']
+    for cname, mirror in pairs:
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in mirror._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append("return 0; }")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    res = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr          # a field named in the mirror but not in the header fails right here
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for cname, mirror in pairs:
+        assert int(got[cname]) == ctypes.sizeof(mirror), cname
+        for fname, _ in mirror._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(mirror, fname).offset, f"{cname}.{fname}"
+
+
+def test_scatter_table_inverts_the_gather_permutations():
+    """policy.scatter_table (the inverse maps f16_ppo_step16 scatters updated parameters through): every blob word that gathers parameter j
+    is listed under j, nothing else is, padding words (perm 0) are never written; more copies than the table holds is an error."""
+    import torch
+
+    from f16_model_b200.policy import scatter_table
+
+    g = torch.Generator().manual_seed(3)
+    n = 500
+    fwd = torch.zeros(700, dtype=torch.long)
+    fwd[torch.randperm(700, generator=g)[:n]] = torch.randperm(n, generator=g) + 1                 # every parameter once, 200 padding words
+    tail = torch.zeros(120, dtype=torch.long)
+    tail[torch.randperm(120, generator=g)[:80]] = torch.randperm(n, generator=g)[:80] + 1          # a subset of the parameters once
+    half = torch.zeros(900, dtype=torch.long)
+    twice = torch.randperm(n, generator=g)[:300] + 1
+    half[torch.randperm(900, generator=g)[:600]] = torch.cat([twice, twice])                       # 300 parameters twice (W2 and W2^T)
+    t = scatter_table(n, fwd, tail, half)
+    assert t.shape == (n, 4) and t.dtype == torch.int32
+    for col, perm, blob_cols in ((0, fwd, (0,)), (1, tail, (1,)), (2, half, (2, 3))):
+        rebuilt = torch.zeros_like(perm)
+        for c in blob_cols:
+            j = torch.nonzero(t[:, c] >= 0).reshape(-1)
+            assert torch.all(rebuilt[t[j, c].long()] == 0)                                         # no word listed twice
+            rebuilt[t[j, c].long()] = j + 1
+        assert torch.equal(rebuilt, perm)
+    with pytest.raises(ValueError):
+        scatter_table(n, torch.cat([fwd, fwd]), tail, half)
