@@ -152,6 +152,7 @@ class PPOTrainer:
         self._update_graph = None
         self._flat = None
         self._fused = bool(self.cfg.fused_update) and envs.obs_layout == "aos"
+        self._pflat_seen = None
         self._peer = None
         if self._fused:
             self._setup_fused()
@@ -496,10 +497,14 @@ class PPOTrainer:
     def _update(self, advantages, returns):
         torch, cfg = self._torch, self.cfg
         self._prepare_update(advantages, returns)
-        if self._fused:                                    # parameters may have been changed from outside (load_agent, ...)
+        if self._fused:
             self._g.zero_()
-            from .policy import pack_train_blob, pack_train_blob16
-            self._train_blob.copy_((pack_train_blob16 if self._fp16 else pack_train_blob)(self.policy.actor_mean, self.policy.critic))
+            # the optimiser kernels keep the weight blobs current; they are re-packed from the torch parameters only when those were changed
+            # from outside since the last update (load_agent, a manual edit): one compare instead of ~40 small packing launches per update
+            if self._pflat_seen is None or not torch.equal(self._pflat_seen, self._pflat):
+                from .policy import pack_train_blob, pack_train_blob16
+                self._train_blob.copy_((pack_train_blob16 if self._fp16 else pack_train_blob)(self.policy.actor_mean, self.policy.critic))
+                self.policy.sync_weights()
         use_graph = cfg.use_cuda_graph and (self.world == 1 or cfg.graph_allreduce)
         if use_graph and self._update_graph is None:
             try:
@@ -537,7 +542,13 @@ class PPOTrainer:
                 n_steps += 1
             if kl_early_stop(self._diag[1], cfg.target_kl, self.world):
                 break
-        self.policy.sync_weights()                                  # refresh the tensor-core weight blob
+        if self._fused:
+            if self._pflat_seen is None:
+                self._pflat_seen = self._pflat.clone()
+            else:
+                self._pflat_seen.copy_(self._pflat)                 # (the optimiser kernels re-packed the blobs with every step)
+        else:
+            self.policy.sync_weights()                              # torch optimiser: refresh the tensor-core weight blobs
         d = self._diag.tolist()
         return dict(old_approx_kl=d[0], approx_kl=d[1], clipfrac=d[2] / max(n_steps, 1), value_loss=d[3], policy_loss=d[4],
                     entropy=d[5])
