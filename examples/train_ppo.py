@@ -71,6 +71,7 @@ def main():
     trainer.train(log=log)
     if rank == 0:
         print("saved:", f16.artifacts.save_agent(agent, args.save_dir, run_name))
+    trainer.close()                 # releases the captured graphs and the peer-memory exchange buffers (must precede destroy_process_group)
     if world > 1:
         torch.distributed.destroy_process_group()
 
