@@ -171,6 +171,7 @@ struct RolloutArgs {
     int K;
     int sample;                   // 0: deterministic actions (eps = 0)
     uint64_t policy_seed;         // key of the exploration-noise stream (the counter is the env's own: id, episode, step)
+    int pace;                     // groups of a CTA admitted to their tanh section at a time (0 = no pacing)
 };
 cudaError_t launch_rollout(const EnvArgs<float> &A, const RolloutArgs &R, bool fast, int n_sm, int pdl, cudaStream_t st);
 

@@ -26,6 +26,8 @@
 // (TrainBlob16), so the rollout's forward pass and the update's forward pass round the same way.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "f16_kernels.cuh"
 #include "f16_policy.h"
 #include "f16_umma.cuh"
@@ -62,6 +64,8 @@ struct alignas(16) RolloutSmem {
     __half a2[kSub][16][kRowsR][8];           // H1: 16 K-chunks (actor 0-7 | critic 8-15) x 128 rows x 8 halfs
     uint64_t bar_tbl, bar_w;
     uint64_t bar_mma[kSub][3];                // per group: layer 1, layer 2 actor, layer 2 critic (one phase flip per step each)
+    uint64_t bar_adm[kSub];                   // per group: admission to the tanh section (pacing, see below)
+    uint32_t adm_tickets, adm_warps_done;     // FIFO tickets taken by groups / warps that have left their tanh section
     uint32_t tmem_base;
     CtaStats stats;
 };
@@ -95,8 +99,12 @@ __global__ void __launch_bounds__(kThreadsR, 1) rollout_kernel(const EnvArgs<flo
         mbar_init(&sm->bar_tbl, 1);
         mbar_init(&sm->bar_w, 1);
 #pragma unroll
-        for (int s = 0; s < kSub; ++s)
+        for (int s = 0; s < kSub; ++s) {
             for (int j = 0; j < 3; ++j) mbar_init(&sm->bar_mma[s][j], 1);
+            mbar_init(&sm->bar_adm[s], 1);
+        }
+        sm->adm_tickets = 0;
+        sm->adm_warps_done = 0;
         sm->stats.count = 0;
         sm->stats.length = 0;
         sm->stats.ret = 0.0;
@@ -230,9 +238,27 @@ __global__ void __launch_bounds__(kThreadsR, 1) rollout_kernel(const EnvArgs<flo
                 u::fence_after_sync();
                 u::mma_f16(tcol, u::desc(a1, kLbo, 128), u::desc(w1, 128 * 16, 128), id_l1, 0u);
                 u::commit(bar1);
+                if (R.pace) {
+                    // Pacing: at most R.pace of the CTA's four groups are inside their tanh section (layer-1 epilogue .. heads) at a time,
+                    // admitted first come, first served.  Left alone, the four warps of a sub-partition -- one of each group -- fall into
+                    // lockstep: all four share the MUFU unit through the tanh phases, then all four sit in the env step with the unit idle
+                    // (period = MUFU work + the rest).  With two groups inside, two warps per sub-partition keep the unit saturated while the
+                    // other two run their env step / MMA round trip (period -> max of the two).  A group is admitted as a whole (its four warps
+                    // wait on bar_adm), so the group barriers inside the section cannot wait for a warp that is still queued.
+                    const uint32_t my = atomicAdd(&sm->adm_tickets, 1u);
+                    const uint32_t need = my >= static_cast<uint32_t>(R.pace) ? 4u * (my - static_cast<uint32_t>(R.pace) + 1u) : 0u;   // warps of the groups ahead that must be out
+                    for (unsigned spin = 0;; ++spin) {
+                        const uint32_t done_w = *reinterpret_cast<volatile uint32_t *>(&sm->adm_warps_done);
+                        if (static_cast<int32_t>(done_w - need) >= 0) break;
+                        if (spin > (1u << 26)) __trap();
+                        __nanosleep(32);
+                    }
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm->bar_adm[sub])) : "memory");
+                }
             }
             RTRACE(1);
             mbar_wait(bar1, phase);
+            if (R.pace) mbar_wait(&sm->bar_adm[sub], phase);
             u::fence_after_sync();
             RTRACE(2);
 #pragma unroll
@@ -293,6 +319,10 @@ __global__ void __launch_bounds__(kThreadsR, 1) rollout_kernel(const EnvArgs<flo
                 head[net] += acc0 + acc1;
             }
             phase ^= 1u;
+            if (R.pace) {   // this warp has left the tanh section
+                __syncwarp();
+                if (lane == 0) atomicAdd(&sm->adm_warps_done, 1u);
+            }
             RTRACE(6);
             const float mean = head[0], value = head[1];
             if (k == K) {   // one forward past the last step: the GAE bootstrap value of the final observation
@@ -407,13 +437,17 @@ struct alignas(16) Policy16Smem {
     __half a2[kSub][16][kRowsR][8];
     uint64_t bar_w;
     uint64_t bar_mma[kSub][3];
+    uint64_t bar_adm[kSub];
+    uint32_t adm_tickets, adm_warps_done;
     uint32_t tmem_base;
 };
 static_assert(offsetof(Policy16Smem, w2) - offsetof(Policy16Smem, w1) == sizeof(TrainBlob16::w1), "w1 | w2 must be contiguous");
 static_assert(offsetof(Policy16Smem, b1) - offsetof(Policy16Smem, w1) == offsetof(TrainBlob16, w2t), "fp32 tail follows w2");
 
+template <int PACE>   // groups admitted to their tanh section at a time (0 = no pacing), see rollout_kernel
 __global__ void __launch_bounds__(kThreadsR, 1) policy_forward16_kernel(const PolicyArgs P, const TrainBlob16 *blob16)
 {
+    constexpr int pace = PACE;
     namespace u = umma;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Policy16Smem *sm = reinterpret_cast<Policy16Smem *>(smem_raw);
@@ -423,8 +457,12 @@ __global__ void __launch_bounds__(kThreadsR, 1) policy_forward16_kernel(const Po
     if (t == 0) {
         mbar_init(&sm->bar_w, 1);
 #pragma unroll
-        for (int s = 0; s < kSub; ++s)
+        for (int s = 0; s < kSub; ++s) {
             for (int j = 0; j < 3; ++j) mbar_init(&sm->bar_mma[s][j], 1);
+            mbar_init(&sm->bar_adm[s], 1);
+        }
+        sm->adm_tickets = 0;
+        sm->adm_warps_done = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -515,6 +553,17 @@ __global__ void __launch_bounds__(kThreadsR, 1) policy_forward16_kernel(const Po
             u::fence_after_sync();
             u::mma_f16(tcol, u::desc(a1, kLbo, 128), u::desc(w1, 128 * 16, 128), id_l1, 0u);
             u::commit(bar1);
+            if (pace) {   // pacing of the tanh section, as in rollout_kernel
+                const uint32_t my = atomicAdd(&sm->adm_tickets, 1u);
+                const uint32_t need = my >= static_cast<uint32_t>(pace) ? 4u * (my - static_cast<uint32_t>(pace) + 1u) : 0u;
+                for (unsigned spin = 0;; ++spin) {
+                    const uint32_t done_w = *reinterpret_cast<volatile uint32_t *>(&sm->adm_warps_done);
+                    if (static_cast<int32_t>(done_w - need) >= 0) break;
+                    if (spin > (1u << 26)) __trap();
+                    __nanosleep(32);
+                }
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm->bar_adm[sub])) : "memory");
+            }
         }
         // the next tile's observation row travels under this tile's work
 #pragma unroll
@@ -527,6 +576,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) policy_forward16_kernel(const Po
             if (P.ep_len) c3 = static_cast<uint32_t>(P.ep_len[i]);
         }
         mbar_wait(bar1, phase);
+        if (pace) mbar_wait(&sm->bar_adm[sub], phase);
         u::fence_after_sync();
 #pragma unroll
         for (int net = 0; net < 2; ++net) {
@@ -577,6 +627,10 @@ __global__ void __launch_bounds__(kThreadsR, 1) policy_forward16_kernel(const Po
             head[net] += acc0 + acc1;
         }
         phase ^= 1u;
+        if (pace) {
+            __syncwarp();
+            if ((t & 31u) == 0) atomicAdd(&sm->adm_warps_done, 1u);
+        }
         if (live) {
             const float mean = head[0];
             if (P.value) P.value[i] = head[1];
@@ -627,7 +681,13 @@ cudaError_t launch_rollout(const EnvArgs<float> &A, const RolloutArgs &R, bool f
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
     lc.numAttrs = pdl ? 1 : 0;
-    cudaError_t e = fast ? cudaLaunchKernelEx(&lc, rollout_kernel<true>, A, R) : cudaLaunchKernelEx(&lc, rollout_kernel<false>, A, R);
+    RolloutArgs Rp = R;
+    static const int pace_env = [] {
+        const char *e = std::getenv("F16B200_ROLLOUT_PACE");   // tuning knob: groups admitted to the tanh section at a time, 0 = no pacing
+        return e ? std::atoi(e) : -1;
+    }();
+    if (pace_env >= 0) Rp.pace = pace_env > 4 ? 4 : pace_env;
+    cudaError_t e = fast ? cudaLaunchKernelEx(&lc, rollout_kernel<true>, A, Rp) : cudaLaunchKernelEx(&lc, rollout_kernel<false>, A, Rp);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
@@ -639,7 +699,9 @@ cudaError_t launch_policy_forward16(const PolicyArgs &P, const TrainBlob16 *blob
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(policy_forward16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Policy16Smem)));
+        cudaError_t e = cudaFuncSetAttribute(policy_forward16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Policy16Smem)));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(policy_forward16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Policy16Smem)));
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
@@ -655,7 +717,10 @@ cudaError_t launch_policy_forward16(const PolicyArgs &P, const TrainBlob16 *blob
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
     lc.numAttrs = pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&lc, policy_forward16_kernel, P, blob16);
+    // pacing pays once every group has several tiles (2^20 rows: 84.3 -> 77.2 us with three of the four groups admitted at a time); with one
+    // or two tiles per group it only delays (65,536 rows: 8.3 -> 9.2 us)
+    const bool paced = groups >= static_cast<int64_t>(n_sm) * kSub * 4;
+    cudaError_t e = paced ? cudaLaunchKernelEx(&lc, policy_forward16_kernel<3>, P, blob16) : cudaLaunchKernelEx(&lc, policy_forward16_kernel<0>, P, blob16);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

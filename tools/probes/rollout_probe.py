@@ -46,7 +46,7 @@ def main():
     for N, K in ((65536, 128), (1 << 20, 16), (4096, 128)):
         us, _ = run(N, K)
         out[f"{N}x{K}"] = {"us": us, "us_per_step": us / K, "env_steps_per_s": N * K / (us * 1e-6)}
-    print(json.dumps(out, indent=1))
+    print(json.dumps({k: {a: round(b, 2) if a != 'env_steps_per_s' else float('%.4g' % b) for a, b in v.items()} for k, v in out.items()}))
 
 
 if __name__ == "__main__":
