@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "f16_policy.h"
 #include "f16_umma.cuh"
@@ -1184,6 +1185,487 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
+// ---------------------------------------------------------------------------
+// ppo_grad16w_kernel: the same tile program as ppo_grad16_kernel with the two slots on their OWN warps -- 512 threads, slot s =
+// warps 8s .. 8s+7, each slot a free-running 256-thread group (named barrier 1 + s) that walks its own tiles through the four
+// stages.  ppo_grad16_kernel interleaves the slots in program order on the same 8 warps: every round trip is hidden, but the SM
+// never holds more than two warps per sub-partition and all of them sit in the same phase (ncu: issue slots 28 % busy, stall
+// samples spread evenly -- latency-bound).  Here a sub-partition holds four warps, two of each slot, and the slots are out of
+// phase by construction: the weight-gradient accumulators (dW2 | db2, dW1 | db1) are shared, so the two issuing warps pass a
+// token -- slot 0's S3 batch of pair j, then slot 1's, then slot 0's of pair j + 1 ... and the same for the S4 batches -- which
+// keeps the accumulation order, and with it every bit of the gradient, fixed, and makes slot 1 trail slot 0 by a fraction of a tile.
+// 128 registers per thread (ppo_grad16_kernel: 226): a thread carries one slot, and the gathered row of its next tile only across S4.
+// ---------------------------------------------------------------------------
+constexpr int kThreadsW = 512;
+
+__device__ __forceinline__ void group_sync(int s) { asm volatile("bar.sync %0, 256;" ::"r"(s + 1) : "memory"); }
+__device__ __forceinline__ void token_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void token_pass(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+template <int OPTS>   // bit 0: slot 1 starts once slot 0 has issued its first layer 2; bit 1: the next tile's gather travels under S3 instead of S4
+__global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGradArgs P, const TrainBlob16 *blob16, float *partials)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TrainSmem16 *sm = reinterpret_cast<TrainSmem16 *>(smem_raw);
+    const unsigned t = threadIdx.x, lane = t & 31u;
+    const unsigned warp = __shfl_sync(0xffffffffu, t >> 5, 0);   // warp-uniform for the compiler (MMA issue on the uniform datapath)
+    const int s = static_cast<int>(warp >> 3);                   // slot = warp group
+    const bool issuer = (warp & 7u) == 0u;                       // warps 0 and 8
+    const unsigned tg = t & 255u, row = tg & (kRows - 1), half = tg >> 7;
+
+    if (t == 0) {
+        mbar_init(&sm->bar_w, 1);
+        mbar_init(&sm->bar_mma[0], 1);
+        mbar_init(&sm->bar_mma[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {   // all 512 TMEM columns, as in ppo_grad16_kernel
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (half == 1) *reinterpret_cast<uint4 *>(sm->a1[s][1][row]) = make_uint4(0u, 0u, 0u, 0u);   // K padding 8..15 of the slot's X operand
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = sm->tmem_base;
+    const TrainBlob16 &W = sm->w;
+    constexpr uint32_t id_l1 = umma_idesc_f16(128, 128, false), id_l2 = umma_idesc_f16(128, 64, false);
+    constexpr uint32_t id_w2 = umma_idesc_f16(128, 128, true), id_w1 = umma_idesc_f16(128, 16, true);
+    const uint32_t w1 = smem_u32(W.w1), w2a = smem_u32(W.w2[0]), w2c = smem_u32(W.w2[1]);
+    const uint32_t w2ta = smem_u32(W.w2t[0]), w2tc = smem_u32(W.w2t[1]);
+    const uint32_t tcol = tmem + s * 128;                                       // the slot's D1 -> D2 -> D3 columns
+    const uint32_t lane_base = tcol + (((warp & 3u) * 32u) << 16) + half * 64;  // this thread's row and net in them
+    uint64_t *bar = &sm->bar_mma[s];
+    unsigned char *a2p = sm->a2[s], *d2p = sm->d2[s];
+    const uint32_t a1u = smem_u32(sm->a1[s]), a2u = smem_u32(a2p), d2u = smem_u32(d2p);
+
+    const unsigned n = static_cast<unsigned>(P.n);
+    const unsigned n_tiles = (n + kRows - 1) / kRows;
+    const float n_f = static_cast<float>(n), inv_n = 1.0f / n_f;
+    const float eps = P.clip_coef;
+
+    float acc_w3a = 0.f, acc_w3b = 0.f;   // dW3 columns 2 lane, 2 lane + 1 of this warp's net (transposing butterfly, see ppo_grad16_kernel)
+    float acc_b3 = 0.f, acc_logstd = 0.f;
+    float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f, st4 = 0.f;
+
+    auto load_index = [&](unsigned tile_) -> int64_t {
+        const unsigned i_ = tile_ * kRows + row;
+        return (tile_ < n_tiles && i_ < n) ? P.mb_idx[i_] : int64_t(-1);
+    };
+    struct RowIn { float v[8]; };   // x[5], a, b, c
+    auto load_row = [&](int64_t src) {
+        RowIn g;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g.v[k] = 0.f;
+        if (src >= 0) {
+            if (P.packed) {            // one aligned 32-byte sector (half 0) / 8 bytes (half 1) per thread
+                if (half == 0) {
+                    const float4 *r = reinterpret_cast<const float4 *>(P.obs + src * 8);
+                    const float4 lo = __ldg(r), hi = __ldg(r + 1);
+                    g.v[0] = lo.x, g.v[1] = lo.y, g.v[2] = lo.z, g.v[3] = lo.w;
+                    g.v[4] = hi.x, g.v[5] = hi.y, g.v[6] = hi.z, g.v[7] = hi.w;
+                } else {
+                    const float2 rv = __ldg(reinterpret_cast<const float2 *>(P.ret + src * 2));
+                    g.v[5] = rv.x, g.v[6] = rv.y;
+                }
+            } else if (half == 0) {
+                const float *o = P.obs + src * 5;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) g.v[k] = o[k];
+                g.v[5] = P.actions[src];
+                g.v[6] = P.logprobs[src];
+                g.v[7] = P.adv[src];
+            } else {
+                g.v[5] = P.ret[src];
+                g.v[6] = P.val[src];
+            }
+        }
+        return g;
+    };
+    auto park_row = [&](float *dst, const RowIn &g) {
+        *reinterpret_cast<float4 *>(dst) = make_float4(g.v[0], g.v[1], g.v[2], g.v[3]);
+        *reinterpret_cast<float4 *>(dst + 4) = make_float4(g.v[4], g.v[5], g.v[6], g.v[7]);
+    };
+
+    // the slot's tiles: blockIdx.x + (2 j + s) gridDim.x; both slots run the same number of rounds (a missing tile = 128 dead rows)
+    const unsigned stride = gridDim.x;
+    const unsigned n_iter = (n_tiles - blockIdx.x + 2 * stride - 1) / (2 * stride);
+    unsigned tile = blockIdx.x + s * stride;
+    // first tile's row and second tile's indices: requested BEFORE the grid dependency resolves (see ppo_grad16_kernel)
+    park_row(sm->stage[0][s][tg], load_row(load_index(tile)));
+    sm->next_idx[s][tg] = load_index(tile + 2 * stride);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (t == 0) {
+        constexpr uint32_t bytes = static_cast<uint32_t>(sizeof(TrainBlob16));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->bar_w)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(&sm->w)),
+                     "l"(blob16), "r"(bytes), "r"(smem_u32(&sm->bar_w))
+                     : "memory");
+    }
+    const float log_std = P.logstd[0], inv_std = __expf(-log_std);
+    const float adv_mean = P.norm_adv ? P.adv_stats[0] : 0.f;
+    const float adv_scale = P.norm_adv ? 1.0f / (P.adv_stats[1] + 1e-8f) : 1.f;
+    mbar_wait(&sm->bar_w, 0);
+    if ((OPTS & 1) && s == 1) asm volatile("bar.sync 7, 288;" ::: "memory");   // slot 1 starts half a tile behind slot 0
+
+    for (unsigned j = 0; j < n_iter; ++j, tile += 2 * stride) {
+        const float *in = sm->stage[j & 1u][s][tg];
+        const bool live = tile < n_tiles && tile * kRows + row < n;
+        const bool first = s == 0 && j == 0;   // this tile's batches initialise the weight-gradient accumulators
+        if (j) {   // the slot's operands are rewritten below: its last batch (dW1) must have completed
+            mbar_wait(bar, 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        // ---- S1: observation row -> X operand (1 in column 5: bias gradients = that column of dZ^T [X | 1]); issue layer 1 ----
+        if (half == 0) {
+            float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f};
+            if (live) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) x[k] = in[k];
+            }
+            *reinterpret_cast<uint4 *>(sm->a1[s][0][row]) = pack8(x);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        group_sync(s);
+        if (issuer && umma::elect_one()) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            umma_f16(tcol, umma_desc(a1u, kRows * 16, 128), umma_desc(w1, 128 * 16, 128), id_l1, 0u);
+            umma_commit(bar);
+        }
+        // ---- S2: H1 = tanh(D1 + b1) -> a2 (fp16); issue layer 2 (into D1's columns) ----
+        mbar_wait(bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            uint32_t ra[32], rb[32];
+            tmem_ld32_issue(lane_base, ra);
+            tmem_ld32_issue(lane_base + 32, rb);
+            tmem_wait_ld();
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {
+                const int col0 = half * 64 + blk * 32;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int jj = col0 + c * 8;
+                    float h[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) h[q] = fast_tanh(__uint_as_float(blk ? rb[c * 8 + q] : ra[c * 8 + q]) + W.b1[jj + q]);
+                    *reinterpret_cast<uint4 *>(a2p + (jj >> 3) * kLboH + row * 16u) = pack8(h);
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        group_sync(s);
+        if (issuer) {
+            if (umma::elect_one()) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(tcol, umma_desc(a2u + k * 2 * kLboH, kLboH, 128), umma_desc(w2a + k * 2 * kHid * 16, kHid * 16, 128), id_l2, k > 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(tcol + 64, umma_desc(a2u + (8 + k * 2) * kLboH, kLboH, 128), umma_desc(w2c + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
+                             k > 0 ? 1u : 0u);
+                umma_commit(bar);
+            }
+            if ((OPTS & 1) && s == 0 && j == 0) {
+                __syncwarp();
+                asm volatile("bar.arrive 7, 288;" ::: "memory");
+            }
+        }
+        // the next tile's row (index fetched one round ago) and the index of the tile after it: they travel under the stage chosen by
+        // OPTS (every stage ends with fence.proxy.async, which waits for the thread's outstanding loads) and are parked before its fence
+        RowIn nr;
+        int64_t ni = -1;
+        if (OPTS & 2) {
+            nr = load_row(sm->next_idx[s][tg]);
+            ni = load_index(tile + 4 * stride);
+        }
+        // ---- S3: H2, head, clipped-PPO loss, dZ2 -> d2; issue D3 = dZ2 W2 (into D2's columns) and the weight gradients dW2, db2 ----
+        mbar_wait(bar, 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            const float s_a = live ? in[5] : 0.f, s_b = live ? in[6] : 0.f, s_c = live ? in[7] : 0.f;
+            // H2 is kept as packed halves between the head and the backward pass (32 registers instead of 64: the slot's whole state must fit
+            // 128 registers; the backward pass reads H1 in fp16 too), the head itself is summed from the fp32 values
+            uint32_t hp[32];
+            float head = W.b3[half];
+            {
+                uint32_t ra[32], rb[32];
+                tmem_ld32_issue(lane_base, ra);
+                tmem_ld32_issue(lane_base + 32, rb);
+                tmem_wait_ld();
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    const int col0 = half * 64 + blk * 32;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float h0 = fast_tanh(__uint_as_float(blk ? rb[2 * c] : ra[2 * c]) + W.b2[col0 + 2 * c]);
+                        const float h1 = fast_tanh(__uint_as_float(blk ? rb[2 * c + 1] : ra[2 * c + 1]) + W.b2[col0 + 2 * c + 1]);
+                        head = fmaf(h0, W.w3[col0 + 2 * c], head);
+                        head = fmaf(h1, W.w3[col0 + 2 * c + 1], head);
+                        const __half2 hh = __floats2half2_rn(h0, h1);
+                        hp[blk * 16 + c] = *reinterpret_cast<const uint32_t *>(&hh);
+                    }
+                }
+            }
+            // clipped-PPO loss; g = d(n * loss) / d head for this row (ppo_model_gsde.py:303-364, as in ppo_grad16_kernel)
+            float g_head = 0.f;
+            if (live) {
+                if (half == 0) {
+                    const float z = (s_a - head) * inv_std;
+                    const float newlp = -0.5f * z * z - log_std - 0.91893853320467274178f;
+                    const float logratio = newlp - s_b;
+                    const float ratio = __expf(logratio);
+                    const float A = (s_c - adv_mean) * adv_scale;
+                    const float lo = 1.0f - eps, hi = 1.0f + eps;
+                    const float rc = fminf(fmaxf(ratio, lo), hi);
+                    const float pg1 = -A * ratio, pg2 = -A * rc;
+                    const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+                    const float g_ratio = pg1 > pg2 ? -A : (pg2 > pg1 ? -A * in_range : -A * (0.5f + 0.5f * in_range));
+                    const float g_lp = g_ratio * ratio;
+                    g_head = g_lp * z * inv_std;
+                    acc_logstd += (g_lp * (z * z - 1.0f) - P.ent_coef) * inv_n;
+                    st0 -= logratio;
+                    st1 += (ratio - 1.0f) - logratio;
+                    st2 += fabsf(ratio - 1.0f) > eps ? 1.f : 0.f;
+                    st4 += fmaxf(pg1, pg2);
+                } else {
+                    const float du = head - s_a;
+                    float g = du, vl = du * du;
+                    if (P.clip_vloss) {
+                        const float dv = head - s_b;
+                        const float vc = s_b + fminf(fmaxf(dv, -eps), eps);
+                        const float dc = vc - s_a, vcl = dc * dc;
+                        const float in_range = (dv >= -eps && dv <= eps) ? 1.f : 0.f;
+                        g = vl > vcl ? du : (vcl > vl ? dc * in_range : 0.5f * du + 0.5f * dc * in_range);
+                        vl = fmaxf(vl, vcl);
+                    }
+                    g_head = P.vf_coef * g;
+                    st3 += 0.5f * vl;
+                }
+            }
+            const float dy = g_head * inv_n;
+            acc_b3 += dy;
+            // n * dZ2 = g * w3 * (1 - H2^2) -> d2 (fp16); dW3 = sum over rows of dy * H2 in fp32: the 64 products of a thread are summed over the
+            // warp's 32 rows by a transposing shuffle butterfly (lane l ends with columns 2l, 2l+1).  Its first level pairs column i with i + 32,
+            // so the columns are walked as chunk pairs (c, c + 4) and only the 32 level-1 sums stay live
+            float h2[32];
+            {
+                const bool upper = (lane & 16u) != 0u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float pl[8], ph[8];
+#pragma unroll
+                    for (int hi = 0; hi < 2; ++hi) {
+                        const int jj = half * 64 + hi * 32 + c * 8;
+                        float g[8];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 h = __half22float2(*reinterpret_cast<const __half2 *>(&hp[hi * 16 + c * 4 + q]));
+                            g[2 * q] = g_head * W.w3[jj + 2 * q] * (1.0f - h.x * h.x);
+                            g[2 * q + 1] = g_head * W.w3[jj + 2 * q + 1] * (1.0f - h.y * h.y);
+                            (hi ? ph : pl)[2 * q] = dy * h.x;
+                            (hi ? ph : pl)[2 * q + 1] = dy * h.y;
+                        }
+                        *reinterpret_cast<uint4 *>(d2p + (jj >> 3) * kLboH + row * 16u) = pack8(g);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) h2[c * 8 + q] = (upper ? ph[q] : pl[q]) + __shfl_xor_sync(0xffffffffu, upper ? pl[q] : ph[q], 16);
+                }
+            }
+#pragma unroll
+            for (int sz = 16; sz >= 2; sz >>= 1) {   // 32 -> 16 -> 8 -> 4 -> 2 values; lanes whose bit sz/2 is set keep the upper half
+                const unsigned o = static_cast<unsigned>(sz) >> 1;
+                const bool upper = (lane & o) != 0u;
+#pragma unroll
+                for (int i = 0; i < sz; ++i) {
+                    const float lo = h2[i], hi = h2[i + sz];
+                    h2[i] = (upper ? hi : lo) + __shfl_xor_sync(0xffffffffu, upper ? lo : hi, o);
+                }
+            }
+            acc_w3a += h2[0];
+            acc_w3b += h2[1];
+        }
+        if (OPTS & 2) {
+            park_row(sm->stage[(j & 1u) ^ 1u][s][tg], nr);
+            sm->next_idx[s][tg] = ni;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // D2 has been read by the whole group: D3 may overwrite it
+        group_sync(s);
+        if (issuer) {
+            // token: the S3 batches of the two slots accumulate into the same dW2 / db2 columns, in the order 0, 1, 0, 1, ...
+            if (s == 0) {
+                if (j) token_wait(4);
+            } else
+                token_wait(3);
+            if (umma::elect_one()) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < 4; ++k)   // D3 = dZ2 * W2 (per net): dZ2 read K-major (rows x features)
+                    umma_f16(tcol, umma_desc(d2u + k * 2 * kLboH, kLboH, 128), umma_desc(w2ta + k * 2 * kHid * 16, kHid * 16, 128), id_l2, k > 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(tcol + 64, umma_desc(d2u + (8 + k * 2) * kLboH, kLboH, 128), umma_desc(w2tc + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
+                             k > 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)   // dW2 += dZ2^T * H1: the same buffers read MN-major (features x rows), 16 rows per MMA
+                    umma_f16(tmem + 256, umma_desc(d2u + k * 256, 128, kLboH), umma_desc(a2u + k * 256, 128, kLboH), id_w2, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)   // db2 += dZ2^T * [X | 1]
+                    umma_f16(tmem + 400, umma_desc(d2u + k * 256, 128, kLboH), umma_desc(a1u + k * 256, 128, kRows * 16), id_w1,
+                             (first && k == 0) ? 0u : 1u);
+                umma_commit(bar);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+            __syncwarp();
+            if (s == 0)
+                token_pass(3);
+            else if (j + 1 < n_iter)
+                token_pass(4);
+        }
+        if (!(OPTS & 2)) {
+            nr = load_row(sm->next_idx[s][tg]);
+            ni = load_index(tile + 4 * stride);
+        }
+        // ---- S4: n * dZ1 = D3 * (1 - H1^2) -> d2 (every MMA that read dZ2 has completed); issue dW1 | db1 += dZ1^T [X | 1] ----
+        mbar_wait(bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            uint32_t ra[32], rb[32];
+            tmem_ld32_issue(lane_base, ra);
+            tmem_ld32_issue(lane_base + 32, rb);
+            tmem_wait_ld();
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {
+                const int col0 = half * 64 + blk * 32;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int jj = col0 + c * 8;
+                    const uint4 raw = *reinterpret_cast<const uint4 *>(a2p + (jj >> 3) * kLboH + row * 16u);
+                    const __half2 *hh = reinterpret_cast<const __half2 *>(&raw);
+                    float g[8];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 h = __half22float2(hh[q]);
+                        g[2 * q] = __uint_as_float(blk ? rb[c * 8 + 2 * q] : ra[c * 8 + 2 * q]) * (1.0f - h.x * h.x);
+                        g[2 * q + 1] = __uint_as_float(blk ? rb[c * 8 + 2 * q + 1] : ra[c * 8 + 2 * q + 1]) * (1.0f - h.y * h.y);
+                    }
+                    *reinterpret_cast<uint4 *>(d2p + (jj >> 3) * kLboH + row * 16u) = pack8(g);
+                }
+            }
+        }
+        if (!(OPTS & 2)) {
+            park_row(sm->stage[(j & 1u) ^ 1u][s][tg], nr);
+            sm->next_idx[s][tg] = ni;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        group_sync(s);
+        if (issuer) {
+            if (s == 0) {
+                if (j) token_wait(6);
+            } else
+                token_wait(5);
+            if (umma::elect_one()) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_f16(tmem + 384, umma_desc(d2u + k * 256, 128, kLboH), umma_desc(a1u + k * 256, 128, kRows * 16), id_w1,
+                             (first && k == 0) ? 0u : 1u);
+                umma_commit(bar);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+            __syncwarp();
+            if (s == 0)
+                token_pass(5);
+            else if (j + 1 < n_iter)
+                token_pass(6);
+        }
+    }
+    mbar_wait(bar, 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();   // both slots have retired: the accumulators are final, the operand buffers are free
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- flush (per-CTA private gradient when `partials` is given, atomics otherwise) ----
+    const bool own = partials != nullptr;
+    PolicyGrad *G = own ? reinterpret_cast<PolicyGrad *>(partials) + blockIdx.x : P.grad;
+    auto put = [&](float *dst, float val) {
+        if (own) *dst = val;
+        else atomicAdd(dst, val);
+    };
+    {
+        // weight-gradient accumulators: TMEM lane = output feature (actor 0-63 | critic 64-127), scaled by n.  dW2: the block of the lane's own
+        // net, 64 columns in four 16-column pieces (one per thread that can reach the lane: 2 slots x 2 halves); dW1 | db1 | db2: slot 0, half 0
+        const unsigned net = row >> 6, jn = row & 63u;
+        const uint32_t lane_acc = tmem + (((warp & 3u) * 32u) << 16);
+        const unsigned piece = static_cast<unsigned>(s) * 2u + half;
+        float v[32];
+        tmem_ld32(lane_acc + 256 + net * 64 + (piece >> 1) * 32, v);   // 32 columns, this thread flushes 16 of them
+        const unsigned c0 = (piece & 1u) * 16u;
+        if (own) {
+            float4 *dst = reinterpret_cast<float4 *>(&G->w2[net][jn][(piece >> 1) * 32 + c0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float4 o;
+                o.x = (c0 ? v[16 + 4 * c] : v[4 * c]) * inv_n;
+                o.y = (c0 ? v[17 + 4 * c] : v[4 * c + 1]) * inv_n;
+                o.z = (c0 ? v[18 + 4 * c] : v[4 * c + 2]) * inv_n;
+                o.w = (c0 ? v[19 + 4 * c] : v[4 * c + 3]) * inv_n;
+                dst[c] = o;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) put(&G->w2[net][jn][(piece >> 1) * 32 + c0 + c], (c0 ? v[16 + c] : v[c]) * inv_n);
+        }
+        if (piece == 0) {
+            tmem_ld32(lane_acc + 384, v);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) put(&G->w1[net][jn][k], v[k] * inv_n);
+            put(&G->b1[net][jn], v[5] * inv_n);
+            put(&G->b2[net][jn], v[16 + 5] * inv_n);
+        }
+    }
+    // dW3 and the scalar sums: the 16 warps meet in shared memory and are added in a fixed order (bit-reproducible gradient)
+    {
+        float *scr = reinterpret_cast<float *>(sm->a2);   // [16 warps][64] dW3 columns, then [16 warps][8] scalars
+        scr[warp * 64 + 2 * lane] = acc_w3a;
+        scr[warp * 64 + 2 * lane + 1] = acc_w3b;
+        float sc[8] = {st0, st1, st2, st3, st4, acc_logstd, half == 0 ? acc_b3 : 0.f, half == 1 ? acc_b3 : 0.f};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float v = sc[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) scr[16 * 64 + warp * 8 + q] = v;
+        }
+        __syncthreads();
+        if (t < 128) {   // net of warp w: (w >> 2) & 1
+            const unsigned net = t >> 6, c = t & 63u;
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a += scr[((k >> 2) * 8 + net * 4 + (k & 3)) * 64 + c];
+            put(&G->w3[net][c], a);
+        } else if (t < 136) {
+            const unsigned q = t - 128;
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < 16; ++w) a += scr[16 * 64 + w * 8 + q];
+            if (q < 5) put(&G->stats[q], a);
+            else if (q == 5) put(&G->logstd, a);
+            else put(&G->b3[q - 6], a);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
 // keyed bijection of [0, n): see f16_ppo_randperm in the header.  Every round is invertible on `bits` bits (odd multiplier, right
 // xor-shift, addition), so the composition is a permutation of [0, 2^bits); values >= n walk the cycle until they fall below n.
 struct PermKey { uint64_t mul[4], add[4]; int shift[4]; int bits; };
@@ -1789,13 +2271,49 @@ cudaError_t launch_ppo_pack_rows(int64_t n, const float *obs, const float *actio
 int ppo_grad_floats_padded() { return (static_cast<int>(sizeof(PolicyGrad) / sizeof(float)) + 31) / 32 * 32; }
 int ppo_grad_reduce_ctas() { return (static_cast<int>(sizeof(PolicyGrad) / sizeof(float)) + 31) / 32; }
 
+// the gradient kernel of a minibatch step: variant chosen once per process (tuning knob F16B200_GRAD16: -1 = ppo_grad16_kernel, 256 threads,
+// slots interleaved in program order; 0..3 = ppo_grad16w_kernel<OPTS>, 512 threads, one warp group per slot)
+static int grad16_variant()
+{
+    static const int v = [] {
+        const char *e = std::getenv("F16B200_GRAD16");
+        return e ? std::atoi(e) : 0;
+    }();
+    return v;
+}
+static cudaError_t configure_grad16()
+{
+    const int bytes = static_cast<int>(sizeof(TrainSmem16));
+    cudaError_t e = cudaFuncSetAttribute(ppo_grad16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ppo_grad16w_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ppo_grad16w_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ppo_grad16w_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ppo_grad16w_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e;
+}
+static cudaError_t launch_grad16_variant(cudaLaunchConfig_t &lc, const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials)
+{
+    const int v = grad16_variant();
+    if (v < 0) {
+        lc.blockDim = dim3(kThreads);
+        return cudaLaunchKernelEx(&lc, ppo_grad16_kernel, P, blob16, partials);
+    }
+    lc.blockDim = dim3(kThreadsW);
+    switch (v & 3) {
+    case 0: return cudaLaunchKernelEx(&lc, ppo_grad16w_kernel<0>, P, blob16, partials);
+    case 1: return cudaLaunchKernelEx(&lc, ppo_grad16w_kernel<1>, P, blob16, partials);
+    case 2: return cudaLaunchKernelEx(&lc, ppo_grad16w_kernel<2>, P, blob16, partials);
+    default: return cudaLaunchKernelEx(&lc, ppo_grad16w_kernel<3>, P, blob16, partials);
+    }
+}
+
 cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials, int n_sm, cudaStream_t st, const PeerArgs *peer)
 {
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(ppo_grad16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TrainSmem16)));
+        cudaError_t e = configure_grad16();
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
@@ -1811,7 +2329,7 @@ cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, f
     lc.stream = st;
     lc.attrs = attr;
     lc.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&lc, ppo_grad16_kernel, P, blob16, partials);
+    cudaError_t e = launch_grad16_variant(lc, P, blob16, partials);
     if (e != cudaSuccess) return e;
     if (partials) {
         constexpr int n_out = static_cast<int>(sizeof(PolicyGrad) / sizeof(float));
@@ -1836,7 +2354,7 @@ cudaError_t launch_ppo_step16(const PpoGradArgs &P, const TrainBlob16 *blob16, f
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(ppo_grad16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TrainSmem16)));
+        cudaError_t e = configure_grad16();
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
@@ -1852,7 +2370,7 @@ cudaError_t launch_ppo_step16(const PpoGradArgs &P, const TrainBlob16 *blob16, f
     lc.stream = st;
     lc.attrs = attr;
     lc.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&lc, ppo_grad16_kernel, P, blob16, partials);
+    cudaError_t e = launch_grad16_variant(lc, P, blob16, partials);
     if (e != cudaSuccess) return e;
     RA.partials = partials;
     RA.n_rows = grid;
