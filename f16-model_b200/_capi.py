@@ -21,7 +21,7 @@ ABI_VERSION = 2
 
 EXPORTS = ["f16_abi_version", "f16_last_error", "f16_init", "f16_launch_geometry", "f16_peak_probe", "f16_env_reset", "f16_env_step",
            "f16_env_step_host", "f16_host_route", "f16_rhs", "f16_model_step", "f16_coeffs", "f16_thrust", "f16_atmosphere",
-           "f16_policy_blob_bytes", "f16_policy_forward", "f16_policy_forward16", "f16_rollout", "f16_ppo_adv_stats", "f16_ppo_train_blob_bytes", "f16_ppo_grad_floats", "f16_ppo_grad", "f16_ppo_train_blob16_bytes", "f16_ppo_grad16_scratch_floats", "f16_ppo_grad16", "f16_ppo_grad16_peer", "f16_ppo_step16", "f16_ppo_step16_sync_bytes", "f16_peer_buffer_bytes", "f16_peer_seq_words", "f16_peer_alloc", "f16_peer_open", "f16_peer_close", "f16_peer_free", "f16_ppo_pack_rows", "f16_ppo_randperm", "f16_ppo_adam",
+           "f16_policy_blob_bytes", "f16_policy_forward", "f16_policy_forward16", "f16_rollout", "f16_ppo_adv_stats", "f16_ppo_train_blob_bytes", "f16_ppo_grad_floats", "f16_ppo_grad", "f16_ppo_train_blob16_bytes", "f16_ppo_grad16_scratch_floats", "f16_ppo_grad16", "f16_ppo_grad16_peer", "f16_ppo_step16", "f16_ppo_step16_sync_bytes", "f16_ppo_epoch16", "f16_ppo_epoch16_sync_bytes", "f16_peer_buffer_bytes", "f16_peer_seq_words", "f16_peer_alloc", "f16_peer_open", "f16_peer_close", "f16_peer_free", "f16_ppo_pack_rows", "f16_ppo_randperm", "f16_ppo_adam",
            "f16_gae", "f16_trim"]
 
 
@@ -126,6 +126,8 @@ def load_library():
     L.f16_ppo_grad16_peer.argtypes = L.f16_ppo_grad.argtypes[:-1] + [vp, C.POINTER(PeerGroup), vp]
     L.f16_ppo_step16.argtypes = [C.POINTER(PpoStep16), vp]
     L.f16_ppo_step16_sync_bytes.argtypes = []
+    L.f16_ppo_epoch16.argtypes = [C.POINTER(PpoStep16), C.c_int, vp]
+    L.f16_ppo_epoch16_sync_bytes.argtypes = []
     L.f16_peer_buffer_bytes.argtypes = [i32]
     L.f16_peer_seq_words.argtypes = []
     L.f16_peer_alloc.argtypes = [i64, C.POINTER(C.c_void_p), vp]

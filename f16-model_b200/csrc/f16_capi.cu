@@ -845,9 +845,10 @@ int f16_ppo_grad16_peer(int64_t n, const void *train_blob16, const void *obs, co
 
 int f16_ppo_step16_sync_bytes(void) { return static_cast<int>((f16::ppo_step16_sync_bytes() + 15) / 16 * 16); }
 
-int f16_ppo_step16(const f16_ppo_step16_args *a, void *stream)
+static int ppo_step16_impl(const f16_ppo_step16_args *a, int n_minibatches, bool epoch, void *stream)
 {
     if (!a) return fail(F16_EINVAL, "args is NULL");
+    if (epoch && (n_minibatches < 1 || a->peer)) return fail(F16_EINVAL, "f16_ppo_epoch16: n_minibatches >= 1 and peer == NULL (single rank)");
     DeviceCtx *c;
     f16::LaunchGeom g;
     int rc = prep(a->n, &c, &g);
@@ -914,10 +915,17 @@ int f16_ppo_step16(const f16_ppo_step16_args *a, void *stream)
     R.diag = static_cast<float *>(a->diag);
     R.inv_rows = static_cast<float>(a->inv_rows);
     R.sync = static_cast<unsigned char *>(a->sync);
-    CUDA_TRY(f16::launch_ppo_step16(P, static_cast<const f16::TrainBlob16 *>(a->train_blob16), static_cast<float *>(a->scratch), R, c->n_sm,
-                                    static_cast<cudaStream_t>(stream)));
+    if (epoch)
+        CUDA_TRY(f16::launch_ppo_epoch16(P, static_cast<const f16::TrainBlob16 *>(a->train_blob16), static_cast<float *>(a->scratch), R, n_minibatches,
+                                         c->n_sm, static_cast<cudaStream_t>(stream)));
+    else
+        CUDA_TRY(f16::launch_ppo_step16(P, static_cast<const f16::TrainBlob16 *>(a->train_blob16), static_cast<float *>(a->scratch), R, c->n_sm,
+                                        static_cast<cudaStream_t>(stream)));
     return F16_OK;
 }
+int f16_ppo_step16(const f16_ppo_step16_args *a, void *stream) { return ppo_step16_impl(a, 1, false, stream); }
+int f16_ppo_epoch16_sync_bytes(void) { return static_cast<int>(f16::ppo_epoch16_sync_bytes()); }
+int f16_ppo_epoch16(const f16_ppo_step16_args *a, int n_minibatches, void *stream) { return ppo_step16_impl(a, n_minibatches, true, stream); }
 
 // ---- exchange buffers in peer memory (CUDA IPC; the ranks of one node) ----
 int64_t f16_peer_buffer_bytes(int world)

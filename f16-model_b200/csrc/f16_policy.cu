@@ -1202,8 +1202,39 @@ __device__ __forceinline__ void group_sync(int s) { asm volatile("bar.sync %0, 2
 __device__ __forceinline__ void token_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void token_pass(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
-template <int OPTS>   // bit 0: slot 1 starts once slot 0 has issued its first layer 2; bit 1: the next tile's gather travels under S3 instead of S4
-__global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGradArgs P, const TrainBlob16 *blob16, float *partials)
+#ifdef F16_GRAD_TRACE
+// debug build only: clock64 at the stage boundaries of CTA 0, warps 0-3 of each slot (trace rows 4 s + (warp & 3)), rounds 2..5
+#define WTRACE(pt)                                                                                                                  \
+    do {                                                                                                                            \
+        if (blockIdx.x == 0 && lane == 0 && (warp & 7u) < 4u && j >= 2 && j < 6) g_grad_trace[s * 4 + (warp & 3u)][j - 2][pt] = clock64(); \
+    } while (0)
+__device__ unsigned long long g_epoch_cta[160][12];   // globaltimer (ns) per CTA at the same points, thread 0, minibatch 2
+__device__ unsigned long long g_epoch_trace[4][12];   // [CTA 0 / last CTA][thread 0 / 256]... rows: (blockIdx.x == 0 ? 0 : 2) + (t == 256), minibatch 2
+#define ETRACE(pt)                                                                                                   \
+    do {                                                                                                             \
+        if (EPOCH && mbi == 2 && (t & 255u) == 0u && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))                \
+            g_epoch_trace[(blockIdx.x == 0 ? 0 : 2) + (t >> 8)][pt] = clock64();                                      \
+        if (EPOCH && mbi == 2 && t == 0 && blockIdx.x < 160) {                                                       \
+            unsigned long long now_;                                                                                 \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                                                 \
+            g_epoch_cta[blockIdx.x][pt] = now_;                                                                      \
+        }                                                                                                            \
+    } while (0)
+#else
+#define WTRACE(pt) do { } while (0)
+#define ETRACE(pt) do { } while (0)
+#endif
+// EPOCH = true: the kernel is persistent over the n_mb minibatches of an epoch and takes the optimiser step itself between two
+// minibatches (cooperative launch, one CTA per SM): after the flush the CTAs meet at a grid-wide counter, every CTA sums the partial
+// gradients of the parameters it owns (n_out / gridDim.x, in 64-parameter passes) and posts its share of the squared norm, a second
+// meeting makes the clip coefficient known everywhere (shares added in a fixed order: bit-identical in every CTA), the owners apply
+// clip_grad_norm_ + Adam(amsgrad) and scatter the new parameters into the three weight blobs (as ppo_reduce_adam_kernel does), and
+// after a third meeting every CTA re-reads the fp16 training blob from L2.  Per minibatch this replaces a kernel boundary, the
+// 289-CTA optimiser launch, the next gradient launch's prologue (TMEM allocation, barrier set-up, weight TMA) and the drain / fill
+// of the SMs around them; the first rows of the next minibatch are gathered under the optimiser step.
+template <bool EPOCH>
+__global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGradArgs P, const TrainBlob16 *blob16, float *partials, const ReduceAdamArgs A,
+                                                                   const int n_mb)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TrainSmem16 *sm = reinterpret_cast<TrainSmem16 *>(smem_raw);
@@ -1244,56 +1275,75 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
     const float n_f = static_cast<float>(n), inv_n = 1.0f / n_f;
     const float eps = P.clip_coef;
 
-    float acc_w3a = 0.f, acc_w3b = 0.f;   // dW3 columns 2 lane, 2 lane + 1 of this warp's net (transposing butterfly, see ppo_grad16_kernel)
-    float acc_b3 = 0.f, acc_logstd = 0.f;
-    float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f, st4 = 0.f;
-
-    auto load_index = [&](unsigned tile_) -> int64_t {
+    // the slot's tiles: blockIdx.x + (2 j + s) gridDim.x, j = 0 .. n_iter - 1; both slots run the same number of rounds (a missing tile = 128
+    // dead rows).  The gather pipeline numbers its rounds through the whole launch: round r = minibatch r / n_iter, tile round r % n_iter, so
+    // with EPOCH the first rows of the next minibatch travel under the last rounds of this one (they do not depend on the optimiser step)
+    const unsigned stride = gridDim.x;
+    const unsigned n_iter = (n_tiles - blockIdx.x + 2 * stride - 1) / (2 * stride);
+    const unsigned tile0 = blockIdx.x + s * stride;
+    const unsigned n_rounds = n_iter * static_cast<unsigned>(n_mb);
+    auto index_addr = [&](unsigned r, bool &ok) -> const int64_t * {   // where the index of this thread's row in round r lives
+        const unsigned mb_ = r / n_iter, tile_ = tile0 + 2 * stride * (r - mb_ * n_iter);
         const unsigned i_ = tile_ * kRows + row;
-        return (tile_ < n_tiles && i_ < n) ? P.mb_idx[i_] : int64_t(-1);
+        ok = r < n_rounds && tile_ < n_tiles && i_ < n;
+        return P.mb_idx + static_cast<size_t>(mb_) * n + i_;
     };
-    struct RowIn { float v[8]; };   // x[5], a, b, c
+    auto load_index = [&](unsigned r) -> int64_t {
+        bool ok;
+        const int64_t *a = index_addr(r, ok);
+        return ok ? *a : int64_t(-1);
+    };
+    // L2 prefetches one round ahead of the gathers (fire and forget: unlike a load they are not waited for by the fences that end every
+    // stage): the row a thread will gather in S4 of this round, and the line of indices it will read there.  Without them a group waits,
+    // once per tile, for the slowest of its 256 random DRAM accesses within the ~1 us of S4 (per-CTA tile loops spread 45 .. 55 us)
+    auto prefetch_row = [&](int64_t src) {
+        if (P.packed && src >= 0) {
+            const void *a = half == 0 ? static_cast<const void *>(P.obs + src * 8) : static_cast<const void *>(P.ret + src * 2);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+    };
+    auto prefetch_index = [&](unsigned r) {
+        bool ok;
+        const int64_t *a = index_addr(r, ok);
+        if (ok && (tg & 15u) == 0u && tg < 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    };
+    // A gathered row: (x[0..3]), (x[4], a, b, c) for the actor half's thread, (ret, val) for the critic half's.  The two halves' loads stay
+    // in SEPARATE registers until they are parked: merged into one array, the compiler joins the two branches with moves that wait for the
+    // load right where it was issued (ncu: the top long-scoreboard stall of the kernel), and the gather no longer travels under S4.
+    struct RowIn { float4 lo, hi; float2 rv; };
     auto load_row = [&](int64_t src) {
         RowIn g;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) g.v[k] = 0.f;
+        g.lo = make_float4(0.f, 0.f, 0.f, 0.f), g.hi = make_float4(0.f, 0.f, 0.f, 0.f), g.rv = make_float2(0.f, 0.f);
         if (src >= 0) {
             if (P.packed) {            // one aligned 32-byte sector (half 0) / 8 bytes (half 1) per thread
                 if (half == 0) {
                     const float4 *r = reinterpret_cast<const float4 *>(P.obs + src * 8);
-                    const float4 lo = __ldg(r), hi = __ldg(r + 1);
-                    g.v[0] = lo.x, g.v[1] = lo.y, g.v[2] = lo.z, g.v[3] = lo.w;
-                    g.v[4] = hi.x, g.v[5] = hi.y, g.v[6] = hi.z, g.v[7] = hi.w;
+                    g.lo = __ldg(r), g.hi = __ldg(r + 1);
                 } else {
-                    const float2 rv = __ldg(reinterpret_cast<const float2 *>(P.ret + src * 2));
-                    g.v[5] = rv.x, g.v[6] = rv.y;
+                    g.rv = __ldg(reinterpret_cast<const float2 *>(P.ret + src * 2));
                 }
             } else if (half == 0) {
                 const float *o = P.obs + src * 5;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) g.v[k] = o[k];
-                g.v[5] = P.actions[src];
-                g.v[6] = P.logprobs[src];
-                g.v[7] = P.adv[src];
+                g.lo = make_float4(o[0], o[1], o[2], o[3]);
+                g.hi = make_float4(o[4], P.actions[src], P.logprobs[src], P.adv[src]);
             } else {
-                g.v[5] = P.ret[src];
-                g.v[6] = P.val[src];
+                g.rv = make_float2(P.ret[src], P.val[src]);
             }
         }
         return g;
     };
-    auto park_row = [&](float *dst, const RowIn &g) {
-        *reinterpret_cast<float4 *>(dst) = make_float4(g.v[0], g.v[1], g.v[2], g.v[3]);
-        *reinterpret_cast<float4 *>(dst + 4) = make_float4(g.v[4], g.v[5], g.v[6], g.v[7]);
+    auto park_row = [&](float *dst, const RowIn &g) {   // [0..4] x (read by the actor half only), [5] a | ret, [6] logprob | val, [7] advantage
+        if (half == 0) {
+            *reinterpret_cast<float4 *>(dst) = g.lo;
+            *reinterpret_cast<float4 *>(dst + 4) = g.hi;
+        } else {
+            *reinterpret_cast<float4 *>(dst + 4) = make_float4(0.f, g.rv.x, g.rv.y, 0.f);
+        }
     };
 
-    // the slot's tiles: blockIdx.x + (2 j + s) gridDim.x; both slots run the same number of rounds (a missing tile = 128 dead rows)
-    const unsigned stride = gridDim.x;
-    const unsigned n_iter = (n_tiles - blockIdx.x + 2 * stride - 1) / (2 * stride);
-    unsigned tile = blockIdx.x + s * stride;
-    // first tile's row and second tile's indices: requested BEFORE the grid dependency resolves (see ppo_grad16_kernel)
-    park_row(sm->stage[0][s][tg], load_row(load_index(tile)));
-    sm->next_idx[s][tg] = load_index(tile + 2 * stride);
+    // first round's row and second round's indices: requested BEFORE the grid dependency resolves (see ppo_grad16_kernel)
+    park_row(sm->stage[0][s][tg], load_row(load_index(0)));
+    sm->next_idx[s][tg] = load_index(1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (t == 0) {
@@ -1303,16 +1353,52 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
                      "l"(blob16), "r"(bytes), "r"(smem_u32(&sm->bar_w))
                      : "memory");
     }
-    const float log_std = P.logstd[0], inv_std = __expf(-log_std);
-    const float adv_mean = P.norm_adv ? P.adv_stats[0] : 0.f;
-    const float adv_scale = P.norm_adv ? 1.0f / (P.adv_stats[1] + 1e-8f) : 1.f;
     mbar_wait(&sm->bar_w, 0);
-    if ((OPTS & 1) && s == 1) asm volatile("bar.sync 7, 288;" ::: "memory");   // slot 1 starts half a tile behind slot 0
 
-    for (unsigned j = 0; j < n_iter; ++j, tile += 2 * stride) {
-        const float *in = sm->stage[j & 1u][s][tg];
+    // ---- EPOCH: grid-wide meetings at one counter (zeroed by the launcher before every launch; a cooperative launch: all CTAs are resident) ----
+    auto grid_meet = [&](unsigned n_meet) {   // n_meet: the number of this meeting in the launch, from 1
+        __threadfence();
+        __syncthreads();
+        if (t == 0) {
+            unsigned long long *arrive = reinterpret_cast<unsigned long long *>(A.sync);
+            atomicAdd(arrive, 1ull);
+            const unsigned long long want = static_cast<unsigned long long>(n_meet) * gridDim.x;
+            unsigned long long t0 = 0ull;
+            for (unsigned spin = 0;; ++spin) {
+                unsigned long long seen;
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(arrive) : "memory");
+                if (seen >= want) break;
+                if ((spin & 1023u) == 1023u) {   // a CTA that never arrives must not hang the GPU: fail loudly after ~10 s
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0ull) t0 = now;
+                    else if (now - t0 > 10000000000ull) __trap();
+                }
+            }
+        }
+        __syncthreads();
+    };
+    const float step0 = EPOCH ? A.step[0] : 0.f;   // read before anybody's first meeting; CTA 0 writes the new value after a step's second meeting
+    unsigned round = 0;                            // rounds of the gather pipeline done so far (all minibatches)
+
+  for (int mbi = 0; mbi < n_mb; ++mbi) {
+    const float log_std = EPOCH ? __ldcg(P.logstd) : P.logstd[0], inv_std = __expf(-log_std);   // EPOCH: a parameter another CTA has just updated
+    const float adv_mean = P.norm_adv ? P.adv_stats[2 * mbi] : 0.f;
+    const float adv_scale = P.norm_adv ? 1.0f / (P.adv_stats[2 * mbi + 1] + 1e-8f) : 1.f;
+    float acc_w3a = 0.f, acc_w3b = 0.f;   // dW3 columns 2 lane, 2 lane + 1 of this warp's net (transposing butterfly, see ppo_grad16_kernel)
+    float acc_b3 = 0.f, acc_logstd = 0.f;
+    float st0 = 0.f, st1 = 0.f, st2 = 0.f, st3 = 0.f, st4 = 0.f;
+    unsigned tile = tile0;
+    ETRACE(0);
+    if (s == 1) asm volatile("bar.sync 7, 288;" ::: "memory");   // slot 1 starts once slot 0 has issued its first layer 2: half a tile behind
+
+    for (unsigned j = 0; j < n_iter; ++j, tile += 2 * stride, ++round) {
+        WTRACE(0);
+        const float *in = sm->stage[round & 1u][s][tg];
         const bool live = tile < n_tiles && tile * kRows + row < n;
         const bool first = s == 0 && j == 0;   // this tile's batches initialise the weight-gradient accumulators
+        prefetch_row(sm->next_idx[s][tg]);
+        prefetch_index(round + 2);
         if (j) {   // the slot's operands are rewritten below: its last batch (dW1) must have completed
             mbar_wait(bar, 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1334,9 +1420,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
             umma_f16(tcol, umma_desc(a1u, kRows * 16, 128), umma_desc(w1, 128 * 16, 128), id_l1, 0u);
             umma_commit(bar);
         }
+        WTRACE(1);
         // ---- S2: H1 = tanh(D1 + b1) -> a2 (fp16); issue layer 2 (into D1's columns) ----
         mbar_wait(bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        WTRACE(2);
         {
             uint32_t ra[32], rb[32];
             tmem_ld32_issue(lane_base, ra);
@@ -1370,22 +1458,16 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
                              k > 0 ? 1u : 0u);
                 umma_commit(bar);
             }
-            if ((OPTS & 1) && s == 0 && j == 0) {
+            if (s == 0 && j == 0) {
                 __syncwarp();
                 asm volatile("bar.arrive 7, 288;" ::: "memory");
             }
         }
-        // the next tile's row (index fetched one round ago) and the index of the tile after it: they travel under the stage chosen by
-        // OPTS (every stage ends with fence.proxy.async, which waits for the thread's outstanding loads) and are parked before its fence
-        RowIn nr;
-        int64_t ni = -1;
-        if (OPTS & 2) {
-            nr = load_row(sm->next_idx[s][tg]);
-            ni = load_index(tile + 4 * stride);
-        }
+        WTRACE(3);
         // ---- S3: H2, head, clipped-PPO loss, dZ2 -> d2; issue D3 = dZ2 W2 (into D2's columns) and the weight gradients dW2, db2 ----
         mbar_wait(bar, 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        WTRACE(4);
         {
             const float s_a = live ? in[5] : 0.f, s_b = live ? in[6] : 0.f, s_c = live ? in[7] : 0.f;
             // H2 is kept as packed halves between the head and the backward pass (32 registers instead of 64: the slot's whole state must fit
@@ -1489,13 +1571,10 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
             acc_w3a += h2[0];
             acc_w3b += h2[1];
         }
-        if (OPTS & 2) {
-            park_row(sm->stage[(j & 1u) ^ 1u][s][tg], nr);
-            sm->next_idx[s][tg] = ni;
-        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // D2 has been read by the whole group: D3 may overwrite it
         group_sync(s);
+        WTRACE(5);
         if (issuer) {
             // token: the S3 batches of the two slots accumulate into the same dW2 / db2 columns, in the order 0, 1, 0, 1, ...
             if (s == 0) {
@@ -1527,13 +1606,15 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
             else if (j + 1 < n_iter)
                 token_pass(4);
         }
-        if (!(OPTS & 2)) {
-            nr = load_row(sm->next_idx[s][tg]);
-            ni = load_index(tile + 4 * stride);
-        }
+        WTRACE(6);
+        // the next tile's row (index fetched one round ago) and the index of the tile after it travel under S4 -- every stage ends with
+        // fence.proxy.async, which waits for the thread's outstanding loads, and S3 has no registers to spare -- and are parked before its fence
+        const RowIn nr = load_row(sm->next_idx[s][tg]);
+        const int64_t ni = load_index(round + 2);
         // ---- S4: n * dZ1 = D3 * (1 - H1^2) -> d2 (every MMA that read dZ2 has completed); issue dW1 | db1 += dZ1^T [X | 1] ----
         mbar_wait(bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        WTRACE(7);
         {
             uint32_t ra[32], rb[32];
             tmem_ld32_issue(lane_base, ra);
@@ -1558,10 +1639,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
                 }
             }
         }
-        if (!(OPTS & 2)) {
-            park_row(sm->stage[(j & 1u) ^ 1u][s][tg], nr);
-            sm->next_idx[s][tg] = ni;
-        }
+        park_row(sm->stage[(round & 1u) ^ 1u][s][tg], nr);
+        sm->next_idx[s][tg] = ni;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         group_sync(s);
@@ -1585,11 +1664,14 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
             else if (j + 1 < n_iter)
                 token_pass(6);
         }
+        WTRACE(8);
     }
     mbar_wait(bar, 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    ETRACE(1);
     __syncthreads();   // both slots have retired: the accumulators are final, the operand buffers are free
+    ETRACE(2);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- flush (per-CTA private gradient when `partials` is given, atomics otherwise) ----
@@ -1661,6 +1743,146 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
             else put(&G->b3[q - 6], a);
         }
     }
+    if constexpr (EPOCH) {
+        // ---- the optimiser step of this minibatch, inside the kernel ----
+        float *scr = reinterpret_cast<float *>(sm->d2);   // both slots have retired: [0, per) reduced gradients, [per, per + 512) staging, 16 more
+        const unsigned nG = gridDim.x;
+        const int per = ((A.n_out + static_cast<int>(nG) - 1) / static_cast<int>(nG) + 63) & ~63;   // parameters (and statistics) a CTA owns
+        const int base = static_cast<int>(blockIdx.x) * per;
+        // Adam's bias corrections (as torch.optim.Adam computes them) -- two powf that depend on the step number only
+        const float step = step0 + static_cast<float>(mbi + 1);
+        float step_size = 0.f, inv_sqrt_bc2 = 0.f;
+        if (static_cast<int>(t) < per) {   // only the warps that own parameters pay for the two powf
+            const float bc1 = 1.0f - powf(A.beta1, step), bc2 = 1.0f - powf(A.beta2, step);
+            step_size = A.lr[0] / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+        }
+        // the owners' optimiser state (this CTA wrote it one step ago) is requested before the meeting
+        float m = 0.f, v = 0.f, vm = 0.f, prm = 0.f;
+        int4 dst = make_int4(-1, -1, -1, -1);
+        if (static_cast<int>(t) < per && base + static_cast<int>(t) < A.n) {
+            const int p = base + static_cast<int>(t);
+            m = A.exp_avg[p], v = A.exp_avg_sq[p], vm = A.max_exp_avg_sq[p], prm = A.param[p];
+            dst = reinterpret_cast<const int4 *>(A.scatter)[p];
+        }
+        ETRACE(3);
+        grid_meet(3u * mbi + 1u);   // every CTA's private gradient is in L2
+        ETRACE(4);
+        for (int c0 = 0; c0 < per; c0 += 64) {   // 64 parameters x 8 groups of partial rows per pass, groups added in a fixed order
+            const int p = base + c0 + static_cast<int>(t & 63u);
+            const unsigned g = t >> 6;
+            float sum = 0.f;
+            if (p < A.n_out) {   // the group's rows b = g, g + 8, ...: all loads of a batch of 20 in flight, then added in row order
+                const float *src = partials + p;
+                for (unsigned b0 = g; b0 < nG; b0 += 160) {
+                    float vals[20];
+#pragma unroll
+                    for (int k = 0; k < 20; ++k) {
+                        const unsigned b = b0 + 8u * k;
+                        vals[k] = b < nG ? __ldcg(src + static_cast<size_t>(b) * A.n_out) : 0.f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 20; ++k) sum += vals[k];
+                }
+            }
+            scr[per + t] = sum;
+            __syncthreads();
+            if (t < 64) {
+                float gsum = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) gsum += scr[per + k * 64 + t];
+                scr[c0 + t] = gsum;
+            }
+            __syncthreads();
+        }
+        {   // clip_grad_norm_: this CTA's share of the squared norm
+            float sq = 0.f;
+            for (int i = static_cast<int>(t); i < per; i += kThreadsW)
+                if (base + i < A.n) sq += scr[i] * scr[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (lane == 0) scr[per + 512 + warp] = sq;
+            __syncthreads();
+            if (t == 0) {
+                float tot = 0.f;
+#pragma unroll
+                for (int w = 0; w < 16; ++w) tot += scr[per + 512 + w];
+                reinterpret_cast<float *>(A.sync + 8)[blockIdx.x] = tot;
+            }
+        }
+        ETRACE(5);
+        grid_meet(3u * mbi + 2u);   // every CTA's share is posted
+        const float *sq_all = reinterpret_cast<const float *>(A.sync + 8);
+        ETRACE(6);
+        float tot = 0.f;
+        for (unsigned c0 = lane; c0 < nG; c0 += 160) {   // five loads in flight per lane, added in a fixed order
+            float sv[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) sv[k] = c0 + 32u * k < nG ? __ldcg(sq_all + c0 + 32u * k) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) tot += sv[k];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        float coef = A.max_grad_norm / (sqrtf(tot) + 1e-6f);
+        coef = coef < 1.0f ? coef : 1.0f;
+        // Adam(amsgrad), as torch.optim.Adam computes it (the arithmetic of ppo_reduce_adam_kernel)
+        for (int i = static_cast<int>(t); i < per; i += kThreadsW) {
+            const int p = base + i;
+            if (p >= A.n_out) break;
+            const float grad = scr[i];
+            A.grad[p] = grad;
+            float pn = 0.f;
+            if (p < A.n) {
+                if (i >= kThreadsW) {   // (only when a CTA owns more than 512 parameters: small grids)
+                    m = A.exp_avg[p], v = A.exp_avg_sq[p], vm = A.max_exp_avg_sq[p], prm = A.param[p];
+                    dst = reinterpret_cast<const int4 *>(A.scatter)[p];
+                }
+                const float gc = grad * coef;
+                const float mn = m + (gc - m) * (1.0f - A.beta1);
+                const float vn = v * A.beta2 + (1.0f - A.beta2) * gc * gc;
+                const float vmax = fmaxf(vm, vn);
+                const float denom = sqrtf(vmax) * inv_sqrt_bc2 + A.eps;
+                pn = prm - step_size * (mn / denom);
+                A.exp_avg[p] = mn;
+                A.exp_avg_sq[p] = vn;
+                A.max_exp_avg_sq[p] = vmax;
+                A.param[p] = pn;
+                if (dst.x >= 0) A.fwd_blob[dst.x] = pn;
+                if (dst.y >= 0) A.tail_blob[dst.y] = pn;
+                if (dst.z >= 0) A.half_blob[dst.z] = __float2half_rn(pn);
+                if (dst.w >= 0) A.half_blob[dst.w] = __float2half_rn(pn);
+            }
+            if (A.diag) {   // the five loss statistics sit right behind the parameters, log-std is the last parameter
+                const int k = p - A.n;
+                if (k >= 0 && k < 5) {
+                    if (k == 2) A.diag[2] += grad * A.inv_rows;
+                    else A.diag[k] = grad * A.inv_rows;
+                }
+                if (p == A.n - 1) A.diag[5] = pn + 1.4189385332046727f;   // Gaussian entropy 0.5 + 0.5 log(2 pi) + log std (after the step)
+            }
+        }
+        if (blockIdx.x == 0 && t == 0) A.step[0] = step;
+        ETRACE(7);
+        grid_meet(3u * mbi + 3u);   // the blobs are complete
+        ETRACE(8);
+        if (mbi + 1 < n_mb) {   // the new weights: L2 -> shared memory (plain loads: the blob was written through the generic proxy a moment ago)
+            const uint4 *src = reinterpret_cast<const uint4 *>(blob16);
+            uint4 *dstw = reinterpret_cast<uint4 *>(&sm->w);
+            constexpr unsigned n16 = sizeof(TrainBlob16) / 16, n_it = (n16 + kThreadsW - 1) / kThreadsW;
+            uint4 wv[n_it];
+#pragma unroll
+            for (unsigned k = 0; k < n_it; ++k)
+                if (t + k * kThreadsW < n16) wv[k] = __ldcg(src + t + k * kThreadsW);
+#pragma unroll
+            for (unsigned k = 0; k < n_it; ++k)
+                if (t + k * kThreadsW < n16) dstw[t + k * kThreadsW] = wv[k];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+        }
+        ETRACE(9);
+    }
+  }   // minibatches
+
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
@@ -2173,6 +2395,14 @@ __global__ void __launch_bounds__(256) gae_kernel(int T, int64_t n, const float 
 }  // namespace
 
 #ifdef F16_GRAD_TRACE
+extern "C" int f16_debug_epoch_cta(unsigned long long *out)
+{
+    return static_cast<int>(cudaMemcpyFromSymbol(out, g_epoch_cta, sizeof(g_epoch_cta)));
+}
+extern "C" int f16_debug_epoch_trace(unsigned long long *out)
+{
+    return static_cast<int>(cudaMemcpyFromSymbol(out, g_epoch_trace, sizeof(g_epoch_trace)));
+}
 extern "C" int f16_debug_grad_trace(unsigned long long *out)
 {
     return static_cast<int>(cudaMemcpyFromSymbol(out, g_grad_trace, sizeof(g_grad_trace)));
@@ -2271,13 +2501,13 @@ cudaError_t launch_ppo_pack_rows(int64_t n, const float *obs, const float *actio
 int ppo_grad_floats_padded() { return (static_cast<int>(sizeof(PolicyGrad) / sizeof(float)) + 31) / 32 * 32; }
 int ppo_grad_reduce_ctas() { return (static_cast<int>(sizeof(PolicyGrad) / sizeof(float)) + 31) / 32; }
 
-// the gradient kernel of a minibatch step: variant chosen once per process (tuning knob F16B200_GRAD16: -1 = ppo_grad16_kernel, 256 threads,
-// slots interleaved in program order; 0..3 = ppo_grad16w_kernel<OPTS>, 512 threads, one warp group per slot)
-static int grad16_variant()
+// the gradient kernel of a minibatch step: ppo_grad16w_kernel (512 threads, one warp group per tile slot); F16B200_GRAD16=-1 selects
+// the 256-thread ppo_grad16_kernel (slots interleaved in program order) for A/B measurements
+static bool grad16_interleaved()
 {
-    static const int v = [] {
+    static const bool v = [] {
         const char *e = std::getenv("F16B200_GRAD16");
-        return e ? std::atoi(e) : 0;
+        return e && std::atoi(e) < 0;
     }();
     return v;
 }
@@ -2285,26 +2515,58 @@ static cudaError_t configure_grad16()
 {
     const int bytes = static_cast<int>(sizeof(TrainSmem16));
     cudaError_t e = cudaFuncSetAttribute(ppo_grad16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ppo_grad16w_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ppo_grad16w_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ppo_grad16w_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ppo_grad16w_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ppo_grad16w_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ppo_grad16w_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     return e;
 }
 static cudaError_t launch_grad16_variant(cudaLaunchConfig_t &lc, const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials)
 {
-    const int v = grad16_variant();
-    if (v < 0) {
+    if (grad16_interleaved()) {
         lc.blockDim = dim3(kThreads);
         return cudaLaunchKernelEx(&lc, ppo_grad16_kernel, P, blob16, partials);
     }
     lc.blockDim = dim3(kThreadsW);
-    switch (v & 3) {
-    case 0: return cudaLaunchKernelEx(&lc, ppo_grad16w_kernel<0>, P, blob16, partials);
-    case 1: return cudaLaunchKernelEx(&lc, ppo_grad16w_kernel<1>, P, blob16, partials);
-    case 2: return cudaLaunchKernelEx(&lc, ppo_grad16w_kernel<2>, P, blob16, partials);
-    default: return cudaLaunchKernelEx(&lc, ppo_grad16w_kernel<3>, P, blob16, partials);
+    ReduceAdamArgs none = {};
+    return cudaLaunchKernelEx(&lc, ppo_grad16w_kernel<false>, P, blob16, partials, none, 1);
+}
+
+size_t ppo_epoch16_sync_bytes() { return 8 + 1024 * sizeof(float); }   // meeting counter + one squared-norm share per CTA
+
+// One launch = the n_mb minibatch steps of an epoch (gradient + reduction + clip + Adam + blob scatter each): ppo_grad16w_kernel<true>.
+// P.mb_idx: n_mb * P.n indices, P.adv_stats: n_mb pairs.  Cooperative launch (the CTAs meet at a grid-wide counter three times per step).
+cudaError_t launch_ppo_epoch16(const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials, ReduceAdamArgs RA, int n_mb, int n_sm, cudaStream_t st)
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = configure_grad16();
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
     }
+    const int64_t tiles = (P.n + kRows - 1) / kRows;
+    const int grid = static_cast<int>(tiles < n_sm ? tiles : n_sm);
+    if (grid > 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(RA.sync, 0, 8, st);   // the meeting counter counts from zero in every launch
+    if (e != cudaSuccess) return e;
+    RA.partials = partials;
+    RA.n_rows = grid;
+    RA.n_out = static_cast<int>(sizeof(PolicyGrad) / sizeof(float));
+    RA.grad = reinterpret_cast<float *>(P.grad);
+    RA.n_pad = ppo_grad_floats_padded();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kThreadsW);
+    lc.dynamicSmemBytes = sizeof(TrainSmem16);
+    lc.stream = st;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    e = cudaLaunchKernelEx(&lc, ppo_grad16w_kernel<true>, P, blob16, partials, RA, n_mb);
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_ppo_grad16(const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials, int n_sm, cudaStream_t st, const PeerArgs *peer)

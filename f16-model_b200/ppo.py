@@ -41,6 +41,8 @@ class PPOConfig:
     fused_precision: str = "fp16"        # tensor-core operands of the fused kernel: "fp16" (weight gradients on the tensor cores too) or "tf32"
     fused_optimizer: bool = True         # fused fp16 update: reduction (+ all-reduce) + clip + Adam + blob re-packing in ONE multi-CTA kernel (f16_ppo_step16)
                                          # instead of the reduction kernel followed by the single-CTA optimiser kernel
+    fused_epoch: bool = True             # single rank, fused fp16 update: ALL minibatch steps of an epoch in ONE persistent cooperative kernel (f16_ppo_epoch16:
+                                         # the optimiser step is taken inside the gradient kernel, between grid-wide meetings) instead of two launches per minibatch
     peer_allreduce: bool = True          # world > 1, fused fp16 update: the gradient all-reduce rides in the gradient-reduction kernel over NVLink peer
                                          # memory (f16_ppo_grad16_peer) instead of an NCCL call per minibatch; falls back to NCCL when the ranks cannot map each other
     graph_allreduce: bool = True         # world > 1: capture the NCCL gradient all-reduce inside the update's CUDA graph (call close() before destroy_process_group)
@@ -307,6 +309,7 @@ class PPOTrainer:
 
             self._scatter = scatter_table(self._n_params, self._fwd_perm, self._train_perm, self._half_perm)
             self._sync16 = torch.zeros(L.f16_ppo_step16_sync_bytes(), dtype=torch.uint8, device=dev)
+            self._sync_epoch = torch.zeros(L.f16_ppo_epoch16_sync_bytes(), dtype=torch.uint8, device=dev)
             self._step16 = _capi.PpoStep16()
         self._params = list(pol.parameters())
         self._adv_stats = torch.zeros(2, device=dev)
@@ -314,9 +317,11 @@ class PPOTrainer:
         self._grad_scratch = torch.empty(max(1, L.f16_ppo_grad16_scratch_floats(dev.index)), device=dev) if self._fp16 else None
         self._adam = [torch.zeros(self._n_params, device=dev) for _ in range(3)] + [torch.zeros(1, device=dev)]   # m, v, vmax, step
 
-    def _fused_minibatch_step(self, mb, adv_stats=None):
+    def _fused_minibatch_step(self, mb, adv_stats=None, epoch_minibatches=0):
         """The same optimiser step in two kernels: forward + loss + backward (ppo_grad_kernel), then clip + Adam + blob
-        re-packing (ppo_adam_kernel); csrc/f16_policy.cu."""
+        re-packing (ppo_adam_kernel); csrc/f16_policy.cu.  With ``epoch_minibatches`` = k > 0 (single rank, fused fp16 optimiser): the k
+        consecutive minibatch steps whose indices start at ``mb`` and whose advantage statistics start at ``adv_stats``, in one
+        persistent kernel (f16_ppo_epoch16)."""
         torch, cfg = self._torch, self.cfg
         b = self._flat
         L = _capi.load_library()
@@ -338,6 +343,8 @@ class PPOTrainer:
                     self._g.data_ptr(), float(cfg.clip_coef), float(cfg.vf_coef), float(cfg.ent_coef),
                     int(bool(cfg.norm_adv)), int(bool(cfg.clip_vloss)))
             peer = self._peer if self._fp16 else None
+            if epoch_minibatches:   # every minibatch step of the epoch in ONE persistent cooperative kernel; `mb` is the first minibatch's slice of the permutation
+                assert self._step16 is not None and self.world == 1
             if self._step16 is not None and (self.world == 1 or peer is not None):   # gradient kernel + ONE kernel for reduction / all-reduce / clip / Adam / blob scatter
                 a = self._step16
                 (a.n, a.train_blob16, a.obs, a.actions, a.logprobs, a.adv, a.ret, a.val, a.mb_idx, a.logstd, a.adv_stats, a.grad, a.clip_coef,
@@ -351,7 +358,11 @@ class PPOTrainer:
                 a.scatter, a.fwd_blob, a.tail_blob, a.half_blob = (self._scatter.data_ptr(), self.policy._blob.data_ptr(),
                                                                     self._blob_tail.data_ptr(), self._train_blob.data_ptr())
                 a.diag, a.inv_rows, a.sync = self._diag.data_ptr(), 1.0 / mb.numel(), self._sync16.data_ptr()
-                _capi.check(L.f16_ppo_step16(C.byref(a), st))
+                if epoch_minibatches:
+                    a.sync = self._sync_epoch.data_ptr()
+                    _capi.check(L.f16_ppo_epoch16(C.byref(a), int(epoch_minibatches), st))
+                else:
+                    _capi.check(L.f16_ppo_step16(C.byref(a), st))
                 return
             if peer is not None:   # ... and the cross-rank mean in the same reduction kernel (peer memory, no NCCL call)
                 _capi.check(L.f16_ppo_grad16_peer(*args, self._grad_scratch.data_ptr(), C.byref(peer.group), st))
@@ -468,8 +479,11 @@ class PPOTrainer:
                         _capi.check(_capi.load_library().f16_ppo_adv_stats(
                             self.minibatch_size, len(starts), self._flat["adv"].data_ptr(), self._perm_buf.data_ptr(),
                             self._adv_stats_epoch.data_ptr(), self._adv_scratch_epoch.data_ptr(), _capi.stream_ptr(self.device)))
-                for k, start in enumerate(starts):
-                    self._fused_minibatch_step(self._perm_buf[start:start + self.minibatch_size], adv_stats=self._adv_stats_epoch[k])
+                if self._step16 is not None and self.world == 1 and self.cfg.fused_epoch:
+                    self._fused_minibatch_step(self._perm_buf[: self.minibatch_size], adv_stats=self._adv_stats_epoch[0], epoch_minibatches=len(starts))
+                else:
+                    for k, start in enumerate(starts):
+                        self._fused_minibatch_step(self._perm_buf[start:start + self.minibatch_size], adv_stats=self._adv_stats_epoch[k])
             else:
                 self._minibatch_step(self._mb_idx)
         with torch.no_grad():                              # undo the warm-up steps IN PLACE (the graph holds these tensors)

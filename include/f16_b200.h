@@ -352,6 +352,18 @@ typedef struct f16_ppo_step16_args {
 int f16_ppo_step16_sync_bytes(void);
 int f16_ppo_step16(const f16_ppo_step16_args *a, void *stream);
 
+/* A whole EPOCH of Agent.train's update loop (control/ppo/ppo_model_gsde.py:295-364: the inner `for start in range(0, batch_size,
+ * minibatch_size)` loop) in ONE persistent cooperative launch on one rank: n_minibatches steps, each the gradient of f16_ppo_grad16
+ * followed by the optimiser step of f16_ppo_step16, with the optimiser step taken INSIDE the kernel -- the CTAs meet at a grid-wide
+ * counter, each sums the partial gradients of the parameters it owns, the squared-norm shares are exchanged, the owners apply
+ * clip_grad_norm_ + Adam(amsgrad) and scatter the new parameters into the three blobs, and every CTA re-reads the training blob.
+ * Arguments as f16_ppo_step16 except: mb_idx holds n_minibatches * n indices (minibatch k reads [k n, (k + 1) n)), adv_stats holds
+ * n_minibatches (mean, std) pairs, peer must be NULL, and sync points to f16_ppo_epoch16_sync_bytes() bytes of its own (not the
+ * buffer f16_ppo_step16 uses; no initialisation needed).  diag, step: as after n_minibatches calls of f16_ppo_step16; grad holds
+ * the last minibatch's gradient and statistics.  The call replays from a CUDA graph. */
+int f16_ppo_epoch16_sync_bytes(void);
+int f16_ppo_epoch16(const f16_ppo_step16_args *a, int n_minibatches, void *stream);
+
 /* The optimiser half of the minibatch step (ppo_model_gsde.py:360-364: clip_grad_norm_(max_grad_norm) then
  * Adam(amsgrad=True).step()) on the flat parameter vector (same field order as the gradient of f16_ppo_grad), followed
  * by re-packing the rollout blob and the training blob from the updated parameters: blob word k = param[perm[k] - 1],

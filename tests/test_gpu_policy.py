@@ -406,3 +406,37 @@ def test_fused_step16_equals_gradient_then_adam(f16):
     assert torch.equal(pol._blob, pack_policy_blob(pol.actor_mean, pol.critic))
     assert torch.equal(a._train_blob, pack_train_blob16(pol.actor_mean, pol.critic))
     assert torch.isfinite(a._diag).all() and abs(a._diag[5].item() - (pol.actor_logstd.item() + 1.4189385332046727)) < 1e-6
+
+
+@pytest.mark.parametrize("n_envs,num_minibatches", [(4096, 4), (512, 8), (32768, 2)])
+def test_fused_epoch16_equals_step16_per_minibatch(f16, n_envs, num_minibatches):
+    """f16_ppo_epoch16 (ALL minibatch steps of an epoch in one persistent cooperative kernel, the optimiser step taken inside it between
+    grid-wide meetings) against f16_ppo_step16 called once per minibatch on the same minibatches: the same gradients (same kernel code,
+    same reduction order), parameters / Adam state equal up to the summation order of the gradient norm, the same diagnostics, and
+    every blob word equal to a fresh packing of the final parameters.  Grids of 128 CTAs (two 64-parameter passes per CTA), 8 CTAs
+    (a CTA owns more than 512 parameters) and 148 CTAs (the production shape)."""
+    from f16_model_b200.policy import pack_policy_blob, pack_train_blob16
+
+    cfg = {"dt": 0.01, "tn": 10, "debug_state": False, "determenistic_ref": False, "scenario": "combo"}
+    trainers, hist = [], []
+    for epoch in (True, False):
+        envs = f16.F16VecEnv(cfg, n_envs, seed=2, fast_math=True)
+        pol = f16.TensorCorePolicy(seed=2, logstd_init=-0.5)
+        tr = f16.PPOTrainer(envs, pol, f16.PPOConfig(num_steps=16, num_minibatches=num_minibatches, update_epochs=3, learning_rate=3e-3,
+                                                     max_grad_norm=0.05, fused_epoch=epoch))
+        hist.append(tr.train(num_updates=2))
+        trainers.append(tr)
+    a, b = trainers
+    n = a._n_params
+    assert float(a._adam[3].item()) == float(b._adam[3].item()) == 2 * 3 * num_minibatches
+    rel = lambda x, y: ((x - y).norm() / (y.norm() + 1e-12)).item()   # noqa: E731
+    assert rel(a._pflat[:n], b._pflat[:n]) < 5e-5, rel(a._pflat[:n], b._pflat[:n])   # up to 48 clipped steps: only the norm's summation order differs
+    for k in range(3):
+        assert rel(a._adam[k], b._adam[k]) < 1e-3
+    assert torch.allclose(a._diag, b._diag, rtol=2e-3, atol=1e-5), (a._diag, b._diag)
+    assert torch.allclose(a._g, b._g, rtol=2e-2, atol=1e-6)          # the last minibatch's gradient and statistics
+    pol = a.policy
+    assert torch.equal(pol._blob, pack_policy_blob(pol.actor_mean, pol.critic))
+    assert torch.equal(a._train_blob, pack_train_blob16(pol.actor_mean, pol.critic))
+    for k in ("value_loss", "approx_kl", "entropy"):
+        assert abs(hist[0][-1][k] - hist[1][-1][k]) <= 2e-3 * max(1.0, abs(hist[1][-1][k])), (k, hist[0][-1][k], hist[1][-1][k])
