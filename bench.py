@@ -817,7 +817,8 @@ def kernel_rooflines(torch, f16, _capi, L, device, rank, world, peaks, peak_kind
         rows = mb.numel()
         us = graph_us(lambda: _capi.check(L.f16_ppo_grad16(*args16, tr._grad_scratch.data_ptr(), st())), reps=10)
         flops = 2.0 * rows * (16 * 128 + 2 * 64 * 64 + 2 * 64 * 64 + 128 * 128 + 16 * 128 + 16 * 128)   # MACs issued per row: fwd L1, L2; dZ2 W2; dW2 (both nets in one M=N=128 product); db2|dW1
-        entry("ppo_grad16_kernel + ppo_grad_reduce (forward + clipped-PPO loss + backward of both MLPs, tcgen05 kind::f16; two tiles in flight per CTA, packed rows)", "mufu",
+        entry("ppo_grad16w_kernel + ppo_grad_reduce (forward + clipped-PPO loss + backward of both MLPs, tcgen05 kind::f16; 512 threads, one warp group per tile slot, "
+              "token-ordered weight-gradient batches, packed rows)", "mufu",
               256 * rows / (us * 1e-6) / 1e9, pipe["mufu_tanh"] / 1e9, "G tanh/s", us, rows,
               peak_kind="MUFU.TANH results/s of f16_peak_probe in this run",
               algorithmic_per_unit="256 tanh per minibatch row (the forward); the backward reuses H1, H2",
@@ -840,8 +841,8 @@ def kernel_rooflines(torch, f16, _capi, L, device, rank, world, peaks, peak_kind
         # the trainer's default minibatch step: gradient kernel + ONE multi-CTA kernel (reduction, clip, Adam, blob scatter)
         if getattr(tr, "_step16", None) is not None:
             us_step = graph_us(lambda: tr._fused_minibatch_step(mb, adv_stats=tr._adv_stats), reps=10)
-            us_grad = [e for e in out if e.get("kernel", "").startswith("ppo_grad16_kernel")][-1]["avg_launch_us"]
-            entry("f16_ppo_step16 = ppo_grad16_kernel + ppo_reduce_adam_kernel (gradient reduction + clip_grad_norm + Adam(amsgrad) + blob scatter in one "
+            us_grad = [e for e in out if e.get("kernel", "").startswith("ppo_grad16w_kernel")][-1]["avg_launch_us"]
+            entry("f16_ppo_step16 = ppo_grad16w_kernel + ppo_reduce_adam_kernel (gradient reduction + clip_grad_norm + Adam(amsgrad) + blob scatter in one "
                   "289-CTA launch with a grid-wide arrival counter): one whole minibatch step, two launches", "mufu",
                   256 * rows / (us_step * 1e-6) / 1e9, pipe["mufu_tanh"] / 1e9, "G tanh/s", us_step, rows,
                   peak_kind="MUFU.TANH results/s of f16_peak_probe in this run",
@@ -849,6 +850,19 @@ def kernel_rooflines(torch, f16, _capi, L, device, rank, world, peaks, peak_kind
                   optimizer_half_us=us_step - us_grad,
                   note="optimizer_half_us = this entry minus the gradient + plain-reduction entry above: what reduction + clip + Adam + re-packing cost "
                        "inside the chain (the separate single-CTA ppo_adam_kernel below costs its whole launch)")
+            # the trainer's default on one rank: ALL minibatch steps of an epoch in one persistent cooperative launch (optimiser step inside the kernel)
+            n_mb = tr.batch_size // tr.minibatch_size
+            tr._adv_stats_epoch[:, 0], tr._adv_stats_epoch[:, 1] = tr._adv_stats[0], tr._adv_stats[1]
+            us_epoch = graph_us(lambda: tr._fused_minibatch_step(tr._perm_buf[: tr.minibatch_size], adv_stats=tr._adv_stats_epoch[0], epoch_minibatches=n_mb),
+                                reps=2, replays=3)
+            us_mb = us_epoch / n_mb
+            entry("f16_ppo_epoch16 = ppo_grad16w_kernel<EPOCH> (persistent over the %d minibatch steps of an epoch: gradient, flush, three grid-wide meetings around "
+                  "reduction / norm / clip + Adam(amsgrad) + blob scatter, weight reload -- ONE cooperative launch per epoch); per MINIBATCH step" % n_mb, "mufu",
+                  256 * rows / (us_mb * 1e-6) / 1e9, pipe["mufu_tanh"] / 1e9, "G tanh/s", us_mb, rows,
+                  peak_kind="MUFU.TANH results/s of f16_peak_probe in this run",
+                  algorithmic_per_unit="256 tanh per minibatch row; the optimiser step has no throughput roofline (9.3 k parameters)",
+                  launch_us=us_epoch, minibatches_per_launch=n_mb, optimizer_half_us=us_mb - us_grad,
+                  note="optimizer_half_us = this entry minus the gradient + plain-reduction entry above (which includes a reduction launch of its own)")
         del tr, envs4, pol4
 
     # ---- trim search (FP64 pipe) ----

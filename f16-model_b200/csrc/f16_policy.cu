@@ -1356,11 +1356,13 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
     mbar_wait(&sm->bar_w, 0);
 
     // ---- EPOCH: grid-wide meetings at one counter (zeroed by the launcher before every launch; a cooperative launch: all CTAs are resident) ----
+    // (the cooperative-groups pattern: the CTA's writes are ordered before thread 0's fence by the CTA barrier, the fence is cumulative;
+    // everything read after a meeting is read with ld.global.cg, past the non-coherent L1)
     auto grid_meet = [&](unsigned n_meet) {   // n_meet: the number of this meeting in the launch, from 1
-        __threadfence();
         __syncthreads();
         if (t == 0) {
             unsigned long long *arrive = reinterpret_cast<unsigned long long *>(A.sync);
+            __threadfence();
             atomicAdd(arrive, 1ull);
             const unsigned long long want = static_cast<unsigned long long>(n_meet) * gridDim.x;
             unsigned long long t0 = 0ull;
@@ -1813,7 +1815,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
         grid_meet(3u * mbi + 2u);   // every CTA's share is posted
         const float *sq_all = reinterpret_cast<const float *>(A.sync + 8);
         ETRACE(6);
+        // (only the warps that own parameters: every warp of every CTA reading the same five lines of L2 took 1.5 us)
         float tot = 0.f;
+        if (static_cast<int>(warp) * 32 < per)
         for (unsigned c0 = lane; c0 < nG; c0 += 160) {   // five loads in flight per lane, added in a fixed order
             float sv[5];
 #pragma unroll
