@@ -711,6 +711,11 @@ struct alignas(16) TrainSmem16 {
     uint64_t bar_mma[2];
     uint32_t tmem_base;
     float red[16];
+    // ppo_grad16w_kernel: the biases ride in the MMAs, as in rollout_kernel: b = hi + lo in fp16 against two columns of ones (layer 1: X columns
+    // 5, 6 and the CTA's copy of W1; layer 2: one more K = 16 MMA per net, A = `ones`, B = `wb2`)
+    alignas(16) __half ones[2][kRows][8];
+    alignas(16) __half wb2[2][2][kHid][8];
+    alignas(16) __half2 w3h[64];      // ppo_grad16w_kernel: the heads' weights as packed halves (actor 0-31 | critic 32-63), for the half2 backward arithmetic
 };
 static_assert(sizeof(TrainSmem16) <= 227 * 1024, "shared memory per CTA");
 
@@ -1255,6 +1260,10 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (half == 1) *reinterpret_cast<uint4 *>(sm->a1[s][1][row]) = make_uint4(0u, 0u, 0u, 0u);   // K padding 8..15 of the slot's X operand
+    if (t < kRows) {   // the layer-2 bias MMA's A operand: k = 0, 1 are 1.0 in every row
+        *reinterpret_cast<uint4 *>(sm->ones[0][t]) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(sm->ones[1][t]) = make_uint4(0u, 0u, 0u, 0u);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1354,6 +1363,24 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
                      : "memory");
     }
     mbar_wait(&sm->bar_w, 0);
+    // derived operands of a freshly loaded blob: biases as (hi, lo) halves into W1's columns 5, 6 and into wb2, w3 as packed halves
+    auto derive_weights = [&]() {
+        if (t < 128) {
+            const float b1v = W.b1[t], b2v = W.b2[t];
+            const __half h1 = __float2half_rn(b1v), h2v = __float2half_rn(b2v);
+            sm->w.w1[0][t][5] = h1;
+            sm->w.w1[0][t][6] = __float2half_rn(b1v - __half2float(h1));
+            const __half2 b2p = __halves2half2(h2v, __float2half_rn(b2v - __half2float(h2v)));
+            *reinterpret_cast<uint4 *>(sm->wb2[t >> 6][0][t & 63u]) = make_uint4(*reinterpret_cast<const uint32_t *>(&b2p), 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(sm->wb2[t >> 6][1][t & 63u]) = make_uint4(0u, 0u, 0u, 0u);
+        } else if (t < 192) {
+            const unsigned c = t - 128;
+            sm->w3h[c] = __floats2half2_rn(W.w3[2 * c], W.w3[2 * c + 1]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    };
+    derive_weights();
 
     // ---- EPOCH: grid-wide meetings at one counter (zeroed by the launcher before every launch; a cooperative launch: all CTAs are resident) ----
     // (the cooperative-groups pattern: the CTA's writes are ordered before thread 0's fence by the CTA barrier, the fence is cumulative;
@@ -1407,7 +1434,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
         }
         // ---- S1: observation row -> X operand (1 in column 5: bias gradients = that column of dZ^T [X | 1]); issue layer 1 ----
         if (half == 0) {
-            float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f};
+            float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1.f, 0.f};   // columns 5, 6: the ones of the bias (hi, lo) rows of W1; column 5 also yields db
             if (live) {
 #pragma unroll
                 for (int k = 0; k < 5; ++k) x[k] = in[k];
@@ -1440,7 +1467,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
                     const int jj = col0 + c * 8;
                     float h[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) h[q] = fast_tanh(__uint_as_float(blk ? rb[c * 8 + q] : ra[c * 8 + q]) + W.b1[jj + q]);
+                    for (int q = 0; q < 8; ++q) h[q] = fast_tanh(__uint_as_float(blk ? rb[c * 8 + q] : ra[c * 8 + q]));   // (b1 came with the MMA)
                     *reinterpret_cast<uint4 *>(a2p + (jj >> 3) * kLboH + row * 16u) = pack8(h);
                 }
             }
@@ -1458,6 +1485,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
                 for (int k = 0; k < 4; ++k)
                     umma_f16(tcol + 64, umma_desc(a2u + (8 + k * 2) * kLboH, kLboH, 128), umma_desc(w2c + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
                              k > 0 ? 1u : 0u);
+#pragma unroll
+                for (int net = 0; net < 2; ++net)   // + b2: ones (k = 0, 1) times (hi, lo)
+                    umma_f16(tcol + net * 64, umma_desc(smem_u32(sm->ones), kRows * 16, 128), umma_desc(smem_u32(sm->wb2[net]), kHid * 16, 128), id_l2, 1u);
                 umma_commit(bar);
             }
             if (s == 0 && j == 0) {
@@ -1486,8 +1516,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
                     const int col0 = half * 64 + blk * 32;
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
-                        const float h0 = fast_tanh(__uint_as_float(blk ? rb[2 * c] : ra[2 * c]) + W.b2[col0 + 2 * c]);
-                        const float h1 = fast_tanh(__uint_as_float(blk ? rb[2 * c + 1] : ra[2 * c + 1]) + W.b2[col0 + 2 * c + 1]);
+                        const float h0 = fast_tanh(__uint_as_float(blk ? rb[2 * c] : ra[2 * c]));   // (b2 came with the MMAs)
+                        const float h1 = fast_tanh(__uint_as_float(blk ? rb[2 * c + 1] : ra[2 * c + 1]));
                         head = fmaf(h0, W.w3[col0 + 2 * c], head);
                         head = fmaf(h1, W.w3[col0 + 2 * c + 1], head);
                         const __half2 hh = __floats2half2_rn(h0, h1);
@@ -1536,25 +1566,31 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
             // n * dZ2 = g * w3 * (1 - H2^2) -> d2 (fp16); dW3 = sum over rows of dy * H2 in fp32: the 64 products of a thread are summed over the
             // warp's 32 rows by a transposing shuffle butterfly (lane l ends with columns 2l, 2l+1).  Its first level pairs column i with i + 32,
             // so the columns are walked as chunk pairs (c, c + 4) and only the 32 level-1 sums stay live
+            // dZ2 is an fp16 tensor-core operand and H2 is held in fp16, so g is computed in packed-half arithmetic -- three HFMA2-pipe instructions
+            // per PAIR of columns (1 - h^2, g_head * w3, their product) instead of eight fp32 ones and a conversion
             float h2[32];
             {
                 const bool upper = (lane & 16u) != 0u;
+                const __half2 gh2 = __float2half2_rn(g_head), one2 = __float2half2_rn(1.0f);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     float pl[8], ph[8];
 #pragma unroll
                     for (int hi = 0; hi < 2; ++hi) {
                         const int jj = half * 64 + hi * 32 + c * 8;
-                        float g[8];
+                        const uint4 w3q = *reinterpret_cast<const uint4 *>(&sm->w3h[jj >> 1]);   // 8 columns of w3 (same address in every lane)
+                        const __half2 *w3p = reinterpret_cast<const __half2 *>(&w3q);
+                        uint4 gq;
+                        __half2 *gp = reinterpret_cast<__half2 *>(&gq);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float2 h = __half22float2(*reinterpret_cast<const __half2 *>(&hp[hi * 16 + c * 4 + q]));
-                            g[2 * q] = g_head * W.w3[jj + 2 * q] * (1.0f - h.x * h.x);
-                            g[2 * q + 1] = g_head * W.w3[jj + 2 * q + 1] * (1.0f - h.y * h.y);
+                            const __half2 hq = *reinterpret_cast<const __half2 *>(&hp[hi * 16 + c * 4 + q]);
+                            gp[q] = __hmul2(__hmul2(gh2, w3p[q]), __hfma2(__hneg2(hq), hq, one2));
+                            const float2 h = __half22float2(hq);
                             (hi ? ph : pl)[2 * q] = dy * h.x;
                             (hi ? ph : pl)[2 * q + 1] = dy * h.y;
                         }
-                        *reinterpret_cast<uint4 *>(d2p + (jj >> 3) * kLboH + row * 16u) = pack8(g);
+                        *reinterpret_cast<uint4 *>(d2p + (jj >> 3) * kLboH + row * 16u) = gq;
                     }
 #pragma unroll
                     for (int q = 0; q < 8; ++q) h2[c * 8 + q] = (upper ? ph[q] : pl[q]) + __shfl_xor_sync(0xffffffffu, upper ? pl[q] : ph[q], 16);
@@ -1630,14 +1666,16 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
                     const int jj = col0 + c * 8;
                     const uint4 raw = *reinterpret_cast<const uint4 *>(a2p + (jj >> 3) * kLboH + row * 16u);
                     const __half2 *hh = reinterpret_cast<const __half2 *>(&raw);
-                    float g[8];
+                    uint4 gq;   // packed-half arithmetic, as in S3: D3 -> fp16, times (1 - h^2)
+                    __half2 *gp = reinterpret_cast<__half2 *>(&gq);
+                    const __half2 one2 = __float2half2_rn(1.0f);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float2 h = __half22float2(hh[q]);
-                        g[2 * q] = __uint_as_float(blk ? rb[c * 8 + 2 * q] : ra[c * 8 + 2 * q]) * (1.0f - h.x * h.x);
-                        g[2 * q + 1] = __uint_as_float(blk ? rb[c * 8 + 2 * q + 1] : ra[c * 8 + 2 * q + 1]) * (1.0f - h.y * h.y);
+                        const __half2 d = __floats2half2_rn(__uint_as_float(blk ? rb[c * 8 + 2 * q] : ra[c * 8 + 2 * q]),
+                                                            __uint_as_float(blk ? rb[c * 8 + 2 * q + 1] : ra[c * 8 + 2 * q + 1]));
+                        gp[q] = __hmul2(d, __hfma2(__hneg2(hh[q]), hh[q], one2));
                     }
-                    *reinterpret_cast<uint4 *>(d2p + (jj >> 3) * kLboH + row * 16u) = pack8(g);
+                    *reinterpret_cast<uint4 *>(d2p + (jj >> 3) * kLboH + row * 16u) = gq;
                 }
             }
         }
@@ -1880,8 +1918,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
 #pragma unroll
             for (unsigned k = 0; k < n_it; ++k)
                 if (t + k * kThreadsW < n16) dstw[t + k * kThreadsW] = wv[k];
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
+            derive_weights();
         }
         ETRACE(9);
     }

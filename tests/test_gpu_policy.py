@@ -434,7 +434,8 @@ def test_fused_epoch16_equals_step16_per_minibatch(f16, n_envs, num_minibatches)
     for k in range(3):
         assert rel(a._adam[k], b._adam[k]) < 1e-3
     assert torch.allclose(a._diag, b._diag, rtol=2e-3, atol=1e-5), (a._diag, b._diag)
-    assert torch.allclose(a._g, b._g, rtol=2e-2, atol=1e-6)          # the last minibatch's gradient and statistics
+    assert rel(a._g[:n], b._g[:n]) < 1e-2, rel(a._g[:n], b._g[:n])   # the last minibatch's gradient (parameters differ by ~1e-5: fp16 roundings flip)
+    assert torch.allclose(a._g[n:], b._g[n:], rtol=2e-3, atol=1e-3)  # and its five summed statistics
     pol = a.policy
     assert torch.equal(pol._blob, pack_policy_blob(pol.actor_mean, pol.critic))
     assert torch.equal(a._train_blob, pack_train_blob16(pol.actor_mean, pol.critic))
