@@ -1563,18 +1563,21 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
             }
             const float dy = g_head * inv_n;
             acc_b3 += dy;
-            // n * dZ2 = g * w3 * (1 - H2^2) -> d2 (fp16); dW3 = sum over rows of dy * H2 in fp32: the 64 products of a thread are summed over the
-            // warp's 32 rows by a transposing shuffle butterfly (lane l ends with columns 2l, 2l+1).  Its first level pairs column i with i + 32,
-            // so the columns are walked as chunk pairs (c, c + 4) and only the 32 level-1 sums stay live
-            // dZ2 is an fp16 tensor-core operand and H2 is held in fp16, so g is computed in packed-half arithmetic -- three HFMA2-pipe instructions
-            // per PAIR of columns (1 - h^2, g_head * w3, their product) instead of eight fp32 ones and a conversion
-            float h2[32];
+            // n * dZ2 = g * w3 * (1 - H2^2) -> d2 (fp16), in packed-half arithmetic (dZ2 is an fp16 tensor-core operand and H2 is held in fp16): three
+            // HFMA2-pipe instructions per PAIR of columns (1 - h^2, g_head * w3, their product) instead of eight fp32 ones and a conversion.
+            // dW3 = sum over rows of dy * H2: the thread's 32 packed products (g_head / 32) * h -- 1 / 32: the sum of a warp's 32 rows stays
+            // within fp16's range whenever g_head itself does -- are summed over the warp's rows by a transposing shuffle butterfly on half2 words
+            // (each level halves the word count and pairs lanes o apart; lane l ends with word l = columns 2l, 2l + 1) and leave the butterfly
+            // as fp32: 31 shuffles per tile instead of the 62 of an fp32 butterfly, no conversions.
+            uint32_t pw[16];
             {
                 const bool upper = (lane & 16u) != 0u;
-                const __half2 gh2 = __float2half2_rn(g_head), one2 = __float2half2_rn(1.0f);
+                const __half2 gh2 = __float2half2_rn(g_head), gs2 = __float2half2_rn(g_head * (1.0f / 32.0f)), one2 = __float2half2_rn(1.0f);
+                auto h2u = [](const __half2 v) { return *reinterpret_cast<const uint32_t *>(&v); };
+                auto u2h = [](const uint32_t v) { return *reinterpret_cast<const __half2 *>(&v); };
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    float pl[8], ph[8];
+                    uint32_t pl[4], ph[4];
 #pragma unroll
                     for (int hi = 0; hi < 2; ++hi) {
                         const int jj = half * 64 + hi * 32 + c * 8;
@@ -1584,30 +1587,29 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
                         __half2 *gp = reinterpret_cast<__half2 *>(&gq);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const __half2 hq = *reinterpret_cast<const __half2 *>(&hp[hi * 16 + c * 4 + q]);
+                            const __half2 hq = u2h(hp[hi * 16 + c * 4 + q]);
                             gp[q] = __hmul2(__hmul2(gh2, w3p[q]), __hfma2(__hneg2(hq), hq, one2));
-                            const float2 h = __half22float2(hq);
-                            (hi ? ph : pl)[2 * q] = dy * h.x;
-                            (hi ? ph : pl)[2 * q + 1] = dy * h.y;
+                            (hi ? ph : pl)[q] = h2u(__hmul2(gs2, hq));
                         }
                         *reinterpret_cast<uint4 *>(d2p + (jj >> 3) * kLboH + row * 16u) = gq;
                     }
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) h2[c * 8 + q] = (upper ? ph[q] : pl[q]) + __shfl_xor_sync(0xffffffffu, upper ? pl[q] : ph[q], 16);
+                    for (int q = 0; q < 4; ++q)   // first level: word e with word e + 16 (columns i and i + 32)
+                        pw[c * 4 + q] = h2u(__hadd2(u2h(upper ? ph[q] : pl[q]), u2h(__shfl_xor_sync(0xffffffffu, upper ? pl[q] : ph[q], 16))));
                 }
-            }
 #pragma unroll
-            for (int sz = 16; sz >= 2; sz >>= 1) {   // 32 -> 16 -> 8 -> 4 -> 2 values; lanes whose bit sz/2 is set keep the upper half
-                const unsigned o = static_cast<unsigned>(sz) >> 1;
-                const bool upper = (lane & o) != 0u;
+                for (int sz = 8; sz >= 1; sz >>= 1) {   // 16 -> 8 -> 4 -> 2 -> 1 words; lanes whose bit sz is set keep the upper half
+                    const bool up = (lane & static_cast<unsigned>(sz)) != 0u;
 #pragma unroll
-                for (int i = 0; i < sz; ++i) {
-                    const float lo = h2[i], hi = h2[i + sz];
-                    h2[i] = (upper ? hi : lo) + __shfl_xor_sync(0xffffffffu, upper ? lo : hi, o);
+                    for (int i = 0; i < sz; ++i) {
+                        const uint32_t lo = pw[i], hi = pw[i + sz];
+                        pw[i] = h2u(__hadd2(u2h(up ? hi : lo), u2h(__shfl_xor_sync(0xffffffffu, up ? lo : hi, sz))));
+                    }
                 }
+                const float2 w3sum = __half22float2(u2h(pw[0]));
+                acc_w3a += w3sum.x * (32.0f * inv_n);
+                acc_w3b += w3sum.y * (32.0f * inv_n);
             }
-            acc_w3a += h2[0];
-            acc_w3b += h2[1];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // D2 has been read by the whole group: D3 may overwrite it
