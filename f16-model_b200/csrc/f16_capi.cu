@@ -848,7 +848,7 @@ int f16_ppo_step16_sync_bytes(void) { return static_cast<int>((f16::ppo_step16_s
 static int ppo_step16_impl(const f16_ppo_step16_args *a, int n_minibatches, bool epoch, void *stream)
 {
     if (!a) return fail(F16_EINVAL, "args is NULL");
-    if (epoch && (n_minibatches < 1 || a->peer)) return fail(F16_EINVAL, "f16_ppo_epoch16: n_minibatches >= 1 and peer == NULL (single rank)");
+    if (epoch && n_minibatches < 1) return fail(F16_EINVAL, "f16_ppo_epoch16: n_minibatches >= 1");
     DeviceCtx *c;
     f16::LaunchGeom g;
     int rc = prep(a->n, &c, &g);

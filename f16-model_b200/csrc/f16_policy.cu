@@ -1832,6 +1832,44 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
                 float gsum = 0.f;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) gsum += scr[per + k * 64 + t];
+                if (A.bufs && p < A.n_pad) {
+                    // the ranks' mean over NVLink peer memory: the exchange of ppo_reduce_adam_kernel<true> ((value, call) words pushed to every
+                    // rank's buffer, own buffer polled, rows added in rank order), with the same call numbering per 32-parameter block (A.seq), so
+                    // f16_ppo_step16 and f16_ppo_epoch16 calls can be mixed on one set of exchange buffers.  (p >> 5 is warp-uniform.)
+                    const int blk = p >> 5;
+                    const uint32_t call = A.seq[blk] + 1u;
+                    const size_t slot_at = static_cast<size_t>(call & 1u) * A.world * A.n_pad;
+                    const size_t mine = slot_at + static_cast<size_t>(A.rank) * A.n_pad + p;
+                    for (int r = 1; r < A.world; ++r) {
+                        uint2 *to = A.bufs[(A.rank + r) % A.world] + mine;
+                        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(to), "r"(__float_as_uint(gsum)), "r"(call) : "memory");
+                    }
+                    const uint2 *own_buf = A.bufs[A.rank] + slot_at + p;
+                    float rsum = 0.f;
+                    unsigned long long t0 = 0ull;
+                    for (int r = 0; r < A.world; ++r) {
+                        float val = gsum;
+                        if (r != A.rank) {
+                            const uint2 *src = own_buf + static_cast<size_t>(r) * A.n_pad;
+                            uint32_t bits, flag;
+                            for (unsigned spin = 0;; ++spin) {
+                                asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(bits), "=r"(flag) : "l"(src) : "memory");
+                                if (flag == call) break;
+                                if ((spin & 1023u) == 1023u) {   // a rank that never arrives: fail loudly after ~10 s
+                                    unsigned long long now;
+                                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                                    if (t0 == 0ull) t0 = now;
+                                    else if (now - t0 > 10000000000ull) __trap();
+                                }
+                            }
+                            val = __uint_as_float(bits);
+                        }
+                        rsum += val;
+                    }
+                    gsum = rsum * (1.0f / static_cast<float>(A.world));
+                    __syncwarp();
+                    if (lane == 0) A.seq[blk] = call;
+                }
                 scr[c0 + t] = gsum;
             }
             __syncthreads();

@@ -41,7 +41,7 @@ class PPOConfig:
     fused_precision: str = "fp16"        # tensor-core operands of the fused kernel: "fp16" (weight gradients on the tensor cores too) or "tf32"
     fused_optimizer: bool = True         # fused fp16 update: reduction (+ all-reduce) + clip + Adam + blob re-packing in ONE multi-CTA kernel (f16_ppo_step16)
                                          # instead of the reduction kernel followed by the single-CTA optimiser kernel
-    fused_epoch: bool = True             # single rank, fused fp16 update: ALL minibatch steps of an epoch in ONE persistent cooperative kernel (f16_ppo_epoch16:
+    fused_epoch: bool = True             # fused fp16 update (one rank, or ranks with the peer-memory exchange): ALL minibatch steps of an epoch in ONE persistent cooperative kernel (f16_ppo_epoch16:
                                          # the optimiser step is taken inside the gradient kernel, between grid-wide meetings) instead of two launches per minibatch
     peer_allreduce: bool = True          # world > 1, fused fp16 update: the gradient all-reduce rides in the gradient-reduction kernel over NVLink peer
                                          # memory (f16_ppo_grad16_peer) instead of an NCCL call per minibatch; falls back to NCCL when the ranks cannot map each other
@@ -344,7 +344,7 @@ class PPOTrainer:
                     int(bool(cfg.norm_adv)), int(bool(cfg.clip_vloss)))
             peer = self._peer if self._fp16 else None
             if epoch_minibatches:   # every minibatch step of the epoch in ONE persistent cooperative kernel; `mb` is the first minibatch's slice of the permutation
-                assert self._step16 is not None and self.world == 1
+                assert self._step16 is not None and (self.world == 1 or peer is not None)
             if self._step16 is not None and (self.world == 1 or peer is not None):   # gradient kernel + ONE kernel for reduction / all-reduce / clip / Adam / blob scatter
                 a = self._step16
                 (a.n, a.train_blob16, a.obs, a.actions, a.logprobs, a.adv, a.ret, a.val, a.mb_idx, a.logstd, a.adv_stats, a.grad, a.clip_coef,
@@ -479,7 +479,7 @@ class PPOTrainer:
                         _capi.check(_capi.load_library().f16_ppo_adv_stats(
                             self.minibatch_size, len(starts), self._flat["adv"].data_ptr(), self._perm_buf.data_ptr(),
                             self._adv_stats_epoch.data_ptr(), self._adv_scratch_epoch.data_ptr(), _capi.stream_ptr(self.device)))
-                if self._step16 is not None and self.world == 1 and self.cfg.fused_epoch:
+                if self._step16 is not None and (self.world == 1 or self._peer is not None) and self.cfg.fused_epoch:
                     self._fused_minibatch_step(self._perm_buf[: self.minibatch_size], adv_stats=self._adv_stats_epoch[0], epoch_minibatches=len(starts))
                 else:
                     for k, start in enumerate(starts):

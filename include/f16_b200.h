@@ -358,8 +358,9 @@ int f16_ppo_step16(const f16_ppo_step16_args *a, void *stream);
  * counter, each sums the partial gradients of the parameters it owns, the squared-norm shares are exchanged, the owners apply
  * clip_grad_norm_ + Adam(amsgrad) and scatter the new parameters into the three blobs, and every CTA re-reads the training blob.
  * Arguments as f16_ppo_step16 except: mb_idx holds n_minibatches * n indices (minibatch k reads [k n, (k + 1) n)), adv_stats holds
- * n_minibatches (mean, std) pairs, peer must be NULL, and sync points to f16_ppo_epoch16_sync_bytes() bytes of its own (not the
- * buffer f16_ppo_step16 uses; no initialisation needed).  diag, step: as after n_minibatches calls of f16_ppo_step16; grad holds
+ * n_minibatches (mean, std) pairs, and sync points to f16_ppo_epoch16_sync_bytes() bytes of its own (not the buffer f16_ppo_step16
+ * uses; no initialisation needed).  With `peer` the reduction phase also takes the ranks' mean over NVLink peer memory (same buffers,
+ * same call numbering as f16_ppo_step16 / f16_ppo_grad16_peer: the calls can be mixed; every rank must launch the same grid).  diag, step: as after n_minibatches calls of f16_ppo_step16; grad holds
  * the last minibatch's gradient and statistics.  The call replays from a CUDA graph. */
 int f16_ppo_epoch16_sync_bytes(void);
 int f16_ppo_epoch16(const f16_ppo_step16_args *a, int n_minibatches, void *stream);

@@ -142,6 +142,17 @@ def _worker(rank, world, port, out):
         res["nccl_trainer_peer"] = tr_n._peer is not None
         res["peer_vs_nccl_params"] = ((flat_n - flat).norm() / flat.norm()).item()
         tr_n.close()
+        # ... and with two launches per minibatch (f16_ppo_step16 with the peer exchange) instead of the persistent epoch kernel, whose reduction
+        # phase makes the same exchange: same parameters up to the summation order of the gradient norm
+        envs_s = make_sharded_env(CFG, 8192 * world, rank, world, dev, seed=1, fast_math=True)
+        pol_s = f16.TensorCorePolicy(device=dev, seed=1, logstd_init=-1.0, env_id_base=shard_range(8192 * world, rank, world)[0])
+        tr_s = f16.PPOTrainer(envs_s, pol_s, f16.PPOConfig(num_steps=32, num_minibatches=8, update_epochs=4, learning_rate=1e-3, target_kl=0.02,
+                                                           fused_epoch=False))
+        tr_s.train(num_updates=3)
+        flat_s = torch.cat([p.detach().reshape(-1) for p in pol_s.parameters()])
+        res["epoch_vs_step16_params"] = ((flat_s - flat).norm() / flat.norm()).item()
+        res["step16_trainer_peer"] = tr_s._peer is not None
+        tr_s.close()
         dist.destroy_process_group()
         out.put((rank, res))
     except Exception as exc:   # surface the failure instead of a silent timeout
@@ -172,3 +183,4 @@ def test_two_rank_ppo_gradient_allreduce():
         assert res["peer_mapped"] and res["trainer_peer"] and not res["nccl_trainer_peer"], res    # NVLink peer mapping works on a B200 box
         assert res["peer_rel_err"] < 1e-6 and res["peer_ranks_equal"] and res["peer_calls"] == 5 + 1 + 4 * 3, res
         assert res["peer_vs_nccl_params"] < 1e-3, res
+        assert res["step16_trainer_peer"] and res["epoch_vs_step16_params"] < 1e-4, res   # epoch kernel (default) vs two launches per minibatch

@@ -68,18 +68,21 @@ def main():
         ok = torch.tensor([1 if torch.equal(ref, flat) else 0], device=dev)
         torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
         same = bool(ok.item())
+    epoch_kernel = bool(getattr(tr, "_step16", None) is not None and cfg.fused_epoch and tr._update_graph and (world == 1 or tr._peer is not None))
     if rank == 0:
         h = hist[-1]
         print(json.dumps({"config": "4: PPO rollout+update, %d envs/GPU x %d steps, %d GPU(s)" % (args.envs, args.num_steps, world),
                           "rollout_env_steps_per_s": h["rollout_sps"] * world, "rollout_s": h["rollout_s"], "update_s": h["update_s"],
                           "minibatches_per_update": cfg.num_minibatches * cfg.update_epochs, "value_loss": h["value_loss"],
                           "approx_kl": h["approx_kl"],
-                          "grad_allreduce": ((("peer memory (NVLink), inside ppo_reduce_adam_kernel (reduction + all-reduce + clip + Adam + blob scatter in one launch)"
+                          "grad_allreduce": ((("peer memory (NVLink), inside the reduction phase of the persistent epoch kernel (f16_ppo_epoch16)" if epoch_kernel else
+                                               "peer memory (NVLink), inside ppo_reduce_adam_kernel (reduction + all-reduce + clip + Adam + blob scatter in one launch)"
                                                if getattr(tr, "_step16", None) is not None else "peer memory (NVLink), fused into ppo_grad_reduce_peer_kernel")
                                               if tr._peer is not None else "nccl")
                                              + (", captured in the update graph" if tr._update_graph else ", eager")) if world > 1 else None,
                           "update_s_all": [round(x["update_s"], 6) for x in hist],
-                          "optimizer": "fused into the reduction kernel (f16_ppo_step16)" if getattr(tr, "_step16", None) is not None else "ppo_adam_kernel (one CTA)",
+                          "optimizer": ("inside the persistent epoch kernel (f16_ppo_epoch16: one cooperative launch per epoch)" if epoch_kernel else
+                                        "fused into the reduction kernel (f16_ppo_step16)" if getattr(tr, "_step16", None) is not None else "ppo_adam_kernel (one CTA)"),
                           "nccl_allreduce_us_per_call_37KB": allreduce_us,
                           "allreduce_share_of_update": (allreduce_us * cfg.num_minibatches * cfg.update_epochs * 1e-6 / h["update_s"]) if allreduce_us else None,
                           "parameters_identical_on_all_ranks": same}), flush=True)
