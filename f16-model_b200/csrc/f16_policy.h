@@ -112,7 +112,7 @@ struct ReduceAdamArgs {
 };
 size_t ppo_step16_sync_bytes();
 cudaError_t launch_ppo_step16(const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials, ReduceAdamArgs RA, int n_sm, cudaStream_t st);
-// the n_mb minibatch steps of an epoch in ONE persistent cooperative launch (single rank): P.mb_idx holds n_mb * P.n indices, P.adv_stats n_mb
+// the n_mb minibatch steps of an epoch in ONE persistent cooperative launch (RA.bufs set: with the cross-rank exchange in its reduction phase): P.mb_idx holds n_mb * P.n indices, P.adv_stats n_mb
 // pairs; RA.sync: ppo_epoch16_sync_bytes() bytes of its own (the launcher zeroes the meeting counter)
 size_t ppo_epoch16_sync_bytes();
 cudaError_t launch_ppo_epoch16(const PpoGradArgs &P, const TrainBlob16 *blob16, float *partials, ReduceAdamArgs RA, int n_mb, int n_sm, cudaStream_t st);
