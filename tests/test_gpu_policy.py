@@ -408,13 +408,13 @@ def test_fused_step16_equals_gradient_then_adam(f16):
     assert torch.isfinite(a._diag).all() and abs(a._diag[5].item() - (pol.actor_logstd.item() + 1.4189385332046727)) < 1e-6
 
 
-@pytest.mark.parametrize("n_envs,num_minibatches", [(4096, 4), (512, 8), (32768, 2)])
+@pytest.mark.parametrize("n_envs,num_minibatches", [(4096, 4), (512, 8), (520, 8), (32768, 2)])
 def test_fused_epoch16_equals_step16_per_minibatch(f16, n_envs, num_minibatches):
     """f16_ppo_epoch16 (ALL minibatch steps of an epoch in one persistent cooperative kernel, the optimiser step taken inside it between
     grid-wide meetings) against f16_ppo_step16 called once per minibatch on the same minibatches: the same gradients (same kernel code,
     same reduction order), parameters / Adam state equal up to the summation order of the gradient norm, the same diagnostics, and
     every blob word equal to a fresh packing of the final parameters.  Grids of 128 CTAs (two 64-parameter passes per CTA), 8 CTAs
-    (a CTA owns more than 512 parameters) and 148 CTAs (the production shape)."""
+    (a CTA owns more than 512 parameters; with 520 envs the minibatch is 1040 rows: a ragged last tile) and 148 CTAs (the production shape)."""
     from f16_model_b200.policy import pack_policy_blob, pack_train_blob16
 
     cfg = {"dt": 0.01, "tn": 10, "debug_state": False, "determenistic_ref": False, "scenario": "combo"}
