@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--tf32-update", type=int, default=0)
     ap.add_argument("--peer", type=int, default=1, help="0: NCCL gradient all-reduce instead of the peer-memory one fused into the reduction kernel")
     ap.add_argument("--only-ppo", action="store_true")
+    ap.add_argument("--learn-fused", type=int, default=1, help="0: torch autograd update in the learning run (comparison curve)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -140,10 +141,11 @@ def main():
         envs = f16.F16VecEnv(det, 4096, device=dev, seed=3, fast_math=True)
         pol = f16.TensorCorePolicy(device=dev, seed=3, logstd_init=-1.0)
         tr = f16.PPOTrainer(envs, pol, f16.PPOConfig(num_steps=250, num_minibatches=16, update_epochs=5, learning_rate=1e-3,
-                                                      clip_coef=0.2, anneal_lr=False))
+                                                      clip_coef=0.2, anneal_lr=False, fused_update=bool(args.learn_fused)))
         hist = tr.train(num_updates=args.learn_updates)
         curve = [round(h["mean_step_reward"], 4) for h in hist]
-        print(json.dumps({"ppo_learning": "4096 envs x 250 steps per update, det. combo reference", "mean_step_reward_per_update": curve,
+        print(json.dumps({"ppo_learning": "4096 envs x 250 steps per update, det. combo reference", "update": "fused kernels (f16_ppo_epoch16)" if args.learn_fused else "torch autograd",
+                          "update_s_last": hist[-1]["update_s"], "mean_step_reward_per_update": curve,
                           "explained_variance_last": hist[-1]["explained_variance"]}), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
