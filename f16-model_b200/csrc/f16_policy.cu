@@ -1200,6 +1200,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad16_kernel(const PpoGradAr
 // token -- slot 0's S3 batch of pair j, then slot 1's, then slot 0's of pair j + 1 ... and the same for the S4 batches -- which
 // keeps the accumulation order, and with it every bit of the gradient, fixed, and makes slot 1 trail slot 0 by a fraction of a tile.
 // 128 registers per thread (ppo_grad16_kernel: 226): a thread carries one slot, and the gathered row of its next tile only across S4.
+// H2 is held as packed halves, dZ2 / dZ1 are computed in packed-half arithmetic (they are fp16 tensor-core operands), dW3 goes through a
+// half2 shuffle butterfly, and the biases ride in the MMAs (hi + lo fp16 split against two columns of ones, as in rollout_kernel).
 // ---------------------------------------------------------------------------
 constexpr int kThreadsW = 512;
 
@@ -1236,7 +1238,8 @@ __device__ unsigned long long g_epoch_trace[4][12];   // [CTA 0 / last CTA][thre
 // clip_grad_norm_ + Adam(amsgrad) and scatter the new parameters into the three weight blobs (as ppo_reduce_adam_kernel does), and
 // after a third meeting every CTA re-reads the fp16 training blob from L2.  Per minibatch this replaces a kernel boundary, the
 // 289-CTA optimiser launch, the next gradient launch's prologue (TMEM allocation, barrier set-up, weight TMA) and the drain / fill
-// of the SMs around them; the first rows of the next minibatch are gathered under the optimiser step.
+// of the SMs around them; the gather pipeline numbers its rounds through the whole launch, so the first rows of the next minibatch
+// travel under the last rounds of this one.  With A.bufs the reduction phase also takes the ranks' mean over NVLink peer memory.
 template <bool EPOCH>
 __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGradArgs P, const TrainBlob16 *blob16, float *partials, const ReduceAdamArgs A,
                                                                    const int n_mb)
