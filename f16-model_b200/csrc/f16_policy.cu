@@ -709,6 +709,7 @@ struct alignas(16) TrainSmem16 {
     int64_t next_idx[2][kThreads];    // minibatch indices of the NEXT pair's rows [slot][thread] (-1: dead row)
     uint64_t bar_w;
     uint64_t bar_mma[2];
+    uint64_t bar_mma2[2];             // ppo_grad16w_kernel: the slot's dW2 | db2 MMAs have completed (its dZ2 / H1 operands may be overwritten)
     uint32_t tmem_base;
     float red[16];
     // ppo_grad16w_kernel: the biases ride in the MMAs, as in rollout_kernel: b = hi + lo in fp16 against two columns of ones (layer 1: X columns
@@ -1256,6 +1257,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
         mbar_init(&sm->bar_w, 1);
         mbar_init(&sm->bar_mma[0], 1);
         mbar_init(&sm->bar_mma[1], 1);
+        mbar_init(&sm->bar_mma2[0], 1);
+        mbar_init(&sm->bar_mma2[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {   // all 512 TMEM columns, as in ppo_grad16_kernel
@@ -1324,23 +1327,24 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
     // load right where it was issued (ncu: the top long-scoreboard stall of the kernel), and the gather no longer travels under S4.
     struct RowIn { float4 lo, hi; float2 rv; };
     auto load_row = [&](int64_t src) {
+        // No zero-initialisation and no `src >= 0` guard around the loads: a value that is either loaded or zero is a predicated move behind the
+        // load, and the thread then waits for the gather where the move sits (ncu: the first instruction of S4).  A dead row (src < 0) gathers
+        // row 0 instead; nothing reads what it parks (S1 and S3 mask dead rows themselves).  Only the fields of the thread's own half are set.
         RowIn g;
-        g.lo = make_float4(0.f, 0.f, 0.f, 0.f), g.hi = make_float4(0.f, 0.f, 0.f, 0.f), g.rv = make_float2(0.f, 0.f);
-        if (src >= 0) {
-            if (P.packed) {            // one aligned 32-byte sector (half 0) / 8 bytes (half 1) per thread
-                if (half == 0) {
-                    const float4 *r = reinterpret_cast<const float4 *>(P.obs + src * 8);
-                    g.lo = __ldg(r), g.hi = __ldg(r + 1);
-                } else {
-                    g.rv = __ldg(reinterpret_cast<const float2 *>(P.ret + src * 2));
-                }
-            } else if (half == 0) {
-                const float *o = P.obs + src * 5;
-                g.lo = make_float4(o[0], o[1], o[2], o[3]);
-                g.hi = make_float4(o[4], P.actions[src], P.logprobs[src], P.adv[src]);
+        const int64_t row_ = src >= 0 ? src : 0;
+        if (P.packed) {            // one aligned 32-byte sector (half 0) / 8 bytes (half 1) per thread
+            if (half == 0) {
+                const float4 *r = reinterpret_cast<const float4 *>(P.obs + row_ * 8);
+                g.lo = __ldg(r), g.hi = __ldg(r + 1);
             } else {
-                g.rv = make_float2(P.ret[src], P.val[src]);
+                g.rv = __ldg(reinterpret_cast<const float2 *>(P.ret + row_ * 2));
             }
+        } else if (half == 0) {
+            const float *o = P.obs + row_ * 5;
+            g.lo = make_float4(o[0], o[1], o[2], o[3]);
+            g.hi = make_float4(o[4], P.actions[row_], P.logprobs[row_], P.adv[row_]);
+        } else {
+            g.rv = make_float2(P.ret[row_], P.val[row_]);
         }
         return g;
     };
@@ -1633,6 +1637,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
                 for (int k = 0; k < 4; ++k)
                     umma_f16(tcol + 64, umma_desc(d2u + (8 + k * 2) * kLboH, kLboH, 128), umma_desc(w2tc + k * 2 * kHid * 16, kHid * 16, 128), id_l2,
                              k > 0 ? 1u : 0u);
+                umma_commit(bar);   // S4's arithmetic starts on D3; its stores into d2 wait for the weight-gradient MMAs below (bar_mma2)
 #pragma unroll
                 for (int k = 0; k < 8; ++k)   // dW2 += dZ2^T * H1: the same buffers read MN-major (features x rows), 16 rows per MMA
                     umma_f16(tmem + 256, umma_desc(d2u + k * 256, 128, kLboH), umma_desc(a2u + k * 256, 128, kLboH), id_w2, (first && k == 0) ? 0u : 1u);
@@ -1640,7 +1645,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
                 for (int k = 0; k < 8; ++k)   // db2 += dZ2^T * [X | 1]
                     umma_f16(tmem + 400, umma_desc(d2u + k * 256, 128, kLboH), umma_desc(a1u + k * 256, 128, kRows * 16), id_w1,
                              (first && k == 0) ? 0u : 1u);
-                umma_commit(bar);
+                umma_commit(&sm->bar_mma2[s]);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             }
             __syncwarp();
@@ -1660,9 +1665,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
         WTRACE(7);
         {
             uint32_t ra[32], rb[32];
+            uint4 gq[8];   // the thread's 64 columns of dZ1 as packed halves
             tmem_ld32_issue(lane_base, ra);
             tmem_ld32_issue(lane_base + 32, rb);
             tmem_wait_ld();
+            const __half2 one2 = __float2half2_rn(1.0f);
 #pragma unroll
             for (int blk = 0; blk < 2; ++blk) {
                 const int col0 = half * 64 + blk * 32;
@@ -1671,18 +1678,25 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
                     const int jj = col0 + c * 8;
                     const uint4 raw = *reinterpret_cast<const uint4 *>(a2p + (jj >> 3) * kLboH + row * 16u);
                     const __half2 *hh = reinterpret_cast<const __half2 *>(&raw);
-                    uint4 gq;   // packed-half arithmetic, as in S3: D3 -> fp16, times (1 - h^2)
-                    __half2 *gp = reinterpret_cast<__half2 *>(&gq);
-                    const __half2 one2 = __float2half2_rn(1.0f);
+                    __half2 *gp = reinterpret_cast<__half2 *>(&gq[blk * 4 + c]);   // packed-half arithmetic, as in S3: D3 -> fp16, times (1 - h^2)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const __half2 d = __floats2half2_rn(__uint_as_float(blk ? rb[c * 8 + 2 * q] : ra[c * 8 + 2 * q]),
                                                             __uint_as_float(blk ? rb[c * 8 + 2 * q + 1] : ra[c * 8 + 2 * q + 1]));
                         gp[q] = __hmul2(d, __hfma2(__hneg2(hh[q]), hh[q], one2));
                     }
-                    *reinterpret_cast<uint4 *>(d2p + (jj >> 3) * kLboH + row * 16u) = gq;
                 }
             }
+            // dZ1 overwrites dZ2, which the slot's dW2 | db2 MMAs (issued behind D3 in the same batch) are still reading: they were given the time of
+            // the arithmetic above; now they must have completed
+            mbar_wait(&sm->bar_mma2[s], round & 1u);
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int jj = half * 64 + blk * 32 + c * 8;
+                    *reinterpret_cast<uint4 *>(d2p + (jj >> 3) * kLboH + row * 16u) = gq[blk * 4 + c];
+                }
         }
         park_row(sm->stage[(round & 1u) ^ 1u][s][tg], nr);
         sm->next_idx[s][tg] = ni;
