@@ -1296,16 +1296,21 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
     const unsigned stride = gridDim.x;
     const unsigned n_iter = (n_tiles - blockIdx.x + 2 * stride - 1) / (2 * stride);
     const unsigned tile0 = blockIdx.x + s * stride;
-    const unsigned n_rounds = n_iter * static_cast<unsigned>(n_mb);
-    auto index_addr = [&](unsigned r, bool &ok) -> const int64_t * {   // where the index of this thread's row in round r lives
-        const unsigned mb_ = r / n_iter, tile_ = tile0 + 2 * stride * (r - mb_ * n_iter);
+    // where the index of this thread's row in tile round jj of minibatch mb_ lives; jj may run up to n_iter + 1 (two rounds ahead of the last
+    // round of a minibatch): it is carried into the following minibatch(es) without a division
+    auto index_addr = [&](unsigned mb_, unsigned jj, bool &ok) -> const int64_t * {
+        if (jj >= n_iter) {
+            jj -= n_iter, ++mb_;
+            if (jj >= n_iter) jj -= n_iter, ++mb_;
+        }
+        const unsigned tile_ = tile0 + 2 * stride * jj;
         const unsigned i_ = tile_ * kRows + row;
-        ok = r < n_rounds && tile_ < n_tiles && i_ < n;
+        ok = mb_ < static_cast<unsigned>(n_mb) && tile_ < n_tiles && i_ < n;
         return P.mb_idx + static_cast<size_t>(mb_) * n + i_;
     };
-    auto load_index = [&](unsigned r) -> int64_t {
+    auto load_index = [&](unsigned mb_, unsigned jj) -> int64_t {
         bool ok;
-        const int64_t *a = index_addr(r, ok);
+        const int64_t *a = index_addr(mb_, jj, ok);
         return ok ? *a : int64_t(-1);
     };
     // L2 prefetches one round ahead of the gathers (fire and forget: unlike a load they are not waited for by the fences that end every
@@ -1317,9 +1322,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
             asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
         }
     };
-    auto prefetch_index = [&](unsigned r) {
+    auto prefetch_index = [&](unsigned mb_, unsigned jj) {
         bool ok;
-        const int64_t *a = index_addr(r, ok);
+        const int64_t *a = index_addr(mb_, jj, ok);
         if (ok && (tg & 15u) == 0u && tg < 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
     };
     // A gathered row: (x[0..3]), (x[4], a, b, c) for the actor half's thread, (ret, val) for the critic half's.  The two halves' loads stay
@@ -1358,8 +1363,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
     };
 
     // first round's row and second round's indices: requested BEFORE the grid dependency resolves (see ppo_grad16_kernel)
-    park_row(sm->stage[0][s][tg], load_row(load_index(0)));
-    sm->next_idx[s][tg] = load_index(1);
+    park_row(sm->stage[0][s][tg], load_row(load_index(0, 0)));
+    sm->next_idx[s][tg] = load_index(0, 1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (t == 0) {
@@ -1434,7 +1439,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
         const bool live = tile < n_tiles && tile * kRows + row < n;
         const bool first = s == 0 && j == 0;   // this tile's batches initialise the weight-gradient accumulators
         prefetch_row(sm->next_idx[s][tg]);
-        prefetch_index(round + 2);
+        prefetch_index(static_cast<unsigned>(mbi), j + 2);
         if (j) {   // the slot's operands are rewritten below: its last batch (dW1) must have completed
             mbar_wait(bar, 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1658,7 +1663,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) ppo_grad16w_kernel(const PpoGrad
         // the next tile's row (index fetched one round ago) and the index of the tile after it travel under S4 -- every stage ends with
         // fence.proxy.async, which waits for the thread's outstanding loads, and S3 has no registers to spare -- and are parked before its fence
         const RowIn nr = load_row(sm->next_idx[s][tg]);
-        const int64_t ni = load_index(round + 2);
+        const int64_t ni = load_index(static_cast<unsigned>(mbi), j + 2);
         // ---- S4: n * dZ1 = D3 * (1 - H1^2) -> d2 (every MMA that read dZ2 has completed); issue dW1 | db1 += dZ1^T [X | 1] ----
         mbar_wait(bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
